@@ -1,0 +1,120 @@
+// Bit reader over an RBSP (emulation-prevention bytes already removed by the host) and the
+// CABAC arithmetic decoding engine (H.264 clause 9.3.3.2).  Single-lane code: one lane of a
+// warp owns a slice.
+#pragma once
+#include "hd.h"
+#include "tables_gen.h"
+
+namespace hwb {
+
+struct BitReader {
+  const uint8_t *base;
+  uint32_t size;     // bytes
+  uint32_t pos;      // next byte to load into the cache
+  uint64_t cache;    // left-aligned: next bit is bit 63
+  int32_t avail;     // valid bits in cache
+  bool overrun;
+};
+
+HWB_HD void br_refill(BitReader &b) {
+  while (b.avail <= 56) {
+    uint64_t v = b.pos < b.size ? b.base[b.pos] : 0;
+    if (b.pos >= b.size + 8) b.overrun = true;
+    b.pos++;
+    b.cache |= v << (56 - b.avail);
+    b.avail += 8;
+  }
+}
+HWB_HD void br_init(BitReader &b, const uint8_t *p, uint32_t size, uint32_t bit_off) {
+  b.base = p; b.size = size; b.pos = bit_off >> 3; b.cache = 0; b.avail = 0; b.overrun = false;
+  br_refill(b);
+  b.cache <<= (bit_off & 7); b.avail -= (bit_off & 7);
+}
+HWB_HD uint32_t br_bitpos(const BitReader &b) { return b.pos * 8 - b.avail; }
+HWB_HD uint32_t br_peek(BitReader &b, int n) {  // n in 1..32
+  if (b.avail < n) br_refill(b);
+  return (uint32_t)(b.cache >> (64 - n));
+}
+HWB_HD void br_skip(BitReader &b, int n) { b.cache <<= n; b.avail -= n; }
+HWB_HD uint32_t br_get(BitReader &b, int n) {
+  if (n == 0) return 0;
+  uint32_t v = br_peek(b, n);
+  br_skip(b, n);
+  return v;
+}
+HWB_HD uint32_t br_get1(BitReader &b) { return br_get(b, 1); }
+HWB_HD uint32_t br_ue(BitReader &b) {
+  uint32_t v = br_peek(b, 32);
+  int lz = clz32(v);
+  if (lz >= 32) { br_skip(b, 32); b.overrun = true; return 0; }
+  br_skip(b, lz);
+  uint32_t r = br_get(b, lz + 1);
+  return r - 1;
+}
+HWB_HD int32_t br_se(BitReader &b) {
+  uint32_t k = br_ue(b);
+  return (k & 1) ? (int32_t)((k + 1) >> 1) : -(int32_t)(k >> 1);
+}
+HWB_HD void br_align(BitReader &b) { br_skip(b, b.avail & 7); }
+// more_rbsp_data(): true unless only the rbsp trailing bits (1 followed by zeros) remain.
+HWB_HD bool br_more_rbsp_data(BitReader &b, uint32_t last_one_bitpos) { return br_bitpos(b) < last_one_bitpos; }
+
+// ------------------------------------------------------------------------------------ CABAC
+struct Cabac {
+  uint32_t range;   // codIRange (9 bits)
+  uint32_t offset;  // codIOffset (9 bits)
+};
+
+HWB_HD void cabac_start(Cabac &c, BitReader &b) {
+  c.range = 510;
+  c.offset = br_get(b, 9);
+}
+
+HWB_HD void cabac_init_states(uint8_t *st, int table, int slice_qp) {
+  const int8_t *mn = cabac_init_mn + table * HWB_CABAC_NCTX * 2;
+  int qp = clip3(0, 51, slice_qp);
+  for (int i = 0; i < HWB_CABAC_NCTX; ++i) {
+    int pre = clip3(1, 126, ((mn[2 * i] * qp) >> 4) + mn[2 * i + 1]);
+    st[i] = pre <= 63 ? (uint8_t)((63 - pre) << 1) : (uint8_t)(((pre - 64) << 1) | 1);
+  }
+}
+
+HWB_HD int cabac_decision(Cabac &c, BitReader &b, uint8_t *state) {
+  uint32_t s = *state;
+  uint32_t p = s >> 1, mps = s & 1;
+  uint32_t rlps = cabac_range_lps[p * 4 + ((c.range >> 6) & 3)];
+  c.range -= rlps;
+  int bin;
+  if (c.offset >= c.range) {
+    bin = (int)(mps ^ 1);
+    c.offset -= c.range;
+    c.range = rlps;
+    if (p == 0) mps ^= 1;
+    *state = (uint8_t)((cabac_trans_lps[p] << 1) | mps);
+  } else {
+    bin = (int)mps;
+    *state = (uint8_t)(((p < 62 ? p + 1 : p) << 1) | mps);
+  }
+  if (c.range < 256) {
+    int sh = clz32(c.range) - 23;
+    c.range <<= sh;
+    c.offset = (c.offset << sh) | br_get(b, sh);
+  }
+  return bin;
+}
+HWB_HD int cabac_bypass(Cabac &c, BitReader &b) {
+  c.offset = (c.offset << 1) | br_get(b, 1);
+  if (c.offset >= c.range) { c.offset -= c.range; return 1; }
+  return 0;
+}
+HWB_HD int cabac_terminate(Cabac &c, BitReader &b) {
+  c.range -= 2;
+  if (c.offset >= c.range) return 1;
+  if (c.range < 256) {
+    c.range <<= 1;
+    c.offset = (c.offset << 1) | br_get(b, 1);
+  }
+  return 0;
+}
+
+}  // namespace hwb

@@ -1,0 +1,1017 @@
+// Slice-data entropy decoding (H.264 clauses 7.3.4-7.3.5, 9.1 Exp-Golomb, 9.2 CAVLC, 9.3 CABAC)
+// and motion-vector derivation (8.4.1, including P_Skip and B direct prediction).
+// One lane owns one slice and walks its macroblocks in raster order; slices of every picture of
+// the chunk are decoded concurrently (entropy decoding needs no pixels).  Output: MbInfo records,
+// coefficient slots, final motion vectors / reference indices per 4x4 / 8x8 block.
+#pragma once
+#include "bits.h"
+#include "ir.h"
+#include "tables_gen.h"
+
+namespace hwb {
+
+enum { NBF_INTRA = 1, NBF_IPCM = 2, NBF_SKIP = 4, NBF_DIRECT16 = 8, NBF_T8 = 16, NBF_I16 = 32, NBF_INXN = 64 };
+enum { REF_UNAVAIL = -2, REF_NONE = -1 };
+
+// What the right / bottom neighbours need to know about a decoded macroblock.
+struct alignas(16) NbCtx {
+  uint8_t flags, cbp, cmode, dirmask;
+  uint32_t cbf;
+  uint8_t nnz_b[4], nnz_r[4];
+  uint8_t cnnz_b[2][2], cnnz_r[2][2];
+  int8_t imode_b[4], imode_r[4];
+  int8_t ref_b[2][4], ref_r[2][4];
+  int16_t mv_b[2][4][2], mv_r[2][4][2];
+  uint8_t mvd_b[2][4][2], mvd_r[2][4][2];
+};
+static_assert(sizeof(NbCtx) == 144, "NbCtx layout");
+
+#define HWB_CI(bx, by) (((by) + 1) * 6 + (bx) + 1)
+
+struct SliceDec {
+  const ChunkCtx *c;
+  const PicDesc *pd;
+  const SliceDesc *sd;
+  int slice_num;  // inside picture
+  BitReader br;
+  Cabac cab;
+  uint8_t *st;  // CABAC context states
+  bool cabac;
+  uint32_t stop_bitpos;
+  int qp;
+  int last_dqp;
+  NbCtx left, topleft;
+  NbCtx *line;  // [mb_w] top context
+  uint32_t coef_next;  // next free slot in the picture arena
+  // ---- current macroblock
+  int mbx, mby, mbaddr;
+  bool availA, availB, availC, availD;
+  int8_t ref_cache[2][30];
+  int16_t mv_cache[2][30][2];
+  uint8_t mvd_cache[2][30][2];
+  uint8_t dir_cache[30];
+  uint8_t nz_cache[30];      // luma total_coeff / coded flag; 0x80 = unavailable
+  uint8_t cnz_cache[2][12];  // chroma 3x4 layouts (by+1)*4 + bx+1 ... only [..][<9] used
+  int8_t im_cache[30];
+  int16_t coef[64];  // staging for one block
+  MbInfo out;
+  int error;
+};
+
+HWB_HD void sd_fail(SliceDec &s, int code) { if (!s.error) s.error = code; }
+
+// ================================================================================ neighbour caches
+HWB_HD void fill_caches(SliceDec &s, bool cur_intra_for_cbf_unused) {
+  (void)cur_intra_for_cbf_unused;
+  const bool B = s.sd->slice_type == SLICE_B;
+  const int nl = B ? 2 : 1;
+  const NbCtx &L = s.left, &T = s.line[s.mbx], &TL = s.topleft;
+  const NbCtx *TRp = s.availC ? &s.line[s.mbx + 1] : nullptr;
+  for (int i = 0; i < 30; ++i) { s.nz_cache[i] = 0x80; s.im_cache[i] = -1; s.dir_cache[i] = 0; }
+  for (int p = 0; p < 2; ++p) for (int i = 0; i < 12; ++i) s.cnz_cache[p][i] = 0x80;
+  for (int l = 0; l < nl; ++l)
+    for (int i = 0; i < 30; ++i) { s.ref_cache[l][i] = REF_UNAVAIL; s.mv_cache[l][i][0] = s.mv_cache[l][i][1] = 0; s.mvd_cache[l][i][0] = s.mvd_cache[l][i][1] = 0; }
+  const bool cip = s.pd->constrained_intra_pred != 0;
+  if (s.availA) {
+    for (int y = 0; y < 4; ++y) {
+      int ci = HWB_CI(-1, y);
+      s.nz_cache[ci] = L.nnz_r[y];
+      s.im_cache[ci] = (L.flags & NBF_INXN) ? L.imode_r[y] : ((cip && !(L.flags & NBF_INTRA)) ? -1 : 2);
+      s.dir_cache[ci] = (L.dirmask >> (4 + y)) & 1;
+      for (int l = 0; l < nl; ++l) {
+        s.ref_cache[l][ci] = L.ref_r[l][y];
+        s.mv_cache[l][ci][0] = L.mv_r[l][y][0]; s.mv_cache[l][ci][1] = L.mv_r[l][y][1];
+        s.mvd_cache[l][ci][0] = L.mvd_r[l][y][0]; s.mvd_cache[l][ci][1] = L.mvd_r[l][y][1];
+      }
+    }
+    for (int p = 0; p < 2; ++p) for (int y = 0; y < 2; ++y) s.cnz_cache[p][(y + 1) * 4] = L.cnnz_r[p][y];
+  }
+  if (s.availB) {
+    for (int x = 0; x < 4; ++x) {
+      int ci = HWB_CI(x, -1);
+      s.nz_cache[ci] = T.nnz_b[x];
+      s.im_cache[ci] = (T.flags & NBF_INXN) ? T.imode_b[x] : ((cip && !(T.flags & NBF_INTRA)) ? -1 : 2);
+      s.dir_cache[ci] = (T.dirmask >> x) & 1;
+      for (int l = 0; l < nl; ++l) {
+        s.ref_cache[l][ci] = T.ref_b[l][x];
+        s.mv_cache[l][ci][0] = T.mv_b[l][x][0]; s.mv_cache[l][ci][1] = T.mv_b[l][x][1];
+        s.mvd_cache[l][ci][0] = T.mvd_b[l][x][0]; s.mvd_cache[l][ci][1] = T.mvd_b[l][x][1];
+      }
+    }
+    for (int p = 0; p < 2; ++p) for (int x = 0; x < 2; ++x) s.cnz_cache[p][x + 1] = T.cnnz_b[p][x];
+  }
+  if (TRp) {
+    int ci = HWB_CI(4, -1);
+    for (int l = 0; l < nl; ++l) { s.ref_cache[l][ci] = TRp->ref_b[l][0]; s.mv_cache[l][ci][0] = TRp->mv_b[l][0][0]; s.mv_cache[l][ci][1] = TRp->mv_b[l][0][1]; }
+  }
+  if (s.availD) {
+    int ci = HWB_CI(-1, -1);
+    for (int l = 0; l < nl; ++l) { s.ref_cache[l][ci] = TL.ref_b[l][3]; s.mv_cache[l][ci][0] = TL.mv_b[l][3][0]; s.mv_cache[l][ci][1] = TL.mv_b[l][3][1]; }
+  }
+}
+
+// ================================================================================ MV prediction
+struct MvRef { int ref; int mx, my; };
+HWB_HD MvRef mv_at(const SliceDec &s, int l, int bx, int by) {
+  int ci = HWB_CI(bx, by);
+  MvRef r; r.ref = s.ref_cache[l][ci]; r.mx = s.mv_cache[l][ci][0]; r.my = s.mv_cache[l][ci][1];
+  return r;
+}
+// Median / directional prediction for the partition whose top-left 4x4 block is (bx,by), width w
+// (in 4x4 units).  shape: 0 = general (median), 1 = 16x8 upper, 2 = 16x8 lower, 3 = 8x16 left, 4 = 8x16 right.
+HWB_HD void pred_mv(const SliceDec &s, int l, int bx, int by, int w, int ref, int shape, int &px, int &py) {
+  MvRef A = mv_at(s, l, bx - 1, by), Bn = mv_at(s, l, bx, by - 1), C = mv_at(s, l, bx + w, by - 1);
+  if (C.ref == REF_UNAVAIL) C = mv_at(s, l, bx - 1, by - 1);
+  if (shape == 1 && Bn.ref == ref) { px = Bn.mx; py = Bn.my; return; }
+  if (shape == 2 && A.ref == ref) { px = A.mx; py = A.my; return; }
+  if (shape == 3 && A.ref == ref) { px = A.mx; py = A.my; return; }
+  if (shape == 4 && C.ref == ref) { px = C.mx; py = C.my; return; }
+  int n = (A.ref == ref) + (Bn.ref == ref) + (C.ref == ref);
+  if (n == 1) {
+    const MvRef &m = A.ref == ref ? A : (Bn.ref == ref ? Bn : C);
+    px = m.mx; py = m.my;
+  } else if (n == 0 && Bn.ref == REF_UNAVAIL && C.ref == REF_UNAVAIL && A.ref != REF_UNAVAIL) {
+    px = A.mx; py = A.my;
+  } else {
+    px = median3(A.mx, Bn.mx, C.mx); py = median3(A.my, Bn.my, C.my);
+  }
+}
+HWB_HD void set_motion(SliceDec &s, int l, int bx, int by, int w, int h, int ref, int mx, int my, int amvdx, int amvdy) {
+  for (int y = by; y < by + h; ++y)
+    for (int x = bx; x < bx + w; ++x) {
+      int ci = HWB_CI(x, y);
+      s.ref_cache[l][ci] = (int8_t)ref;
+      s.mv_cache[l][ci][0] = (int16_t)mx; s.mv_cache[l][ci][1] = (int16_t)my;
+      s.mvd_cache[l][ci][0] = (uint8_t)amvdx; s.mvd_cache[l][ci][1] = (uint8_t)amvdy;
+    }
+}
+
+// ================================================================================ B direct prediction
+// Block until macroblock `mbaddr` of picture `colpic` has final motion data (its slice has
+// published progress beyond it).  Slices take tickets in decode order, so the producer is always
+// resident or finished: no deadlock.
+HWB_HD void wait_col_mb(const SliceDec &s, int colpic, int mbaddr) {
+#if HWB_DEVICE_BUILD
+  const PicDesc &cp = s.c->pics[colpic];
+  int k = cp.first_slice;
+  for (int i = 1; i < cp.num_slices; ++i) if (s.c->slices[cp.first_slice + i].first_mb <= mbaddr) k = cp.first_slice + i;
+  volatile int32_t *p = s.c->entropy_prog + k;
+  while (*p <= mbaddr) { __nanosleep(200); }
+  __threadfence();
+#else
+  (void)s; (void)colpic; (void)mbaddr;
+#endif
+}
+HWB_HD int minpos(int a, int b) { return (a >= 0 && b >= 0) ? (a < b ? a : b) : (a > b ? a : b); }
+
+// Fills dref[2][4] / dmv[2][16][2] (raster 4x4) for the quadrants in `qmask`.
+HWB_FN void direct_predict(SliceDec &s, int qmask, int8_t dref[2][4], int16_t dmv[2][16][2]) {
+  const ChunkCtx &c = *s.c;
+  const SliceDesc &sd = *s.sd;
+  const int colf = sd.ref_frame[1][0];
+  wait_col_mb(s, colf, s.mbaddr);
+  const bool col_intra = ld_u8_cg(&pic_mbinfo(c, colf)[s.mbaddr].mbtype) != MB_INTER;
+  const bool col_has_l1 = c.pics[colf].has_inter == 2;
+  const int8_t *cr0 = pic_refidx(c, colf, 0) + (uint64_t)s.mbaddr * 4, *cr1 = pic_refidx(c, colf, 1) + (uint64_t)s.mbaddr * 4;
+  const int16_t *cp0 = pic_refpic(c, colf, 0) + (uint64_t)s.mbaddr * 4, *cp1 = pic_refpic(c, colf, 1) + (uint64_t)s.mbaddr * 4;
+  const int16_t *cm0 = pic_mv(c, colf, 0) + (uint64_t)s.mbaddr * 32, *cm1 = pic_mv(c, colf, 1) + (uint64_t)s.mbaddr * 32;
+  const bool inf8 = s.pd->direct_8x8_inference != 0;
+  int ref[2] = {0, 0}, pmx[2] = {0, 0}, pmy[2] = {0, 0};
+  if (sd.direct_spatial) {
+    for (int l = 0; l < 2; ++l) {
+      MvRef A = mv_at(s, l, -1, 0), Bn = mv_at(s, l, 0, -1), C = mv_at(s, l, 4, -1);
+      if (C.ref == REF_UNAVAIL) C = mv_at(s, l, -1, -1);
+      // MinPositive chain; unavailable (-2) and unused (-1) both count as negative
+      int r = minpos(A.ref, minpos(Bn.ref, C.ref));
+      ref[l] = r < 0 ? -1 : r;
+    }
+    if (ref[0] < 0 && ref[1] < 0) { ref[0] = ref[1] = 0; }
+    else {
+      for (int l = 0; l < 2; ++l)
+        if (ref[l] >= 0) pred_mv(s, l, 0, 0, 4, ref[l], 0, pmx[l], pmy[l]);
+    }
+  }
+  const bool l1_short = !((sd.ref_long[1] >> 0) & 1);
+  for (int q = 0; q < 4; ++q) {
+    if (!((qmask >> q) & 1)) continue;
+    for (int k = 0; k < 4; ++k) {
+      int bx = (q & 1) * 2 + (k & 1), by = (q >> 1) * 2 + (k >> 1);
+      int cbx = bx, cby = by;
+      if (inf8) { cbx = (q & 1) * 3; cby = (q >> 1) * 3; }
+      int cq = (cby >> 1) * 2 + (cbx >> 1), cbr = cby * 4 + cbx;
+      int refcol = -1, colpicref = -1, cmx = 0, cmy = 0;
+      if (!col_intra) {
+        int rc0 = ld_i8_cg(cr0 + cq);
+        if (rc0 >= 0) { refcol = rc0; colpicref = ld_i16_cg(cp0 + cq); cmx = ld_i16_cg(cm0 + cbr * 2); cmy = ld_i16_cg(cm0 + cbr * 2 + 1); }
+        else if (col_has_l1) { refcol = ld_i8_cg(cr1 + cq); colpicref = ld_i16_cg(cp1 + cq); cmx = ld_i16_cg(cm1 + cbr * 2); cmy = ld_i16_cg(cm1 + cbr * 2 + 1); }
+      }
+      int br = by * 4 + bx;
+      if (sd.direct_spatial) {
+        bool colzero = l1_short && refcol == 0 && cmx >= -1 && cmx <= 1 && cmy >= -1 && cmy <= 1;
+        for (int l = 0; l < 2; ++l) {
+          dref[l][q] = (int8_t)ref[l];
+          bool z = ref[l] < 0 || (ref[l] == 0 && colzero);
+          dmv[l][br][0] = (int16_t)(z ? 0 : pmx[l]); dmv[l][br][1] = (int16_t)(z ? 0 : pmy[l]);
+        }
+      } else {
+        int r0 = 0;
+        if (refcol >= 0) {
+          r0 = 0;
+          for (int i = 0; i < sd.num_ref[0]; ++i) if (sd.ref_frame[0][i] == colpicref) { r0 = i; break; }
+        }
+        dref[0][q] = (int8_t)r0; dref[1][q] = 0;
+        int poc0 = sd.ref_poc[0][r0], poc1 = sd.ref_poc[1][0];
+        int tb = clip3(-128, 127, s.pd->poc - poc0), td = clip3(-128, 127, poc1 - poc0);
+        if (((sd.ref_long[0] >> r0) & 1) || td == 0) {
+          dmv[0][br][0] = (int16_t)cmx; dmv[0][br][1] = (int16_t)cmy; dmv[1][br][0] = dmv[1][br][1] = 0;
+        } else {
+          int tx = (16384 + iabs(td / 2)) / td;
+          int dsf = clip3(-1024, 1023, (tb * tx + 32) >> 6);
+          int mx0 = (dsf * cmx + 128) >> 8, my0 = (dsf * cmy + 128) >> 8;
+          dmv[0][br][0] = (int16_t)mx0; dmv[0][br][1] = (int16_t)my0;
+          dmv[1][br][0] = (int16_t)(mx0 - cmx); dmv[1][br][1] = (int16_t)(my0 - cmy);
+        }
+      }
+    }
+  }
+}
+
+HWB_HD void apply_direct(SliceDec &s, int l, int q, const int8_t dref[2][4], const int16_t dmv[2][16][2]) {
+  for (int k = 0; k < 4; ++k) {
+    int bx = (q & 1) * 2 + (k & 1), by = (q >> 1) * 2 + (k >> 1), br = by * 4 + bx;
+    set_motion(s, l, bx, by, 1, 1, dref[l][q], dmv[l][br][0], dmv[l][br][1], 0, 0);
+    s.dir_cache[HWB_CI(bx, by)] = 1;
+  }
+}
+
+// ================================================================================ CAVLC residual
+HWB_HD int cavlc_nc(int na, int nb) {
+  bool a = na != 0x80, b = nb != 0x80;
+  if (a && b) return (na + nb + 1) >> 1;
+  return a ? na : (b ? nb : 0);
+}
+
+// Decodes one residual block.  Levels are written to s.coef (zeroed first) at dezigzagged positions
+// given by `scan` (scan[start+i]); for 8x8-interleaved blocks scan8 != nullptr: position =
+// scan8[4*i + sub].  Returns total_coeff.
+HWB_FN int cavlc_residual(SliceDec &s, int nC, int max_coeff, int start, const uint8_t *scan, const uint8_t *scan8, int sub) {
+  BitReader &b = s.br;
+  int total, t1;
+  if (nC < 0) {
+    uint32_t e = cavlc_chroma_dc_token[br_peek(b, 8)];
+    if (!e) { sd_fail(s, 10); return 0; }
+    br_skip(b, e >> 8); total = (e & 255) >> 2; t1 = e & 3;
+  } else if (nC >= 8) {
+    uint32_t e = cavlc_coeff_token_flc[br_peek(b, 6)];
+    if (!e) { sd_fail(s, 11); return 0; }
+    br_skip(b, 6); total = (e & 255) >> 2; t1 = e & 3;
+  } else {
+    int tab = nC < 2 ? 0 : (nC < 4 ? 1 : 2);
+    uint32_t v = br_peek(b, 16);
+    int lz = clz32(v) - 16;
+    if (lz >= 16) { sd_fail(s, 12); return 0; }
+    uint32_t suf = (v >> (12 - lz)) & 7;  // the 3 bits after the leading 1 (16-bit window, lz<=12 ok)
+    if (lz > 12) suf = (v << (lz - 12)) & 7;
+    uint32_t e = cavlc_coeff_token_lz[tab * 128 + lz * 8 + suf];
+    if (!e) { sd_fail(s, 13); return 0; }
+    br_skip(b, e >> 8); total = (e & 255) >> 2; t1 = e & 3;
+  }
+  if (total == 0) return 0;
+  if (total > max_coeff) { sd_fail(s, 14); return 0; }
+  int level[16];
+  int suffix_len = (total > 10 && t1 < 3) ? 1 : 0;
+  for (int i = 0; i < total; ++i) {
+    if (i < t1) { level[i] = br_get1(b) ? -1 : 1; continue; }
+    uint32_t v = br_peek(b, 32);
+    int prefix = clz32(v);
+    if (prefix > 25) { sd_fail(s, 15); return 0; }
+    br_skip(b, prefix + 1);
+    int code = (prefix < 15 ? prefix : 15) << suffix_len;
+    int ssz = suffix_len;
+    if (prefix == 14 && suffix_len == 0) ssz = 4;
+    if (prefix >= 15) ssz = prefix - 3;
+    if (ssz) code += (int)br_get(b, ssz);
+    if (prefix >= 15 && suffix_len == 0) code += 15;
+    if (prefix >= 16) code += (1 << (prefix - 3)) - 4096;
+    if (i == t1 && t1 < 3) code += 2;
+    int lv = (code & 1) ? (-code - 1) >> 1 : (code + 2) >> 1;
+    level[i] = lv;
+    if (suffix_len == 0) suffix_len = 1;
+    if (iabs(lv) > (3 << (suffix_len - 1)) && suffix_len < 6) suffix_len++;
+  }
+  int zeros_left = 0;
+  if (total < max_coeff) {
+    if (nC < 0) {
+      uint32_t e = cavlc_chroma_dc_total_zeros[(total - 1) * 8 + br_peek(b, 3)];
+      br_skip(b, e >> 8); zeros_left = e & 255;
+    } else {
+      uint32_t e = cavlc_total_zeros[(total - 1) * 512 + br_peek(b, 9)];
+      if (!e) { sd_fail(s, 16); return 0; }
+      br_skip(b, e >> 8); zeros_left = e & 255;
+    }
+  }
+  int idx = total + zeros_left - 1;  // scan index of the highest-frequency coefficient
+  if (idx >= max_coeff) { sd_fail(s, 17); return 0; }
+  for (int i = 0; i < total; ++i) {
+    int pos = scan8 ? scan8[4 * idx + sub] : scan[start + idx];
+    s.coef[pos] = (int16_t)level[i];
+    if (i + 1 < total) {
+      int run = 0;
+      if (zeros_left > 0) {
+        uint32_t e = cavlc_run_before[(zeros_left < 7 ? zeros_left - 1 : 6) * 2048 + br_peek(b, 11)];
+        if (!e) { sd_fail(s, 18); return 0; }
+        br_skip(b, e >> 8); run = e & 255;
+        zeros_left -= run;
+        if (zeros_left < 0) { sd_fail(s, 19); return 0; }
+      }
+      idx -= 1 + run;
+    }
+  }
+  return total;
+}
+
+// ================================================================================ CABAC residual
+HWB_FN int cabac_residual(SliceDec &s, int cat, int max_coeff, int start, const uint8_t *scan) {
+  // cat: 0 I16 DC, 1 I16 AC, 2 luma 4x4, 3 chroma DC, 4 chroma AC, 5 luma 8x8
+  const int sig_off = cat == 0 ? 105 : cat == 1 ? 120 : cat == 2 ? 134 : cat == 3 ? 149 : cat == 4 ? 152 : 402;
+  const int last_off = cat == 0 ? 166 : cat == 1 ? 181 : cat == 2 ? 195 : cat == 3 ? 210 : cat == 4 ? 213 : 417;
+  const int abs_off = cat == 0 ? 227 : cat == 1 ? 237 : cat == 2 ? 247 : cat == 3 ? 257 : cat == 4 ? 266 : 426;
+  uint8_t index[64];
+  int n = 0;
+  int i = 0;
+  for (; i < max_coeff - 1; ++i) {
+    int sctx = cat == 5 ? cabac_sig8x8_ctx[i] : (cat == 3 ? (i < 2 ? i : 2) : i);
+    if (cabac_decision(s.cab, s.br, s.st + sig_off + sctx)) {
+      index[n++] = (uint8_t)i;
+      int lctx = cat == 5 ? cabac_last8x8_ctx[i] : (cat == 3 ? (i < 2 ? i : 2) : i);
+      if (cabac_decision(s.cab, s.br, s.st + last_off + lctx)) break;
+    }
+  }
+  if (i == max_coeff - 1) index[n++] = (uint8_t)i;
+  int eq1 = 0, gt1 = 0;
+  for (int k = n - 1; k >= 0; --k) {
+    int ctx0 = gt1 ? 0 : (eq1 < 3 ? 1 + eq1 : 4);
+    int absv;
+    if (!cabac_decision(s.cab, s.br, s.st + abs_off + ctx0)) {
+      absv = 1; eq1++;
+    } else {
+      int cmax = cat == 3 ? 3 : 4;
+      int ctx1 = 5 + (gt1 < cmax ? gt1 : cmax);
+      absv = 2;
+      while (absv < 15 && cabac_decision(s.cab, s.br, s.st + abs_off + ctx1)) absv++;
+      if (absv >= 15) {
+        int kk = 0;
+        while (cabac_bypass(s.cab, s.br)) { absv += 1 << kk; kk++; if (kk > 20) { sd_fail(s, 30); return n; } }
+        while (kk--) absv += cabac_bypass(s.cab, s.br) << kk;
+      }
+      gt1++;
+    }
+    int sign = cabac_bypass(s.cab, s.br);
+    s.coef[scan[start + index[k]]] = (int16_t)(sign ? -absv : absv);
+  }
+  return n;
+}
+
+// ================================================================================ output helpers
+HWB_HD void coef_clear(SliceDec &s, int n) { for (int i = 0; i < n; ++i) s.coef[i] = 0; }
+// Append s.coef[0..16*nslots) to the arena and mark item bits [bit, bit+nslots).
+HWB_HD void coef_emit(SliceDec &s, int bit, int nslots) {
+  int16_t *dst = pic_coefs(*s.c, s.pd->frame) + (uint64_t)s.coef_next * 16;
+  for (int i = 0; i < nslots * 16; ++i) dst[i] = s.coef[i];
+  s.coef_next += nslots;
+  s.out.nzmask |= ((1u << nslots) - 1u) << bit;
+}
+
+// identity scan for blocks whose coefficients are already in raster order
+HWB_TABLE uint8_t scan_ident4[4] = {0, 1, 2, 3};
+
+// ================================================================================ residual (both modes)
+// nnz[] receives total_coeff per luma block (raster) and chroma block.
+HWB_FN void decode_residual(SliceDec &s, bool i16, int cbp, bool t8, uint8_t nnz_l[16], uint8_t nnz_c[2][4]) {
+  const bool cabac = s.cabac;
+  const bool intra = s.out.mbtype != MB_INTER;
+  const int cbf_unavail = intra ? 1 : 0;
+  for (int i = 0; i < 16; ++i) nnz_l[i] = 0;
+  for (int p = 0; p < 2; ++p) for (int i = 0; i < 4; ++i) nnz_c[p][i] = 0;
+  if (i16) {
+    int coded = 1;
+    if (cabac) {
+      int a = s.availA ? ((s.left.flags & NBF_IPCM) ? 1 : (s.left.cbf >> NZ_LUMA_DC) & 1) : cbf_unavail;
+      int bq = s.availB ? ((s.line[s.mbx].flags & NBF_IPCM) ? 1 : (s.line[s.mbx].cbf >> NZ_LUMA_DC) & 1) : cbf_unavail;
+      coded = cabac_decision(s.cab, s.br, s.st + 85 + 0 + a + 2 * bq);
+    }
+    if (coded) {
+      coef_clear(s, 16);
+      int n = cabac ? cabac_residual(s, 0, 16, 0, zigzag4x4)
+                    : cavlc_residual(s, cavlc_nc(s.nz_cache[HWB_CI(-1, 0)], s.nz_cache[HWB_CI(0, -1)]), 16, 0, zigzag4x4, nullptr, 0);
+      if (n) coef_emit(s, NZ_LUMA_DC, 1);
+    }
+  }
+  for (int q = 0; q < 4; ++q) {
+    if (!((cbp >> q) & 1)) continue;
+    if (t8) {
+      int n = 0;
+      coef_clear(s, 64);
+      if (cabac) {
+        n = cabac_residual(s, 5, 64, 0, zigzag8x8);
+        for (int k = 0; k < 4; ++k) {
+          int bx = (q & 1) * 2 + (k & 1), by = (q >> 1) * 2 + (k >> 1);
+          nnz_l[by * 4 + bx] = (uint8_t)(n > 16 ? 16 : n); s.nz_cache[HWB_CI(bx, by)] = nnz_l[by * 4 + bx];
+        }
+      } else {
+        for (int k = 0; k < 4; ++k) {
+          int bx = (q & 1) * 2 + (k & 1), by = (q >> 1) * 2 + (k >> 1);
+          int nc = cavlc_nc(s.nz_cache[HWB_CI(bx - 1, by)], s.nz_cache[HWB_CI(bx, by - 1)]);
+          int m = cavlc_residual(s, nc, 16, 0, nullptr, zigzag8x8, k);
+          nnz_l[by * 4 + bx] = (uint8_t)m; s.nz_cache[HWB_CI(bx, by)] = (uint8_t)m;
+          n += m;
+        }
+      }
+      if (n) coef_emit(s, NZ_LUMA0 + q * 4, 4);
+    } else {
+      for (int k = 0; k < 4; ++k) {
+        int z = q * 4 + k, bx = z2x(z), by = z2y(z);
+        int na = s.nz_cache[HWB_CI(bx - 1, by)], nb = s.nz_cache[HWB_CI(bx, by - 1)];
+        int n = 0, coded = 1;
+        if (cabac) {
+          int a = na == 0x80 ? cbf_unavail : (na != 0), bq = nb == 0x80 ? cbf_unavail : (nb != 0);
+          coded = cabac_decision(s.cab, s.br, s.st + 85 + (i16 ? 4 : 8) + a + 2 * bq);
+        }
+        if (coded) {
+          coef_clear(s, 16);
+          if (cabac) n = cabac_residual(s, i16 ? 1 : 2, i16 ? 15 : 16, i16 ? 1 : 0, zigzag4x4);
+          else n = cavlc_residual(s, cavlc_nc(na, nb), i16 ? 15 : 16, i16 ? 1 : 0, zigzag4x4, nullptr, 0);
+          if (n) coef_emit(s, NZ_LUMA0 + z, 1);
+        }
+        nnz_l[by * 4 + bx] = (uint8_t)n; s.nz_cache[HWB_CI(bx, by)] = (uint8_t)n;
+      }
+    }
+  }
+  if (cbp & 0x30) {
+    for (int p = 0; p < 2; ++p) {
+      int coded = 1;
+      int bit = p ? NZ_CR_DC : NZ_CB_DC;
+      if (cabac) {
+        int a = s.availA ? ((s.left.flags & NBF_IPCM) ? 1 : (s.left.cbf >> bit) & 1) : cbf_unavail;
+        int bq = s.availB ? ((s.line[s.mbx].flags & NBF_IPCM) ? 1 : (s.line[s.mbx].cbf >> bit) & 1) : cbf_unavail;
+        coded = cabac_decision(s.cab, s.br, s.st + 85 + 12 + a + 2 * bq);
+      }
+      if (coded) {
+        coef_clear(s, 16);
+        int n = cabac ? cabac_residual(s, 3, 4, 0, scan_ident4) : cavlc_residual(s, -1, 4, 0, scan_ident4, nullptr, 0);
+        if (n) coef_emit(s, bit, 1);
+      }
+    }
+  }
+  if (cbp & 0x20) {
+    for (int p = 0; p < 2; ++p)
+      for (int k = 0; k < 4; ++k) {
+        int bx = k & 1, by = k >> 1;
+        int na = s.cnz_cache[p][(by + 1) * 4 + bx], nb = s.cnz_cache[p][by * 4 + bx + 1];
+        int n = 0, coded = 1;
+        if (cabac) {
+          int a = na == 0x80 ? cbf_unavail : (na != 0), bq = nb == 0x80 ? cbf_unavail : (nb != 0);
+          coded = cabac_decision(s.cab, s.br, s.st + 85 + 16 + a + 2 * bq);
+        }
+        if (coded) {
+          coef_clear(s, 16);
+          n = cabac ? cabac_residual(s, 4, 15, 1, zigzag4x4) : cavlc_residual(s, cavlc_nc(na, nb), 15, 1, zigzag4x4, nullptr, 0);
+          if (n) coef_emit(s, (p ? NZ_CR0 : NZ_CB0) + k, 1);
+        }
+        nnz_c[p][k] = (uint8_t)n; s.cnz_cache[p][(by + 1) * 4 + bx + 1] = (uint8_t)n;
+      }
+  }
+}
+
+// ================================================================================ CABAC syntax elements
+HWB_HD int cabac_intra_mb_type(SliceDec &s, int base, bool islice) {
+  uint8_t *st = s.st + base;
+  if (islice) {
+    int ctx = 0;
+    if (s.availA && !(s.left.flags & NBF_INXN)) ctx++;
+    if (s.availB && !(s.line[s.mbx].flags & NBF_INXN)) ctx++;
+    if (!cabac_decision(s.cab, s.br, st + ctx)) return 0;
+    st += 2;
+  } else {
+    if (!cabac_decision(s.cab, s.br, st)) return 0;
+  }
+  if (cabac_terminate(s.cab, s.br)) return 25;
+  int t = 1;
+  t += 12 * cabac_decision(s.cab, s.br, st + 1);
+  if (cabac_decision(s.cab, s.br, st + 2)) t += 4 + 4 * cabac_decision(s.cab, s.br, st + 2 + (islice ? 1 : 0));
+  t += 2 * cabac_decision(s.cab, s.br, st + 3 + (islice ? 1 : 0));
+  t += cabac_decision(s.cab, s.br, st + 3 + (islice ? 2 : 0));
+  return t;
+}
+
+HWB_HD int cabac_b_mb_type(SliceDec &s) {
+  int ctx = 0;
+  if (s.availA && !(s.left.flags & NBF_DIRECT16)) ctx++;
+  if (s.availB && !(s.line[s.mbx].flags & NBF_DIRECT16)) ctx++;
+  uint8_t *st = s.st + 27;
+  if (!cabac_decision(s.cab, s.br, st + ctx)) return 0;
+  if (!cabac_decision(s.cab, s.br, st + 3)) return 1 + cabac_decision(s.cab, s.br, st + 5);
+  int bits = cabac_decision(s.cab, s.br, st + 4) << 3;
+  bits |= cabac_decision(s.cab, s.br, st + 5) << 2;
+  bits |= cabac_decision(s.cab, s.br, st + 5) << 1;
+  bits |= cabac_decision(s.cab, s.br, st + 5);
+  if (bits < 8) return bits + 3;
+  if (bits == 13) return 23 + cabac_intra_mb_type(s, 32, false);
+  if (bits == 14) return 11;
+  if (bits == 15) return 22;
+  bits = (bits << 1) | cabac_decision(s.cab, s.br, st + 5);
+  return bits - 4;
+}
+
+HWB_HD int cabac_b_sub_type(SliceDec &s) {
+  uint8_t *st = s.st + 36;
+  if (!cabac_decision(s.cab, s.br, st)) return 0;
+  if (!cabac_decision(s.cab, s.br, st + 1)) return 1 + cabac_decision(s.cab, s.br, st + 3);
+  int t = 3;
+  if (cabac_decision(s.cab, s.br, st + 2)) {
+    if (cabac_decision(s.cab, s.br, st + 3)) return 11 + cabac_decision(s.cab, s.br, st + 3);
+    t += 4;
+  }
+  t += 2 * cabac_decision(s.cab, s.br, st + 3);
+  t += cabac_decision(s.cab, s.br, st + 3);
+  return t;
+}
+
+HWB_HD int cabac_ref_idx(SliceDec &s, int l, int bx, int by) {
+  int ra = s.ref_cache[l][HWB_CI(bx - 1, by)], rb = s.ref_cache[l][HWB_CI(bx, by - 1)];
+  int ctx = 0;
+  if (ra > 0 && !s.dir_cache[HWB_CI(bx - 1, by)]) ctx++;
+  if (rb > 0 && !s.dir_cache[HWB_CI(bx, by - 1)]) ctx += 2;
+  int ref = 0;
+  while (cabac_decision(s.cab, s.br, s.st + 54 + ctx)) {
+    ref++;
+    ctx = (ctx >> 2) + 4;
+    if (ref >= 32) { sd_fail(s, 40); return 0; }
+  }
+  return ref;
+}
+
+HWB_HD int cabac_mvd(SliceDec &s, int base, int amvd, int &absout) {
+  int inc = amvd < 3 ? 0 : (amvd > 32 ? 2 : 1);
+  if (!cabac_decision(s.cab, s.br, s.st + base + inc)) { absout = 0; return 0; }
+  int mvd = 1, ctx = base + 3;
+  while (mvd < 9 && cabac_decision(s.cab, s.br, s.st + ctx)) { if (mvd < 4) ctx++; mvd++; }
+  if (mvd >= 9) {
+    int k = 3;
+    while (cabac_bypass(s.cab, s.br)) { mvd += 1 << k; k++; if (k > 24) { sd_fail(s, 41); return 0; } }
+    while (k--) mvd += cabac_bypass(s.cab, s.br) << k;
+  }
+  absout = mvd < 70 ? mvd : 70;
+  return cabac_bypass(s.cab, s.br) ? -mvd : mvd;
+}
+
+HWB_HD int cabac_cbp(SliceDec &s) {
+  const NbCtx &L = s.left, &T = s.line[s.mbx];
+  // luma: cbp bits of neighbours; unavailable / I_PCM behave as "all coded"
+  int cbpa = s.availA ? ((L.flags & NBF_IPCM) ? 0x2F : L.cbp) : 0x0F;
+  int cbpb = s.availB ? ((T.flags & NBF_IPCM) ? 0x2F : T.cbp) : 0x0F;
+  int cbp = 0;
+  for (int b8 = 0; b8 < 4; ++b8) {
+    int a = (b8 & 1) ? !((cbp >> (b8 - 1)) & 1) : !((cbpa >> (b8 + 1)) & 1);
+    int bq = (b8 & 2) ? !((cbp >> (b8 - 2)) & 1) : !((cbpb >> (b8 + 2)) & 1);
+    cbp |= cabac_decision(s.cab, s.br, s.st + 73 + a + 2 * bq) << b8;
+  }
+  int ca = s.availA ? (cbpa >> 4) & 3 : 0, cb = s.availB ? (cbpb >> 4) & 3 : 0;
+  int ctx = (ca > 0) + 2 * (cb > 0);
+  if (cabac_decision(s.cab, s.br, s.st + 77 + ctx)) {
+    ctx = 4 + (ca == 2) + 2 * (cb == 2);
+    cbp |= (1 + cabac_decision(s.cab, s.br, s.st + 77 + ctx)) << 4;
+  }
+  return cbp;
+}
+
+HWB_HD int cabac_dqp(SliceDec &s) {
+  int ctx = s.last_dqp != 0, val = 0;
+  while (cabac_decision(s.cab, s.br, s.st + 60 + ctx)) {
+    ctx = 2 + (ctx >> 1);
+    val++;
+    if (val > 104) { sd_fail(s, 42); return 0; }
+  }
+  return (val & 1) ? (val + 1) >> 1 : -((val + 1) >> 1);
+}
+
+HWB_HD int cabac_chroma_mode(SliceDec &s) {
+  int ctx = 0;
+  if (s.availA && s.left.cmode != 0) ctx++;
+  if (s.availB && s.line[s.mbx].cmode != 0) ctx++;
+  if (!cabac_decision(s.cab, s.br, s.st + 64 + ctx)) return 0;
+  if (!cabac_decision(s.cab, s.br, s.st + 64 + 3)) return 1;
+  return 2 + cabac_decision(s.cab, s.br, s.st + 64 + 3);
+}
+
+// ================================================================================ macroblock layer
+// prediction flags (1 L0, 2 L1, 3 Bi) of the two partitions of B 16x8 / 8x16 types, by (mb_type-4)>>1
+HWB_TABLE uint8_t b_part_pred[18] = {1, 1, 2, 2, 1, 2, 2, 1, 1, 3, 2, 3, 3, 1, 3, 2, 3, 3};
+
+HWB_HD int read_ref(SliceDec &s, int l, int bx, int by) {
+  int nref = s.sd->num_ref[l];
+  if (nref <= 1) return 0;
+  if (s.cabac) return cabac_ref_idx(s, l, bx, by);
+  if (nref == 2) return br_get1(s.br) ^ 1;
+  return (int)br_ue(s.br);
+}
+
+HWB_HD void read_mvd_and_set(SliceDec &s, int l, int bx, int by, int w, int h, int ref, int shape) {
+  int px, py;
+  pred_mv(s, l, bx, by, w, ref, shape, px, py);
+  int dx, dy, ax = 0, ay = 0;
+  if (s.cabac) {
+    int sa = s.mvd_cache[l][HWB_CI(bx - 1, by)][0] + s.mvd_cache[l][HWB_CI(bx, by - 1)][0];
+    int sb = s.mvd_cache[l][HWB_CI(bx - 1, by)][1] + s.mvd_cache[l][HWB_CI(bx, by - 1)][1];
+    dx = cabac_mvd(s, 40, sa, ax);
+    dy = cabac_mvd(s, 47, sb, ay);
+  } else {
+    dx = br_se(s.br); dy = br_se(s.br);
+  }
+  set_motion(s, l, bx, by, w, h, ref, px + dx, py + dy, ax, ay);
+}
+
+// Decode one macroblock; s.mbx/mby/mbaddr and availability set by caller.  `skipped`: P_Skip/B_Skip.
+HWB_FN void decode_mb(SliceDec &s, bool skipped) {
+  const ChunkCtx &c = *s.c;
+  const SliceDesc &sd = *s.sd;
+  const int st = sd.slice_type;
+  const bool B = st == SLICE_B;
+  const int nl = B ? 2 : 1;
+  fill_caches(s, false);
+  MbInfo &o = s.out;
+  o.mbtype = MB_INTER; o.qp = (uint8_t)s.qp; o.cbp = 0; o.flags = 0; o.imode = 0; o.cmode = 0;
+  o.slice = (uint16_t)s.slice_num; o.nzmask = 0; o.coef_off = s.coef_next;
+  for (int i = 0; i < 16; ++i) o.i4modes[i] = 2;
+  uint8_t nnz_l[16], nnz_c[2][4];
+  for (int i = 0; i < 16; ++i) nnz_l[i] = 0;
+  for (int p = 0; p < 2; ++p) for (int i = 0; i < 4; ++i) nnz_c[p][i] = 0;
+  int8_t imodes_r[16];  // raster intra modes (-1 = not I_NxN)
+  for (int i = 0; i < 16; ++i) imodes_r[i] = -1;
+  bool direct16 = false;
+  uint32_t dirq = 0;  // quadrants predicted in direct mode
+  int8_t dref[2][4];
+  int16_t dmv[2][16][2];
+  bool is_pcm = false;
+
+  if (skipped) {
+    o.flags |= MBF_SKIP;
+    s.last_dqp = 0;
+    if (!B) {
+      int mx = 0, my = 0;
+      MvRef A = mv_at(s, 0, -1, 0), Bn = mv_at(s, 0, 0, -1);
+      if (!(A.ref == REF_UNAVAIL || Bn.ref == REF_UNAVAIL || (A.ref == 0 && A.mx == 0 && A.my == 0) || (Bn.ref == 0 && Bn.mx == 0 && Bn.my == 0)))
+        pred_mv(s, 0, 0, 0, 4, 0, 0, mx, my);
+      set_motion(s, 0, 0, 0, 4, 4, 0, mx, my, 0, 0);
+    } else {
+      direct16 = true; dirq = 15;
+      direct_predict(s, 15, dref, dmv);
+      for (int l = 0; l < 2; ++l) for (int q = 0; q < 4; ++q) apply_direct(s, l, q, dref, dmv);
+    }
+  } else {
+    // ---------------- mb_type
+    int mbt;
+    if (s.cabac) {
+      if (st == SLICE_I) mbt = cabac_intra_mb_type(s, 3, true);
+      else if (st == SLICE_P) {
+        if (!cabac_decision(s.cab, s.br, s.st + 14)) {
+          if (!cabac_decision(s.cab, s.br, s.st + 15)) mbt = 3 * cabac_decision(s.cab, s.br, s.st + 16);
+          else mbt = 2 - cabac_decision(s.cab, s.br, s.st + 17);
+        } else mbt = 5 + cabac_intra_mb_type(s, 17, false);
+      } else mbt = cabac_b_mb_type(s);
+    } else mbt = (int)br_ue(s.br);
+    int imbt = -1;  // intra mb_type 0..25
+    if (st == SLICE_I) imbt = mbt;
+    else if (st == SLICE_P && mbt >= 5) imbt = mbt - 5;
+    else if (B && mbt >= 23) imbt = mbt - 23;
+    if (imbt > 25 || (st == SLICE_P && mbt > 30) || (B && mbt > 48)) { sd_fail(s, 50); return; }
+
+    if (imbt == 25) {
+      // ---------------- I_PCM
+      is_pcm = true;
+      o.mbtype = MB_IPCM; o.qp = 0; o.cbp = 0x2F;
+      br_align(s.br);
+      uint8_t *dst = (uint8_t *)(pic_coefs(c, s.pd->frame) + (uint64_t)s.coef_next * 16);
+      for (int i = 0; i < 384; ++i) dst[i] = (uint8_t)br_get(s.br, 8);
+      s.coef_next += 12; o.nzmask = 0xFFF;
+      if (s.cabac) cabac_start(s.cab, s.br);
+      for (int i = 0; i < 16; ++i) nnz_l[i] = 16;
+      for (int p = 0; p < 2; ++p) for (int i = 0; i < 4; ++i) nnz_c[p][i] = 16;
+      s.last_dqp = 0;
+    } else if (imbt >= 0) {
+      // ---------------- intra
+      bool t8 = false;
+      int cbp;
+      if (imbt == 0) {
+        if (s.pd->transform8x8_mode) {
+          if (s.cabac) {
+            int ctx = (s.availA && (s.left.flags & NBF_T8)) + (s.availB && (s.line[s.mbx].flags & NBF_T8));
+            t8 = cabac_decision(s.cab, s.br, s.st + 399 + ctx) != 0;
+          } else t8 = br_get1(s.br) != 0;
+        }
+        o.mbtype = t8 ? MB_I8x8 : MB_I4x4;
+        if (t8) o.flags |= MBF_T8x8;
+        const int nb = t8 ? 4 : 16;
+        for (int k = 0; k < nb; ++k) {
+          int bx = t8 ? (k & 1) * 2 : z2x(k), by = t8 ? (k >> 1) * 2 : z2y(k);
+          int ma = s.im_cache[HWB_CI(bx - 1, by)], mb_ = s.im_cache[HWB_CI(bx, by - 1)];
+          int pred = (ma < 0 || mb_ < 0) ? 2 : (ma < mb_ ? ma : mb_);
+          int mode;
+          if (s.cabac) {
+            if (cabac_decision(s.cab, s.br, s.st + 68)) mode = pred;
+            else {
+              int rem = cabac_decision(s.cab, s.br, s.st + 69);
+              rem |= cabac_decision(s.cab, s.br, s.st + 69) << 1;
+              rem |= cabac_decision(s.cab, s.br, s.st + 69) << 2;
+              mode = rem < pred ? rem : rem + 1;
+            }
+          } else {
+            if (br_get1(s.br)) mode = pred;
+            else { int rem = (int)br_get(s.br, 3); mode = rem < pred ? rem : rem + 1; }
+          }
+          o.i4modes[k] = (uint8_t)mode;
+          int wd = t8 ? 2 : 1;
+          for (int y = by; y < by + wd; ++y) for (int x = bx; x < bx + wd; ++x) { s.im_cache[HWB_CI(x, y)] = (int8_t)mode; imodes_r[y * 4 + x] = (int8_t)mode; }
+        }
+      } else {
+        o.mbtype = MB_I16x16;
+        o.imode = (uint8_t)((imbt - 1) & 3);
+      }
+      o.cmode = (uint8_t)(s.cabac ? cabac_chroma_mode(s) : (int)br_ue(s.br));
+      if (o.cmode > 3) { sd_fail(s, 51); return; }
+      if (imbt == 0) {
+        if (s.cabac) cbp = cabac_cbp(s);
+        else { uint32_t k = br_ue(s.br); if (k > 47) { sd_fail(s, 52); return; } cbp = golomb_to_intra_cbp[k]; }
+      } else {
+        cbp = (((imbt - 1) / 4) % 3) << 4 | ((imbt - 1) >= 12 ? 15 : 0);
+      }
+      o.cbp = (uint8_t)cbp;
+      if (cbp || imbt > 0) {
+        int dqp = s.cabac ? cabac_dqp(s) : br_se(s.br);
+        s.last_dqp = dqp;
+        s.qp = (s.qp + dqp + 52) % 52;
+      } else s.last_dqp = 0;
+      o.qp = (uint8_t)s.qp;
+      decode_residual(s, imbt > 0, cbp, t8, nnz_l, nnz_c);
+    } else {
+      // ---------------- inter
+      int cbp;
+      bool t8_allowed = true;
+      int sub[4] = {0, 0, 0, 0};
+      if (B && mbt == 0) {
+        direct16 = true; dirq = 15;
+        direct_predict(s, 15, dref, dmv);
+        for (int l = 0; l < 2; ++l) for (int q = 0; q < 4; ++q) apply_direct(s, l, q, dref, dmv);
+        t8_allowed = s.pd->direct_8x8_inference != 0;
+      } else if ((!B && mbt >= 3) || (B && mbt == 22)) {
+        // 8x8 with sub-macroblock types
+        for (int q = 0; q < 4; ++q) {
+          if (s.cabac) {
+            if (B) sub[q] = cabac_b_sub_type(s);
+            else sub[q] = cabac_decision(s.cab, s.br, s.st + 21) ? 0 : (!cabac_decision(s.cab, s.br, s.st + 22) ? 1 : (cabac_decision(s.cab, s.br, s.st + 23) ? 2 : 3));
+          } else sub[q] = (int)br_ue(s.br);
+          if (sub[q] > (B ? 12 : 3)) { sd_fail(s, 53); return; }
+          if (B && sub[q] == 0) dirq |= 1u << q;
+        }
+        if (dirq) direct_predict(s, (int)dirq, dref, dmv);
+        // sub shapes: 0: 8x8, 1: 8x4, 2: 4x8, 3: 4x4; pred flags: 1 L0, 2 L1, 3 Bi
+        int shape[4], pf[4];
+        for (int q = 0; q < 4; ++q) {
+          if (!B) { shape[q] = sub[q]; pf[q] = 1; }
+          else if (sub[q] == 0) { shape[q] = 0; pf[q] = 0; }
+          else {
+            int t = sub[q];
+            shape[q] = t <= 3 ? 0 : (t >= 10 ? 3 : ((t & 1) ? 2 : 1));
+            pf[q] = t <= 3 ? t : (t >= 10 ? t - 9 : ((t - 4) >> 1) + 1);
+          }
+          if (shape[q] != 0) t8_allowed = false;
+          if (B && sub[q] == 0 && !s.pd->direct_8x8_inference) t8_allowed = false;
+        }
+        int refs[2][4];
+        const bool ref0_only = !B && mbt == 4 && !s.cabac;  // P_8x8ref0 (CAVLC only)
+        for (int l = 0; l < nl; ++l)
+          for (int q = 0; q < 4; ++q) {
+            refs[l][q] = -1;
+            if ((dirq >> q) & 1) continue;
+            if (pf[q] & (1 << l)) {
+              refs[l][q] = ref0_only ? 0 : read_ref(s, l, (q & 1) * 2, (q >> 1) * 2);
+              if (refs[l][q] >= sd.num_ref[l]) { sd_fail(s, 54); return; }
+            }
+            // make the reference visible for later ref_idx contexts of this list
+            int bx = (q & 1) * 2, by = (q >> 1) * 2;
+            for (int y = by; y < by + 2; ++y) for (int x = bx; x < bx + 2; ++x) s.ref_cache[l][HWB_CI(x, y)] = (int8_t)(refs[l][q] >= 0 ? refs[l][q] : REF_NONE);
+          }
+        // references of not-yet-decoded quadrants must look unavailable for C-neighbour lookups
+        for (int l = 0; l < nl; ++l) {
+          for (int q = 0; q < 4; ++q) {
+            int bx = (q & 1) * 2, by = (q >> 1) * 2;
+            for (int y = by; y < by + 2; ++y) for (int x = bx; x < bx + 2; ++x) s.ref_cache[l][HWB_CI(x, y)] = REF_UNAVAIL;
+          }
+          for (int q = 0; q < 4; ++q) {
+            int bx = (q & 1) * 2, by = (q >> 1) * 2;
+            if ((dirq >> q) & 1) { apply_direct(s, l, q, dref, dmv); continue; }
+            if (refs[l][q] < 0) { set_motion(s, l, bx, by, 2, 2, REF_NONE, 0, 0, 0, 0); continue; }
+            int r = refs[l][q];
+            switch (shape[q]) {
+              case 0: read_mvd_and_set(s, l, bx, by, 2, 2, r, 0); break;
+              case 1: read_mvd_and_set(s, l, bx, by, 2, 1, r, 0); read_mvd_and_set(s, l, bx, by + 1, 2, 1, r, 0); break;
+              case 2: read_mvd_and_set(s, l, bx, by, 1, 2, r, 0); read_mvd_and_set(s, l, bx + 1, by, 1, 2, r, 0); break;
+              default:
+                for (int k = 0; k < 4; ++k) read_mvd_and_set(s, l, bx + (k & 1), by + (k >> 1), 1, 1, r, 0);
+            }
+          }
+        }
+      } else {
+        // 16x16, 16x8, 8x16
+        int shape, pf0, pf1;
+        if (!B) { shape = mbt; pf0 = pf1 = 1; }
+        else if (mbt <= 3) { shape = 0; pf0 = pf1 = mbt; }
+        else {
+          shape = (mbt & 1) ? 2 : 1;
+          int k = (mbt - 4) >> 1;
+          pf0 = b_part_pred[k * 2]; pf1 = b_part_pred[k * 2 + 1];
+        }
+        const int np = shape == 0 ? 1 : 2;
+        int refs[2][2];
+        for (int l = 0; l < nl; ++l)
+          for (int p = 0; p < np; ++p) {
+            int pf = p ? pf1 : pf0;
+            int bx = (shape == 2 && p) ? 2 : 0, by = (shape == 1 && p) ? 2 : 0;
+            int w = shape == 2 ? 2 : 4, h = shape == 1 ? 2 : 4;
+            refs[l][p] = -1;
+            if (pf & (1 << l)) {
+              refs[l][p] = read_ref(s, l, bx, by);
+              if (refs[l][p] >= sd.num_ref[l]) { sd_fail(s, 55); return; }
+            }
+            for (int y = by; y < by + h; ++y) for (int x = bx; x < bx + w; ++x) s.ref_cache[l][HWB_CI(x, y)] = (int8_t)(refs[l][p] >= 0 ? refs[l][p] : REF_NONE);
+          }
+        for (int l = 0; l < nl; ++l) {
+          for (int i = 0; i < 16; ++i) s.ref_cache[l][HWB_CI(i & 3, i >> 2)] = REF_UNAVAIL;
+          for (int p = 0; p < np; ++p) {
+            int bx = (shape == 2 && p) ? 2 : 0, by = (shape == 1 && p) ? 2 : 0;
+            int w = shape == 2 ? 2 : 4, h = shape == 1 ? 2 : 4;
+            if (refs[l][p] < 0) { set_motion(s, l, bx, by, w, h, REF_NONE, 0, 0, 0, 0); continue; }
+            int sh = shape == 0 ? 0 : (shape == 1 ? 1 + p : 3 + p);
+            read_mvd_and_set(s, l, bx, by, w, h, refs[l][p], sh);
+          }
+        }
+      }
+      // ---------------- cbp, transform size, qp delta, residual
+      if (s.cabac) cbp = cabac_cbp(s);
+      else { uint32_t k = br_ue(s.br); if (k > 47) { sd_fail(s, 56); return; } cbp = golomb_to_inter_cbp[k]; }
+      o.cbp = (uint8_t)cbp;
+      bool t8 = false;
+      if ((cbp & 15) && s.pd->transform8x8_mode && t8_allowed) {
+        if (s.cabac) {
+          int ctx = (s.availA && (s.left.flags & NBF_T8)) + (s.availB && (s.line[s.mbx].flags & NBF_T8));
+          t8 = cabac_decision(s.cab, s.br, s.st + 399 + ctx) != 0;
+        } else t8 = br_get1(s.br) != 0;
+      }
+      if (t8) o.flags |= MBF_T8x8;
+      if (cbp) {
+        int dqp = s.cabac ? cabac_dqp(s) : br_se(s.br);
+        s.last_dqp = dqp;
+        s.qp = (s.qp + dqp + 52) % 52;
+      } else s.last_dqp = 0;
+      o.qp = (uint8_t)s.qp;
+      decode_residual(s, false, cbp, t8, nnz_l, nnz_c);
+    }
+  }
+
+  // ---------------- write outputs
+  const int f = s.pd->frame;
+  pic_mbinfo(c, f)[s.mbaddr] = o;
+  const bool inter = o.mbtype == MB_INTER;
+  if (inter) {
+    for (int l = 0; l < nl; ++l) {
+      int16_t *mvo = pic_mv(c, f, l) + (uint64_t)s.mbaddr * 32;
+      int8_t *ro = pic_refidx(c, f, l) + (uint64_t)s.mbaddr * 4;
+      int16_t *po = pic_refpic(c, f, l) + (uint64_t)s.mbaddr * 4;
+      for (int i = 0; i < 16; ++i) { int ci = HWB_CI(i & 3, i >> 2); mvo[2 * i] = s.mv_cache[l][ci][0]; mvo[2 * i + 1] = s.mv_cache[l][ci][1]; }
+      for (int q = 0; q < 4; ++q) {
+        int r = s.ref_cache[l][HWB_CI((q & 1) * 2, (q >> 1) * 2)];
+        ro[q] = (int8_t)r;
+        po[q] = r >= 0 ? sd.ref_frame[l][r] : (int16_t)-1;
+      }
+    }
+    if (!B && s.pd->has_inter == 2) {
+      int8_t *ro = pic_refidx(c, f, 1) + (uint64_t)s.mbaddr * 4;
+      int16_t *po = pic_refpic(c, f, 1) + (uint64_t)s.mbaddr * 4;
+      for (int q = 0; q < 4; ++q) { ro[q] = -1; po[q] = -1; }
+    }
+  }
+  // ---------------- neighbour context for the macroblocks to come
+  NbCtx n;
+  n.flags = (uint8_t)((inter ? 0 : NBF_INTRA) | (is_pcm ? NBF_IPCM : 0) | (skipped ? NBF_SKIP : 0) | (direct16 ? NBF_DIRECT16 : 0) |
+                      ((o.flags & MBF_T8x8) ? NBF_T8 : 0) | (o.mbtype == MB_I16x16 ? NBF_I16 : 0) | ((o.mbtype == MB_I4x4 || o.mbtype == MB_I8x8) ? NBF_INXN : 0));
+  n.cbp = o.cbp; n.cmode = o.cmode; n.cbf = is_pcm ? 0x7FFFFFFu : o.nzmask;
+  n.dirmask = 0;
+  for (int i = 0; i < 4; ++i) {
+    n.nnz_b[i] = nnz_l[12 + i]; n.nnz_r[i] = nnz_l[i * 4 + 3];
+    n.imode_b[i] = imodes_r[12 + i]; n.imode_r[i] = imodes_r[i * 4 + 3];
+    if (s.dir_cache[HWB_CI(i, 3)]) n.dirmask |= 1u << i;
+    if (s.dir_cache[HWB_CI(3, i)]) n.dirmask |= 16u << i;
+    for (int l = 0; l < 2; ++l) {
+      bool on = inter && l < nl;
+      int cb = HWB_CI(i, 3), cr = HWB_CI(3, i);
+      n.ref_b[l][i] = on ? s.ref_cache[l][cb] : (int8_t)REF_NONE;
+      n.ref_r[l][i] = on ? s.ref_cache[l][cr] : (int8_t)REF_NONE;
+      for (int k = 0; k < 2; ++k) {
+        n.mv_b[l][i][k] = on ? s.mv_cache[l][cb][k] : (int16_t)0; n.mv_r[l][i][k] = on ? s.mv_cache[l][cr][k] : (int16_t)0;
+        n.mvd_b[l][i][k] = on ? s.mvd_cache[l][cb][k] : (uint8_t)0; n.mvd_r[l][i][k] = on ? s.mvd_cache[l][cr][k] : (uint8_t)0;
+      }
+    }
+  }
+  for (int p = 0; p < 2; ++p) { n.cnnz_b[p][0] = nnz_c[p][2]; n.cnnz_b[p][1] = nnz_c[p][3]; n.cnnz_r[p][0] = nnz_c[p][1]; n.cnnz_r[p][1] = nnz_c[p][3]; }
+  s.topleft = s.line[s.mbx];
+  s.line[s.mbx] = n;
+  s.left = n;
+}
+
+// ================================================================================ slice
+HWB_FN void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states) {
+  SliceDec s;
+  s.c = &c; s.sd = &c.slices[slice_idx]; s.pd = &c.pics[s.sd->pic];
+  s.slice_num = slice_idx - s.pd->first_slice;
+  s.cabac = s.pd->cabac != 0;
+  s.st = cabac_states;
+  s.error = 0;
+  const SliceDesc &sd = *s.sd;
+  const uint8_t *data = c.bitstream + sd.data_off;
+  br_init(s.br, data, sd.data_size, sd.bit_off);
+  // position of the rbsp_stop_one_bit
+  {
+    int n = (int)sd.data_size;
+    while (n > 0 && data[n - 1] == 0) --n;
+    uint32_t last = n > 0 ? data[n - 1] : 0x80;
+    int tz = 0;
+    while (!((last >> tz) & 1)) ++tz;
+    s.stop_bitpos = (uint32_t)(n > 0 ? (n - 1) * 8 + (7 - tz) : 0);
+  }
+  s.qp = sd.qp; s.last_dqp = 0;
+  s.line = (NbCtx *)(c.ectx + (uint64_t)slice_idx * c.ectx_stride);
+  // the arena region of a slice starts at its first macroblock's worst-case offset
+  s.coef_next = (uint32_t)sd.first_mb * SLOTS_PER_MB;
+  if (s.cabac) {
+    br_align(s.br);
+    cabac_init_states(s.st, sd.slice_type == SLICE_I ? 0 : 1 + sd.cabac_init_idc, sd.qp);
+    cabac_start(s.cab, s.br);
+  }
+  const int first = sd.first_mb;
+  int addr = first;
+  bool end = false;
+  // CAVLC mb_skip_run state: -1 = read a new run before the next macroblock, 0 = the next
+  // macroblock is coded, >0 = macroblocks still to skip
+  int run = -1;
+  while (!end && addr < c.nmb) {
+    s.mbaddr = addr; s.mbx = addr % c.mb_w; s.mby = addr / c.mb_w;
+    s.availA = s.mbx > 0 && addr - 1 >= first;
+    s.availB = addr - c.mb_w >= first;
+    s.availC = s.mbx < c.mb_w - 1 && addr - c.mb_w + 1 >= first;
+    s.availD = s.mbx > 0 && addr - c.mb_w - 1 >= first;
+    bool skipped = false;
+    if (sd.slice_type != SLICE_I) {
+      if (s.cabac) {
+        int ctx = (s.availA && !(s.left.flags & NBF_SKIP)) + (s.availB && !(s.line[s.mbx].flags & NBF_SKIP));
+        skipped = cabac_decision(s.cab, s.br, s.st + (sd.slice_type == SLICE_B ? 24 : 11) + ctx) != 0;
+      } else {
+        if (run < 0) {
+          run = (int)br_ue(s.br);
+          if (run > c.nmb - addr) { sd_fail(s, 60); break; }
+        }
+        if (run > 0) { skipped = true; run--; }
+      }
+    }
+    decode_mb(s, skipped);
+    if (s.error || s.br.overrun) break;
+    if (s.cabac) {
+      end = cabac_terminate(s.cab, s.br) != 0;
+    } else if (skipped) {
+      if (run == 0 && !br_more_rbsp_data(s.br, s.stop_bitpos)) end = true;
+    } else {
+      run = -1;
+      if (!br_more_rbsp_data(s.br, s.stop_bitpos)) end = true;
+    }
+    addr++;
+    if (addr % c.mb_w == 0 || end || addr == c.nmb) {
+#if HWB_DEVICE_BUILD
+      __threadfence();
+      *((volatile int32_t *)(c.entropy_prog + slice_idx)) = (end || addr == c.nmb) ? c.nmb : addr;
+#else
+      c.entropy_prog[slice_idx] = (end || addr == c.nmb) ? c.nmb : addr;
+#endif
+    }
+  }
+  if (s.error || s.br.overrun) {
+#if HWB_DEVICE_BUILD
+    atomicExch(c.error_flag, s.error ? s.error : 99);
+    __threadfence();
+    *((volatile int32_t *)(c.entropy_prog + slice_idx)) = c.nmb;  // never leave consumers spinning
+#else
+    *c.error_flag = s.error ? s.error : 99;
+    c.entropy_prog[slice_idx] = c.nmb;
+#endif
+  }
+}
+
+}  // namespace hwb
