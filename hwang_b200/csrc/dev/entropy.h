@@ -69,6 +69,8 @@ HWB_HD void fill_caches(SliceDec &s, bool cur_intra_for_cbf_unused) {
   const NbCtx *TRp = s.availC ? &s.line[s.mbx + 1] : nullptr;
   for (int i = 0; i < 30; ++i) { s.nz_cache[i] = 0x80; s.im_cache[i] = -1; s.dir_cache[i] = 0; }
   for (int p = 0; p < 2; ++p) for (int i = 0; i < 12; ++i) s.cnz_cache[p][i] = 0x80;
+  for (int i = 0; i < 16; ++i) s.nz_cache[HWB_CI(i & 3, i >> 2)] = 0;  // own blocks: available, nothing coded yet
+  for (int p = 0; p < 2; ++p) for (int i = 0; i < 4; ++i) s.cnz_cache[p][((i >> 1) + 1) * 4 + (i & 1) + 1] = 0;
   for (int l = 0; l < nl; ++l)
     for (int i = 0; i < 30; ++i) { s.ref_cache[l][i] = REF_UNAVAIL; s.mv_cache[l][i][0] = s.mv_cache[l][i][1] = 0; s.mvd_cache[l][i][0] = s.mvd_cache[l][i][1] = 0; }
   const bool cip = s.pd->constrained_intra_pred != 0;
@@ -604,6 +606,65 @@ HWB_HD int cabac_chroma_mode(SliceDec &s) {
   return 2 + cabac_decision(s.cab, s.br, s.st + 64 + 3);
 }
 
+// Publish a decoded macroblock: MbInfo, final motion data, and the neighbour context for the
+// macroblocks to come.  Shared by the decoder and by the stream generator's entropy writer.
+HWB_FN void finish_mb(SliceDec &s, const uint8_t nnz_l[16], const uint8_t nnz_c[2][4], const int8_t imodes_r[16],
+                      bool skipped, bool direct16, bool is_pcm) {
+  const ChunkCtx &c = *s.c;
+  const SliceDesc &sd = *s.sd;
+  const bool B = sd.slice_type == SLICE_B;
+  const int nl = B ? 2 : 1;
+  MbInfo &o = s.out;
+  // ---------------- write outputs
+  const int f = s.pd->frame;
+  pic_mbinfo(c, f)[s.mbaddr] = o;
+  const bool inter = o.mbtype == MB_INTER;
+  if (inter) {
+    for (int l = 0; l < nl; ++l) {
+      int16_t *mvo = pic_mv(c, f, l) + (uint64_t)s.mbaddr * 32;
+      int8_t *ro = pic_refidx(c, f, l) + (uint64_t)s.mbaddr * 4;
+      int16_t *po = pic_refpic(c, f, l) + (uint64_t)s.mbaddr * 4;
+      for (int i = 0; i < 16; ++i) { int ci = HWB_CI(i & 3, i >> 2); mvo[2 * i] = s.mv_cache[l][ci][0]; mvo[2 * i + 1] = s.mv_cache[l][ci][1]; }
+      for (int q = 0; q < 4; ++q) {
+        int r = s.ref_cache[l][HWB_CI((q & 1) * 2, (q >> 1) * 2)];
+        ro[q] = (int8_t)r;
+        po[q] = r >= 0 ? sd.ref_frame[l][r] : (int16_t)-1;
+      }
+    }
+    if (!B && s.pd->has_inter == 2) {
+      int8_t *ro = pic_refidx(c, f, 1) + (uint64_t)s.mbaddr * 4;
+      int16_t *po = pic_refpic(c, f, 1) + (uint64_t)s.mbaddr * 4;
+      for (int q = 0; q < 4; ++q) { ro[q] = -1; po[q] = -1; }
+    }
+  }
+  // ---------------- neighbour context for the macroblocks to come
+  NbCtx n;
+  n.flags = (uint8_t)((inter ? 0 : NBF_INTRA) | (is_pcm ? NBF_IPCM : 0) | (skipped ? NBF_SKIP : 0) | (direct16 ? NBF_DIRECT16 : 0) |
+                      ((o.flags & MBF_T8x8) ? NBF_T8 : 0) | (o.mbtype == MB_I16x16 ? NBF_I16 : 0) | ((o.mbtype == MB_I4x4 || o.mbtype == MB_I8x8) ? NBF_INXN : 0));
+  n.cbp = o.cbp; n.cmode = o.cmode; n.cbf = is_pcm ? 0x7FFFFFFu : o.nzmask;
+  n.dirmask = 0;
+  for (int i = 0; i < 4; ++i) {
+    n.nnz_b[i] = nnz_l[12 + i]; n.nnz_r[i] = nnz_l[i * 4 + 3];
+    n.imode_b[i] = imodes_r[12 + i]; n.imode_r[i] = imodes_r[i * 4 + 3];
+    if (s.dir_cache[HWB_CI(i, 3)]) n.dirmask |= 1u << i;
+    if (s.dir_cache[HWB_CI(3, i)]) n.dirmask |= 16u << i;
+    for (int l = 0; l < 2; ++l) {
+      bool on = inter && l < nl;
+      int cb = HWB_CI(i, 3), cr = HWB_CI(3, i);
+      n.ref_b[l][i] = on ? s.ref_cache[l][cb] : (int8_t)REF_NONE;
+      n.ref_r[l][i] = on ? s.ref_cache[l][cr] : (int8_t)REF_NONE;
+      for (int k = 0; k < 2; ++k) {
+        n.mv_b[l][i][k] = on ? s.mv_cache[l][cb][k] : (int16_t)0; n.mv_r[l][i][k] = on ? s.mv_cache[l][cr][k] : (int16_t)0;
+        n.mvd_b[l][i][k] = on ? s.mvd_cache[l][cb][k] : (uint8_t)0; n.mvd_r[l][i][k] = on ? s.mvd_cache[l][cr][k] : (uint8_t)0;
+      }
+    }
+  }
+  for (int p = 0; p < 2; ++p) { n.cnnz_b[p][0] = nnz_c[p][2]; n.cnnz_b[p][1] = nnz_c[p][3]; n.cnnz_r[p][0] = nnz_c[p][1]; n.cnnz_r[p][1] = nnz_c[p][3]; }
+  s.topleft = s.line[s.mbx];
+  s.line[s.mbx] = n;
+  s.left = n;
+}
+
 // ================================================================================ macroblock layer
 // prediction flags (1 L0, 2 L1, 3 Bi) of the two partitions of B 16x8 / 8x16 types, by (mb_type-4)>>1
 HWB_TABLE uint8_t b_part_pred[18] = {1, 1, 2, 2, 1, 2, 2, 1, 1, 3, 2, 3, 3, 1, 3, 2, 3, 3};
@@ -878,54 +939,7 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
     }
   }
 
-  // ---------------- write outputs
-  const int f = s.pd->frame;
-  pic_mbinfo(c, f)[s.mbaddr] = o;
-  const bool inter = o.mbtype == MB_INTER;
-  if (inter) {
-    for (int l = 0; l < nl; ++l) {
-      int16_t *mvo = pic_mv(c, f, l) + (uint64_t)s.mbaddr * 32;
-      int8_t *ro = pic_refidx(c, f, l) + (uint64_t)s.mbaddr * 4;
-      int16_t *po = pic_refpic(c, f, l) + (uint64_t)s.mbaddr * 4;
-      for (int i = 0; i < 16; ++i) { int ci = HWB_CI(i & 3, i >> 2); mvo[2 * i] = s.mv_cache[l][ci][0]; mvo[2 * i + 1] = s.mv_cache[l][ci][1]; }
-      for (int q = 0; q < 4; ++q) {
-        int r = s.ref_cache[l][HWB_CI((q & 1) * 2, (q >> 1) * 2)];
-        ro[q] = (int8_t)r;
-        po[q] = r >= 0 ? sd.ref_frame[l][r] : (int16_t)-1;
-      }
-    }
-    if (!B && s.pd->has_inter == 2) {
-      int8_t *ro = pic_refidx(c, f, 1) + (uint64_t)s.mbaddr * 4;
-      int16_t *po = pic_refpic(c, f, 1) + (uint64_t)s.mbaddr * 4;
-      for (int q = 0; q < 4; ++q) { ro[q] = -1; po[q] = -1; }
-    }
-  }
-  // ---------------- neighbour context for the macroblocks to come
-  NbCtx n;
-  n.flags = (uint8_t)((inter ? 0 : NBF_INTRA) | (is_pcm ? NBF_IPCM : 0) | (skipped ? NBF_SKIP : 0) | (direct16 ? NBF_DIRECT16 : 0) |
-                      ((o.flags & MBF_T8x8) ? NBF_T8 : 0) | (o.mbtype == MB_I16x16 ? NBF_I16 : 0) | ((o.mbtype == MB_I4x4 || o.mbtype == MB_I8x8) ? NBF_INXN : 0));
-  n.cbp = o.cbp; n.cmode = o.cmode; n.cbf = is_pcm ? 0x7FFFFFFu : o.nzmask;
-  n.dirmask = 0;
-  for (int i = 0; i < 4; ++i) {
-    n.nnz_b[i] = nnz_l[12 + i]; n.nnz_r[i] = nnz_l[i * 4 + 3];
-    n.imode_b[i] = imodes_r[12 + i]; n.imode_r[i] = imodes_r[i * 4 + 3];
-    if (s.dir_cache[HWB_CI(i, 3)]) n.dirmask |= 1u << i;
-    if (s.dir_cache[HWB_CI(3, i)]) n.dirmask |= 16u << i;
-    for (int l = 0; l < 2; ++l) {
-      bool on = inter && l < nl;
-      int cb = HWB_CI(i, 3), cr = HWB_CI(3, i);
-      n.ref_b[l][i] = on ? s.ref_cache[l][cb] : (int8_t)REF_NONE;
-      n.ref_r[l][i] = on ? s.ref_cache[l][cr] : (int8_t)REF_NONE;
-      for (int k = 0; k < 2; ++k) {
-        n.mv_b[l][i][k] = on ? s.mv_cache[l][cb][k] : (int16_t)0; n.mv_r[l][i][k] = on ? s.mv_cache[l][cr][k] : (int16_t)0;
-        n.mvd_b[l][i][k] = on ? s.mvd_cache[l][cb][k] : (uint8_t)0; n.mvd_r[l][i][k] = on ? s.mvd_cache[l][cr][k] : (uint8_t)0;
-      }
-    }
-  }
-  for (int p = 0; p < 2; ++p) { n.cnnz_b[p][0] = nnz_c[p][2]; n.cnnz_b[p][1] = nnz_c[p][3]; n.cnnz_r[p][0] = nnz_c[p][1]; n.cnnz_r[p][1] = nnz_c[p][3]; }
-  s.topleft = s.line[s.mbx];
-  s.line[s.mbx] = n;
-  s.left = n;
+  finish_mb(s, nnz_l, nnz_c, imodes_r, skipped, direct16, is_pcm);
 }
 
 // ================================================================================ slice

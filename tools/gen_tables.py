@@ -233,7 +233,7 @@ v4 = np.zeros((6, 16), np.uint8)
 for q in range(6):
     for i in range(16):
         x, y = i & 3, i >> 2
-        v4[q, i] = dq4[q, 0 if (x % 2 == 0 and y % 2 == 0) else (1 if (x % 2 == 1 and y % 2 == 1) else 2)]
+        v4[q, i] = dq4[q, (x & 1) + (y & 1)]  # {both even: 10.., one odd: 13.., both odd: 16..}
 emit('dequant4_v', v4)
 scan8 = [0, 3, 4, 3, 3, 1, 5, 1, 4, 5, 2, 5, 3, 1, 5, 1]
 v8 = np.zeros((6, 64), np.uint8)
