@@ -1,0 +1,274 @@
+// CUDA side of the decoder: kernels for sm_100a and the thin C-ABI (csrc/dev/devapi.h) the C++ host
+// calls.  No tensor cores (there is no dense contraction on this path): the kernels are
+// integer/byte work organised around the two structural constraints of H.264 decoding:
+//   * entropy decoding is serial per slice  -> one warp per slice, every slice of every picture of
+//     the chunk in flight at once, handed out in decode order by an atomic ticket (which also makes
+//     the B-direct co-located-picture wait deadlock-free);
+//   * intra prediction and deblocking depend on the left / top / top-right macroblocks
+//     -> one warp per macroblock row, rows of a picture form a wavefront synchronised through
+//        per-row progress counters in global memory, many pictures (all pictures of one dependency
+//        level of the chunk) per launch so the wavefronts of different pictures fill the 148 SMs.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <string>
+
+#include "../dev/deblock.h"
+#include "../dev/devapi.h"
+#include "../dev/entropy.h"
+#include "../dev/recon.h"
+#include "../dev/rgb.h"
+
+using namespace hwb;
+
+namespace {
+
+constexpr int kWarpsPerBlock = 4;
+constexpr int kThreads = kWarpsPerBlock * 32;
+
+__device__ __forceinline__ int warp_ticket(int32_t *ticket) {
+  int t = 0;
+  if ((threadIdx.x & 31) == 0) t = atomicAdd(ticket, 1);
+  return __shfl_sync(0xffffffffu, t, 0);
+}
+
+// ------------------------------------------------------------------------------------ entropy
+__global__ void __launch_bounds__(kThreads) entropy_kernel(ChunkCtx c, int32_t *ticket) {
+  __shared__ uint8_t states[kWarpsPerBlock][464];
+  const int w = threadIdx.x >> 5;
+  for (;;) {
+    const int s = warp_ticket(ticket);
+    if (s >= c.num_slices) return;
+    if ((threadIdx.x & 31) == 0) decode_slice(c, s, states[w]);
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------ reconstruction
+__device__ __forceinline__ void wait_progress(const int32_t *p, int need) {
+  if ((threadIdx.x & 31) == 0) {
+    while (*((volatile const int32_t *)p) < need) __nanosleep(64);
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void publish_progress(int32_t *p, int v) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {
+    __threadfence();
+    *((volatile int32_t *)p) = v;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) recon_kernel(ChunkCtx c, const int32_t *pics, int npics, int32_t *ticket) {
+  __shared__ ReconScratch sm[kWarpsPerBlock];
+  ReconScratch *my = &sm[threadIdx.x >> 5];
+  const int total = npics * c.mb_h;
+  for (;;) {
+    const int t = warp_ticket(ticket);
+    if (t >= total) return;
+    const int pic = pics[t / c.mb_h], y = t % c.mb_h;
+    const MbInfo *mbs = pic_mbinfo(c, c.pics[pic].frame);
+    int32_t *prog = c.recon_prog + (size_t)pic * c.mb_h;
+    for (int x = 0; x < c.mb_w; ++x) {
+      // intra macroblocks read the unfiltered row above up to the top-right neighbour
+      if (y > 0 && mbs[y * c.mb_w + x].mbtype != MB_INTER) wait_progress(prog + y - 1, x + 2 < c.mb_w ? x + 2 : c.mb_w);
+      recon_mb(c, pic, x, y, my);
+      publish_progress(prog + y, x + 1);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) deblock_kernel(ChunkCtx c, const int32_t *pics, int npics, int32_t *ticket) {
+  __shared__ DeblockScratch sm[kWarpsPerBlock];
+  DeblockScratch *my = &sm[threadIdx.x >> 5];
+  const int total = npics * c.mb_h;
+  for (;;) {
+    const int t = warp_ticket(ticket);
+    if (t >= total) return;
+    const int pic = pics[t / c.mb_h], y = t % c.mb_h;
+    int32_t *prog = c.dbl_prog + (size_t)pic * c.mb_h;
+    for (int x = 0; x < c.mb_w; ++x) {
+      if (y > 0) wait_progress(prog + y - 1, x + 2 < c.mb_w ? x + 2 : c.mb_w);
+      deblock_mb(c, pic, x, y, my);
+      publish_progress(prog + y, x + 1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ output
+__global__ void __launch_bounds__(256) rgb24_kernel(ChunkCtx c, int frame, int crop_x, int crop_y, int w, int h, uint8_t *dst) {
+  const int nx = (w + 15) >> 4;
+  const int total = nx * h;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+    rgb24_item(c, frame, crop_x, crop_y, w, h, dst, i % nx, i / nx);
+}
+
+__global__ void __launch_bounds__(256) yuv_kernel(ChunkCtx c, int frame, int crop_x, int crop_y, int w, int h, uint8_t *dst) {
+  const int total = w * h + 2 * (w / 2) * (h / 2);
+  const uint8_t *Y = frame_y(c, frame), *U = frame_cb(c, frame), *V = frame_cr(c, frame);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    if (i < w * h) dst[i] = Y[(size_t)(crop_y + i / w) * c.wc + crop_x + i % w];
+    else {
+      int k = i - w * h, cw = w / 2, ch = h / 2;
+      const uint8_t *P = k < cw * ch ? U : V;
+      if (k >= cw * ch) k -= cw * ch;
+      dst[i] = P[(size_t)(crop_y / 2 + k / cw) * (c.wc / 2) + crop_x / 2 + k % cw];
+    }
+  }
+}
+
+}  // namespace
+
+// ========================================================================================= C-ABI
+struct hwb_dev {
+  int device = 0;
+  int sms = 148;
+  cudaStream_t streams[HWB_NUM_STREAMS];
+  std::string err;
+  std::atomic<uint64_t> launches{0};
+};
+struct hwb_event { cudaEvent_t ev; };
+
+#define HWB_CUDA(d, expr)                                                                             \
+  do {                                                                                                \
+    cudaError_t e__ = (expr);                                                                         \
+    if (e__ != cudaSuccess) { (d)->err = std::string(#expr) + ": " + cudaGetErrorString(e__); return 1; } \
+  } while (0)
+
+extern "C" {
+
+int hwb_dev_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int hwb_dev_open(int device, hwb_dev **out) {
+  *out = nullptr;
+  int n = hwb_dev_count();
+  if (device < 0 || device >= n) return 1;
+  if (cudaSetDevice(device) != cudaSuccess) return 1;
+  hwb_dev *d = new hwb_dev();
+  d->device = device;
+  cudaDeviceGetAttribute(&d->sms, cudaDevAttrMultiProcessorCount, device);
+  for (int i = 0; i < HWB_NUM_STREAMS; ++i)
+    if (cudaStreamCreateWithFlags(&d->streams[i], cudaStreamNonBlocking) != cudaSuccess) { delete d; return 1; }
+  *out = d;
+  return 0;
+}
+void hwb_dev_close(hwb_dev *d) {
+  if (!d) return;
+  cudaSetDevice(d->device);
+  for (int i = 0; i < HWB_NUM_STREAMS; ++i) cudaStreamDestroy(d->streams[i]);
+  delete d;
+}
+const char *hwb_dev_error(hwb_dev *d) { return d->err.c_str(); }
+
+void *hwb_dev_malloc(hwb_dev *d, size_t n) {
+  cudaSetDevice(d->device);
+  void *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, n ? n : 1);
+  if (e != cudaSuccess) { d->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); cudaGetLastError(); return nullptr; }
+  return p;
+}
+void hwb_dev_free(hwb_dev *d, void *p) { cudaSetDevice(d->device); cudaFree(p); }
+void *hwb_dev_malloc_host(hwb_dev *d, size_t n) {
+  cudaSetDevice(d->device);
+  void *p = nullptr;
+  cudaError_t e = cudaHostAlloc(&p, n ? n : 1, cudaHostAllocPortable);
+  if (e != cudaSuccess) { d->err = std::string("cudaHostAlloc: ") + cudaGetErrorString(e); cudaGetLastError(); return nullptr; }
+  return p;
+}
+void hwb_dev_free_host(hwb_dev *d, void *p) { cudaSetDevice(d->device); cudaFreeHost(p); }
+int hwb_dev_is_pinned(hwb_dev *d, const void *p) {
+  cudaPointerAttributes a;
+  cudaSetDevice(d->device);
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return a.type == cudaMemoryTypeHost ? 1 : 0;
+}
+
+int hwb_dev_h2d(hwb_dev *d, int s, void *dst, const void *src, size_t n) {
+  cudaSetDevice(d->device);
+  HWB_CUDA(d, cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, d->streams[s]));
+  return 0;
+}
+int hwb_dev_d2h(hwb_dev *d, int s, void *dst, const void *src, size_t n) {
+  cudaSetDevice(d->device);
+  HWB_CUDA(d, cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, d->streams[s]));
+  return 0;
+}
+int hwb_dev_memset(hwb_dev *d, int s, void *dst, int v, size_t n) {
+  cudaSetDevice(d->device);
+  HWB_CUDA(d, cudaMemsetAsync(dst, v, n, d->streams[s]));
+  return 0;
+}
+
+static int grid_for(hwb_dev *d, int work_warps, int blocks_per_sm) {
+  int blocks = (work_warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  int cap = d->sms * blocks_per_sm;  // a multiple of the SM count; warps loop over tickets
+  return blocks < cap ? (blocks < 1 ? 1 : blocks) : cap;
+}
+
+int hwb_dev_entropy(hwb_dev *d, int s, const ChunkCtx *c, int32_t *ticket) {
+  cudaSetDevice(d->device);
+  entropy_kernel<<<grid_for(d, c->num_slices, 8), kThreads, 0, d->streams[s]>>>(*c, ticket);
+  HWB_CUDA(d, cudaGetLastError());
+  d->launches++;
+  return 0;
+}
+int hwb_dev_recon(hwb_dev *d, int s, const ChunkCtx *c, const int32_t *pics, int npics, int32_t *ticket) {
+  cudaSetDevice(d->device);
+  recon_kernel<<<grid_for(d, npics * c->mb_h, 8), kThreads, 0, d->streams[s]>>>(*c, pics, npics, ticket);
+  HWB_CUDA(d, cudaGetLastError());
+  d->launches++;
+  return 0;
+}
+int hwb_dev_deblock(hwb_dev *d, int s, const ChunkCtx *c, const int32_t *pics, int npics, int32_t *ticket) {
+  cudaSetDevice(d->device);
+  deblock_kernel<<<grid_for(d, npics * c->mb_h, 8), kThreads, 0, d->streams[s]>>>(*c, pics, npics, ticket);
+  HWB_CUDA(d, cudaGetLastError());
+  d->launches++;
+  return 0;
+}
+int hwb_dev_rgb24(hwb_dev *d, int s, const ChunkCtx *c, int frame, int crop_x, int crop_y, int w, int h, uint8_t *dst) {
+  cudaSetDevice(d->device);
+  int items = ((w + 15) / 16) * h;
+  int blocks = (items + 255) / 256;
+  if (blocks > d->sms * 8) blocks = d->sms * 8;
+  rgb24_kernel<<<blocks, 256, 0, d->streams[s]>>>(*c, frame, crop_x, crop_y, w, h, dst);
+  HWB_CUDA(d, cudaGetLastError());
+  d->launches++;
+  return 0;
+}
+int hwb_dev_yuv(hwb_dev *d, int s, const ChunkCtx *c, int frame, int crop_x, int crop_y, int w, int h, uint8_t *dst) {
+  cudaSetDevice(d->device);
+  yuv_kernel<<<d->sms * 4, 256, 0, d->streams[s]>>>(*c, frame, crop_x, crop_y, w, h, dst);
+  HWB_CUDA(d, cudaGetLastError());
+  d->launches++;
+  return 0;
+}
+
+hwb_event *hwb_dev_event_create(hwb_dev *d) {
+  cudaSetDevice(d->device);
+  hwb_event *e = new hwb_event();
+  if (cudaEventCreate(&e->ev) != cudaSuccess) { delete e; return nullptr; }
+  return e;
+}
+void hwb_dev_event_destroy(hwb_dev *d, hwb_event *e) { if (!e) return; cudaSetDevice(d->device); cudaEventDestroy(e->ev); delete e; }
+int hwb_dev_event_record(hwb_dev *d, hwb_event *e, int s) { cudaSetDevice(d->device); HWB_CUDA(d, cudaEventRecord(e->ev, d->streams[s])); return 0; }
+int hwb_dev_event_done(hwb_dev *d, hwb_event *e) {
+  cudaSetDevice(d->device);
+  cudaError_t r = cudaEventQuery(e->ev);
+  if (r == cudaSuccess) return 1;
+  if (r == cudaErrorNotReady) { cudaGetLastError(); return 0; }
+  d->err = std::string("cudaEventQuery: ") + cudaGetErrorString(r);
+  return -1;
+}
+int hwb_dev_event_sync(hwb_dev *d, hwb_event *e) { cudaSetDevice(d->device); HWB_CUDA(d, cudaEventSynchronize(e->ev)); return 0; }
+int hwb_dev_stream_wait(hwb_dev *d, int s, hwb_event *e) { cudaSetDevice(d->device); HWB_CUDA(d, cudaStreamWaitEvent(d->streams[s], e->ev, 0)); return 0; }
+int hwb_dev_stream_sync(hwb_dev *d, int s) { cudaSetDevice(d->device); HWB_CUDA(d, cudaStreamSynchronize(d->streams[s])); return 0; }
+int hwb_dev_event_elapsed(hwb_dev *d, hwb_event *a, hwb_event *b, float *ms) { cudaSetDevice(d->device); HWB_CUDA(d, cudaEventElapsedTime(ms, a->ev, b->ev)); return 0; }
+uint64_t hwb_dev_launch_count(hwb_dev *d) { return d->launches.load(); }
+}

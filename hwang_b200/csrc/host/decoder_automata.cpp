@@ -1,0 +1,157 @@
+#include "decoder_automata.h"
+
+namespace hwang {
+
+DecoderAutomata *DecoderAutomata::make_instance(DeviceHandle device_handle, int32_t num_devices, VideoDecoderType decoder_type) {
+  // reference: decoder_automata.cpp:44-53
+  VideoDecoderInterface *decoder = VideoDecoderFactory::make_from_config(device_handle, num_devices, decoder_type);
+  if (decoder == nullptr) return nullptr;
+  return new DecoderAutomata(device_handle, num_devices, decoder_type, decoder);
+}
+
+DecoderAutomata *DecoderAutomata::make_with_decoder(VideoDecoderInterface *decoder) {
+  if (decoder == nullptr) return nullptr;
+  return new DecoderAutomata(CPU_DEVICE, 1, VideoDecoderType::B200, decoder);
+}
+
+DecoderAutomata::DecoderAutomata(DeviceHandle device_handle, int32_t num_devices, VideoDecoderType decoder_type, VideoDecoderInterface *decoder)
+    : device_handle_(device_handle), num_devices_(num_devices), decoder_type_(decoder_type), decoder_(decoder) {
+  feeder_thread_ = std::thread(&DecoderAutomata::feeder, this);
+}
+
+DecoderAutomata::~DecoderAutomata() {
+  // reference: decoder_automata.cpp:55-78 (drain, flush, join)
+  stop_feeder();
+  {
+    std::unique_lock<std::mutex> lk(mu_);
+    quit_ = true;
+  }
+  cv_.notify_all();
+  feeder_thread_.join();
+  decoder_->flush();
+  while (decoder_->decoded_frames_buffered() > 0) { if (!decoder_->discard_frame().ok) break; }
+}
+
+void DecoderAutomata::stop_feeder() {
+  abort_ = true;
+  std::unique_lock<std::mutex> lk(mu_);
+  cv_.wait(lk, [&] { return parked_; });
+  work_ = false;
+  abort_ = false;
+}
+
+Result DecoderAutomata::validate(const std::vector<EncodedData> &encoded_data) const {
+  for (auto &d : encoded_data) {
+    if (d.end_keyframe < d.start_keyframe) return Result(false, "EncodedData: end_keyframe < start_keyframe");
+    const uint64_t n = d.end_keyframe - d.start_keyframe;
+    if (d.sample_offsets.size() < n || d.sample_sizes.size() < n) return Result(false, "EncodedData: sample tables shorter than the interval");
+    for (uint64_t i = 0; i < n; ++i)
+      if (d.sample_offsets[i] + d.sample_sizes[i] > d.encoded_video.size()) return Result(false, "EncodedData: sample outside encoded_video");
+    uint64_t prev = 0;
+    bool first = true;
+    for (uint64_t v : d.valid_frames) {
+      if (v < d.start_keyframe || v >= d.end_keyframe) return Result(false, "EncodedData: valid frame outside the interval");
+      if (!first && v <= prev) return Result(false, "EncodedData: valid_frames must be strictly ascending");
+      prev = v; first = false;
+    }
+    if (d.width != encoded_data[0].width || d.height != encoded_data[0].height || d.format != encoded_data[0].format)
+      return Result(false, "EncodedData: all intervals must share width/height/format");
+  }
+  return Result();
+}
+
+Result DecoderAutomata::initialize(const std::vector<EncodedData> &encoded_data, const std::vector<uint8_t> &extradata) {
+  // reference: decoder_automata.cpp:80-118
+  stop_feeder();
+  decoder_->flush();
+  while (decoder_->decoded_frames_buffered() > 0) HWANG_RETURN_ON_ERROR(decoder_->discard_frame());
+  decoder_->wait_until_frames_copied();
+  result_set_ = false;
+  feeder_result_ = Result();
+  encoded_data_.clear();
+  interval_ = 0; popped_ = 0; valid_idx_ = 0;
+  if (encoded_data.empty()) return Result();
+  HWANG_RETURN_ON_ERROR(validate(encoded_data));
+  encoded_data_ = encoded_data;
+  info_.width = encoded_data_[0].width; info_.height = encoded_data_[0].height; info_.format = encoded_data_[0].format;
+  frame_size_ = (size_t)info_.width * info_.height * 3;
+  HWANG_RETURN_ON_ERROR(decoder_->configure(info_, extradata));
+  {
+    std::unique_lock<std::mutex> lk(mu_);
+    work_ = true;
+    parked_ = false;
+  }
+  cv_.notify_all();
+  return Result();
+}
+
+void DecoderAutomata::feeder() {
+  // reference: decoder_automata.cpp:259-404
+  for (;;) {
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      parked_ = true;
+      cv_.notify_all();
+      cv_.wait(lk, [&] { return quit_ || (work_ && !parked_) ; });
+      if (quit_) return;
+    }
+    bool failed = false;
+    for (size_t di = 0; di < encoded_data_.size() && !abort_ && !failed; ++di) {
+      const EncodedData &d = encoded_data_[di];
+      const uint64_t n = d.end_keyframe - d.start_keyframe;
+      size_t next_kf = 0;
+      for (uint64_t i = 0; i < n && !abort_; ++i) {
+        while (!abort_ && decoder_->decoded_frames_buffered() > MAX_BUFFERED_FRAMES) std::this_thread::yield();
+        if (abort_) break;
+        const uint64_t frame = d.start_keyframe + i;
+        bool is_keyframe = false;
+        while (next_kf < d.keyframes.size() && d.keyframes[next_kf] < frame) next_kf++;
+        if (next_kf < d.keyframes.size() && d.keyframes[next_kf] == frame) { is_keyframe = true; next_kf++; }
+        Result r = decoder_->feed(d.encoded_video.data() + d.sample_offsets[i], (size_t)d.sample_sizes[i], is_keyframe);
+        if (!r.ok) { feeder_result_ = r; result_set_ = true; failed = true; break; }
+      }
+      if (abort_ || failed) break;
+      // end of interval: everything fed must become poppable (reference :383-397)
+      Result r = decoder_->feed(nullptr, 0, false);
+      if (r.ok) r = decoder_->flush();
+      if (!r.ok) { feeder_result_ = r; result_set_ = true; failed = true; }
+    }
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      work_ = false;
+    }
+  }
+}
+
+Result DecoderAutomata::get_frames(uint8_t *buffer, int32_t num_frames) {
+  // reference: decoder_automata.cpp:120-252
+  int32_t got = 0;
+  while (got < num_frames) {
+    if (result_set_) return feeder_result_;
+    // advance past exhausted intervals (their unwanted tail frames are popped and dropped)
+    if (interval_ >= encoded_data_.size()) return Result(false, "get_frames: requested more frames than the intervals contain");
+    const EncodedData &d = encoded_data_[interval_];
+    const uint64_t total = d.end_keyframe - d.start_keyframe;
+    if (popped_ >= total) { interval_++; popped_ = 0; valid_idx_ = 0; continue; }
+    if (valid_idx_ >= d.valid_frames.size()) {
+      // nothing more wanted here: make sure later intervals still hold wanted frames before waiting on this tail
+      bool more = false;
+      for (size_t j = interval_ + 1; j < encoded_data_.size(); ++j) more |= !encoded_data_[j].valid_frames.empty();
+      if (!more) return Result(false, "get_frames: requested more frames than the intervals contain");
+    }
+    if (decoder_->decoded_frames_buffered() <= 0) { std::this_thread::yield(); continue; }
+    const uint64_t frame = d.start_keyframe + popped_;
+    if (valid_idx_ < d.valid_frames.size() && d.valid_frames[valid_idx_] == frame) {
+      HWANG_RETURN_ON_ERROR(decoder_->get_frame(buffer + (size_t)got * frame_size_, frame_size_));
+      valid_idx_++; got++;
+    } else {
+      HWANG_RETURN_ON_ERROR(decoder_->discard_frame());
+    }
+    popped_++;
+  }
+  HWANG_RETURN_ON_ERROR(decoder_->wait_until_frames_copied());
+  if (result_set_) return feeder_result_;
+  return Result();
+}
+
+}  // namespace hwang

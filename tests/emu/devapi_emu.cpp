@@ -1,0 +1,86 @@
+// TEST INFRASTRUCTURE ONLY.  Host emulation of the CUDA-side C-ABI (hwang_b200/csrc/dev/devapi.h):
+// the very same device functions (entropy.h / recon.h / deblock.h / rgb.h, compiled with a plain C++
+// compiler, lanes run as loops) executed serially in ticket order.  It exists so that the CPU-only
+// test tier can exercise the decode core and the host scheduler bit-exactly against the oracle on
+// machines without a GPU.  It is built into tests/emu/libhwb_emu.so, never into the product library
+// (hwang_b200/libhwang_b200.so links csrc/cuda/kernels.cu instead and fails loudly without a GPU).
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+
+#include "../../hwang_b200/csrc/dev/deblock.h"
+#include "../../hwang_b200/csrc/dev/devapi.h"
+#include "../../hwang_b200/csrc/dev/entropy.h"
+#include "../../hwang_b200/csrc/dev/recon.h"
+#include "../../hwang_b200/csrc/dev/rgb.h"
+
+using namespace hwb;
+
+struct hwb_dev { std::string err; uint64_t launches = 0; };
+struct hwb_event { int dummy; };
+
+extern "C" {
+
+int hwb_dev_count(void) { return 1; }
+int hwb_dev_open(int, hwb_dev **out) { *out = new hwb_dev(); return 0; }
+void hwb_dev_close(hwb_dev *d) { delete d; }
+const char *hwb_dev_error(hwb_dev *d) { return d->err.c_str(); }
+void *hwb_dev_malloc(hwb_dev *, size_t n) { return malloc(n ? n : 1); }
+void hwb_dev_free(hwb_dev *, void *p) { free(p); }
+void *hwb_dev_malloc_host(hwb_dev *, size_t n) { return malloc(n ? n : 1); }
+void hwb_dev_free_host(hwb_dev *, void *p) { free(p); }
+int hwb_dev_is_pinned(hwb_dev *, const void *) { return 0; }
+int hwb_dev_h2d(hwb_dev *, int, void *dst, const void *src, size_t n) { memcpy(dst, src, n); return 0; }
+int hwb_dev_d2h(hwb_dev *, int, void *dst, const void *src, size_t n) { memcpy(dst, src, n); return 0; }
+int hwb_dev_memset(hwb_dev *, int, void *dst, int v, size_t n) { memset(dst, v, n); return 0; }
+
+int hwb_dev_entropy(hwb_dev *d, int, const ChunkCtx *c, int32_t *) {
+  uint8_t states[1024];
+  for (int s = 0; s < c->num_slices; ++s) decode_slice(*c, s, states);
+  d->launches++;
+  return 0;
+}
+int hwb_dev_recon(hwb_dev *d, int, const ChunkCtx *c, const int32_t *pics, int npics, int32_t *) {
+  ReconScratch sm;
+  for (int i = 0; i < npics; ++i)
+    for (int y = 0; y < c->mb_h; ++y)
+      for (int x = 0; x < c->mb_w; ++x) recon_mb(*c, pics[i], x, y, &sm);
+  d->launches++;
+  return 0;
+}
+int hwb_dev_deblock(hwb_dev *d, int, const ChunkCtx *c, const int32_t *pics, int npics, int32_t *) {
+  DeblockScratch sm;
+  for (int i = 0; i < npics; ++i)
+    for (int y = 0; y < c->mb_h; ++y)
+      for (int x = 0; x < c->mb_w; ++x) deblock_mb(*c, pics[i], x, y, &sm);
+  d->launches++;
+  return 0;
+}
+int hwb_dev_rgb24(hwb_dev *d, int, const ChunkCtx *c, int frame, int crop_x, int crop_y, int w, int h, uint8_t *dst) {
+  for (int y = 0; y < h; ++y)
+    for (int x16 = 0; x16 < (w + 15) / 16; ++x16) rgb24_item(*c, frame, crop_x, crop_y, w, h, dst, x16, y);
+  d->launches++;
+  return 0;
+}
+int hwb_dev_yuv(hwb_dev *d, int, const ChunkCtx *c, int frame, int crop_x, int crop_y, int w, int h, uint8_t *dst) {
+  const uint8_t *Y = frame_y(*c, frame), *U = frame_cb(*c, frame), *V = frame_cr(*c, frame);
+  for (int y = 0; y < h; ++y) memcpy(dst + (size_t)y * w, Y + (size_t)(crop_y + y) * c->wc + crop_x, w);
+  uint8_t *du = dst + (size_t)w * h, *dv = du + (size_t)(w / 2) * (h / 2);
+  for (int y = 0; y < h / 2; ++y) {
+    memcpy(du + (size_t)y * (w / 2), U + (size_t)(crop_y / 2 + y) * (c->wc / 2) + crop_x / 2, w / 2);
+    memcpy(dv + (size_t)y * (w / 2), V + (size_t)(crop_y / 2 + y) * (c->wc / 2) + crop_x / 2, w / 2);
+  }
+  d->launches++;
+  return 0;
+}
+
+hwb_event *hwb_dev_event_create(hwb_dev *) { return new hwb_event(); }
+void hwb_dev_event_destroy(hwb_dev *, hwb_event *e) { delete e; }
+int hwb_dev_event_record(hwb_dev *, hwb_event *, int) { return 0; }
+int hwb_dev_event_done(hwb_dev *, hwb_event *) { return 1; }
+int hwb_dev_event_sync(hwb_dev *, hwb_event *) { return 0; }
+int hwb_dev_stream_wait(hwb_dev *, int, hwb_event *) { return 0; }
+int hwb_dev_stream_sync(hwb_dev *, int) { return 0; }
+int hwb_dev_event_elapsed(hwb_dev *, hwb_event *, hwb_event *, float *ms) { *ms = 0; return 0; }
+uint64_t hwb_dev_launch_count(hwb_dev *d) { return d->launches; }
+}
