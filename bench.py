@@ -1,0 +1,349 @@
+#!/usr/bin/env python3
+"""Benchmark of the hot path: 1080p H.264 (Main, CABAC, GOP 30) dense decode of a 3000-frame clip,
+BASELINE.json configs[1].  One "step" = one pass over the whole clip: every picture entropy-decoded,
+reconstructed, deblocked, and every frame converted to RGB24.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA kernels through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's ffmpeg CPU path on the host cores
+
+JSON line keys: see the task contract.  `value` = frames/s with the bitstream resident in HBM and RGB24
+left in HBM (device timeline, CUDA events); `e2e` = the same clip through DecoderAutomata.get_frames with
+HOST buffers: host parse + H2D + decode + D2H of every RGB frame inside the timed region.
+"""
+import argparse
+import io
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, WC, HC = 1920, 1080, 1920, 1088
+GOP = 30
+CLIP_KW = dict(width=W, height=H, gop=GOP, profile=1, bframes=0, num_ref=2, qp=27, seed=2, slices=1, intra_in_p_pct=2)
+
+
+def clip_path(frames):
+    d = os.path.join(ROOT, 'tests', '_cache')
+    os.makedirs(d, exist_ok=True)
+    return os.path.join(d, 'bench_1080p_main_cabac_gop30_%d.mp4' % frames)
+
+
+def get_clip(frames):
+    p = clip_path(frames)
+    if not os.path.exists(p):
+        from hwang_b200 import build
+        build.build_gen()
+        from hwang_b200.testing import streamgen
+        t = time.time()
+        data = streamgen.generate(frames=frames, **CLIP_KW)
+        with open(p + '.tmp', 'wb') as f:
+            f.write(data)
+        os.replace(p + '.tmp', p)
+        sys.stderr.write('[bench] generated %s: %.1f MB in %.1fs\n' % (os.path.basename(p), len(data) / 1e6, time.time() - t))
+    with open(p, 'rb') as f:
+        return f.read()
+
+
+def algorithmic_bytes(frames):
+    """recon write (1.5*Wc*Hc) + one reference read for inter pictures + RGB24 write for returned frames."""
+    fs = WC * HC * 3 // 2
+    n_i = (frames + GOP - 1) // GOP
+    return frames * fs + (frames - n_i) * fs + frames * W * H * 3
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.stop_flag = False
+
+    def run(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + q, '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split('\n')[0]
+                f = [x.strip() for x in out.split(',')]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:6]):
+                    if v.lower().startswith('active'):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def result(self):
+        s = sorted(self.samples)
+        return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+_G = {}
+
+
+def _ref_worker(job):
+    """Decode whole keyframe-delimited intervals with one libavcodec instance (threads=1, the reference default:
+    video_decoder_factory.cpp:89-92) and convert every frame to RGB24 with sws_scale (software_video_decoder.cpp:325)."""
+    from oracle import ffmpeg_oracle as fo
+    gops = job
+    nls, sps, pps = fo.parse_avcc(_G['avcc'])
+    sws = fo.SwsRgb24(W, H)
+    n = [0]
+
+    def sink(yuv):
+        sws(*yuv)
+        n[0] += 1
+    for g in gops:
+        dec = fo.FFmpegH264(threads=1)
+        for i in range(g * GOP, min((g + 1) * GOP, len(_G['samples']))):
+            dec.send(fo.avcc_to_annexb(_G['samples'][i], nls, sps, pps, i % GOP == 0), sink)
+        dec.send(None, sink)
+        dec.flush()
+        dec.close()
+    sws.close()
+    return n[0]
+
+
+def cpu_reference_fps(mp4, gops, procs):
+    """frames/s of the reference CPU path over the given GOPs using `procs` worker processes."""
+    from oracle import mp4_simple
+    idx = mp4_simple.index_mp4(mp4)
+    _G['avcc'] = idx['avcc']
+    _G['samples'] = [mp4[o:o + s] for o, s in zip(idx['offsets'], idx['sizes'])]
+    jobs = [gops[i::procs] for i in range(procs)]
+    jobs = [j for j in jobs if j]
+    ctx = mp.get_context('fork')
+    with ctx.Pool(len(jobs)) as pool:
+        pool.map(_ref_worker, [[]] * len(jobs))  # warm: import + library load in every worker
+        t = time.perf_counter()
+        n = sum(pool.map(_ref_worker, jobs))
+        dt = time.perf_counter() - t
+    return n / dt, n, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from oracle import ffmpeg_oracle as fo
+    mp4 = get_clip(args.frames)
+    procs = os.cpu_count() or 1
+    ngop = (args.frames + GOP - 1) // GOP
+    sample_gops = list(range(min(ngop, max(procs, 16))))
+    for _ in range(args.warmup):
+        cpu_reference_fps(mp4, sample_gops[:procs], procs)
+    t0 = time.perf_counter()
+    vals = []
+    for _ in range(args.steps):
+        fps, n, dt = cpu_reference_fps(mp4, sample_gops, procs)
+        vals.append(fps)
+    total = time.perf_counter() - t0
+    v = sum(vals) / len(vals)
+    sample = '%d GOPs (%d frames) of the clip per step, %d worker processes x libavcodec threads=1 + sws_scale RGB24 per frame' % (
+        len(sample_gops), len(sample_gops) * GOP, procs)
+    line = {
+        'impl': 'reference', 'metric': '1080p H.264 decoded frames/s', 'value': v, 'unit': 'frames/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 * total / max(1, args.steps), 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic (in-repo generator, not libx264)',
+        'config': workload_config(args, len(mp4)),
+        'cpu_baseline': {'value': v, 'unit': 'frames/s', 'cores': procs, 'kind': 'port', 'sample': sample + '; ' + fo.ffmpeg_version()},
+        'e2e': {'value': v, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, clip_bytes):
+    return {'workload': '1080p H.264 Main CABAC GOP30 dense sequential decode of %d frames (BASELINE configs[1])' % args.frames,
+            'frames': args.frames, 'resolution': '1920x1080', 'gop': GOP, 'entropy': 'CABAC', 'profile': 'Main',
+            'bits_per_frame': round(8.0 * clip_bytes / args.frames), 'generator_seed': CLIP_KW['seed'],
+            'l2': 'inputs larger than L2 (frame buffers %.1f GB per step)' % (args.frames * WC * HC * 1.5 / 1e9),
+            'parallelism': 'gop-sharded, no collective'}
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import hwang_b200 as hw
+    from hwang_b200 import _lib
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    if not os.path.exists(_lib.PRODUCT_LIB):
+        if rank == 0:
+            from hwang_b200 import build
+            build.build_product()
+        if dist:
+            dist.barrier()
+    _lib.use_library(_lib.PRODUCT_LIB)  # fails loudly if the CUDA library is missing
+    if hw.device_count() <= local:
+        raise SystemExit('bench.py: no CUDA device %d (there is no CPU fallback)' % local)
+    if rank == 0:
+        get_clip(args.frames)
+    if dist:
+        dist.barrier()
+    mp4 = get_clip(args.frames)
+    index = hw.index_video(io.BytesIO(mp4))
+    offs, sizes = index.sample_offsets(), index.sample_sizes()
+    kf = set(index.keyframe_indices())
+    samples = [mp4[o:o + s] for o, s in zip(offs, sizes)]
+    n = len(samples)
+    L = _lib.lib()
+
+    def barrier():
+        torch.cuda.synchronize(local)
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize(local)
+
+    # ---- device-resident pass: one chunk = the whole clip, RGB24 left in HBM
+    dec = hw.VideoDecoder(local)
+    dec.set_chunk_pictures(1 << 30)
+
+    def device_step():
+        dec.configure(W, H, index.format(), index.metadata_bytes())
+        for i, s in enumerate(samples):
+            dec.feed(s, i in kf)
+        dec.feed(None)
+        dec.flush()
+        for _ in range(n):
+            dec.get_frame_device()
+        dec.wait_until_frames_copied()
+
+    # ---- end-to-end pass: DecoderAutomata.get_frames into pinned host buffers, 64 frames per call
+    auto = hw.DecoderAutomata(hw.DeviceHandle(hw.DeviceType.GPU, local), 1, hw.VideoDecoderType.B200)
+    ed = hw.EncodedData()
+    ed.width, ed.height, ed.format = W, H, index.format()
+    ed.start_keyframe, ed.end_keyframe = 0, n
+    ed.sample_offsets = [o - offs[0] for o in offs]
+    ed.sample_sizes = sizes
+    ed.keyframes = sorted(kf)
+    ed.valid_frames = list(range(n))
+    ed.encoded_video = mp4[offs[0]:offs[-1] + sizes[-1]]
+    batch = 64
+    fs = W * H * 3
+    pinned = hw.api.PinnedBuffer(fs * batch)
+    checksum = [0]
+
+    def e2e_step():
+        auto.initialize([ed], index.metadata_bytes())
+        done = 0
+        while done < n:
+            k = min(batch, n - done)
+            if L.hwb_automata_get_frames(auto._h, pinned.ptr, k) != 0:
+                raise RuntimeError(L.hwb_automata_last_error(auto._h).decode())
+            checksum[0] ^= int(pinned.array[fs * (k - 1) + 12345])  # touch the result on the host
+            done += k
+
+    for _ in range(args.warmup):
+        device_step()
+        e2e_step()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    # timed: device-resident
+    s0 = dec.stats()
+    barrier()
+    for _ in range(args.steps):
+        device_step()
+    barrier()
+    s1 = dec.stats()
+    # timed: end to end
+    a0 = auto.stats()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    a1 = auto.stats()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    d = {k: s1[k] - s0[k] for k in s1}
+    dev_ms = d['decode_ms'] + d['rgb_ms']  # device timeline (CUDA events on the launching streams)
+    times = torch.tensor([dev_ms / 1000.0, t_e2e], dtype=torch.float64, device='cuda:%d' % local)
+    if dist:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_s, e2e_s = float(times[0]), float(times[1])
+    if rank != 0:
+        return
+    frames_total = n * args.steps * world
+    value = frames_total / dev_s
+    e2e_value = frames_total / e2e_s
+    stage = {'entropy': (d['entropy_ms'], d['entropy_launches']), 'recon': (d['recon_ms'], d['recon_launches']),
+             'deblock': (d['deblock_ms'], d['deblock_launches']), 'rgb24': (d['rgb_ms'], d['rgb_launches'])}
+    dom = max(stage, key=lambda k: stage[k][0])
+    dom_ms, dom_launches = stage[dom]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    alg = algorithmic_bytes(n) * args.steps
+    # achieved = algorithmic bytes handled per launch of the dominant kernel / its average launch duration
+    achieved = (alg / max(1, dom_launches)) / (dom_ms / max(1, dom_launches) / 1000.0) / 1e9 if dom_ms > 0 else 0.0
+    cpu = None
+    if world == 1 or True:
+        procs = os.cpu_count() or 1
+        ngop = (n + GOP - 1) // GOP
+        gops = list(range(min(ngop, max(procs, 16))))
+        from oracle import ffmpeg_oracle as fo
+        fps, cn, cdt = cpu_reference_fps(mp4, gops, procs)
+        cpu = {'value': fps, 'unit': 'frames/s', 'cores': procs, 'kind': 'port',
+               'sample': '%d frames (%d GOPs) of the same clip, %d processes x libavcodec threads=1 + sws_scale RGB24, %.1fs; %s' % (
+                   cn, len(gops), procs, cdt, fo.ffmpeg_version())}
+    line = {
+        'metric': '1080p H.264 decoded frames/s', 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1000.0 * dev_s / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic (in-repo generator, not libx264)',
+        'config': workload_config(args, len(mp4)),
+        'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': (a1['h2d_bytes'] - a0['h2d_bytes']) // args.steps,
+                'd2h_bytes_per_step': (a1['d2h_bytes'] - a0['d2h_bytes']) // args.steps, 'ms_per_step': 1000.0 * e2e_s / args.steps},
+        'gpu_launches': int(d['kernel_launches'] + (a1['kernel_launches'] - a0['kernel_launches'])),
+        'roofline': {'bound': 'hbm', 'kernel': dom + '_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                     'frac': achieved / peak, 'traffic': None, 'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback',
+                     'whole_pipeline_frac': (alg / dev_s / 1e9) / peak,
+                     'stage_ms_per_step': {k: v[0] / args.steps for k, v in stage.items()}},
+        'cpu_baseline': cpu,
+        'clocks': sampler.result(),
+        'checksum': checksum[0],
+    }
+    print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours')
+    ap.add_argument('--frames', type=int, default=int(os.environ.get('HWB_BENCH_FRAMES', '3000')))
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -20,7 +20,8 @@ c_u64p = ctypes.POINTER(ctypes.c_uint64)
 class Stats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint64) for n in ('pictures_decoded', 'frames_returned', 'chunks', 'bitstream_bytes',
                                                'kernel_launches', 'h2d_bytes', 'd2h_bytes', 'algorithmic_bytes')] + \
-               [('decode_ms', ctypes.c_double)]
+               [(n, ctypes.c_double) for n in ('decode_ms', 'entropy_ms', 'recon_ms', 'deblock_ms', 'rgb_ms')] + \
+               [(n, ctypes.c_uint64) for n in ('entropy_launches', 'recon_launches', 'deblock_launches', 'rgb_launches')]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -32,6 +32,7 @@ void B200VideoDecoder::release_all() {
   hwb_dev_stream_sync(dev_, HWB_STREAM_COPY);
   auto drop = [&](std::unique_ptr<Chunk> &c) {
     if (!c) return;
+    for (auto e : c->stage_ev) hwb_dev_event_destroy(dev_, e);
     if (c->ev_begin) hwb_dev_event_destroy(dev_, c->ev_begin);
     if (c->ev_done) hwb_dev_event_destroy(dev_, c->ev_done);
     if (c->slab.base) hwb_dev_free(dev_, c->slab.base);
@@ -50,6 +51,8 @@ void B200VideoDecoder::release_all() {
     rgb_dev_[i] = rgb_pinned_[i] = nullptr;
   }
   pending_.clear();
+  for (auto &e : rgb_ev_) { hwb_dev_event_destroy(dev_, e.first); hwb_dev_event_destroy(dev_, e.second); }
+  rgb_ev_.clear();
   live_bytes_ = 0;
   ring_bytes_ = 0;
 }
@@ -166,7 +169,6 @@ Result B200VideoDecoder::submit_current() {
   ch->ev_begin = hwb_dev_event_create(dev_);
   ch->ev_done = hwb_dev_event_create(dev_);
   int rc = 0;
-  rc |= hwb_dev_event_record(dev_, ch->ev_begin, st);
   ch->bitstream.resize(ch->bitstream.size() + 64, 0);  // read-ahead padding for the bit readers
   rc |= hwb_dev_h2d(dev_, st, b + o_bits, ch->bitstream.data(), ch->bitstream.size());
   rc |= hwb_dev_h2d(dev_, st, b + o_pics, ch->pics.data(), (size_t)P * sizeof(PicDesc));
@@ -174,13 +176,19 @@ Result B200VideoDecoder::submit_current() {
   rc |= hwb_dev_h2d(dev_, st, b + o_levels, level_list.data(), (size_t)P * 4);
   rc |= hwb_dev_memset(dev_, st, sync, 0, n_sync * 4);
   stats_.h2d_bytes += ch->bitstream.size() + (size_t)P * sizeof(PicDesc) + (size_t)S * sizeof(SliceDesc) + (size_t)P * 4;
+  rc |= hwb_dev_event_record(dev_, ch->ev_begin, st);  // inputs are resident in HBM from here on
+  auto mark = [&]() { if (profile_) { hwb_event *e = hwb_dev_event_create(dev_); hwb_dev_event_record(dev_, e, st); ch->stage_ev.push_back(e); } };
+  mark();
   rc |= hwb_dev_entropy(dev_, st, &c, tickets);
+  mark();
   size_t lo = 0;
   for (int l = 0; l < nlevels; ++l) {
     const int n = (int)by_level[l].size();
     const int32_t *pl = (const int32_t *)(b + o_levels) + lo;
     rc |= hwb_dev_recon(dev_, st, &c, pl, n, tickets + 1 + 2 * l);
+    mark();
     rc |= hwb_dev_deblock(dev_, st, &c, pl, n, tickets + 2 + 2 * l);
+    mark();
     lo += n;
   }
   rc |= hwb_dev_event_record(dev_, ch->ev_done, st);
@@ -210,6 +218,15 @@ Result B200VideoDecoder::finish_chunk(Chunk &c) {
   hwb_dev_stream_sync(dev_, HWB_STREAM_COPY);
   float ms = 0;
   if (hwb_dev_event_elapsed(dev_, c.ev_begin, c.ev_done, &ms) == 0) stats_.decode_ms += ms;
+  for (size_t i = 1; i < c.stage_ev.size(); ++i) {
+    float t = 0;
+    if (hwb_dev_event_elapsed(dev_, c.stage_ev[i - 1], c.stage_ev[i], &t) != 0) continue;
+    if (i == 1) { stats_.entropy_ms += t; stats_.entropy_launches++; }
+    else if (i % 2 == 0) { stats_.recon_ms += t; stats_.recon_launches++; }
+    else { stats_.deblock_ms += t; stats_.deblock_launches++; }
+  }
+  for (auto e : c.stage_ev) hwb_dev_event_destroy(dev_, e);
+  c.stage_ev.clear();
   stats_.algorithmic_bytes += c.alg_bytes;
   c.finished = true; c.checked = true;
   if (flag) { sticky_error_ = "B200 decoder: corrupt or unsupported bitstream (device error code " + std::to_string(flag) + ")"; return Result(false, sticky_error_); }
@@ -247,6 +264,12 @@ void B200VideoDecoder::retire_front() {
 
 void B200VideoDecoder::drain_copies() {
   hwb_dev_stream_sync(dev_, HWB_STREAM_COPY);
+  for (auto &e : rgb_ev_) {
+    float t = 0;
+    if (hwb_dev_event_elapsed(dev_, e.first, e.second, &t) == 0) { stats_.rgb_ms += t; stats_.rgb_launches++; }
+    hwb_dev_event_destroy(dev_, e.first); hwb_dev_event_destroy(dev_, e.second);
+  }
+  rgb_ev_.clear();
   for (auto &p : pending_) if (p.pinned) memcpy(p.user, p.pinned, p.size);
   pending_.clear();
   ring_next_ = 0;
@@ -278,8 +301,11 @@ Result B200VideoDecoder::pop_common(int mode, uint8_t *buf, size_t size, uint8_t
   if ((int)pending_.size() >= kRing || ring_next_ >= kRing) drain_copies();
   const int slot = ring_next_++;
   int rc;
+  hwb_event *r0 = nullptr, *r1 = nullptr;
+  if (profile_ && mode != 1) { r0 = hwb_dev_event_create(dev_); r1 = hwb_dev_event_create(dev_); hwb_dev_event_record(dev_, r0, HWB_STREAM_COPY); }
   if (mode == 1) rc = hwb_dev_yuv(dev_, HWB_STREAM_COPY, &c.ctx, frame, stream_.crop_left(), stream_.crop_top(), (int)width_, (int)height_, rgb_dev_[slot]);
   else rc = hwb_dev_rgb24(dev_, HWB_STREAM_COPY, &c.ctx, frame, stream_.crop_left(), stream_.crop_top(), (int)width_, (int)height_, rgb_dev_[slot]);
+  if (r1) { hwb_dev_event_record(dev_, r1, HWB_STREAM_COPY); rgb_ev_.push_back({r0, r1}); }
   if (mode == 2) {
     *dev_out = rgb_dev_[slot];
     pending_.push_back({nullptr, nullptr, 0});

@@ -25,6 +25,8 @@ struct B200Stats {
   uint64_t h2d_bytes = 0, d2h_bytes = 0;
   uint64_t algorithmic_bytes = 0;  // recon write + one reference read + RGB write
   double decode_ms = 0;            // device time of the decode stages (CUDA events), summed over chunks
+  double entropy_ms = 0, recon_ms = 0, deblock_ms = 0, rgb_ms = 0;
+  uint64_t entropy_launches = 0, recon_launches = 0, deblock_launches = 0, rgb_launches = 0;
 };
 
 class B200VideoDecoder : public VideoDecoderInterface {
@@ -64,6 +66,7 @@ class B200VideoDecoder : public VideoDecoderInterface {
     Slab slab;
     hwb::ChunkCtx ctx;
     hwb_event *ev_begin = nullptr, *ev_done = nullptr;
+    std::vector<hwb_event *> stage_ev;  // boundaries: [0] before entropy, [1] after entropy, then after each recon / deblock launch
     bool submitted = false, finished = false, checked = false;
     int32_t *error_dev = nullptr;
     uint64_t alg_bytes = 0;
@@ -97,6 +100,8 @@ class B200VideoDecoder : public VideoDecoderInterface {
   size_t ring_bytes_ = 0;
   int ring_next_ = 0;
   std::vector<PendingCopy> pending_;
+  std::vector<std::pair<hwb_event *, hwb_event *>> rgb_ev_;  // per pending RGB launch
+  bool profile_ = true;
   B200Stats stats_;
   std::string sticky_error_;
 };

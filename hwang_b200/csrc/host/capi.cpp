@@ -31,6 +31,8 @@ void fill_stats(const B200Stats &s, hwb_stats *o) {
   o->pictures_decoded = s.pictures_decoded; o->frames_returned = s.frames_returned; o->chunks = s.chunks; o->bitstream_bytes = s.bitstream_bytes;
   o->kernel_launches = s.kernel_launches; o->h2d_bytes = s.h2d_bytes; o->d2h_bytes = s.d2h_bytes; o->algorithmic_bytes = s.algorithmic_bytes;
   o->decode_ms = s.decode_ms;
+  o->entropy_ms = s.entropy_ms; o->recon_ms = s.recon_ms; o->deblock_ms = s.deblock_ms; o->rgb_ms = s.rgb_ms;
+  o->entropy_launches = s.entropy_launches; o->recon_launches = s.recon_launches; o->deblock_launches = s.deblock_launches; o->rgb_launches = s.rgb_launches;
 }
 }  // namespace
 

@@ -35,8 +35,7 @@ DecoderAutomata::~DecoderAutomata() {
 void DecoderAutomata::stop_feeder() {
   abort_ = true;
   std::unique_lock<std::mutex> lk(mu_);
-  cv_.wait(lk, [&] { return parked_; });
-  work_ = false;
+  cv_.wait(lk, [&] { return parked_ && !work_; });
   abort_ = false;
 }
 
@@ -78,8 +77,7 @@ Result DecoderAutomata::initialize(const std::vector<EncodedData> &encoded_data,
   HWANG_RETURN_ON_ERROR(decoder_->configure(info_, extradata));
   {
     std::unique_lock<std::mutex> lk(mu_);
-    work_ = true;
-    parked_ = false;
+    work_ = true;  // consumed by the feeder; no lost wake-up even if the thread has not reached its wait yet
   }
   cv_.notify_all();
   return Result();
@@ -92,8 +90,10 @@ void DecoderAutomata::feeder() {
       std::unique_lock<std::mutex> lk(mu_);
       parked_ = true;
       cv_.notify_all();
-      cv_.wait(lk, [&] { return quit_ || (work_ && !parked_) ; });
+      cv_.wait(lk, [&] { return quit_ || work_; });
       if (quit_) return;
+      work_ = false;
+      parked_ = false;
     }
     bool failed = false;
     for (size_t di = 0; di < encoded_data_.size() && !abort_ && !failed; ++di) {
@@ -115,10 +115,6 @@ void DecoderAutomata::feeder() {
       Result r = decoder_->feed(nullptr, 0, false);
       if (r.ok) r = decoder_->flush();
       if (!r.ok) { feeder_result_ = r; result_set_ = true; failed = true; }
-    }
-    {
-      std::unique_lock<std::mutex> lk(mu_);
-      work_ = false;
     }
   }
 }

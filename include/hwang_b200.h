@@ -62,6 +62,8 @@ int hwb_decoder_set_chunk_pictures(hwb_decoder *d, int n); /* pictures per GPU b
 typedef struct hwb_stats {
   uint64_t pictures_decoded, frames_returned, chunks, bitstream_bytes, kernel_launches, h2d_bytes, d2h_bytes, algorithmic_bytes;
   double decode_ms; /* device time of the decode stages, CUDA events */
+  double entropy_ms, recon_ms, deblock_ms, rgb_ms; /* per-stage device time (CUDA events on the launching stream) */
+  uint64_t entropy_launches, recon_launches, deblock_launches, rgb_launches;
 } hwb_stats;
 int hwb_decoder_get_stats(hwb_decoder *d, hwb_stats *out);
 

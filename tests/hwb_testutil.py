@@ -1,0 +1,70 @@
+"""Shared helpers for the parity tests: generate a clip, decode it with the oracle and with our decoder."""
+import io
+
+import numpy as np
+
+import hwang_b200 as hw
+from hwang_b200.testing import streamgen
+from oracle import ffmpeg_oracle as fo
+
+
+def make_clip(**kw):
+    mp4 = streamgen.generate(**kw)
+    index = hw.index_video(io.BytesIO(mp4))
+    offs, sizes = index.sample_offsets(), index.sample_sizes()
+    kf = set(index.keyframe_indices())
+    samples = [mp4[o:o + s] for o, s in zip(offs, sizes)]
+    return mp4, index, samples, [i in kf for i in range(len(samples))]
+
+
+def oracle_frames(index, samples, keyflags):
+    return fo.decode_samples(index.metadata_bytes(), samples, keyflags)
+
+
+def decode_yuv(index, samples, keyflags, chunk_pictures=None):
+    dec = hw.VideoDecoder(0)
+    if chunk_pictures:
+        dec.set_chunk_pictures(chunk_pictures)
+    dec.configure(index.frame_width(), index.frame_height(), index.format(), index.metadata_bytes())
+    for s, k in zip(samples, keyflags):
+        dec.feed(s, k)
+    dec.feed(None)
+    dec.flush()
+    out = []
+    while dec.frames_ready() > 0:
+        out.append(dec.get_frame_yuv())
+    return out, dec
+
+
+def flat(yuv):
+    y, u, v = yuv
+    return np.concatenate([y.ravel(), u.ravel(), v.ravel()])
+
+
+def assert_yuv_parity(kw, chunk_pictures=None):
+    mp4, index, samples, kf = make_clip(**kw)
+    ref = oracle_frames(index, samples, kf)
+    got, dec = decode_yuv(index, samples, kf, chunk_pictures)
+    assert len(got) == len(ref) == kw['frames']
+    for i, (g, r) in enumerate(zip(got, ref)):
+        assert np.array_equal(g, flat(r)), 'frame %d differs from libavcodec (%s)' % (i, kw)
+    return dec
+
+
+FEATURE_CLIPS = {
+    'cbp_cavlc_multislice_ipcm': dict(frames=20, gop=10, width=320, height=240, seed=11, num_ref=2, slices=3, qp_jitter=3,
+                                      ipcm_per_100k=2000, intra_in_p_pct=10),
+    'cbp_constrained_intra_poc2': dict(frames=12, gop=12, deblock=3, width=176, height=144, seed=12, num_ref=4, slices=2,
+                                       constrained_intra=1, chroma_qp_offset=3, poc_type=2, intra_in_p_pct=20),
+    'main_cabac_p': dict(frames=20, gop=10, width=320, height=240, profile=1, seed=21, num_ref=3, slices=2, qp_jitter=3,
+                         ipcm_per_100k=2000, intra_in_p_pct=10, cabac_init_idc=-1, deblock=3),
+    'high_cabac_b_spatial_scaling': dict(frames=24, gop=12, width=320, height=240, profile=2, seed=31, num_ref=3, slices=2,
+                                         qp_jitter=3, ipcm_per_100k=1000, intra_in_p_pct=8, cabac_init_idc=-1, deblock=3,
+                                         bframes=2, weighted=2, scaling_lists=1, chroma_qp_offset=-2),
+    'high_cavlc_b_temporal': dict(frames=24, gop=12, width=320, height=240, profile=2, seed=32, num_ref=4, slices=3,
+                                  qp_jitter=2, intra_in_p_pct=5, bframes=3, direct_spatial=0, weighted=2, cabac=0),
+    'main_weighted_p': dict(frames=16, gop=16, width=352, height=288, profile=1, seed=33, num_ref=2, bframes=1, weighted=1, qp=34),
+    'deblock_off_and_slice_edges': dict(frames=8, gop=8, width=160, height=128, profile=1, seed=35, slices=4, deblock=2),
+    'tiny_16x16': dict(frames=5, gop=5, width=16, height=16, profile=1, seed=36, bframes=1),
+    'cropped_1080': dict(frames=4, gop=4, width=1920, height=1080, profile=2, seed=34, num_ref=2, bframes=2, qp=30),
+}

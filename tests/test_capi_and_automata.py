@@ -1,0 +1,119 @@
+"""CPU tier: the C ABI library loads and exports every symbol include/hwang_b200.h declares; automaton logic."""
+import io
+import os
+import re
+
+import numpy as np
+import pytest
+
+import hwang_b200 as hw
+from hwang_b200 import _lib
+from oracle import ffmpeg_oracle as fo
+import hwb_testutil as util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    with open(os.path.join(ROOT, 'include', 'hwang_b200.h')) as f:
+        src = re.sub(r'/\*.*?\*/', '', f.read(), flags=re.S)
+    return sorted(set(re.findall(r'\b(hwb_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_header_and_binding_agree():
+    assert declared_symbols() == sorted(_lib.SIGNATURES)
+
+
+def test_product_library_exports_every_declared_symbol():
+    """No compute call: on the CPU box this only checks that the CUDA-linked library loads and exports the ABI."""
+    import ctypes
+    from hwang_b200 import build
+    build.build_product()
+    lib = ctypes.CDLL(_lib.PRODUCT_LIB)
+    for name in declared_symbols():
+        assert hasattr(lib, name), name
+    lib.hwb_version.restype = ctypes.c_char_p
+    assert b'sm_100a' in lib.hwb_version()
+
+
+def test_product_has_no_cpu_fallback():
+    """Without a CUDA device the product library must refuse to build a decoder (never decode on the CPU)."""
+    import ctypes
+    lib = ctypes.CDLL(_lib.PRODUCT_LIB)
+    if lib.hwb_device_count() > 0:
+        pytest.skip('a GPU is present')
+    h = ctypes.c_void_p()
+    assert lib.hwb_decoder_create(1, 0, 1, 3, ctypes.byref(h)) != 0 and not h
+    lib.hwb_automata_create.restype = ctypes.c_void_p
+    assert not lib.hwb_automata_create(1, 0, 1, 3)
+
+
+def test_factory_rejects_other_backends(emu):
+    L = _lib.lib()
+    assert L.hwb_has_decoder_type(hw.VideoDecoderType.B200) == 1
+    assert L.hwb_has_decoder_type(hw.VideoDecoderType.SOFTWARE) == 0
+    with pytest.raises(RuntimeError):
+        hw.DecoderAutomata(hw.DeviceHandle(hw.DeviceType.CPU, 0), 1, hw.VideoDecoderType.SOFTWARE)
+
+
+def test_unsupported_codec_and_bad_extradata(emu):
+    dec = hw.VideoDecoder(0)
+    with pytest.raises(RuntimeError, match='Unsupported video codec'):
+        dec.configure(64, 48, 'hev1', b'\x01' * 16)
+    with pytest.raises(RuntimeError):
+        dec.configure(64, 48, 'avc1', b'\x00' * 4)
+
+
+def test_sparse_retrieval_shapes(emu, built):
+    """The reference tests' request shapes (decoder_automata_test.cpp:233-245, :287, :442-445) on a small clip:
+    ranges across GOPs, a single-frame gather, get_frames in batches, several intervals in one initialize."""
+    kw = dict(width=96, height=80, frames=60, gop=6, profile=1, bframes=1, seed=77, qp=30)
+    mp4, index, samples, kf = util.make_clip(**kw)
+    ref = [fo.yuv420_to_rgb24(*f) for f in util.oracle_frames(index, samples, kf)]
+    dec = hw.Decoder(io.BytesIO(mp4), video_index=index)
+    for rows in ([0], [59], [25], list(range(0, 10)) + list(range(30, 55)), list(range(0, 60, 17)), list(range(60)), [5, 6, 7, 41]):
+        frames = dec.retrieve(rows)
+        assert len(frames) == len(rows)
+        for r, f in zip(rows, frames):
+            assert np.array_equal(np.asarray(f), ref[r]), (rows, r)
+    # all intervals handed to one initialize, frames pulled in batches that straddle interval boundaries
+    rows = [1, 2, 13, 14, 15, 40, 58]
+    ivs = hw.slice_into_video_intervals(index, rows)
+    offs, sizes = index.sample_offsets(), index.sample_sizes()
+    eds = []
+    for (s, e), valid in ivs:
+        d = hw.EncodedData()
+        d.width, d.height, d.format = kw['width'], kw['height'], index.format()
+        d.start_keyframe, d.end_keyframe = s, e
+        d.sample_offsets = [o - offs[s] for o in offs[s:e]]
+        d.sample_sizes = sizes[s:e]
+        d.keyframes = [k for k in index.keyframe_indices() if s <= k <= e]
+        d.valid_frames = valid
+        d.encoded_video = mp4[offs[s]:offs[e - 1] + sizes[e - 1]]
+        eds.append(d)
+    assert len(eds) > 1
+    auto = hw.DecoderAutomata(hw.DeviceHandle(hw.DeviceType.GPU, 0), 1, hw.VideoDecoderType.B200)
+    auto.initialize(eds, index.metadata_bytes())
+    got = []
+    for n in (3, 1, 3):
+        got += auto.get_frames(index, n)
+    for r, f in zip(rows, got):
+        assert np.array_equal(np.asarray(f), ref[r])
+    with pytest.raises(RuntimeError):
+        auto.get_frames(index, 1)  # more than the intervals hold
+    # re-initialize resets everything
+    auto.initialize(eds[:1], index.metadata_bytes())
+    f = auto.get_frames(index, 1)
+    assert np.array_equal(np.asarray(f[0]), ref[rows[0]])
+
+
+def test_corrupt_stream_reports_error(emu, built):
+    kw = dict(width=64, height=48, frames=6, gop=6, profile=1, seed=9)
+    mp4, index, samples, kf = util.make_clip(**kw)
+    dec = hw.VideoDecoder(0)
+    dec.configure(64, 48, 'avc1', index.metadata_bytes())
+    with pytest.raises(RuntimeError):
+        dec.feed(samples[1], False)  # interval must start at an IDR
+    dec.configure(64, 48, 'avc1', index.metadata_bytes())
+    with pytest.raises(RuntimeError):
+        dec.feed(samples[0][:20], True)  # NAL length runs past the sample

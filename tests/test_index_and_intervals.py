@@ -1,0 +1,144 @@
+"""CPU tier: MP4IndexCreator / VideoIndex / slice_into_video_intervals against the reference's own outputs
+(tests/golden/*.json, produced by oracle/_ref/ref_tool) and the oracle restatements."""
+import glob
+import io
+import json
+import os
+
+import numpy as np
+import pytest
+
+import hwang_b200 as hw
+from hwang_b200.testing import streamgen
+from oracle import intervals as oiv, mp4_simple
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+NAMES = sorted(os.path.basename(p)[:-5] for p in glob.glob(os.path.join(GOLDEN, '*.json')))
+
+
+def load(name):
+    with open(os.path.join(GOLDEN, name + '.mp4'), 'rb') as f:
+        mp4 = f.read()
+    with open(os.path.join(GOLDEN, name + '.json')) as f:
+        return mp4, json.load(f)
+
+
+def run_indexer(mp4, step=1024):
+    """the 1 KiB pull loop of hwang/mp4_index_creator_test.cpp:36-41"""
+    ic = hw.MP4IndexCreator(len(mp4))
+    off, size = 0, step
+    guard = 0
+    while not ic.is_done():
+        _, off, size = ic.feed(mp4[off:off + size], size)
+        guard += 1
+        assert guard < 100000
+    return ic
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_index_matches_reference_index_creator(emu, name):
+    mp4, g = load(name)
+    ic = run_indexer(mp4)
+    assert not ic.is_error(), ic.error_message()
+    vi = ic.get_video_index()
+    ri = g['reference_index']
+    assert vi.sample_offsets() == ri['offsets']
+    assert vi.sample_sizes() == ri['sizes']
+    assert vi.keyframe_indices() == ri['keyframes']
+    assert vi.metadata_bytes().hex() == ri['metadata_hex']
+    assert (vi.frame_width(), vi.frame_height(), vi.format(), vi.frames()) == (ri['width'], ri['height'], ri['format'], ri['frames'])
+    assert (vi.timescale(), vi.duration()) == (ri['timescale'], ri['duration'])
+    # and the python oracle walker agrees
+    o = mp4_simple.index_mp4(mp4)
+    assert (o['offsets'], o['sizes'], o['keyframes']) == (ri['offsets'], ri['sizes'], ri['keyframes'])
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_slice_into_video_intervals_matches_reference(emu, name):
+    mp4, g = load(name)
+    vi = run_indexer(mp4).get_video_index()
+    for case in g['reference_intervals']:
+        got = hw.slice_into_video_intervals(vi, case['rows'])
+        assert got == [((d['start'], d['end']), d['rows']) for d in case['intervals']]
+
+
+def test_intervals_property_random(emu):
+    rng = np.random.default_rng(5)
+    for trial in range(200):
+        n = int(rng.integers(1, 200))
+        gop = int(rng.integers(1, 20))
+        kfs = list(range(0, n, gop))
+        sizes = [int(x) for x in rng.integers(1, 50, n)]
+        offs, o = [], 100
+        for i in range(n):
+            if i in kfs and rng.random() < 0.3:
+                o += int(rng.integers(1, 10))  # gap: GOP not byte-adjacent
+            offs.append(o)
+            o += sizes[i]
+        rows = sorted(set(int(x) for x in rng.integers(0, n, int(rng.integers(1, 40)))))
+        vi = hw.VideoIndex.create(30, n, 64, 48, 'avc1', offs, sizes, kfs, b'\x01')
+        got = hw.slice_into_video_intervals(vi, rows)
+        assert got == oiv.slice_into_video_intervals(offs, sizes, kfs, n, rows)
+        # properties: every row appears once, inside its interval, intervals start/end on keyframes
+        flat = [r for _, rs in got for r in rs]
+        assert flat == rows
+        for (s, e), rs in got:
+            assert s in kfs and (e in kfs or e == n) and all(s <= r < e for r in rs)
+
+
+def test_video_index_serialization_is_protobuf_compatible(emu):
+    """wire-compat with hwang/hwang_descriptors.proto:5-15, checked with the python protobuf runtime"""
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+    fd = descriptor_pb2.FileDescriptorProto()
+    fd.name = 'hwang_descriptors.proto'
+    fd.package = 'hwang.proto'
+    fd.syntax = 'proto3'
+    m = fd.message_type.add()
+    m.name = 'VideoIndex'
+    T = descriptor_pb2.FieldDescriptorProto
+    for name, num, typ, rep in (('timescale', 7, T.TYPE_UINT32, False), ('duration', 8, T.TYPE_UINT64, False),
+                                ('frame_width', 1, T.TYPE_UINT32, False), ('frame_height', 2, T.TYPE_UINT32, False),
+                                ('format', 9, T.TYPE_STRING, False), ('sample_offsets', 3, T.TYPE_UINT64, True),
+                                ('sample_sizes', 4, T.TYPE_UINT64, True), ('keyframe_indices', 5, T.TYPE_UINT64, True),
+                                ('metadata_bytes', 6, T.TYPE_BYTES, False)):
+        f = m.field.add()
+        f.name, f.number, f.type = name, num, typ
+        f.label = T.LABEL_REPEATED if rep else T.LABEL_OPTIONAL
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(fd)
+    cls = message_factory.GetMessageClass(pool.FindMessageTypeByName('hwang.proto.VideoIndex'))
+    offs = [0, 300, 70000, 1 << 33]
+    sizes = [300, 5, 128, 9]
+    vi = hw.VideoIndex.create(90000, 1 << 35, 1920, 1080, 'avc1', offs, sizes, [0, 2], bytes(range(40)))
+    blob = vi.serialize()
+    msg = cls()
+    msg.ParseFromString(blob)
+    assert list(msg.sample_offsets) == offs and list(msg.sample_sizes) == sizes and list(msg.keyframe_indices) == [0, 2]
+    assert (msg.timescale, msg.duration, msg.frame_width, msg.frame_height, msg.format) == (90000, 1 << 35, 1920, 1080, 'avc1')
+    assert msg.metadata_bytes == bytes(range(40))
+    assert msg.SerializeToString() == blob  # byte-identical to the canonical protobuf encoding
+    back = hw.VideoIndex.deserialize(msg.SerializeToString())
+    assert back.sample_offsets() == offs and back.keyframe_indices() == [0, 2] and back.metadata_bytes() == bytes(range(40))
+    assert back.fps() == pytest.approx(4 / ((1 << 35) / 90000))
+
+
+def test_indexer_error_paths(emu, built):
+    mp4 = streamgen.generate(width=64, height=48, frames=4, gop=4)
+    # truncated file: EOF inside moov
+    cut = mp4[:200]
+    ic = run_indexer(cut)
+    assert ic.is_error() and ic.error_message()
+    # unsupported brand
+    bad = bytearray(mp4)
+    for tag in (b'isom', b'iso2', b'avc1', b'mp41'):
+        i = bad.find(tag, 0, 40)
+        while i >= 0:
+            bad[i:i + 4] = b'qt  '
+            i = bad.find(tag, 0, 40)
+    ic = run_indexer(bytes(bad))
+    assert ic.is_error() and 'brands' in ic.error_message()
+    # different pull granularities give the same index
+    a = run_indexer(mp4, 1024).get_video_index()
+    b = run_indexer(mp4, 64).get_video_index()
+    c = run_indexer(mp4, 1 << 20).get_video_index()
+    assert a.sample_offsets() == b.sample_offsets() == c.sample_offsets()
