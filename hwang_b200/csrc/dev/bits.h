@@ -17,6 +17,17 @@ struct BitReader {
 };
 
 HWB_HD void br_refill(BitReader &b) {
+#if HWB_DEVICE_BUILD
+  // Device: the byte position is always word aligned (see br_init) and this is only called with avail <= 32, so a
+  // refill is one 32-bit load through the read-only path.  Slice data starts on a 16-byte boundary and the chunk
+  // bitstream is padded, so reading a few bytes past the slice is safe.
+  uint32_t w = __ldg((const uint32_t *)(b.base + b.pos));
+  w = __byte_perm(w, 0, 0x0123);
+  if (b.pos >= b.size + 8) b.overrun = true;
+  b.cache |= (uint64_t)w << (32 - b.avail);
+  b.avail += 32;
+  b.pos += 4;
+#else
   while (b.avail <= 56) {
     uint64_t v = b.pos < b.size ? b.base[b.pos] : 0;
     if (b.pos >= b.size + 8) b.overrun = true;
@@ -24,11 +35,20 @@ HWB_HD void br_refill(BitReader &b) {
     b.cache |= v << (56 - b.avail);
     b.avail += 8;
   }
+#endif
 }
 HWB_HD void br_init(BitReader &b, const uint8_t *p, uint32_t size, uint32_t bit_off) {
-  b.base = p; b.size = size; b.pos = bit_off >> 3; b.cache = 0; b.avail = 0; b.overrun = false;
+  b.base = p; b.size = size; b.cache = 0; b.avail = 0; b.overrun = false;
+#if HWB_DEVICE_BUILD
+  b.pos = (bit_off >> 3) & ~3u;
+  br_refill(b);
+  const int skip = (int)(bit_off - b.pos * 8 + 32);  // pos already advanced by 4
+  b.cache <<= skip; b.avail -= skip;
+#else
+  b.pos = bit_off >> 3;
   br_refill(b);
   b.cache <<= (bit_off & 7); b.avail -= (bit_off & 7);
+#endif
 }
 HWB_HD uint32_t br_bitpos(const BitReader &b) { return b.pos * 8 - b.avail; }
 HWB_HD uint32_t br_peek(BitReader &b, int n) {  // n in 1..32

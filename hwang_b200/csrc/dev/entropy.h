@@ -3,12 +3,28 @@
 // One lane owns one slice and walks its macroblocks in raster order; slices of every picture of
 // the chunk are decoded concurrently (entropy decoding needs no pixels).  Output: MbInfo records,
 // coefficient slots, final motion vectors / reference indices per 4x4 / 8x8 block.
-#pragma once
+// The file may be included several times with different (HWB_ENT_NS, HWB_ENT_MODE) pairs: the CUDA side compiles a
+// CABAC-only and a CAVLC-only copy of the slice decoder (each a fraction of the code, which matters because this kernel
+// is instruction-fetch bound) next to the generic one; host builds use the generic runtime-flag version only.
 #include "bits.h"
 #include "ir.h"
 #include "tables_gen.h"
 
+#ifndef HWB_ENT_NS
+#define HWB_ENT_NS ent
+#define HWB_ENT_MODE (-1)
+#endif
+#undef HWB_IS_CABAC
+#if HWB_ENT_MODE == 1
+#define HWB_IS_CABAC(s) true
+#elif HWB_ENT_MODE == 0
+#define HWB_IS_CABAC(s) false
+#else
+#define HWB_IS_CABAC(s) ((s).cabac)
+#endif
+
 namespace hwb {
+namespace HWB_ENT_NS {
 
 enum { NBF_INTRA = 1, NBF_IPCM = 2, NBF_SKIP = 4, NBF_DIRECT16 = 8, NBF_T8 = 16, NBF_I16 = 32, NBF_INXN = 64 };
 enum { REF_UNAVAIL = -2, REF_NONE = -1 };
@@ -53,15 +69,36 @@ struct SliceDec {
   uint8_t nz_cache[30];      // luma total_coeff / coded flag; 0x80 = unavailable
   uint8_t cnz_cache[2][12];  // chroma 3x4 layouts (by+1)*4 + bx+1 ... only [..][<9] used
   int8_t im_cache[30];
-  int16_t coef[64];  // staging for one block
+  alignas(16) int16_t coef[64];  // staging for one block
   MbInfo out;
   int error;
+  // Per-macroblock scratch.  It lives here (not on the stack) because on the GPU this struct is placed in
+  // shared memory: with one active lane per warp, thread-local memory (interleaved across the 32 lanes)
+  // touches a different cache line per word and thrashes L1.
+  uint8_t nnz_l[16], nnz_c[2][4];
+  int8_t imodes_r[16];
+  int8_t dref[2][4];
+  int16_t dmv[2][16][2];
+  int16_t level[16];
+  uint8_t index[64];
+  int8_t refs[2][4];
+  int8_t sub[4], shape[4], pf[4];
 };
 
 HWB_HD void sd_fail(SliceDec &s, int code) { if (!s.error) s.error = code; }
 
+// Out-of-line engine access for the macroblock-layer syntax (tens of call sites): keeps the kernel small enough for
+// the instruction cache.  The residual loops use the inlined, register-resident versions instead.
+HWB_FN int cabac_bin_p(SliceDec &s, uint8_t *st) { return cabac_decision(s.cab, s.br, st); }
+HWB_HD int cabac_bin(SliceDec &s, int ctx) { return cabac_bin_p(s, s.st + ctx); }
+HWB_FN int cabac_byp(SliceDec &s) { return cabac_bypass(s.cab, s.br); }
+HWB_FN int cabac_term(SliceDec &s) { return cabac_terminate(s.cab, s.br); }
+HWB_FN uint32_t s_ue(SliceDec &s) { return br_ue(s.br); }
+HWB_FN int32_t s_se(SliceDec &s) { return br_se(s.br); }
+HWB_FN uint32_t s_get(SliceDec &s, int n) { return br_get(s.br, n); }
+
 // ================================================================================ neighbour caches
-HWB_HD void fill_caches(SliceDec &s, bool cur_intra_for_cbf_unused) {
+HWB_FN void fill_caches(SliceDec &s, bool cur_intra_for_cbf_unused) {
   (void)cur_intra_for_cbf_unused;
   const bool B = s.sd->slice_type == SLICE_B;
   const int nl = B ? 2 : 1;
@@ -121,7 +158,7 @@ HWB_HD MvRef mv_at(const SliceDec &s, int l, int bx, int by) {
 }
 // Median / directional prediction for the partition whose top-left 4x4 block is (bx,by), width w
 // (in 4x4 units).  shape: 0 = general (median), 1 = 16x8 upper, 2 = 16x8 lower, 3 = 8x16 left, 4 = 8x16 right.
-HWB_HD void pred_mv(const SliceDec &s, int l, int bx, int by, int w, int ref, int shape, int &px, int &py) {
+HWB_FN void pred_mv(const SliceDec &s, int l, int bx, int by, int w, int ref, int shape, int &px, int &py) {
   MvRef A = mv_at(s, l, bx - 1, by), Bn = mv_at(s, l, bx, by - 1), C = mv_at(s, l, bx + w, by - 1);
   if (C.ref == REF_UNAVAIL) C = mv_at(s, l, bx - 1, by - 1);
   if (shape == 1 && Bn.ref == ref) { px = Bn.mx; py = Bn.my; return; }
@@ -138,7 +175,7 @@ HWB_HD void pred_mv(const SliceDec &s, int l, int bx, int by, int w, int ref, in
     px = median3(A.mx, Bn.mx, C.mx); py = median3(A.my, Bn.my, C.my);
   }
 }
-HWB_HD void set_motion(SliceDec &s, int l, int bx, int by, int w, int h, int ref, int mx, int my, int amvdx, int amvdy) {
+HWB_FN void set_motion(SliceDec &s, int l, int bx, int by, int w, int h, int ref, int mx, int my, int amvdx, int amvdy) {
   for (int y = by; y < by + h; ++y)
     for (int x = bx; x < bx + w; ++x) {
       int ci = HWB_CI(x, y);
@@ -238,7 +275,7 @@ HWB_FN void direct_predict(SliceDec &s, int qmask, int8_t dref[2][4], int16_t dm
   }
 }
 
-HWB_HD void apply_direct(SliceDec &s, int l, int q, const int8_t dref[2][4], const int16_t dmv[2][16][2]) {
+HWB_FN void apply_direct(SliceDec &s, int l, int q, const int8_t dref[2][4], const int16_t dmv[2][16][2]) {
   for (int k = 0; k < 4; ++k) {
     int bx = (q & 1) * 2 + (k & 1), by = (q >> 1) * 2 + (k >> 1), br = by * 4 + bx;
     set_motion(s, l, bx, by, 1, 1, dref[l][q], dmv[l][br][0], dmv[l][br][1], 0, 0);
@@ -256,9 +293,9 @@ HWB_HD int cavlc_nc(int na, int nb) {
 // Decodes one residual block.  Levels are written to s.coef (zeroed first) at dezigzagged positions
 // given by `scan` (scan[start+i]); for 8x8-interleaved blocks scan8 != nullptr: position =
 // scan8[4*i + sub].  Returns total_coeff.
-HWB_FN int cavlc_residual(SliceDec &s, int nC, int max_coeff, int start, const uint8_t *scan, const uint8_t *scan8, int sub) {
-  BitReader &b = s.br;
+HWB_HD int cavlc_residual_impl(SliceDec &s, BitReader &b, int nC, int max_coeff, int start, const uint8_t *scan, const uint8_t *scan8, int sub) {
   int total, t1;
+  int16_t *level = s.level;
   if (nC < 0) {
     uint32_t e = cavlc_chroma_dc_token[br_peek(b, 8)];
     if (!e) { sd_fail(s, 10); return 0; }
@@ -280,10 +317,9 @@ HWB_FN int cavlc_residual(SliceDec &s, int nC, int max_coeff, int start, const u
   }
   if (total == 0) return 0;
   if (total > max_coeff) { sd_fail(s, 14); return 0; }
-  int level[16];
   int suffix_len = (total > 10 && t1 < 3) ? 1 : 0;
   for (int i = 0; i < total; ++i) {
-    if (i < t1) { level[i] = br_get1(b) ? -1 : 1; continue; }
+    if (i < t1) { level[i] = (int16_t)(br_get1(b) ? -1 : 1); continue; }
     uint32_t v = br_peek(b, 32);
     int prefix = clz32(v);
     if (prefix > 25) { sd_fail(s, 15); return 0; }
@@ -297,7 +333,7 @@ HWB_FN int cavlc_residual(SliceDec &s, int nC, int max_coeff, int start, const u
     if (prefix >= 16) code += (1 << (prefix - 3)) - 4096;
     if (i == t1 && t1 < 3) code += 2;
     int lv = (code & 1) ? (-code - 1) >> 1 : (code + 2) >> 1;
-    level[i] = lv;
+    level[i] = (int16_t)lv;
     if (suffix_len == 0) suffix_len = 1;
     if (iabs(lv) > (3 << (suffix_len - 1)) && suffix_len < 6) suffix_len++;
   }
@@ -316,7 +352,7 @@ HWB_FN int cavlc_residual(SliceDec &s, int nC, int max_coeff, int start, const u
   if (idx >= max_coeff) { sd_fail(s, 17); return 0; }
   for (int i = 0; i < total; ++i) {
     int pos = scan8 ? scan8[4 * idx + sub] : scan[start + idx];
-    s.coef[pos] = (int16_t)level[i];
+    s.coef[pos] = level[i];
     if (i + 1 < total) {
       int run = 0;
       if (zeros_left > 0) {
@@ -331,53 +367,73 @@ HWB_FN int cavlc_residual(SliceDec &s, int nC, int max_coeff, int start, const u
   }
   return total;
 }
+// The bit reader is copied into registers for the duration of the block (s lives in shared memory on the GPU).
+HWB_FN int cavlc_residual(SliceDec &s, int nC, int max_coeff, int start, const uint8_t *scan, const uint8_t *scan8, int sub) {
+  BitReader b = s.br;
+  int r = cavlc_residual_impl(s, b, nC, max_coeff, start, scan, scan8, sub);
+  s.br = b;
+  return r;
+}
 
 // ================================================================================ CABAC residual
-HWB_FN int cabac_residual(SliceDec &s, int cat, int max_coeff, int start, const uint8_t *scan) {
+HWB_TABLE uint8_t ctx_inc_identity[16] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15};
+HWB_TABLE uint8_t ctx_inc_chroma_dc[4] = {0, 1, 2, 2};
+HWB_HD int cabac_residual_impl(SliceDec &s, Cabac &cab, BitReader &br, uint8_t *st, int cat, int max_coeff, int start, const uint8_t *scan) {
   // cat: 0 I16 DC, 1 I16 AC, 2 luma 4x4, 3 chroma DC, 4 chroma AC, 5 luma 8x8
   const int sig_off = cat == 0 ? 105 : cat == 1 ? 120 : cat == 2 ? 134 : cat == 3 ? 149 : cat == 4 ? 152 : 402;
   const int last_off = cat == 0 ? 166 : cat == 1 ? 181 : cat == 2 ? 195 : cat == 3 ? 210 : cat == 4 ? 213 : 417;
   const int abs_off = cat == 0 ? 227 : cat == 1 ? 237 : cat == 2 ? 247 : cat == 3 ? 257 : cat == 4 ? 266 : 426;
-  uint8_t index[64];
+  uint8_t *index = s.index;
+  const uint8_t *sig_tab = cat == 5 ? cabac_sig8x8_ctx : (cat == 3 ? ctx_inc_chroma_dc : ctx_inc_identity);
+  const uint8_t *last_tab = cat == 5 ? cabac_last8x8_ctx : (cat == 3 ? ctx_inc_chroma_dc : ctx_inc_identity);
+  uint8_t *sig_st = st + sig_off, *last_st = st + last_off;
   int n = 0;
   int i = 0;
+#pragma unroll 1
   for (; i < max_coeff - 1; ++i) {
-    int sctx = cat == 5 ? cabac_sig8x8_ctx[i] : (cat == 3 ? (i < 2 ? i : 2) : i);
-    if (cabac_decision(s.cab, s.br, s.st + sig_off + sctx)) {
+    if (cabac_decision(cab, br, sig_st + sig_tab[i])) {
       index[n++] = (uint8_t)i;
-      int lctx = cat == 5 ? cabac_last8x8_ctx[i] : (cat == 3 ? (i < 2 ? i : 2) : i);
-      if (cabac_decision(s.cab, s.br, s.st + last_off + lctx)) break;
+      if (cabac_decision(cab, br, last_st + last_tab[i])) break;
     }
   }
   if (i == max_coeff - 1) index[n++] = (uint8_t)i;
   int eq1 = 0, gt1 = 0;
+#pragma unroll 1
   for (int k = n - 1; k >= 0; --k) {
     int ctx0 = gt1 ? 0 : (eq1 < 3 ? 1 + eq1 : 4);
     int absv;
-    if (!cabac_decision(s.cab, s.br, s.st + abs_off + ctx0)) {
+    if (!cabac_decision(cab, br, st + abs_off + ctx0)) {
       absv = 1; eq1++;
     } else {
       int cmax = cat == 3 ? 3 : 4;
       int ctx1 = 5 + (gt1 < cmax ? gt1 : cmax);
       absv = 2;
-      while (absv < 15 && cabac_decision(s.cab, s.br, s.st + abs_off + ctx1)) absv++;
+#pragma unroll 1
+      while (absv < 15 && cabac_decision(cab, br, st + abs_off + ctx1)) absv++;
       if (absv >= 15) {
         int kk = 0;
-        while (cabac_bypass(s.cab, s.br)) { absv += 1 << kk; kk++; if (kk > 20) { sd_fail(s, 30); return n; } }
-        while (kk--) absv += cabac_bypass(s.cab, s.br) << kk;
+        while (cabac_bypass(cab, br)) { absv += 1 << kk; kk++; if (kk > 20) { sd_fail(s, 30); return n; } }
+        while (kk--) absv += cabac_bypass(cab, br) << kk;
       }
       gt1++;
     }
-    int sign = cabac_bypass(s.cab, s.br);
+    int sign = cabac_bypass(cab, br);
     s.coef[scan[start + index[k]]] = (int16_t)(sign ? -absv : absv);
   }
   return n;
 }
+HWB_FN int cabac_residual(SliceDec &s, int cat, int max_coeff, int start, const uint8_t *scan) {
+  Cabac cab = s.cab;
+  BitReader br = s.br;
+  int n = cabac_residual_impl(s, cab, br, s.st, cat, max_coeff, start, scan);
+  s.cab = cab; s.br = br;
+  return n;
+}
 
 // ================================================================================ output helpers
-HWB_HD void coef_clear(SliceDec &s, int n) { for (int i = 0; i < n; ++i) s.coef[i] = 0; }
+HWB_FN void coef_clear(SliceDec &s, int n) { for (int i = 0; i < n; ++i) s.coef[i] = 0; }
 // Append s.coef[0..16*nslots) to the arena and mark item bits [bit, bit+nslots).
-HWB_HD void coef_emit(SliceDec &s, int bit, int nslots) {
+HWB_FN void coef_emit(SliceDec &s, int bit, int nslots) {
   int16_t *dst = pic_coefs(*s.c, s.pd->frame) + (uint64_t)s.coef_next * 16;
   for (int i = 0; i < nslots * 16; ++i) dst[i] = s.coef[i];
   s.coef_next += nslots;
@@ -390,7 +446,7 @@ HWB_TABLE uint8_t scan_ident4[4] = {0, 1, 2, 3};
 // ================================================================================ residual (both modes)
 // nnz[] receives total_coeff per luma block (raster) and chroma block.
 HWB_FN void decode_residual(SliceDec &s, bool i16, int cbp, bool t8, uint8_t nnz_l[16], uint8_t nnz_c[2][4]) {
-  const bool cabac = s.cabac;
+  const bool cabac = HWB_IS_CABAC(s);
   const bool intra = s.out.mbtype != MB_INTER;
   const int cbf_unavail = intra ? 1 : 0;
   for (int i = 0; i < 16; ++i) nnz_l[i] = 0;
@@ -400,7 +456,7 @@ HWB_FN void decode_residual(SliceDec &s, bool i16, int cbp, bool t8, uint8_t nnz
     if (cabac) {
       int a = s.availA ? ((s.left.flags & NBF_IPCM) ? 1 : (s.left.cbf >> NZ_LUMA_DC) & 1) : cbf_unavail;
       int bq = s.availB ? ((s.line[s.mbx].flags & NBF_IPCM) ? 1 : (s.line[s.mbx].cbf >> NZ_LUMA_DC) & 1) : cbf_unavail;
-      coded = cabac_decision(s.cab, s.br, s.st + 85 + 0 + a + 2 * bq);
+      coded = cabac_bin(s, 85 + 0 + a + 2 * bq);
     }
     if (coded) {
       coef_clear(s, 16);
@@ -437,7 +493,7 @@ HWB_FN void decode_residual(SliceDec &s, bool i16, int cbp, bool t8, uint8_t nnz
         int n = 0, coded = 1;
         if (cabac) {
           int a = na == 0x80 ? cbf_unavail : (na != 0), bq = nb == 0x80 ? cbf_unavail : (nb != 0);
-          coded = cabac_decision(s.cab, s.br, s.st + 85 + (i16 ? 4 : 8) + a + 2 * bq);
+          coded = cabac_bin(s, 85 + (i16 ? 4 : 8) + a + 2 * bq);
         }
         if (coded) {
           coef_clear(s, 16);
@@ -456,7 +512,7 @@ HWB_FN void decode_residual(SliceDec &s, bool i16, int cbp, bool t8, uint8_t nnz
       if (cabac) {
         int a = s.availA ? ((s.left.flags & NBF_IPCM) ? 1 : (s.left.cbf >> bit) & 1) : cbf_unavail;
         int bq = s.availB ? ((s.line[s.mbx].flags & NBF_IPCM) ? 1 : (s.line[s.mbx].cbf >> bit) & 1) : cbf_unavail;
-        coded = cabac_decision(s.cab, s.br, s.st + 85 + 12 + a + 2 * bq);
+        coded = cabac_bin(s, 85 + 12 + a + 2 * bq);
       }
       if (coded) {
         coef_clear(s, 16);
@@ -473,7 +529,7 @@ HWB_FN void decode_residual(SliceDec &s, bool i16, int cbp, bool t8, uint8_t nnz
         int n = 0, coded = 1;
         if (cabac) {
           int a = na == 0x80 ? cbf_unavail : (na != 0), bq = nb == 0x80 ? cbf_unavail : (nb != 0);
-          coded = cabac_decision(s.cab, s.br, s.st + 85 + 16 + a + 2 * bq);
+          coded = cabac_bin(s, 85 + 16 + a + 2 * bq);
         }
         if (coded) {
           coef_clear(s, 16);
@@ -486,66 +542,67 @@ HWB_FN void decode_residual(SliceDec &s, bool i16, int cbp, bool t8, uint8_t nnz
 }
 
 // ================================================================================ CABAC syntax elements
-HWB_HD int cabac_intra_mb_type(SliceDec &s, int base, bool islice) {
+HWB_FN int cabac_intra_mb_type(SliceDec &s, int base, bool islice) {
   uint8_t *st = s.st + base;
   if (islice) {
     int ctx = 0;
     if (s.availA && !(s.left.flags & NBF_INXN)) ctx++;
     if (s.availB && !(s.line[s.mbx].flags & NBF_INXN)) ctx++;
-    if (!cabac_decision(s.cab, s.br, st + ctx)) return 0;
+    if (!cabac_bin_p(s, st + ctx)) return 0;
     st += 2;
   } else {
-    if (!cabac_decision(s.cab, s.br, st)) return 0;
+    if (!cabac_bin_p(s, st)) return 0;
   }
-  if (cabac_terminate(s.cab, s.br)) return 25;
+  if (cabac_term(s)) return 25;
   int t = 1;
-  t += 12 * cabac_decision(s.cab, s.br, st + 1);
-  if (cabac_decision(s.cab, s.br, st + 2)) t += 4 + 4 * cabac_decision(s.cab, s.br, st + 2 + (islice ? 1 : 0));
-  t += 2 * cabac_decision(s.cab, s.br, st + 3 + (islice ? 1 : 0));
-  t += cabac_decision(s.cab, s.br, st + 3 + (islice ? 2 : 0));
+  t += 12 * cabac_bin_p(s, st + 1);
+  if (cabac_bin_p(s, st + 2)) t += 4 + 4 * cabac_bin_p(s, st + 2 + (islice ? 1 : 0));
+  t += 2 * cabac_bin_p(s, st + 3 + (islice ? 1 : 0));
+  t += cabac_bin_p(s, st + 3 + (islice ? 2 : 0));
   return t;
 }
 
-HWB_HD int cabac_b_mb_type(SliceDec &s) {
+HWB_FN int cabac_b_mb_type(SliceDec &s) {
   int ctx = 0;
   if (s.availA && !(s.left.flags & NBF_DIRECT16)) ctx++;
   if (s.availB && !(s.line[s.mbx].flags & NBF_DIRECT16)) ctx++;
   uint8_t *st = s.st + 27;
-  if (!cabac_decision(s.cab, s.br, st + ctx)) return 0;
-  if (!cabac_decision(s.cab, s.br, st + 3)) return 1 + cabac_decision(s.cab, s.br, st + 5);
-  int bits = cabac_decision(s.cab, s.br, st + 4) << 3;
-  bits |= cabac_decision(s.cab, s.br, st + 5) << 2;
-  bits |= cabac_decision(s.cab, s.br, st + 5) << 1;
-  bits |= cabac_decision(s.cab, s.br, st + 5);
+  if (!cabac_bin_p(s, st + ctx)) return 0;
+  if (!cabac_bin_p(s, st + 3)) return 1 + cabac_bin_p(s, st + 5);
+  int bits = cabac_bin_p(s, st + 4) << 3;
+  bits |= cabac_bin_p(s, st + 5) << 2;
+  bits |= cabac_bin_p(s, st + 5) << 1;
+  bits |= cabac_bin_p(s, st + 5);
   if (bits < 8) return bits + 3;
   if (bits == 13) return 23 + cabac_intra_mb_type(s, 32, false);
   if (bits == 14) return 11;
   if (bits == 15) return 22;
-  bits = (bits << 1) | cabac_decision(s.cab, s.br, st + 5);
+  bits = (bits << 1) | cabac_bin_p(s, st + 5);
   return bits - 4;
 }
 
-HWB_HD int cabac_b_sub_type(SliceDec &s) {
+HWB_FN int cabac_b_sub_type(SliceDec &s) {
   uint8_t *st = s.st + 36;
-  if (!cabac_decision(s.cab, s.br, st)) return 0;
-  if (!cabac_decision(s.cab, s.br, st + 1)) return 1 + cabac_decision(s.cab, s.br, st + 3);
+  if (!cabac_bin_p(s, st)) return 0;
+  if (!cabac_bin_p(s, st + 1)) return 1 + cabac_bin_p(s, st + 3);
   int t = 3;
-  if (cabac_decision(s.cab, s.br, st + 2)) {
-    if (cabac_decision(s.cab, s.br, st + 3)) return 11 + cabac_decision(s.cab, s.br, st + 3);
+  if (cabac_bin_p(s, st + 2)) {
+    if (cabac_bin_p(s, st + 3)) return 11 + cabac_bin_p(s, st + 3);
     t += 4;
   }
-  t += 2 * cabac_decision(s.cab, s.br, st + 3);
-  t += cabac_decision(s.cab, s.br, st + 3);
+  t += 2 * cabac_bin_p(s, st + 3);
+  t += cabac_bin_p(s, st + 3);
   return t;
 }
 
-HWB_HD int cabac_ref_idx(SliceDec &s, int l, int bx, int by) {
+HWB_FN int cabac_ref_idx(SliceDec &s, int l, int bx, int by) {
   int ra = s.ref_cache[l][HWB_CI(bx - 1, by)], rb = s.ref_cache[l][HWB_CI(bx, by - 1)];
   int ctx = 0;
   if (ra > 0 && !s.dir_cache[HWB_CI(bx - 1, by)]) ctx++;
   if (rb > 0 && !s.dir_cache[HWB_CI(bx, by - 1)]) ctx += 2;
   int ref = 0;
-  while (cabac_decision(s.cab, s.br, s.st + 54 + ctx)) {
+#pragma unroll 1
+  while (cabac_bin(s, 54 + ctx)) {
     ref++;
     ctx = (ctx >> 2) + 4;
     if (ref >= 32) { sd_fail(s, 40); return 0; }
@@ -553,21 +610,22 @@ HWB_HD int cabac_ref_idx(SliceDec &s, int l, int bx, int by) {
   return ref;
 }
 
-HWB_HD int cabac_mvd(SliceDec &s, int base, int amvd, int &absout) {
+HWB_FN int cabac_mvd(SliceDec &s, int base, int amvd, int &absout) {
   int inc = amvd < 3 ? 0 : (amvd > 32 ? 2 : 1);
-  if (!cabac_decision(s.cab, s.br, s.st + base + inc)) { absout = 0; return 0; }
+  if (!cabac_bin(s, base + inc)) { absout = 0; return 0; }
   int mvd = 1, ctx = base + 3;
-  while (mvd < 9 && cabac_decision(s.cab, s.br, s.st + ctx)) { if (mvd < 4) ctx++; mvd++; }
+#pragma unroll 1
+  while (mvd < 9 && cabac_bin(s, ctx)) { if (mvd < 4) ctx++; mvd++; }
   if (mvd >= 9) {
     int k = 3;
-    while (cabac_bypass(s.cab, s.br)) { mvd += 1 << k; k++; if (k > 24) { sd_fail(s, 41); return 0; } }
-    while (k--) mvd += cabac_bypass(s.cab, s.br) << k;
+    while (cabac_byp(s)) { mvd += 1 << k; k++; if (k > 24) { sd_fail(s, 41); return 0; } }
+    while (k--) mvd += cabac_byp(s) << k;
   }
   absout = mvd < 70 ? mvd : 70;
-  return cabac_bypass(s.cab, s.br) ? -mvd : mvd;
+  return cabac_byp(s) ? -mvd : mvd;
 }
 
-HWB_HD int cabac_cbp(SliceDec &s) {
+HWB_FN int cabac_cbp(SliceDec &s) {
   const NbCtx &L = s.left, &T = s.line[s.mbx];
   // luma: cbp bits of neighbours; unavailable / I_PCM behave as "all coded"
   int cbpa = s.availA ? ((L.flags & NBF_IPCM) ? 0x2F : L.cbp) : 0x0F;
@@ -576,20 +634,20 @@ HWB_HD int cabac_cbp(SliceDec &s) {
   for (int b8 = 0; b8 < 4; ++b8) {
     int a = (b8 & 1) ? !((cbp >> (b8 - 1)) & 1) : !((cbpa >> (b8 + 1)) & 1);
     int bq = (b8 & 2) ? !((cbp >> (b8 - 2)) & 1) : !((cbpb >> (b8 + 2)) & 1);
-    cbp |= cabac_decision(s.cab, s.br, s.st + 73 + a + 2 * bq) << b8;
+    cbp |= cabac_bin(s, 73 + a + 2 * bq) << b8;
   }
   int ca = s.availA ? (cbpa >> 4) & 3 : 0, cb = s.availB ? (cbpb >> 4) & 3 : 0;
   int ctx = (ca > 0) + 2 * (cb > 0);
-  if (cabac_decision(s.cab, s.br, s.st + 77 + ctx)) {
+  if (cabac_bin(s, 77 + ctx)) {
     ctx = 4 + (ca == 2) + 2 * (cb == 2);
-    cbp |= (1 + cabac_decision(s.cab, s.br, s.st + 77 + ctx)) << 4;
+    cbp |= (1 + cabac_bin(s, 77 + ctx)) << 4;
   }
   return cbp;
 }
 
-HWB_HD int cabac_dqp(SliceDec &s) {
+HWB_FN int cabac_dqp(SliceDec &s) {
   int ctx = s.last_dqp != 0, val = 0;
-  while (cabac_decision(s.cab, s.br, s.st + 60 + ctx)) {
+  while (cabac_bin(s, 60 + ctx)) {
     ctx = 2 + (ctx >> 1);
     val++;
     if (val > 104) { sd_fail(s, 42); return 0; }
@@ -597,13 +655,13 @@ HWB_HD int cabac_dqp(SliceDec &s) {
   return (val & 1) ? (val + 1) >> 1 : -((val + 1) >> 1);
 }
 
-HWB_HD int cabac_chroma_mode(SliceDec &s) {
+HWB_FN int cabac_chroma_mode(SliceDec &s) {
   int ctx = 0;
   if (s.availA && s.left.cmode != 0) ctx++;
   if (s.availB && s.line[s.mbx].cmode != 0) ctx++;
-  if (!cabac_decision(s.cab, s.br, s.st + 64 + ctx)) return 0;
-  if (!cabac_decision(s.cab, s.br, s.st + 64 + 3)) return 1;
-  return 2 + cabac_decision(s.cab, s.br, s.st + 64 + 3);
+  if (!cabac_bin(s, 64 + ctx)) return 0;
+  if (!cabac_bin(s, 64 + 3)) return 1;
+  return 2 + cabac_bin(s, 64 + 3);
 }
 
 // Publish a decoded macroblock: MbInfo, final motion data, and the neighbour context for the
@@ -669,25 +727,25 @@ HWB_FN void finish_mb(SliceDec &s, const uint8_t nnz_l[16], const uint8_t nnz_c[
 // prediction flags (1 L0, 2 L1, 3 Bi) of the two partitions of B 16x8 / 8x16 types, by (mb_type-4)>>1
 HWB_TABLE uint8_t b_part_pred[18] = {1, 1, 2, 2, 1, 2, 2, 1, 1, 3, 2, 3, 3, 1, 3, 2, 3, 3};
 
-HWB_HD int read_ref(SliceDec &s, int l, int bx, int by) {
+HWB_FN int read_ref(SliceDec &s, int l, int bx, int by) {
   int nref = s.sd->num_ref[l];
   if (nref <= 1) return 0;
-  if (s.cabac) return cabac_ref_idx(s, l, bx, by);
-  if (nref == 2) return br_get1(s.br) ^ 1;
-  return (int)br_ue(s.br);
+  if (HWB_IS_CABAC(s)) return cabac_ref_idx(s, l, bx, by);
+  if (nref == 2) return s_get(s, 1) ^ 1;
+  return (int)s_ue(s);
 }
 
-HWB_HD void read_mvd_and_set(SliceDec &s, int l, int bx, int by, int w, int h, int ref, int shape) {
+HWB_FN void read_mvd_and_set(SliceDec &s, int l, int bx, int by, int w, int h, int ref, int shape) {
   int px, py;
   pred_mv(s, l, bx, by, w, ref, shape, px, py);
   int dx, dy, ax = 0, ay = 0;
-  if (s.cabac) {
+  if (HWB_IS_CABAC(s)) {
     int sa = s.mvd_cache[l][HWB_CI(bx - 1, by)][0] + s.mvd_cache[l][HWB_CI(bx, by - 1)][0];
     int sb = s.mvd_cache[l][HWB_CI(bx - 1, by)][1] + s.mvd_cache[l][HWB_CI(bx, by - 1)][1];
     dx = cabac_mvd(s, 40, sa, ax);
     dy = cabac_mvd(s, 47, sb, ay);
   } else {
-    dx = br_se(s.br); dy = br_se(s.br);
+    dx = s_se(s); dy = s_se(s);
   }
   set_motion(s, l, bx, by, w, h, ref, px + dx, py + dy, ax, ay);
 }
@@ -704,15 +762,16 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
   o.mbtype = MB_INTER; o.qp = (uint8_t)s.qp; o.cbp = 0; o.flags = 0; o.imode = 0; o.cmode = 0;
   o.slice = (uint16_t)s.slice_num; o.nzmask = 0; o.coef_off = s.coef_next;
   for (int i = 0; i < 16; ++i) o.i4modes[i] = 2;
-  uint8_t nnz_l[16], nnz_c[2][4];
+  uint8_t *nnz_l = s.nnz_l;
+  uint8_t (*nnz_c)[4] = s.nnz_c;
   for (int i = 0; i < 16; ++i) nnz_l[i] = 0;
   for (int p = 0; p < 2; ++p) for (int i = 0; i < 4; ++i) nnz_c[p][i] = 0;
-  int8_t imodes_r[16];  // raster intra modes (-1 = not I_NxN)
+  int8_t *imodes_r = s.imodes_r;  // raster intra modes (-1 = not I_NxN)
   for (int i = 0; i < 16; ++i) imodes_r[i] = -1;
   bool direct16 = false;
   uint32_t dirq = 0;  // quadrants predicted in direct mode
-  int8_t dref[2][4];
-  int16_t dmv[2][16][2];
+  int8_t (*dref)[4] = s.dref;
+  int16_t (*dmv)[16][2] = s.dmv;
   bool is_pcm = false;
 
   if (skipped) {
@@ -732,15 +791,15 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
   } else {
     // ---------------- mb_type
     int mbt;
-    if (s.cabac) {
+    if (HWB_IS_CABAC(s)) {
       if (st == SLICE_I) mbt = cabac_intra_mb_type(s, 3, true);
       else if (st == SLICE_P) {
-        if (!cabac_decision(s.cab, s.br, s.st + 14)) {
-          if (!cabac_decision(s.cab, s.br, s.st + 15)) mbt = 3 * cabac_decision(s.cab, s.br, s.st + 16);
-          else mbt = 2 - cabac_decision(s.cab, s.br, s.st + 17);
+        if (!cabac_bin(s, 14)) {
+          if (!cabac_bin(s, 15)) mbt = 3 * cabac_bin(s, 16);
+          else mbt = 2 - cabac_bin(s, 17);
         } else mbt = 5 + cabac_intra_mb_type(s, 17, false);
       } else mbt = cabac_b_mb_type(s);
-    } else mbt = (int)br_ue(s.br);
+    } else mbt = (int)s_ue(s);
     int imbt = -1;  // intra mb_type 0..25
     if (st == SLICE_I) imbt = mbt;
     else if (st == SLICE_P && mbt >= 5) imbt = mbt - 5;
@@ -753,9 +812,9 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
       o.mbtype = MB_IPCM; o.qp = 0; o.cbp = 0x2F;
       br_align(s.br);
       uint8_t *dst = (uint8_t *)(pic_coefs(c, s.pd->frame) + (uint64_t)s.coef_next * 16);
-      for (int i = 0; i < 384; ++i) dst[i] = (uint8_t)br_get(s.br, 8);
+      for (int i = 0; i < 384; ++i) dst[i] = (uint8_t)s_get(s, 8);
       s.coef_next += 12; o.nzmask = 0xFFF;
-      if (s.cabac) cabac_start(s.cab, s.br);
+      if (HWB_IS_CABAC(s)) cabac_start(s.cab, s.br);
       for (int i = 0; i < 16; ++i) nnz_l[i] = 16;
       for (int p = 0; p < 2; ++p) for (int i = 0; i < 4; ++i) nnz_c[p][i] = 16;
       s.last_dqp = 0;
@@ -765,10 +824,10 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
       int cbp;
       if (imbt == 0) {
         if (s.pd->transform8x8_mode) {
-          if (s.cabac) {
+          if (HWB_IS_CABAC(s)) {
             int ctx = (s.availA && (s.left.flags & NBF_T8)) + (s.availB && (s.line[s.mbx].flags & NBF_T8));
-            t8 = cabac_decision(s.cab, s.br, s.st + 399 + ctx) != 0;
-          } else t8 = br_get1(s.br) != 0;
+            t8 = cabac_bin(s, 399 + ctx) != 0;
+          } else t8 = s_get(s, 1) != 0;
         }
         o.mbtype = t8 ? MB_I8x8 : MB_I4x4;
         if (t8) o.flags |= MBF_T8x8;
@@ -778,17 +837,17 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
           int ma = s.im_cache[HWB_CI(bx - 1, by)], mb_ = s.im_cache[HWB_CI(bx, by - 1)];
           int pred = (ma < 0 || mb_ < 0) ? 2 : (ma < mb_ ? ma : mb_);
           int mode;
-          if (s.cabac) {
-            if (cabac_decision(s.cab, s.br, s.st + 68)) mode = pred;
+          if (HWB_IS_CABAC(s)) {
+            if (cabac_bin(s, 68)) mode = pred;
             else {
-              int rem = cabac_decision(s.cab, s.br, s.st + 69);
-              rem |= cabac_decision(s.cab, s.br, s.st + 69) << 1;
-              rem |= cabac_decision(s.cab, s.br, s.st + 69) << 2;
+              int rem = cabac_bin(s, 69);
+              rem |= cabac_bin(s, 69) << 1;
+              rem |= cabac_bin(s, 69) << 2;
               mode = rem < pred ? rem : rem + 1;
             }
           } else {
-            if (br_get1(s.br)) mode = pred;
-            else { int rem = (int)br_get(s.br, 3); mode = rem < pred ? rem : rem + 1; }
+            if (s_get(s, 1)) mode = pred;
+            else { int rem = (int)s_get(s, 3); mode = rem < pred ? rem : rem + 1; }
           }
           o.i4modes[k] = (uint8_t)mode;
           int wd = t8 ? 2 : 1;
@@ -798,17 +857,17 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
         o.mbtype = MB_I16x16;
         o.imode = (uint8_t)((imbt - 1) & 3);
       }
-      o.cmode = (uint8_t)(s.cabac ? cabac_chroma_mode(s) : (int)br_ue(s.br));
+      o.cmode = (uint8_t)(HWB_IS_CABAC(s) ? cabac_chroma_mode(s) : (int)s_ue(s));
       if (o.cmode > 3) { sd_fail(s, 51); return; }
       if (imbt == 0) {
-        if (s.cabac) cbp = cabac_cbp(s);
-        else { uint32_t k = br_ue(s.br); if (k > 47) { sd_fail(s, 52); return; } cbp = golomb_to_intra_cbp[k]; }
+        if (HWB_IS_CABAC(s)) cbp = cabac_cbp(s);
+        else { uint32_t k = s_ue(s); if (k > 47) { sd_fail(s, 52); return; } cbp = golomb_to_intra_cbp[k]; }
       } else {
         cbp = (((imbt - 1) / 4) % 3) << 4 | ((imbt - 1) >= 12 ? 15 : 0);
       }
       o.cbp = (uint8_t)cbp;
       if (cbp || imbt > 0) {
-        int dqp = s.cabac ? cabac_dqp(s) : br_se(s.br);
+        int dqp = HWB_IS_CABAC(s) ? cabac_dqp(s) : s_se(s);
         s.last_dqp = dqp;
         s.qp = (s.qp + dqp + 52) % 52;
       } else s.last_dqp = 0;
@@ -818,7 +877,8 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
       // ---------------- inter
       int cbp;
       bool t8_allowed = true;
-      int sub[4] = {0, 0, 0, 0};
+      int8_t *sub = s.sub;
+      sub[0] = sub[1] = sub[2] = sub[3] = 0;
       if (B && mbt == 0) {
         direct16 = true; dirq = 15;
         direct_predict(s, 15, dref, dmv);
@@ -827,35 +887,35 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
       } else if ((!B && mbt >= 3) || (B && mbt == 22)) {
         // 8x8 with sub-macroblock types
         for (int q = 0; q < 4; ++q) {
-          if (s.cabac) {
-            if (B) sub[q] = cabac_b_sub_type(s);
-            else sub[q] = cabac_decision(s.cab, s.br, s.st + 21) ? 0 : (!cabac_decision(s.cab, s.br, s.st + 22) ? 1 : (cabac_decision(s.cab, s.br, s.st + 23) ? 2 : 3));
-          } else sub[q] = (int)br_ue(s.br);
+          if (HWB_IS_CABAC(s)) {
+            if (B) sub[q] = (int8_t)cabac_b_sub_type(s);
+            else sub[q] = (int8_t)(cabac_bin(s, 21) ? 0 : (!cabac_bin(s, 22) ? 1 : (cabac_bin(s, 23) ? 2 : 3)));
+          } else sub[q] = (int8_t)s_ue(s);
           if (sub[q] > (B ? 12 : 3)) { sd_fail(s, 53); return; }
           if (B && sub[q] == 0) dirq |= 1u << q;
         }
         if (dirq) direct_predict(s, (int)dirq, dref, dmv);
         // sub shapes: 0: 8x8, 1: 8x4, 2: 4x8, 3: 4x4; pred flags: 1 L0, 2 L1, 3 Bi
-        int shape[4], pf[4];
+        int8_t *shape = s.shape, *pf = s.pf;
         for (int q = 0; q < 4; ++q) {
           if (!B) { shape[q] = sub[q]; pf[q] = 1; }
           else if (sub[q] == 0) { shape[q] = 0; pf[q] = 0; }
           else {
             int t = sub[q];
-            shape[q] = t <= 3 ? 0 : (t >= 10 ? 3 : ((t & 1) ? 2 : 1));
-            pf[q] = t <= 3 ? t : (t >= 10 ? t - 9 : ((t - 4) >> 1) + 1);
+            shape[q] = (int8_t)(t <= 3 ? 0 : (t >= 10 ? 3 : ((t & 1) ? 2 : 1)));
+            pf[q] = (int8_t)(t <= 3 ? t : (t >= 10 ? t - 9 : ((t - 4) >> 1) + 1));
           }
           if (shape[q] != 0) t8_allowed = false;
           if (B && sub[q] == 0 && !s.pd->direct_8x8_inference) t8_allowed = false;
         }
-        int refs[2][4];
-        const bool ref0_only = !B && mbt == 4 && !s.cabac;  // P_8x8ref0 (CAVLC only)
+        int8_t (*refs)[4] = s.refs;
+        const bool ref0_only = !B && mbt == 4 && !HWB_IS_CABAC(s);  // P_8x8ref0 (CAVLC only)
         for (int l = 0; l < nl; ++l)
           for (int q = 0; q < 4; ++q) {
             refs[l][q] = -1;
             if ((dirq >> q) & 1) continue;
             if (pf[q] & (1 << l)) {
-              refs[l][q] = ref0_only ? 0 : read_ref(s, l, (q & 1) * 2, (q >> 1) * 2);
+              refs[l][q] = (int8_t)(ref0_only ? 0 : read_ref(s, l, (q & 1) * 2, (q >> 1) * 2));
               if (refs[l][q] >= sd.num_ref[l]) { sd_fail(s, 54); return; }
             }
             // make the reference visible for later ref_idx contexts of this list
@@ -893,7 +953,7 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
           pf0 = b_part_pred[k * 2]; pf1 = b_part_pred[k * 2 + 1];
         }
         const int np = shape == 0 ? 1 : 2;
-        int refs[2][2];
+        int8_t (*refs)[4] = s.refs;
         for (int l = 0; l < nl; ++l)
           for (int p = 0; p < np; ++p) {
             int pf = p ? pf1 : pf0;
@@ -901,7 +961,7 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
             int w = shape == 2 ? 2 : 4, h = shape == 1 ? 2 : 4;
             refs[l][p] = -1;
             if (pf & (1 << l)) {
-              refs[l][p] = read_ref(s, l, bx, by);
+              refs[l][p] = (int8_t)read_ref(s, l, bx, by);
               if (refs[l][p] >= sd.num_ref[l]) { sd_fail(s, 55); return; }
             }
             for (int y = by; y < by + h; ++y) for (int x = bx; x < bx + w; ++x) s.ref_cache[l][HWB_CI(x, y)] = (int8_t)(refs[l][p] >= 0 ? refs[l][p] : REF_NONE);
@@ -918,19 +978,19 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
         }
       }
       // ---------------- cbp, transform size, qp delta, residual
-      if (s.cabac) cbp = cabac_cbp(s);
-      else { uint32_t k = br_ue(s.br); if (k > 47) { sd_fail(s, 56); return; } cbp = golomb_to_inter_cbp[k]; }
+      if (HWB_IS_CABAC(s)) cbp = cabac_cbp(s);
+      else { uint32_t k = s_ue(s); if (k > 47) { sd_fail(s, 56); return; } cbp = golomb_to_inter_cbp[k]; }
       o.cbp = (uint8_t)cbp;
       bool t8 = false;
       if ((cbp & 15) && s.pd->transform8x8_mode && t8_allowed) {
-        if (s.cabac) {
+        if (HWB_IS_CABAC(s)) {
           int ctx = (s.availA && (s.left.flags & NBF_T8)) + (s.availB && (s.line[s.mbx].flags & NBF_T8));
-          t8 = cabac_decision(s.cab, s.br, s.st + 399 + ctx) != 0;
-        } else t8 = br_get1(s.br) != 0;
+          t8 = cabac_bin(s, 399 + ctx) != 0;
+        } else t8 = s_get(s, 1) != 0;
       }
       if (t8) o.flags |= MBF_T8x8;
       if (cbp) {
-        int dqp = s.cabac ? cabac_dqp(s) : br_se(s.br);
+        int dqp = HWB_IS_CABAC(s) ? cabac_dqp(s) : s_se(s);
         s.last_dqp = dqp;
         s.qp = (s.qp + dqp + 52) % 52;
       } else s.last_dqp = 0;
@@ -943,8 +1003,8 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
 }
 
 // ================================================================================ slice
-HWB_FN void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states) {
-  SliceDec s;
+HWB_FN void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states, SliceDec *state) {
+  SliceDec &s = *state;
   s.c = &c; s.sd = &c.slices[slice_idx]; s.pd = &c.pics[s.sd->pic];
   s.slice_num = slice_idx - s.pd->first_slice;
   s.cabac = s.pd->cabac != 0;
@@ -966,7 +1026,7 @@ HWB_FN void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states
   s.line = (NbCtx *)(c.ectx + (uint64_t)slice_idx * c.ectx_stride);
   // the arena region of a slice starts at its first macroblock's worst-case offset
   s.coef_next = (uint32_t)sd.first_mb * SLOTS_PER_MB;
-  if (s.cabac) {
+  if (HWB_IS_CABAC(s)) {
     br_align(s.br);
     cabac_init_states(s.st, sd.slice_type == SLICE_I ? 0 : 1 + sd.cabac_init_idc, sd.qp);
     cabac_start(s.cab, s.br);
@@ -985,12 +1045,12 @@ HWB_FN void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states
     s.availD = s.mbx > 0 && addr - c.mb_w - 1 >= first;
     bool skipped = false;
     if (sd.slice_type != SLICE_I) {
-      if (s.cabac) {
+      if (HWB_IS_CABAC(s)) {
         int ctx = (s.availA && !(s.left.flags & NBF_SKIP)) + (s.availB && !(s.line[s.mbx].flags & NBF_SKIP));
-        skipped = cabac_decision(s.cab, s.br, s.st + (sd.slice_type == SLICE_B ? 24 : 11) + ctx) != 0;
+        skipped = cabac_bin(s, (sd.slice_type == SLICE_B ? 24 : 11) + ctx) != 0;
       } else {
         if (run < 0) {
-          run = (int)br_ue(s.br);
+          run = (int)s_ue(s);
           if (run > c.nmb - addr) { sd_fail(s, 60); break; }
         }
         if (run > 0) { skipped = true; run--; }
@@ -998,8 +1058,8 @@ HWB_FN void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states
     }
     decode_mb(s, skipped);
     if (s.error || s.br.overrun) break;
-    if (s.cabac) {
-      end = cabac_terminate(s.cab, s.br) != 0;
+    if (HWB_IS_CABAC(s)) {
+      end = cabac_term(s) != 0;
     } else if (skipped) {
       if (run == 0 && !br_more_rbsp_data(s.br, s.stop_bitpos)) end = true;
     } else {
@@ -1028,4 +1088,9 @@ HWB_FN void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states
   }
 }
 
+}  // namespace HWB_ENT_NS
+#ifndef HWB_ENT_DEFAULT_IMPORTED
+#define HWB_ENT_DEFAULT_IMPORTED
+using namespace ent;
+#endif
 }  // namespace hwb

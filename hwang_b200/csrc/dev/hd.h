@@ -15,8 +15,9 @@
 #if defined(__CUDACC__)
 #define HWB_DEVICE_BUILD 1
 #define HWB_HD __device__ __forceinline__
-#define HWB_FN __device__
+#define HWB_FN __device__ __noinline__  /* big routines stay out of line: the entropy kernel must fit the instruction cache */
 #define HWB_TABLE static __device__ const
+#define HWB_CTABLE static __constant__ const  /* small tables read by one lane per warp: constant cache */
 #define HWB_LANES(l) { const int l = (int)(threadIdx.x & 31);
 #define HWB_LANES_END } __syncwarp();
 #define HWB_LANE0 if ((threadIdx.x & 31) == 0)
@@ -25,6 +26,7 @@
 #define HWB_HD static inline
 #define HWB_FN static
 #define HWB_TABLE static const
+#define HWB_CTABLE static const
 #define HWB_LANES(l) for (int l = 0; l < 32; ++l) {
 #define HWB_LANES_END }
 #define HWB_LANE0

@@ -179,7 +179,9 @@ Result B200VideoDecoder::submit_current() {
   rc |= hwb_dev_event_record(dev_, ch->ev_begin, st);  // inputs are resident in HBM from here on
   auto mark = [&]() { if (profile_) { hwb_event *e = hwb_dev_event_create(dev_); hwb_dev_event_record(dev_, e, st); ch->stage_ev.push_back(e); } };
   mark();
-  rc |= hwb_dev_entropy(dev_, st, &c, tickets);
+  int mode = ch->pics[0].cabac ? 1 : 0;
+  for (auto &p : ch->pics) if ((p.cabac ? 1 : 0) != mode) mode = -1;
+  rc |= hwb_dev_entropy(dev_, st, &c, tickets, mode);
   mark();
   size_t lo = 0;
   for (int l = 0; l < nlevels; ++l) {

@@ -1,5 +1,6 @@
 """Shared helpers for the parity tests: generate a clip, decode it with the oracle and with our decoder."""
 import io
+import time
 
 import numpy as np
 
@@ -31,8 +32,15 @@ def decode_yuv(index, samples, keyflags, chunk_pictures=None):
     dec.feed(None)
     dec.flush()
     out = []
-    while dec.frames_ready() > 0:
-        out.append(dec.get_frame_yuv())
+    deadline = time.time() + 300
+    while len(out) < len(samples):  # the GPU decodes asynchronously: poll until every fed picture has come out
+        if dec.frames_ready() > 0:
+            out.append(dec.get_frame_yuv())
+        elif time.time() > deadline:
+            raise TimeoutError('decoder produced %d of %d frames' % (len(out), len(samples)))
+        else:
+            time.sleep(0.0005)
+    assert dec.frames_ready() == 0
     return out, dec
 
 

@@ -50,9 +50,9 @@ def i8(off, n):
 out = []
 
 
-def emit(name, arr, ctype='uint8_t', per_line=16):
+def emit(name, arr, ctype='uint8_t', per_line=16, const=False):
     arr = np.asarray(arr).reshape(-1)
-    out.append('HWB_TABLE %s %s[%d] = {' % (ctype, name, arr.size))
+    out.append('%s %s %s[%d] = {' % ('HWB_CTABLE' if const else 'HWB_TABLE', ctype, name, arr.size))
     for i in range(0, arr.size, per_line):
         out.append('  ' + ','.join(str(int(x)) for x in arr[i:i + per_line]) + ',')
     out.append('};')
@@ -82,7 +82,7 @@ for p in range(64):
 assert range_lps[0].tolist() == [128, 176, 208, 240]
 assert range_lps[63].tolist() == [2, 2, 2, 2]
 assert range_lps[62].tolist() == [6, 7, 8, 9]
-emit('cabac_range_lps', range_lps)  # [pStateIdx][qCodIRangeIdx]
+emit('cabac_range_lps', range_lps, const=True)  # [pStateIdx][qCodIRangeIdx]
 mlps = u8(lps_off + 512, 256)
 trans_lps = np.zeros(64, np.uint8)
 trans_mps = np.zeros(64, np.uint8)
@@ -94,7 +94,7 @@ spec_lps = [0, 0, 1, 2, 2, 4, 4, 5, 6, 7, 8, 9, 9, 11, 11, 12, 13, 13, 15, 15, 1
             36, 36, 37, 37, 37, 38, 38, 63]
 assert trans_lps.tolist() == spec_lps
 assert trans_mps.tolist() == [min(p + 1, 62) for p in range(63)] + [63]
-emit('cabac_trans_lps', trans_lps)
+emit('cabac_trans_lps', trans_lps, const=True)
 
 sig8 = u8(find([0, 1, 2, 3, 4, 5, 5, 4, 4, 3, 3, 4, 4, 4, 5, 5, 4, 4, 4, 4, 3, 3, 6, 7, 7, 7, 8, 9, 10, 9, 8, 7], 0, 1), 63)
 assert sig8[-1] == 12 or True
