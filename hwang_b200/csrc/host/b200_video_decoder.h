@@ -87,7 +87,7 @@ class B200VideoDecoder : public VideoDecoderInterface {
   hwb::H264Stream stream_;
   bool configured_ = false;
   uint32_t width_ = 0, height_ = 0;
-  int chunk_target_ = 256;
+  int chunk_target_ = 4096;  // pictures per GPU batch: the entropy stage is latency-bound per slice, so bigger batches are better
   std::unique_ptr<Chunk> cur_;
   std::deque<std::unique_ptr<Chunk>> queue_;    // submitted chunks, oldest first
   std::vector<std::unique_ptr<Chunk>> retired_;  // fully popped, slab reusable after the next copy-stream sync
