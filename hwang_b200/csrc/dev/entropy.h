@@ -29,20 +29,27 @@ namespace HWB_ENT_NS {
 enum { NBF_INTRA = 1, NBF_IPCM = 2, NBF_SKIP = 4, NBF_DIRECT16 = 8, NBF_T8 = 16, NBF_I16 = 32, NBF_INXN = 64 };
 enum { REF_UNAVAIL = -2, REF_NONE = -1 };
 
-// What the right / bottom neighbours need to know about a decoded macroblock.
+// What the macroblocks below (below-left / below-right) need to know about a decoded macroblock: its bottom
+// edge.  The right edge never leaves the caches: the next macroblock of the row shifts it into its left column.
 struct alignas(16) NbCtx {
-  uint8_t flags, cbp, cmode, dirmask;
-  uint32_t cbf;
-  uint8_t nnz_b[4], nnz_r[4];
-  uint8_t cnnz_b[2][2], cnnz_r[2][2];
-  int8_t imode_b[4], imode_r[4];
-  int8_t ref_b[2][4], ref_r[2][4];
-  int16_t mv_b[2][4][2], mv_r[2][4][2];
-  uint8_t mvd_b[2][4][2], mvd_r[2][4][2];
+  uint8_t flags, cbp, cmode, dirmask;  // dirmask bit x: bottom-row block x was predicted in direct mode
+  uint32_t cbf;                        // nzmask-style coded flags (I_PCM: all ones)
+  uint8_t cnnz_b[2][2];
+  uint8_t pad[4];
+  uint8_t nnz_b[4];
+  int8_t imode_b[4];  // effective Intra4x4PredMode for the neighbour derivation (2 = not I_NxN, -1 = unusable)
+  int8_t ref_b[2][4];
+  int16_t mv_b[2][4][2];
+  uint8_t mvd_b[2][4][2];
 };
-static_assert(sizeof(NbCtx) == 144, "NbCtx layout");
+static_assert(sizeof(NbCtx) == 80, "NbCtx layout");
+struct LeftCtx { uint8_t flags, cbp, cmode, pad; uint32_t cbf; };
 
-#define HWB_CI(bx, by) (((by) + 1) * 6 + (bx) + 1)
+// Neighbour caches: 5 rows x 8 columns per array (row 0 = blocks above, columns 4..7 = the macroblock, column 3 =
+// left neighbours, column 8 == next row's column 0 = "top-right of the last column", permanently unavailable
+// except for row 0 where it holds the top-right macroblock's block).  Rows of 4 blocks are word / 16-byte aligned.
+#define HWB_CI(bx, by) (((by) + 1) * 8 + (bx) + 4)
+enum { HWB_CACHE_N = 48 };
 
 struct SliceDec {
   const ChunkCtx *c;
@@ -56,27 +63,27 @@ struct SliceDec {
   uint32_t stop_bitpos;
   int qp;
   int last_dqp;
-  NbCtx left, topleft;
+  LeftCtx left;
+  int8_t tl_ref[2];        // top-left macroblock's bottom-right block (saved before its line entry is overwritten)
+  int16_t tl_mv[2][2];
   NbCtx *line;  // [mb_w] top context
   uint32_t coef_next;  // next free slot in the picture arena
   // ---- current macroblock
   int mbx, mby, mbaddr;
   bool availA, availB, availC, availD;
-  int8_t ref_cache[2][30];
-  int16_t mv_cache[2][30][2];
-  uint8_t mvd_cache[2][30][2];
-  uint8_t dir_cache[30];
-  uint8_t nz_cache[30];      // luma total_coeff / coded flag; 0x80 = unavailable
-  uint8_t cnz_cache[2][12];  // chroma 3x4 layouts (by+1)*4 + bx+1 ... only [..][<9] used
-  int8_t im_cache[30];
+  alignas(16) int16_t mv_cache[2][HWB_CACHE_N][2];
+  alignas(16) uint8_t mvd_cache[2][HWB_CACHE_N][2];
+  alignas(16) int8_t ref_cache[2][HWB_CACHE_N];
+  alignas(16) uint8_t dir_cache[HWB_CACHE_N];
+  alignas(16) uint8_t nz_cache[HWB_CACHE_N];  // luma total_coeff / coded flag; 0x80 = unavailable
+  alignas(16) int8_t im_cache[HWB_CACHE_N];
+  uint8_t cnz_cache[2][12];  // chroma 3x4 layouts: (by+1)*4 + bx+1
   alignas(16) int16_t coef[64];  // staging for one block
   MbInfo out;
   int error;
   // Per-macroblock scratch.  It lives here (not on the stack) because on the GPU this struct is placed in
   // shared memory: with one active lane per warp, thread-local memory (interleaved across the 32 lanes)
   // touches a different cache line per word and thrashes L1.
-  uint8_t nnz_l[16], nnz_c[2][4];
-  int8_t imodes_r[16];
   int8_t dref[2][4];
   int16_t dmv[2][16][2];
   int16_t level[16];
@@ -98,55 +105,85 @@ HWB_FN int32_t s_se(SliceDec &s) { return br_se(s.br); }
 HWB_FN uint32_t s_get(SliceDec &s, int n) { return br_get(s.br, n); }
 
 // ================================================================================ neighbour caches
-HWB_FN void fill_caches(SliceDec &s, bool cur_intra_for_cbf_unused) {
-  (void)cur_intra_for_cbf_unused;
-  const bool B = s.sd->slice_type == SLICE_B;
-  const int nl = B ? 2 : 1;
-  const NbCtx &L = s.left, &T = s.line[s.mbx], &TL = s.topleft;
-  const NbCtx *TRp = s.availC ? &s.line[s.mbx + 1] : nullptr;
-  for (int i = 0; i < 30; ++i) { s.nz_cache[i] = 0x80; s.im_cache[i] = -1; s.dir_cache[i] = 0; }
+HWB_HD void cpy4(void *d, const void *s) { *(uint32_t *)d = *(const uint32_t *)s; }
+HWB_HD void set4(void *d, uint32_t v) { *(uint32_t *)d = v; }
+HWB_HD void cpy8(void *d, const void *s) { *(uint64_t *)d = *(const uint64_t *)s; }
+HWB_HD void cpy16(void *d, const void *s) {
+#if HWB_DEVICE_BUILD
+  *(uint4 *)d = *(const uint4 *)s;
+#else
+  memcpy(d, s, 16);
+#endif
+}
+
+// Called once per slice before the first macroblock: entries that never change.
+HWB_FN void init_caches(SliceDec &s) {
+  for (int l = 0; l < 2; ++l)
+    for (int i = 0; i < HWB_CACHE_N; ++i) { s.ref_cache[l][i] = REF_UNAVAIL; s.mv_cache[l][i][0] = s.mv_cache[l][i][1] = 0; s.mvd_cache[l][i][0] = s.mvd_cache[l][i][1] = 0; }
+  for (int i = 0; i < HWB_CACHE_N; ++i) { s.nz_cache[i] = 0x80; s.im_cache[i] = -1; s.dir_cache[i] = 0; }
   for (int p = 0; p < 2; ++p) for (int i = 0; i < 12; ++i) s.cnz_cache[p][i] = 0x80;
-  for (int i = 0; i < 16; ++i) s.nz_cache[HWB_CI(i & 3, i >> 2)] = 0;  // own blocks: available, nothing coded yet
-  for (int p = 0; p < 2; ++p) for (int i = 0; i < 4; ++i) s.cnz_cache[p][((i >> 1) + 1) * 4 + (i & 1) + 1] = 0;
-  for (int l = 0; l < nl; ++l)
-    for (int i = 0; i < 30; ++i) { s.ref_cache[l][i] = REF_UNAVAIL; s.mv_cache[l][i][0] = s.mv_cache[l][i][1] = 0; s.mvd_cache[l][i][0] = s.mvd_cache[l][i][1] = 0; }
-  const bool cip = s.pd->constrained_intra_pred != 0;
+}
+
+// Per macroblock: the left column is the previous macroblock's right column (still in the caches), the top row
+// comes from the slice's line buffer, the interior is reset.
+HWB_FN void fill_caches(SliceDec &s, bool unused) {
+  (void)unused;
+  const int nl = s.sd->slice_type == SLICE_B ? 2 : (s.sd->slice_type == SLICE_P ? 1 : 0);
   if (s.availA) {
     for (int y = 0; y < 4; ++y) {
-      int ci = HWB_CI(-1, y);
-      s.nz_cache[ci] = L.nnz_r[y];
-      s.im_cache[ci] = (L.flags & NBF_INXN) ? L.imode_r[y] : ((cip && !(L.flags & NBF_INTRA)) ? -1 : 2);
-      s.dir_cache[ci] = (L.dirmask >> (4 + y)) & 1;
+      const int d = HWB_CI(-1, y), f = HWB_CI(3, y);
+      s.nz_cache[d] = s.nz_cache[f]; s.im_cache[d] = s.im_cache[f]; s.dir_cache[d] = s.dir_cache[f];
       for (int l = 0; l < nl; ++l) {
-        s.ref_cache[l][ci] = L.ref_r[l][y];
-        s.mv_cache[l][ci][0] = L.mv_r[l][y][0]; s.mv_cache[l][ci][1] = L.mv_r[l][y][1];
-        s.mvd_cache[l][ci][0] = L.mvd_r[l][y][0]; s.mvd_cache[l][ci][1] = L.mvd_r[l][y][1];
+        s.ref_cache[l][d] = s.ref_cache[l][f];
+        cpy4(s.mv_cache[l][d], s.mv_cache[l][f]);
+        *(uint16_t *)s.mvd_cache[l][d] = *(const uint16_t *)s.mvd_cache[l][f];
       }
     }
-    for (int p = 0; p < 2; ++p) for (int y = 0; y < 2; ++y) s.cnz_cache[p][(y + 1) * 4] = L.cnnz_r[p][y];
+    for (int p = 0; p < 2; ++p) { s.cnz_cache[p][4] = s.cnz_cache[p][6]; s.cnz_cache[p][8] = s.cnz_cache[p][10]; }
+  } else {
+    for (int y = 0; y < 4; ++y) {
+      const int d = HWB_CI(-1, y);
+      s.nz_cache[d] = 0x80; s.im_cache[d] = -1; s.dir_cache[d] = 0;
+      for (int l = 0; l < nl; ++l) { s.ref_cache[l][d] = REF_UNAVAIL; set4(s.mv_cache[l][d], 0); *(uint16_t *)s.mvd_cache[l][d] = 0; }
+    }
+    for (int p = 0; p < 2; ++p) { s.cnz_cache[p][4] = 0x80; s.cnz_cache[p][8] = 0x80; }
   }
+  const int top = HWB_CI(0, -1);
   if (s.availB) {
-    for (int x = 0; x < 4; ++x) {
-      int ci = HWB_CI(x, -1);
-      s.nz_cache[ci] = T.nnz_b[x];
-      s.im_cache[ci] = (T.flags & NBF_INXN) ? T.imode_b[x] : ((cip && !(T.flags & NBF_INTRA)) ? -1 : 2);
-      s.dir_cache[ci] = (T.dirmask >> x) & 1;
-      for (int l = 0; l < nl; ++l) {
-        s.ref_cache[l][ci] = T.ref_b[l][x];
-        s.mv_cache[l][ci][0] = T.mv_b[l][x][0]; s.mv_cache[l][ci][1] = T.mv_b[l][x][1];
-        s.mvd_cache[l][ci][0] = T.mvd_b[l][x][0]; s.mvd_cache[l][ci][1] = T.mvd_b[l][x][1];
-      }
+    const NbCtx &T = s.line[s.mbx];
+    cpy4(s.nz_cache + top, T.nnz_b);
+    cpy4(s.im_cache + top, T.imode_b);
+    const uint32_t dm = T.dirmask;
+    set4(s.dir_cache + top, (dm & 1) | ((dm & 2) << 7) | ((dm & 4) << 14) | ((dm & 8) << 21));
+    for (int l = 0; l < nl; ++l) {
+      cpy4(s.ref_cache[l] + top, T.ref_b[l]);
+      cpy16(s.mv_cache[l][top], T.mv_b[l]);
+      cpy8(s.mvd_cache[l][top], T.mvd_b[l]);
     }
-    for (int p = 0; p < 2; ++p) for (int x = 0; x < 2; ++x) s.cnz_cache[p][x + 1] = T.cnnz_b[p][x];
+    for (int p = 0; p < 2; ++p) { s.cnz_cache[p][1] = T.cnnz_b[p][0]; s.cnz_cache[p][2] = T.cnnz_b[p][1]; }
+  } else {
+    set4(s.nz_cache + top, 0x80808080u); set4(s.im_cache + top, 0xFFFFFFFFu); set4(s.dir_cache + top, 0);
+    for (int l = 0; l < nl; ++l) {
+      set4(s.ref_cache[l] + top, 0xFEFEFEFEu);
+      for (int x = 0; x < 4; ++x) set4(s.mv_cache[l][top + x], 0);
+      for (int x = 0; x < 4; ++x) *(uint16_t *)s.mvd_cache[l][top + x] = 0;
+    }
+    for (int p = 0; p < 2; ++p) { s.cnz_cache[p][1] = 0x80; s.cnz_cache[p][2] = 0x80; }
   }
-  if (TRp) {
-    int ci = HWB_CI(4, -1);
-    for (int l = 0; l < nl; ++l) { s.ref_cache[l][ci] = TRp->ref_b[l][0]; s.mv_cache[l][ci][0] = TRp->mv_b[l][0][0]; s.mv_cache[l][ci][1] = TRp->mv_b[l][0][1]; }
+  for (int l = 0; l < nl; ++l) {
+    const int tr = HWB_CI(4, -1), tl = HWB_CI(-1, -1);
+    if (s.availC) { const NbCtx &R = s.line[s.mbx + 1]; s.ref_cache[l][tr] = R.ref_b[l][0]; cpy4(s.mv_cache[l][tr], R.mv_b[l][0]); }
+    else { s.ref_cache[l][tr] = REF_UNAVAIL; set4(s.mv_cache[l][tr], 0); }
+    if (s.availD) { s.ref_cache[l][tl] = s.tl_ref[l]; cpy4(s.mv_cache[l][tl], s.tl_mv[l]); }
+    else { s.ref_cache[l][tl] = REF_UNAVAIL; set4(s.mv_cache[l][tl], 0); }
   }
-  if (s.availD) {
-    int ci = HWB_CI(-1, -1);
-    for (int l = 0; l < nl; ++l) { s.ref_cache[l][ci] = TL.ref_b[l][3]; s.mv_cache[l][ci][0] = TL.mv_b[l][3][0]; s.mv_cache[l][ci][1] = TL.mv_b[l][3][1]; }
+  // interior: nothing coded yet, nothing direct, references "not decoded yet"
+  for (int y = 0; y < 4; ++y) {
+    const int r = HWB_CI(0, y);
+    set4(s.nz_cache + r, 0); set4(s.dir_cache + r, 0);
+    for (int l = 0; l < nl; ++l) set4(s.ref_cache[l] + r, 0xFEFEFEFEu);
   }
+  for (int p = 0; p < 2; ++p) { s.cnz_cache[p][5] = s.cnz_cache[p][6] = s.cnz_cache[p][9] = s.cnz_cache[p][10] = 0; }
 }
 
 // ================================================================================ MV prediction
@@ -431,11 +468,17 @@ HWB_FN int cabac_residual(SliceDec &s, int cat, int max_coeff, int start, const 
 }
 
 // ================================================================================ output helpers
-HWB_FN void coef_clear(SliceDec &s, int n) { for (int i = 0; i < n; ++i) s.coef[i] = 0; }
+HWB_FN void coef_clear(SliceDec &s, int n) {
+#if HWB_DEVICE_BUILD
+  for (int i = 0; i < n; i += 8) *(uint4 *)(s.coef + i) = make_uint4(0, 0, 0, 0);
+#else
+  for (int i = 0; i < n; ++i) s.coef[i] = 0;
+#endif
+}
 // Append s.coef[0..16*nslots) to the arena and mark item bits [bit, bit+nslots).
 HWB_FN void coef_emit(SliceDec &s, int bit, int nslots) {
   int16_t *dst = pic_coefs(*s.c, s.pd->frame) + (uint64_t)s.coef_next * 16;
-  for (int i = 0; i < nslots * 16; ++i) dst[i] = s.coef[i];
+  for (int i = 0; i < nslots * 2; ++i) cpy16(dst + 8 * i, s.coef + 8 * i);
   s.coef_next += nslots;
   s.out.nzmask |= ((1u << nslots) - 1u) << bit;
 }
@@ -445,12 +488,10 @@ HWB_TABLE uint8_t scan_ident4[4] = {0, 1, 2, 3};
 
 // ================================================================================ residual (both modes)
 // nnz[] receives total_coeff per luma block (raster) and chroma block.
-HWB_FN void decode_residual(SliceDec &s, bool i16, int cbp, bool t8, uint8_t nnz_l[16], uint8_t nnz_c[2][4]) {
+HWB_FN void decode_residual(SliceDec &s, bool i16, int cbp, bool t8) {
   const bool cabac = HWB_IS_CABAC(s);
   const bool intra = s.out.mbtype != MB_INTER;
   const int cbf_unavail = intra ? 1 : 0;
-  for (int i = 0; i < 16; ++i) nnz_l[i] = 0;
-  for (int p = 0; p < 2; ++p) for (int i = 0; i < 4; ++i) nnz_c[p][i] = 0;
   if (i16) {
     int coded = 1;
     if (cabac) {
@@ -474,14 +515,14 @@ HWB_FN void decode_residual(SliceDec &s, bool i16, int cbp, bool t8, uint8_t nnz
         n = cabac_residual(s, 5, 64, 0, zigzag8x8);
         for (int k = 0; k < 4; ++k) {
           int bx = (q & 1) * 2 + (k & 1), by = (q >> 1) * 2 + (k >> 1);
-          nnz_l[by * 4 + bx] = (uint8_t)(n > 16 ? 16 : n); s.nz_cache[HWB_CI(bx, by)] = nnz_l[by * 4 + bx];
+          s.nz_cache[HWB_CI(bx, by)] = (uint8_t)(n > 16 ? 16 : n);
         }
       } else {
         for (int k = 0; k < 4; ++k) {
           int bx = (q & 1) * 2 + (k & 1), by = (q >> 1) * 2 + (k >> 1);
           int nc = cavlc_nc(s.nz_cache[HWB_CI(bx - 1, by)], s.nz_cache[HWB_CI(bx, by - 1)]);
           int m = cavlc_residual(s, nc, 16, 0, nullptr, zigzag8x8, k);
-          nnz_l[by * 4 + bx] = (uint8_t)m; s.nz_cache[HWB_CI(bx, by)] = (uint8_t)m;
+          s.nz_cache[HWB_CI(bx, by)] = (uint8_t)m;
           n += m;
         }
       }
@@ -501,7 +542,7 @@ HWB_FN void decode_residual(SliceDec &s, bool i16, int cbp, bool t8, uint8_t nnz
           else n = cavlc_residual(s, cavlc_nc(na, nb), i16 ? 15 : 16, i16 ? 1 : 0, zigzag4x4, nullptr, 0);
           if (n) coef_emit(s, NZ_LUMA0 + z, 1);
         }
-        nnz_l[by * 4 + bx] = (uint8_t)n; s.nz_cache[HWB_CI(bx, by)] = (uint8_t)n;
+        s.nz_cache[HWB_CI(bx, by)] = (uint8_t)n;
       }
     }
   }
@@ -536,7 +577,7 @@ HWB_FN void decode_residual(SliceDec &s, bool i16, int cbp, bool t8, uint8_t nnz
           n = cabac ? cabac_residual(s, 4, 15, 1, zigzag4x4) : cavlc_residual(s, cavlc_nc(na, nb), 15, 1, zigzag4x4, nullptr, 0);
           if (n) coef_emit(s, (p ? NZ_CR0 : NZ_CB0) + k, 1);
         }
-        nnz_c[p][k] = (uint8_t)n; s.cnz_cache[p][(by + 1) * 4 + bx + 1] = (uint8_t)n;
+        s.cnz_cache[p][(by + 1) * 4 + bx + 1] = (uint8_t)n;
       }
   }
 }
@@ -626,7 +667,8 @@ HWB_FN int cabac_mvd(SliceDec &s, int base, int amvd, int &absout) {
 }
 
 HWB_FN int cabac_cbp(SliceDec &s) {
-  const NbCtx &L = s.left, &T = s.line[s.mbx];
+  const LeftCtx &L = s.left;
+  const NbCtx &T = s.line[s.mbx];
   // luma: cbp bits of neighbours; unavailable / I_PCM behave as "all coded"
   int cbpa = s.availA ? ((L.flags & NBF_IPCM) ? 0x2F : L.cbp) : 0x0F;
   int cbpb = s.availB ? ((T.flags & NBF_IPCM) ? 0x2F : T.cbp) : 0x0F;
@@ -664,25 +706,42 @@ HWB_FN int cabac_chroma_mode(SliceDec &s) {
   return 2 + cabac_bin(s, 64 + 3);
 }
 
-// Publish a decoded macroblock: MbInfo, final motion data, and the neighbour context for the
-// macroblocks to come.  Shared by the decoder and by the stream generator's entropy writer.
-HWB_FN void finish_mb(SliceDec &s, const uint8_t nnz_l[16], const uint8_t nnz_c[2][4], const int8_t imodes_r[16],
-                      bool skipped, bool direct16, bool is_pcm) {
+// Publish a decoded macroblock: MbInfo, final motion data, and the neighbour context for the macroblocks to come.
+// The caches must hold the macroblock's total_coeff (nz/cnz), intra modes (I_NxN only), motion and direct flags.
+// Shared by the decoder and by the stream generator's entropy writer.
+HWB_FN void finish_mb(SliceDec &s, bool skipped, bool direct16, bool is_pcm) {
   const ChunkCtx &c = *s.c;
   const SliceDesc &sd = *s.sd;
   const bool B = sd.slice_type == SLICE_B;
-  const int nl = B ? 2 : 1;
+  const int nl = B ? 2 : (sd.slice_type == SLICE_P ? 1 : 0);
   MbInfo &o = s.out;
-  // ---------------- write outputs
   const int f = s.pd->frame;
-  pic_mbinfo(c, f)[s.mbaddr] = o;
   const bool inter = o.mbtype == MB_INTER;
+  const bool inxn = o.mbtype == MB_I4x4 || o.mbtype == MB_I8x8;
+  // ---- normalise the interior so that the right column / bottom row say what neighbours must see
+  if (!inter) {
+    for (int l = 0; l < nl; ++l)
+      for (int y = 0; y < 4; ++y) {
+        const int r = HWB_CI(0, y);
+        set4(s.ref_cache[l] + r, 0xFFFFFFFFu);
+        for (int x = 0; x < 4; ++x) { set4(s.mv_cache[l][r + x], 0); *(uint16_t *)s.mvd_cache[l][r + x] = 0; }
+      }
+  }
+  if (!inxn) {
+    const uint32_t v = (inter && s.pd->constrained_intra_pred) ? 0xFFFFFFFFu : 0x02020202u;
+    for (int y = 0; y < 4; ++y) set4(s.im_cache + HWB_CI(0, y), v);
+  }
+  // ---- outputs
+  {
+    MbInfo *dst = pic_mbinfo(c, f) + s.mbaddr;
+    cpy16(dst, &o); cpy16((uint8_t *)dst + 16, (const uint8_t *)&o + 16);
+  }
   if (inter) {
     for (int l = 0; l < nl; ++l) {
       int16_t *mvo = pic_mv(c, f, l) + (uint64_t)s.mbaddr * 32;
+      for (int y = 0; y < 4; ++y) cpy16(mvo + 8 * y, s.mv_cache[l][HWB_CI(0, y)]);
       int8_t *ro = pic_refidx(c, f, l) + (uint64_t)s.mbaddr * 4;
       int16_t *po = pic_refpic(c, f, l) + (uint64_t)s.mbaddr * 4;
-      for (int i = 0; i < 16; ++i) { int ci = HWB_CI(i & 3, i >> 2); mvo[2 * i] = s.mv_cache[l][ci][0]; mvo[2 * i + 1] = s.mv_cache[l][ci][1]; }
       for (int q = 0; q < 4; ++q) {
         int r = s.ref_cache[l][HWB_CI((q & 1) * 2, (q >> 1) * 2)];
         ro[q] = (int8_t)r;
@@ -690,37 +749,30 @@ HWB_FN void finish_mb(SliceDec &s, const uint8_t nnz_l[16], const uint8_t nnz_c[
       }
     }
     if (!B && s.pd->has_inter == 2) {
-      int8_t *ro = pic_refidx(c, f, 1) + (uint64_t)s.mbaddr * 4;
+      set4(pic_refidx(c, f, 1) + (uint64_t)s.mbaddr * 4, 0xFFFFFFFFu);
       int16_t *po = pic_refpic(c, f, 1) + (uint64_t)s.mbaddr * 4;
-      for (int q = 0; q < 4; ++q) { ro[q] = -1; po[q] = -1; }
+      for (int q = 0; q < 4; ++q) po[q] = -1;
     }
   }
-  // ---------------- neighbour context for the macroblocks to come
-  NbCtx n;
-  n.flags = (uint8_t)((inter ? 0 : NBF_INTRA) | (is_pcm ? NBF_IPCM : 0) | (skipped ? NBF_SKIP : 0) | (direct16 ? NBF_DIRECT16 : 0) |
-                      ((o.flags & MBF_T8x8) ? NBF_T8 : 0) | (o.mbtype == MB_I16x16 ? NBF_I16 : 0) | ((o.mbtype == MB_I4x4 || o.mbtype == MB_I8x8) ? NBF_INXN : 0));
-  n.cbp = o.cbp; n.cmode = o.cmode; n.cbf = is_pcm ? 0x7FFFFFFu : o.nzmask;
-  n.dirmask = 0;
-  for (int i = 0; i < 4; ++i) {
-    n.nnz_b[i] = nnz_l[12 + i]; n.nnz_r[i] = nnz_l[i * 4 + 3];
-    n.imode_b[i] = imodes_r[12 + i]; n.imode_r[i] = imodes_r[i * 4 + 3];
-    if (s.dir_cache[HWB_CI(i, 3)]) n.dirmask |= 1u << i;
-    if (s.dir_cache[HWB_CI(3, i)]) n.dirmask |= 16u << i;
-    for (int l = 0; l < 2; ++l) {
-      bool on = inter && l < nl;
-      int cb = HWB_CI(i, 3), cr = HWB_CI(3, i);
-      n.ref_b[l][i] = on ? s.ref_cache[l][cb] : (int8_t)REF_NONE;
-      n.ref_r[l][i] = on ? s.ref_cache[l][cr] : (int8_t)REF_NONE;
-      for (int k = 0; k < 2; ++k) {
-        n.mv_b[l][i][k] = on ? s.mv_cache[l][cb][k] : (int16_t)0; n.mv_r[l][i][k] = on ? s.mv_cache[l][cr][k] : (int16_t)0;
-        n.mvd_b[l][i][k] = on ? s.mvd_cache[l][cb][k] : (uint8_t)0; n.mvd_r[l][i][k] = on ? s.mvd_cache[l][cr][k] : (uint8_t)0;
-      }
-    }
+  // ---- neighbour context: bottom edge to the line buffer (after saving what the next macroblock's top-left needs)
+  NbCtx &n = s.line[s.mbx];
+  for (int l = 0; l < nl; ++l) { s.tl_ref[l] = n.ref_b[l][3]; cpy4(s.tl_mv[l], n.mv_b[l][3]); }
+  const uint8_t flags = (uint8_t)((inter ? 0 : NBF_INTRA) | (is_pcm ? NBF_IPCM : 0) | (skipped ? NBF_SKIP : 0) | (direct16 ? NBF_DIRECT16 : 0) |
+                                  ((o.flags & MBF_T8x8) ? NBF_T8 : 0) | (o.mbtype == MB_I16x16 ? NBF_I16 : 0) | (inxn ? NBF_INXN : 0));
+  const int bot = HWB_CI(0, 3);
+  uint32_t dm = 0;
+  for (int x = 0; x < 4; ++x) if (s.dir_cache[bot + x]) dm |= 1u << x;
+  const uint32_t cbf = is_pcm ? 0x7FFFFFFu : o.nzmask;
+  n.flags = flags; n.cbp = o.cbp; n.cmode = o.cmode; n.dirmask = (uint8_t)dm; n.cbf = cbf;
+  for (int p = 0; p < 2; ++p) { n.cnnz_b[p][0] = s.cnz_cache[p][9]; n.cnnz_b[p][1] = s.cnz_cache[p][10]; }
+  cpy4(n.nnz_b, s.nz_cache + bot);
+  cpy4(n.imode_b, s.im_cache + bot);
+  for (int l = 0; l < nl; ++l) {
+    cpy4(n.ref_b[l], s.ref_cache[l] + bot);
+    cpy16(n.mv_b[l], s.mv_cache[l][bot]);
+    cpy8(n.mvd_b[l], s.mvd_cache[l][bot]);
   }
-  for (int p = 0; p < 2; ++p) { n.cnnz_b[p][0] = nnz_c[p][2]; n.cnnz_b[p][1] = nnz_c[p][3]; n.cnnz_r[p][0] = nnz_c[p][1]; n.cnnz_r[p][1] = nnz_c[p][3]; }
-  s.topleft = s.line[s.mbx];
-  s.line[s.mbx] = n;
-  s.left = n;
+  s.left.flags = flags; s.left.cbp = o.cbp; s.left.cmode = o.cmode; s.left.cbf = cbf;
 }
 
 // ================================================================================ macroblock layer
@@ -762,12 +814,6 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
   o.mbtype = MB_INTER; o.qp = (uint8_t)s.qp; o.cbp = 0; o.flags = 0; o.imode = 0; o.cmode = 0;
   o.slice = (uint16_t)s.slice_num; o.nzmask = 0; o.coef_off = s.coef_next;
   for (int i = 0; i < 16; ++i) o.i4modes[i] = 2;
-  uint8_t *nnz_l = s.nnz_l;
-  uint8_t (*nnz_c)[4] = s.nnz_c;
-  for (int i = 0; i < 16; ++i) nnz_l[i] = 0;
-  for (int p = 0; p < 2; ++p) for (int i = 0; i < 4; ++i) nnz_c[p][i] = 0;
-  int8_t *imodes_r = s.imodes_r;  // raster intra modes (-1 = not I_NxN)
-  for (int i = 0; i < 16; ++i) imodes_r[i] = -1;
   bool direct16 = false;
   uint32_t dirq = 0;  // quadrants predicted in direct mode
   int8_t (*dref)[4] = s.dref;
@@ -815,8 +861,8 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
       for (int i = 0; i < 384; ++i) dst[i] = (uint8_t)s_get(s, 8);
       s.coef_next += 12; o.nzmask = 0xFFF;
       if (HWB_IS_CABAC(s)) cabac_start(s.cab, s.br);
-      for (int i = 0; i < 16; ++i) nnz_l[i] = 16;
-      for (int p = 0; p < 2; ++p) for (int i = 0; i < 4; ++i) nnz_c[p][i] = 16;
+      for (int y = 0; y < 4; ++y) set4(s.nz_cache + HWB_CI(0, y), 0x10101010u);
+      for (int p = 0; p < 2; ++p) { s.cnz_cache[p][5] = s.cnz_cache[p][6] = s.cnz_cache[p][9] = s.cnz_cache[p][10] = 16; }
       s.last_dqp = 0;
     } else if (imbt >= 0) {
       // ---------------- intra
@@ -851,7 +897,7 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
           }
           o.i4modes[k] = (uint8_t)mode;
           int wd = t8 ? 2 : 1;
-          for (int y = by; y < by + wd; ++y) for (int x = bx; x < bx + wd; ++x) { s.im_cache[HWB_CI(x, y)] = (int8_t)mode; imodes_r[y * 4 + x] = (int8_t)mode; }
+          for (int y = by; y < by + wd; ++y) for (int x = bx; x < bx + wd; ++x) s.im_cache[HWB_CI(x, y)] = (int8_t)mode;
         }
       } else {
         o.mbtype = MB_I16x16;
@@ -872,7 +918,7 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
         s.qp = (s.qp + dqp + 52) % 52;
       } else s.last_dqp = 0;
       o.qp = (uint8_t)s.qp;
-      decode_residual(s, imbt > 0, cbp, t8, nnz_l, nnz_c);
+      decode_residual(s, imbt > 0, cbp, t8);
     } else {
       // ---------------- inter
       int cbp;
@@ -995,11 +1041,11 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
         s.qp = (s.qp + dqp + 52) % 52;
       } else s.last_dqp = 0;
       o.qp = (uint8_t)s.qp;
-      decode_residual(s, false, cbp, t8, nnz_l, nnz_c);
+      decode_residual(s, false, cbp, t8);
     }
   }
 
-  finish_mb(s, nnz_l, nnz_c, imodes_r, skipped, direct16, is_pcm);
+  finish_mb(s, skipped, direct16, is_pcm);
 }
 
 // ================================================================================ slice
@@ -1023,6 +1069,7 @@ HWB_FN void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states
     s.stop_bitpos = (uint32_t)(n > 0 ? (n - 1) * 8 + (7 - tz) : 0);
   }
   s.qp = sd.qp; s.last_dqp = 0;
+  init_caches(s);
   s.line = (NbCtx *)(c.ectx + (uint64_t)slice_idx * c.ectx_stride);
   // the arena region of a slice starts at its first macroblock's worst-case offset
   s.coef_next = (uint32_t)sd.first_mb * SLOTS_PER_MB;

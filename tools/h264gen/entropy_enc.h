@@ -152,7 +152,7 @@ inline int cabac_write_block(SliceEnc &e, const int *c, int cat, int max_coeff) 
 
 // ------------------------------------------------------------------ residual (mirrors decode_residual)
 // Coefficients are read back from the arena slots written by the generator (raw levels, raster order).
-inline void write_residual(SliceEnc &e, bool i16, int cbp, bool t8, uint8_t nnz_l[16], uint8_t nnz_c[2][4]) {
+inline void write_residual(SliceEnc &e, bool i16, int cbp, bool t8) {
   SliceDec &s = e.s;
   const bool cabac = e.cabac;
   const MbInfo &o = s.out;
@@ -163,8 +163,6 @@ inline void write_residual(SliceEnc &e, bool i16, int cbp, bool t8, uint8_t nnz_
     return ((o.nzmask >> bit) & 1) ? arena + 16 * popc32(o.nzmask & ((1u << bit) - 1)) : nullptr;
   };
   int c[64];
-  for (int i = 0; i < 16; ++i) nnz_l[i] = 0;
-  for (int p = 0; p < 2; ++p) for (int i = 0; i < 4; ++i) nnz_c[p][i] = 0;
   if (i16) {
     const int16_t *sl = slot(NZ_LUMA_DC);
     for (int i = 0; i < 16; ++i) c[i] = sl ? sl[zigzag4x4[i]] : 0;
@@ -185,14 +183,14 @@ inline void write_residual(SliceEnc &e, bool i16, int cbp, bool t8, uint8_t nnz_
         int n = cabac_write_block(e, c, 5, 64);
         for (int k = 0; k < 4; ++k) {
           int bx = (q & 1) * 2 + (k & 1), by = (q >> 1) * 2 + (k >> 1);
-          nnz_l[by * 4 + bx] = (uint8_t)(n > 16 ? 16 : n); s.nz_cache[HWB_CI(bx, by)] = nnz_l[by * 4 + bx];
+          s.nz_cache[HWB_CI(bx, by)] = (uint8_t)(n > 16 ? 16 : n);
         }
       } else {
         for (int k = 0; k < 4; ++k) {
           int bx = (q & 1) * 2 + (k & 1), by = (q >> 1) * 2 + (k >> 1);
           for (int i = 0; i < 16; ++i) c[i] = sl ? sl[zigzag8x8[4 * i + k]] : 0;
           int m = cavlc_write_block(e, c, 16, cavlc_nc(s.nz_cache[HWB_CI(bx - 1, by)], s.nz_cache[HWB_CI(bx, by - 1)]));
-          nnz_l[by * 4 + bx] = (uint8_t)m; s.nz_cache[HWB_CI(bx, by)] = (uint8_t)m;
+          s.nz_cache[HWB_CI(bx, by)] = (uint8_t)m;
         }
       }
     } else {
@@ -207,7 +205,7 @@ inline void write_residual(SliceEnc &e, bool i16, int cbp, bool t8, uint8_t nnz_
           e.ce.decision(85 + (i16 ? 4 : 8) + a + 2 * bq, sl != nullptr);
           if (sl) n = cabac_write_block(e, c, i16 ? 1 : 2, mc);
         } else n = cavlc_write_block(e, c, mc, cavlc_nc(na, nb));
-        nnz_l[by * 4 + bx] = (uint8_t)n; s.nz_cache[HWB_CI(bx, by)] = (uint8_t)n;
+        s.nz_cache[HWB_CI(bx, by)] = (uint8_t)n;
       }
     }
   }
@@ -237,7 +235,7 @@ inline void write_residual(SliceEnc &e, bool i16, int cbp, bool t8, uint8_t nnz_
           e.ce.decision(85 + 16 + a + 2 * bq, sl != nullptr);
           if (sl) n = cabac_write_block(e, c, 4, 15);
         } else n = cavlc_write_block(e, c, 15, cavlc_nc(na, nb));
-        nnz_c[p][k] = (uint8_t)n; s.cnz_cache[p][(by + 1) * 4 + bx + 1] = (uint8_t)n;
+        s.cnz_cache[p][(by + 1) * 4 + bx + 1] = (uint8_t)n;
       }
   }
 }
@@ -356,7 +354,8 @@ inline void w_cbp(SliceEnc &e, int cbp, bool intra) {
     for (int k = 0; k < 48; ++k) if (tab[k] == cbp) { e.bw.ue((uint32_t)k); return; }
     assert(0);
   }
-  const NbCtx &L = s.left, &T = s.line[s.mbx];
+  const LeftCtx &L = s.left;
+  const NbCtx &T = s.line[s.mbx];
   int cbpa = s.availA ? ((L.flags & NBF_IPCM) ? 0x2F : L.cbp) : 0x0F;
   int cbpb = s.availB ? ((T.flags & NBF_IPCM) ? 0x2F : T.cbp) : 0x0F;
   for (int b8 = 0; b8 < 4; ++b8) {
@@ -396,11 +395,6 @@ inline void encode_mb(SliceEnc &e, const MbEnc &m) {
   const bool B = st == SLICE_B;
   const int nl = B ? 2 : 1;
   MbInfo &o = s.out;
-  uint8_t nnz_l[16], nnz_c[2][4];
-  for (int i = 0; i < 16; ++i) nnz_l[i] = 0;
-  for (int p = 0; p < 2; ++p) for (int i = 0; i < 4; ++i) nnz_c[p][i] = 0;
-  int8_t imodes_r[16];
-  for (int i = 0; i < 16; ++i) imodes_r[i] = -1;
   bool direct16 = false, is_pcm = false;
   uint32_t dirq = 0;
   int8_t dref[2][4];
@@ -449,8 +443,8 @@ inline void encode_mb(SliceEnc &e, const MbEnc &m) {
       e.bw.align_zero();
       for (int i = 0; i < 384; ++i) e.bw.put(m.pcm[i], 8);
       if (e.cabac) e.ce.start(&e.bw);
-      for (int i = 0; i < 16; ++i) nnz_l[i] = 16;
-      for (int p = 0; p < 2; ++p) for (int i = 0; i < 4; ++i) nnz_c[p][i] = 16;
+      for (int y = 0; y < 4; ++y) set4(s.nz_cache + HWB_CI(0, y), 0x10101010u);
+      for (int p = 0; p < 2; ++p) { s.cnz_cache[p][5] = s.cnz_cache[p][6] = s.cnz_cache[p][9] = s.cnz_cache[p][10] = 16; }
       s.last_dqp = 0;
     } else if (m.imbt >= 0) {
       if (m.imbt == 0) {
@@ -468,7 +462,7 @@ inline void encode_mb(SliceEnc &e, const MbEnc &m) {
             else { e.bw.put1(0); e.bw.put((uint32_t)rem, 3); }
           }
           int wd = m.t8 ? 2 : 1;
-          for (int y = by; y < by + wd; ++y) for (int x = bx; x < bx + wd; ++x) { s.im_cache[HWB_CI(x, y)] = (int8_t)mode; imodes_r[y * 4 + x] = (int8_t)mode; }
+          for (int y = by; y < by + wd; ++y) for (int x = bx; x < bx + wd; ++x) s.im_cache[HWB_CI(x, y)] = (int8_t)mode;
         }
       }
       if (e.cabac) {
@@ -482,7 +476,7 @@ inline void encode_mb(SliceEnc &e, const MbEnc &m) {
       if (m.cbp || m.imbt > 0) { w_dqp(e, m.dqp); s.last_dqp = m.dqp; s.qp = (s.qp + m.dqp + 52) % 52; }
       else s.last_dqp = 0;
       assert(o.qp == s.qp);
-      write_residual(e, m.imbt > 0, m.cbp, m.t8, nnz_l, nnz_c);
+      write_residual(e, m.imbt > 0, m.cbp, m.t8);
     } else {
       bool t8_allowed = true;
       if (B && m.mbt == 0) {
@@ -563,7 +557,7 @@ inline void encode_mb(SliceEnc &e, const MbEnc &m) {
       if (m.cbp) { w_dqp(e, m.dqp); s.last_dqp = m.dqp; s.qp = (s.qp + m.dqp + 52) % 52; }
       else s.last_dqp = 0;
       assert(o.qp == s.qp);
-      write_residual(e, false, m.cbp, m.t8, nnz_l, nnz_c);
+      write_residual(e, false, m.cbp, m.t8);
     }
   }
   // the motion data the caches now hold must be exactly what reconstruction used
@@ -581,7 +575,7 @@ inline void encode_mb(SliceEnc &e, const MbEnc &m) {
       }
     }
   }
-  finish_mb(s, nnz_l, nnz_c, imodes_r, m.skipped, direct16, is_pcm);
+  finish_mb(s, m.skipped, direct16, is_pcm);
 }
 
 }  // namespace gen
