@@ -82,7 +82,7 @@ __device__ __forceinline__ void publish_progress(int32_t *p, int v) {
   }
 }
 
-__global__ void __launch_bounds__(kThreads) recon_kernel(ChunkCtx c, const int32_t *pics, int npics, int32_t *ticket) {
+__global__ void __launch_bounds__(kThreads, 4) recon_kernel(ChunkCtx c, const int32_t *pics, int npics, int32_t *ticket) {
   __shared__ ReconScratch sm[kWarpsPerBlock];
   ReconScratch *my = &sm[threadIdx.x >> 5];
   const int total = npics * c.mb_h;

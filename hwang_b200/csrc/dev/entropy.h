@@ -65,7 +65,7 @@ struct SliceDec {
   int last_dqp;
   LeftCtx left;
   int8_t tl_ref[2];        // top-left macroblock's bottom-right block (saved before its line entry is overwritten)
-  int16_t tl_mv[2][2];
+  alignas(4) int16_t tl_mv[2][2];  // copied as 32-bit words
   NbCtx *line;  // [mb_w] top context
   uint32_t coef_next;  // next free slot in the picture arena
   // ---- current macroblock

@@ -237,10 +237,13 @@ Result B200VideoDecoder::finish_chunk(Chunk &c) {
 
 int B200VideoDecoder::frames_ready() {
   std::lock_guard<std::mutex> lk(mu_);
+  if (!sticky_error_.empty()) return -1;
   int n = 0;
   for (auto &c : queue_) {
     if (!c->finished) {
-      if (hwb_dev_event_done(dev_, c->ev_done) == 1) c->finished = true;
+      int st = hwb_dev_event_done(dev_, c->ev_done);
+      if (st < 0) { sticky_error_ = std::string("B200 decoder: CUDA error: ") + hwb_dev_error(dev_); return -1; }
+      if (st == 1) c->finished = true;
       else break;  // chunks complete in order
     }
     n += (int)(c->order.size() - c->next_out);
@@ -254,6 +257,7 @@ int B200VideoDecoder::frames_ready() {
 // at 8 ("at least this many frames are ready") unless a lot of device memory is already in flight.
 int B200VideoDecoder::decoded_frames_buffered() {
   int n = frames_ready();
+  if (n < 0) return 1;  // error state: let the consumer pop, get_frame / discard_frame report the error
   std::lock_guard<std::mutex> lk(mu_);
   if (live_bytes_ > kLiveBudget) return n;
   return n > 8 ? 8 : n;

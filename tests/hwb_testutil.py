@@ -34,7 +34,8 @@ def decode_yuv(index, samples, keyflags, chunk_pictures=None):
     out = []
     deadline = time.time() + 300
     while len(out) < len(samples):  # the GPU decodes asynchronously: poll until every fed picture has come out
-        if dec.frames_ready() > 0:
+        n = dec.frames_ready()
+        if n != 0:  # negative = decoder error: get_frame_yuv raises with the message
             out.append(dec.get_frame_yuv())
         elif time.time() > deadline:
             raise TimeoutError('decoder produced %d of %d frames' % (len(out), len(samples)))

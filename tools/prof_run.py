@@ -21,7 +21,7 @@ for r in range(reps):
     dec.feed(None); dec.flush()
     n = 0
     while n < frames:
-        if dec.frames_ready() > 0:
+        if dec.frames_ready() != 0:
             dec.get_frame_device(); n += 1
         else:
             time.sleep(0.001)
