@@ -70,7 +70,7 @@ HWB_ENTROPY_KERNEL(entropy_cavlc_kernel, hwb::ent_cavlc)  // every picture of th
 // ------------------------------------------------------------------------------------ reconstruction
 __device__ __forceinline__ void wait_progress(const int32_t *p, int need) {
   if ((threadIdx.x & 31) == 0) {
-    while (*((volatile const int32_t *)p) < need) __nanosleep(64);
+    while (*((volatile const int32_t *)p) < need) __nanosleep(200);
   }
   __syncwarp();
 }
@@ -89,14 +89,19 @@ __global__ void __launch_bounds__(kThreads, 4) recon_kernel(ChunkCtx c, const in
   for (;;) {
     const int t = warp_ticket(ticket);
     if (t >= total) return;
-    const int pic = pics[t / c.mb_h], y = t % c.mb_h;
+    // row-major over the pictures of the level: consecutive tickets are the same row of different pictures, so a
+    // row's predecessor (same picture, row above) was handed out npics tickets earlier and is far ahead
+    const int pic = pics[t % npics], y = t / npics;
     const MbInfo *mbs = pic_mbinfo(c, c.pics[pic].frame);
     int32_t *prog = c.recon_prog + (size_t)pic * c.mb_h;
+    const bool has_inter = c.pics[pic].has_inter != 0;
     for (int x = 0; x < c.mb_w; ++x) {
       // intra macroblocks read the unfiltered row above up to the top-right neighbour
       if (y > 0 && mbs[y * c.mb_w + x].mbtype != MB_INTER) wait_progress(prog + y - 1, x + 2 < c.mb_w ? x + 2 : c.mb_w);
       recon_mb(c, pic, x, y, my);
-      publish_progress(prog + y, x + 1);
+      // only intra macroblocks of the row below consume this; pictures with inter slices have few of them, so the
+      // fence + flag store is amortised over 4 macroblocks there
+      if (!has_inter || (x & 3) == 3 || x == c.mb_w - 1) publish_progress(prog + y, x + 1);
     }
   }
 }
@@ -108,7 +113,7 @@ __global__ void __launch_bounds__(kThreads) deblock_kernel(ChunkCtx c, const int
   for (;;) {
     const int t = warp_ticket(ticket);
     if (t >= total) return;
-    const int pic = pics[t / c.mb_h], y = t % c.mb_h;
+    const int pic = pics[t % npics], y = t / npics;
     int32_t *prog = c.dbl_prog + (size_t)pic * c.mb_h;
     for (int x = 0; x < c.mb_w; ++x) {
       if (y > 0) wait_progress(prog + y - 1, x + 2 < c.mb_w ? x + 2 : c.mb_w);

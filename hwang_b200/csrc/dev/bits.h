@@ -99,33 +99,30 @@ HWB_HD void cabac_init_states(uint8_t *st, int table, int slice_qp) {
   }
 }
 
+// Branch-free binary decision (9.3.3.2.1): one fused table entry gives rangeLPS and both successor states.
 HWB_HD int cabac_decision(Cabac &c, BitReader &b, uint8_t *state) {
-  uint32_t s = *state;
-  uint32_t p = s >> 1, mps = s & 1;
-  uint32_t rlps = cabac_range_lps[p * 4 + ((c.range >> 6) & 3)];
-  c.range -= rlps;
-  int bin;
-  if (c.offset >= c.range) {
-    bin = (int)(mps ^ 1);
-    c.offset -= c.range;
-    c.range = rlps;
-    if (p == 0) mps ^= 1;
-    *state = (uint8_t)((cabac_trans_lps[p] << 1) | mps);
-  } else {
-    bin = (int)mps;
-    *state = (uint8_t)(((p < 62 ? p + 1 : p) << 1) | mps);
-  }
-  if (c.range < 256) {
-    int sh = clz32(c.range) - 23;
-    c.range <<= sh;
-    c.offset = (c.offset << sh) | br_get(b, sh);
-  }
-  return bin;
+  if (b.avail < 16) br_refill(b);
+  const uint32_t s = *state;
+  const uint32_t e = cabac_fused[s * 4 + ((c.range >> 6) & 3)];
+  const uint32_t rlps = e & 0xff;
+  const uint32_t rmps = c.range - rlps;
+  const bool lps = c.offset >= rmps;
+  c.offset = lps ? c.offset - rmps : c.offset;
+  c.range = lps ? rlps : rmps;
+  *state = (uint8_t)(lps ? (e >> 8) : (e >> 16));
+  const int sh = clz32(c.range) - 23;  // renormalisation shift, 0 when range >= 256
+  c.range <<= sh;
+  c.offset = (c.offset << sh) | (uint32_t)((b.cache >> 1) >> (63 - sh));
+  b.cache <<= sh; b.avail -= sh;
+  return (int)((s & 1) ^ (lps ? 1u : 0u));
 }
 HWB_HD int cabac_bypass(Cabac &c, BitReader &b) {
-  c.offset = (c.offset << 1) | br_get(b, 1);
-  if (c.offset >= c.range) { c.offset -= c.range; return 1; }
-  return 0;
+  if (b.avail < 16) br_refill(b);
+  c.offset = (c.offset << 1) | (uint32_t)(b.cache >> 63);
+  b.cache <<= 1; b.avail -= 1;
+  const bool one = c.offset >= c.range;
+  c.offset -= one ? c.range : 0u;
+  return one ? 1 : 0;
 }
 HWB_HD int cabac_terminate(Cabac &c, BitReader &b) {
   c.range -= 2;

@@ -118,9 +118,13 @@ HWB_HD void cpy16(void *d, const void *s) {
 
 // Called once per slice before the first macroblock: entries that never change.
 HWB_FN void init_caches(SliceDec &s) {
+#pragma unroll 1
   for (int l = 0; l < 2; ++l)
+#pragma unroll 1
     for (int i = 0; i < HWB_CACHE_N; ++i) { s.ref_cache[l][i] = REF_UNAVAIL; s.mv_cache[l][i][0] = s.mv_cache[l][i][1] = 0; s.mvd_cache[l][i][0] = s.mvd_cache[l][i][1] = 0; }
+#pragma unroll 1
   for (int i = 0; i < HWB_CACHE_N; ++i) { s.nz_cache[i] = 0x80; s.im_cache[i] = -1; s.dir_cache[i] = 0; }
+#pragma unroll 1
   for (int p = 0; p < 2; ++p) for (int i = 0; i < 12; ++i) s.cnz_cache[p][i] = 0x80;
 }
 
@@ -130,22 +134,28 @@ HWB_FN void fill_caches(SliceDec &s, bool unused) {
   (void)unused;
   const int nl = s.sd->slice_type == SLICE_B ? 2 : (s.sd->slice_type == SLICE_P ? 1 : 0);
   if (s.availA) {
+#pragma unroll 1
     for (int y = 0; y < 4; ++y) {
       const int d = HWB_CI(-1, y), f = HWB_CI(3, y);
       s.nz_cache[d] = s.nz_cache[f]; s.im_cache[d] = s.im_cache[f]; s.dir_cache[d] = s.dir_cache[f];
+#pragma unroll 1
       for (int l = 0; l < nl; ++l) {
         s.ref_cache[l][d] = s.ref_cache[l][f];
         cpy4(s.mv_cache[l][d], s.mv_cache[l][f]);
         *(uint16_t *)s.mvd_cache[l][d] = *(const uint16_t *)s.mvd_cache[l][f];
       }
     }
+#pragma unroll 1
     for (int p = 0; p < 2; ++p) { s.cnz_cache[p][4] = s.cnz_cache[p][6]; s.cnz_cache[p][8] = s.cnz_cache[p][10]; }
   } else {
+#pragma unroll 1
     for (int y = 0; y < 4; ++y) {
       const int d = HWB_CI(-1, y);
       s.nz_cache[d] = 0x80; s.im_cache[d] = -1; s.dir_cache[d] = 0;
+#pragma unroll 1
       for (int l = 0; l < nl; ++l) { s.ref_cache[l][d] = REF_UNAVAIL; set4(s.mv_cache[l][d], 0); *(uint16_t *)s.mvd_cache[l][d] = 0; }
     }
+#pragma unroll 1
     for (int p = 0; p < 2; ++p) { s.cnz_cache[p][4] = 0x80; s.cnz_cache[p][8] = 0x80; }
   }
   const int top = HWB_CI(0, -1);
@@ -155,21 +165,28 @@ HWB_FN void fill_caches(SliceDec &s, bool unused) {
     cpy4(s.im_cache + top, T.imode_b);
     const uint32_t dm = T.dirmask;
     set4(s.dir_cache + top, (dm & 1) | ((dm & 2) << 7) | ((dm & 4) << 14) | ((dm & 8) << 21));
+#pragma unroll 1
     for (int l = 0; l < nl; ++l) {
       cpy4(s.ref_cache[l] + top, T.ref_b[l]);
       cpy16(s.mv_cache[l][top], T.mv_b[l]);
       cpy8(s.mvd_cache[l][top], T.mvd_b[l]);
     }
+#pragma unroll 1
     for (int p = 0; p < 2; ++p) { s.cnz_cache[p][1] = T.cnnz_b[p][0]; s.cnz_cache[p][2] = T.cnnz_b[p][1]; }
   } else {
     set4(s.nz_cache + top, 0x80808080u); set4(s.im_cache + top, 0xFFFFFFFFu); set4(s.dir_cache + top, 0);
+#pragma unroll 1
     for (int l = 0; l < nl; ++l) {
       set4(s.ref_cache[l] + top, 0xFEFEFEFEu);
+#pragma unroll 1
       for (int x = 0; x < 4; ++x) set4(s.mv_cache[l][top + x], 0);
+#pragma unroll 1
       for (int x = 0; x < 4; ++x) *(uint16_t *)s.mvd_cache[l][top + x] = 0;
     }
+#pragma unroll 1
     for (int p = 0; p < 2; ++p) { s.cnz_cache[p][1] = 0x80; s.cnz_cache[p][2] = 0x80; }
   }
+#pragma unroll 1
   for (int l = 0; l < nl; ++l) {
     const int tr = HWB_CI(4, -1), tl = HWB_CI(-1, -1);
     if (s.availC) { const NbCtx &R = s.line[s.mbx + 1]; s.ref_cache[l][tr] = R.ref_b[l][0]; cpy4(s.mv_cache[l][tr], R.mv_b[l][0]); }
@@ -178,11 +195,14 @@ HWB_FN void fill_caches(SliceDec &s, bool unused) {
     else { s.ref_cache[l][tl] = REF_UNAVAIL; set4(s.mv_cache[l][tl], 0); }
   }
   // interior: nothing coded yet, nothing direct, references "not decoded yet"
+#pragma unroll 1
   for (int y = 0; y < 4; ++y) {
     const int r = HWB_CI(0, y);
     set4(s.nz_cache + r, 0); set4(s.dir_cache + r, 0);
+#pragma unroll 1
     for (int l = 0; l < nl; ++l) set4(s.ref_cache[l] + r, 0xFEFEFEFEu);
   }
+#pragma unroll 1
   for (int p = 0; p < 2; ++p) { s.cnz_cache[p][5] = s.cnz_cache[p][6] = s.cnz_cache[p][9] = s.cnz_cache[p][10] = 0; }
 }
 
@@ -506,6 +526,7 @@ HWB_FN void decode_residual(SliceDec &s, bool i16, int cbp, bool t8) {
       if (n) coef_emit(s, NZ_LUMA_DC, 1);
     }
   }
+#pragma unroll 1
   for (int q = 0; q < 4; ++q) {
     if (!((cbp >> q) & 1)) continue;
     if (t8) {
@@ -513,11 +534,13 @@ HWB_FN void decode_residual(SliceDec &s, bool i16, int cbp, bool t8) {
       coef_clear(s, 64);
       if (cabac) {
         n = cabac_residual(s, 5, 64, 0, zigzag8x8);
+#pragma unroll 1
         for (int k = 0; k < 4; ++k) {
           int bx = (q & 1) * 2 + (k & 1), by = (q >> 1) * 2 + (k >> 1);
           s.nz_cache[HWB_CI(bx, by)] = (uint8_t)(n > 16 ? 16 : n);
         }
       } else {
+#pragma unroll 1
         for (int k = 0; k < 4; ++k) {
           int bx = (q & 1) * 2 + (k & 1), by = (q >> 1) * 2 + (k >> 1);
           int nc = cavlc_nc(s.nz_cache[HWB_CI(bx - 1, by)], s.nz_cache[HWB_CI(bx, by - 1)]);
@@ -528,6 +551,7 @@ HWB_FN void decode_residual(SliceDec &s, bool i16, int cbp, bool t8) {
       }
       if (n) coef_emit(s, NZ_LUMA0 + q * 4, 4);
     } else {
+#pragma unroll 1
       for (int k = 0; k < 4; ++k) {
         int z = q * 4 + k, bx = z2x(z), by = z2y(z);
         int na = s.nz_cache[HWB_CI(bx - 1, by)], nb = s.nz_cache[HWB_CI(bx, by - 1)];
@@ -547,6 +571,7 @@ HWB_FN void decode_residual(SliceDec &s, bool i16, int cbp, bool t8) {
     }
   }
   if (cbp & 0x30) {
+#pragma unroll 1
     for (int p = 0; p < 2; ++p) {
       int coded = 1;
       int bit = p ? NZ_CR_DC : NZ_CB_DC;
@@ -563,7 +588,9 @@ HWB_FN void decode_residual(SliceDec &s, bool i16, int cbp, bool t8) {
     }
   }
   if (cbp & 0x20) {
+#pragma unroll 1
     for (int p = 0; p < 2; ++p)
+#pragma unroll 1
       for (int k = 0; k < 4; ++k) {
         int bx = k & 1, by = k >> 1;
         int na = s.cnz_cache[p][(by + 1) * 4 + bx], nb = s.cnz_cache[p][by * 4 + bx + 1];
@@ -720,15 +747,19 @@ HWB_FN void finish_mb(SliceDec &s, bool skipped, bool direct16, bool is_pcm) {
   const bool inxn = o.mbtype == MB_I4x4 || o.mbtype == MB_I8x8;
   // ---- normalise the interior so that the right column / bottom row say what neighbours must see
   if (!inter) {
+#pragma unroll 1
     for (int l = 0; l < nl; ++l)
+#pragma unroll 1
       for (int y = 0; y < 4; ++y) {
         const int r = HWB_CI(0, y);
         set4(s.ref_cache[l] + r, 0xFFFFFFFFu);
+#pragma unroll 1
         for (int x = 0; x < 4; ++x) { set4(s.mv_cache[l][r + x], 0); *(uint16_t *)s.mvd_cache[l][r + x] = 0; }
       }
   }
   if (!inxn) {
     const uint32_t v = (inter && s.pd->constrained_intra_pred) ? 0xFFFFFFFFu : 0x02020202u;
+#pragma unroll 1
     for (int y = 0; y < 4; ++y) set4(s.im_cache + HWB_CI(0, y), v);
   }
   // ---- outputs
@@ -737,11 +768,14 @@ HWB_FN void finish_mb(SliceDec &s, bool skipped, bool direct16, bool is_pcm) {
     cpy16(dst, &o); cpy16((uint8_t *)dst + 16, (const uint8_t *)&o + 16);
   }
   if (inter) {
+#pragma unroll 1
     for (int l = 0; l < nl; ++l) {
       int16_t *mvo = pic_mv(c, f, l) + (uint64_t)s.mbaddr * 32;
+#pragma unroll 1
       for (int y = 0; y < 4; ++y) cpy16(mvo + 8 * y, s.mv_cache[l][HWB_CI(0, y)]);
       int8_t *ro = pic_refidx(c, f, l) + (uint64_t)s.mbaddr * 4;
       int16_t *po = pic_refpic(c, f, l) + (uint64_t)s.mbaddr * 4;
+#pragma unroll 1
       for (int q = 0; q < 4; ++q) {
         int r = s.ref_cache[l][HWB_CI((q & 1) * 2, (q >> 1) * 2)];
         ro[q] = (int8_t)r;
@@ -751,22 +785,27 @@ HWB_FN void finish_mb(SliceDec &s, bool skipped, bool direct16, bool is_pcm) {
     if (!B && s.pd->has_inter == 2) {
       set4(pic_refidx(c, f, 1) + (uint64_t)s.mbaddr * 4, 0xFFFFFFFFu);
       int16_t *po = pic_refpic(c, f, 1) + (uint64_t)s.mbaddr * 4;
+#pragma unroll 1
       for (int q = 0; q < 4; ++q) po[q] = -1;
     }
   }
   // ---- neighbour context: bottom edge to the line buffer (after saving what the next macroblock's top-left needs)
   NbCtx &n = s.line[s.mbx];
+#pragma unroll 1
   for (int l = 0; l < nl; ++l) { s.tl_ref[l] = n.ref_b[l][3]; cpy4(s.tl_mv[l], n.mv_b[l][3]); }
   const uint8_t flags = (uint8_t)((inter ? 0 : NBF_INTRA) | (is_pcm ? NBF_IPCM : 0) | (skipped ? NBF_SKIP : 0) | (direct16 ? NBF_DIRECT16 : 0) |
                                   ((o.flags & MBF_T8x8) ? NBF_T8 : 0) | (o.mbtype == MB_I16x16 ? NBF_I16 : 0) | (inxn ? NBF_INXN : 0));
   const int bot = HWB_CI(0, 3);
   uint32_t dm = 0;
+#pragma unroll 1
   for (int x = 0; x < 4; ++x) if (s.dir_cache[bot + x]) dm |= 1u << x;
   const uint32_t cbf = is_pcm ? 0x7FFFFFFu : o.nzmask;
   n.flags = flags; n.cbp = o.cbp; n.cmode = o.cmode; n.dirmask = (uint8_t)dm; n.cbf = cbf;
+#pragma unroll 1
   for (int p = 0; p < 2; ++p) { n.cnnz_b[p][0] = s.cnz_cache[p][9]; n.cnnz_b[p][1] = s.cnz_cache[p][10]; }
   cpy4(n.nnz_b, s.nz_cache + bot);
   cpy4(n.imode_b, s.im_cache + bot);
+#pragma unroll 1
   for (int l = 0; l < nl; ++l) {
     cpy4(n.ref_b[l], s.ref_cache[l] + bot);
     cpy16(n.mv_b[l], s.mv_cache[l][bot]);
@@ -813,6 +852,7 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
   MbInfo &o = s.out;
   o.mbtype = MB_INTER; o.qp = (uint8_t)s.qp; o.cbp = 0; o.flags = 0; o.imode = 0; o.cmode = 0;
   o.slice = (uint16_t)s.slice_num; o.nzmask = 0; o.coef_off = s.coef_next;
+#pragma unroll 1
   for (int i = 0; i < 16; ++i) o.i4modes[i] = 2;
   bool direct16 = false;
   uint32_t dirq = 0;  // quadrants predicted in direct mode
@@ -832,6 +872,7 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
     } else {
       direct16 = true; dirq = 15;
       direct_predict(s, 15, dref, dmv);
+#pragma unroll 1
       for (int l = 0; l < 2; ++l) for (int q = 0; q < 4; ++q) apply_direct(s, l, q, dref, dmv);
     }
   } else {
@@ -858,10 +899,13 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
       o.mbtype = MB_IPCM; o.qp = 0; o.cbp = 0x2F;
       br_align(s.br);
       uint8_t *dst = (uint8_t *)(pic_coefs(c, s.pd->frame) + (uint64_t)s.coef_next * 16);
+#pragma unroll 1
       for (int i = 0; i < 384; ++i) dst[i] = (uint8_t)s_get(s, 8);
       s.coef_next += 12; o.nzmask = 0xFFF;
       if (HWB_IS_CABAC(s)) cabac_start(s.cab, s.br);
+#pragma unroll 1
       for (int y = 0; y < 4; ++y) set4(s.nz_cache + HWB_CI(0, y), 0x10101010u);
+#pragma unroll 1
       for (int p = 0; p < 2; ++p) { s.cnz_cache[p][5] = s.cnz_cache[p][6] = s.cnz_cache[p][9] = s.cnz_cache[p][10] = 16; }
       s.last_dqp = 0;
     } else if (imbt >= 0) {
@@ -878,6 +922,7 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
         o.mbtype = t8 ? MB_I8x8 : MB_I4x4;
         if (t8) o.flags |= MBF_T8x8;
         const int nb = t8 ? 4 : 16;
+#pragma unroll 1
         for (int k = 0; k < nb; ++k) {
           int bx = t8 ? (k & 1) * 2 : z2x(k), by = t8 ? (k >> 1) * 2 : z2y(k);
           int ma = s.im_cache[HWB_CI(bx - 1, by)], mb_ = s.im_cache[HWB_CI(bx, by - 1)];
@@ -897,6 +942,7 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
           }
           o.i4modes[k] = (uint8_t)mode;
           int wd = t8 ? 2 : 1;
+#pragma unroll 1
           for (int y = by; y < by + wd; ++y) for (int x = bx; x < bx + wd; ++x) s.im_cache[HWB_CI(x, y)] = (int8_t)mode;
         }
       } else {
@@ -928,10 +974,12 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
       if (B && mbt == 0) {
         direct16 = true; dirq = 15;
         direct_predict(s, 15, dref, dmv);
+#pragma unroll 1
         for (int l = 0; l < 2; ++l) for (int q = 0; q < 4; ++q) apply_direct(s, l, q, dref, dmv);
         t8_allowed = s.pd->direct_8x8_inference != 0;
       } else if ((!B && mbt >= 3) || (B && mbt == 22)) {
         // 8x8 with sub-macroblock types
+#pragma unroll 1
         for (int q = 0; q < 4; ++q) {
           if (HWB_IS_CABAC(s)) {
             if (B) sub[q] = (int8_t)cabac_b_sub_type(s);
@@ -943,6 +991,7 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
         if (dirq) direct_predict(s, (int)dirq, dref, dmv);
         // sub shapes: 0: 8x8, 1: 8x4, 2: 4x8, 3: 4x4; pred flags: 1 L0, 2 L1, 3 Bi
         int8_t *shape = s.shape, *pf = s.pf;
+#pragma unroll 1
         for (int q = 0; q < 4; ++q) {
           if (!B) { shape[q] = sub[q]; pf[q] = 1; }
           else if (sub[q] == 0) { shape[q] = 0; pf[q] = 0; }
@@ -956,7 +1005,9 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
         }
         int8_t (*refs)[4] = s.refs;
         const bool ref0_only = !B && mbt == 4 && !HWB_IS_CABAC(s);  // P_8x8ref0 (CAVLC only)
+#pragma unroll 1
         for (int l = 0; l < nl; ++l)
+#pragma unroll 1
           for (int q = 0; q < 4; ++q) {
             refs[l][q] = -1;
             if ((dirq >> q) & 1) continue;
@@ -966,14 +1017,19 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
             }
             // make the reference visible for later ref_idx contexts of this list
             int bx = (q & 1) * 2, by = (q >> 1) * 2;
+#pragma unroll 1
             for (int y = by; y < by + 2; ++y) for (int x = bx; x < bx + 2; ++x) s.ref_cache[l][HWB_CI(x, y)] = (int8_t)(refs[l][q] >= 0 ? refs[l][q] : REF_NONE);
           }
         // references of not-yet-decoded quadrants must look unavailable for C-neighbour lookups
+#pragma unroll 1
         for (int l = 0; l < nl; ++l) {
+#pragma unroll 1
           for (int q = 0; q < 4; ++q) {
             int bx = (q & 1) * 2, by = (q >> 1) * 2;
+#pragma unroll 1
             for (int y = by; y < by + 2; ++y) for (int x = bx; x < bx + 2; ++x) s.ref_cache[l][HWB_CI(x, y)] = REF_UNAVAIL;
           }
+#pragma unroll 1
           for (int q = 0; q < 4; ++q) {
             int bx = (q & 1) * 2, by = (q >> 1) * 2;
             if ((dirq >> q) & 1) { apply_direct(s, l, q, dref, dmv); continue; }
@@ -984,6 +1040,7 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
               case 1: read_mvd_and_set(s, l, bx, by, 2, 1, r, 0); read_mvd_and_set(s, l, bx, by + 1, 2, 1, r, 0); break;
               case 2: read_mvd_and_set(s, l, bx, by, 1, 2, r, 0); read_mvd_and_set(s, l, bx + 1, by, 1, 2, r, 0); break;
               default:
+#pragma unroll 1
                 for (int k = 0; k < 4; ++k) read_mvd_and_set(s, l, bx + (k & 1), by + (k >> 1), 1, 1, r, 0);
             }
           }
@@ -1000,7 +1057,9 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
         }
         const int np = shape == 0 ? 1 : 2;
         int8_t (*refs)[4] = s.refs;
+#pragma unroll 1
         for (int l = 0; l < nl; ++l)
+#pragma unroll 1
           for (int p = 0; p < np; ++p) {
             int pf = p ? pf1 : pf0;
             int bx = (shape == 2 && p) ? 2 : 0, by = (shape == 1 && p) ? 2 : 0;
@@ -1010,10 +1069,14 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
               refs[l][p] = (int8_t)read_ref(s, l, bx, by);
               if (refs[l][p] >= sd.num_ref[l]) { sd_fail(s, 55); return; }
             }
+#pragma unroll 1
             for (int y = by; y < by + h; ++y) for (int x = bx; x < bx + w; ++x) s.ref_cache[l][HWB_CI(x, y)] = (int8_t)(refs[l][p] >= 0 ? refs[l][p] : REF_NONE);
           }
+#pragma unroll 1
         for (int l = 0; l < nl; ++l) {
+#pragma unroll 1
           for (int i = 0; i < 16; ++i) s.ref_cache[l][HWB_CI(i & 3, i >> 2)] = REF_UNAVAIL;
+#pragma unroll 1
           for (int p = 0; p < np; ++p) {
             int bx = (shape == 2 && p) ? 2 : 0, by = (shape == 1 && p) ? 2 : 0;
             int w = shape == 2 ? 2 : 4, h = shape == 1 ? 2 : 4;

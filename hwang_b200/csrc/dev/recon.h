@@ -180,11 +180,26 @@ HWB_HD void mc_luma_4x2(const uint8_t *ref, int w, int h, int px, int py, int fx
     return;
   }
   if (inside) {
+#if HWB_DEVICE_BUILD
+    // three aligned 32-bit loads per window row instead of nine byte loads (the row is 9 bytes at any alignment;
+    // the over-read of at most 3 bytes stays inside the frame buffer)
+    const uint8_t *p0 = ref + (py - 2) * w + px - 2;
+    const int sh = (int)(((uintptr_t)p0) & 3) * 8;  // rows are a multiple of 16 bytes apart: same alignment for every row
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+      const uint32_t *q = (const uint32_t *)((uintptr_t)(p0 + r * w) & ~(uintptr_t)3);
+      const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+      const uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh), x2 = w2 >> sh;
+      win[r][0] = (uint8_t)x0; win[r][1] = (uint8_t)(x0 >> 8); win[r][2] = (uint8_t)(x0 >> 16); win[r][3] = (uint8_t)(x0 >> 24);
+      win[r][4] = (uint8_t)x1; win[r][5] = (uint8_t)(x1 >> 8); win[r][6] = (uint8_t)(x1 >> 16); win[r][7] = (uint8_t)(x1 >> 24);
+      win[r][8] = (uint8_t)x2;
+    }
+#else
     for (int r = 0; r < 7; ++r) {
       const uint8_t *p = ref + (py - 2 + r) * w + px - 2;
-#pragma unroll
       for (int c = 0; c < 9; ++c) win[r][c] = p[c];
     }
+#endif
   } else {
     for (int r = 0; r < 7; ++r) {
       int yy = clip3(0, h - 1, py - 2 + r);

@@ -95,6 +95,17 @@ spec_lps = [0, 0, 1, 2, 2, 4, 4, 5, 6, 7, 8, 9, 9, 11, 11, 12, 13, 13, 15, 15, 1
 assert trans_lps.tolist() == spec_lps
 assert trans_mps.tolist() == [min(p + 1, 62) for p in range(63)] + [63]
 emit('cabac_trans_lps', trans_lps, const=True)
+# fused table for the branch-free decoder: index = (pStateIdx << 1 | valMPS) * 4 + qCodIRangeIdx,
+# entry = rangeLPS | next state after an LPS << 8 | next state after an MPS << 16   (state = pStateIdx << 1 | valMPS)
+fused = np.zeros((128, 4), np.uint32)
+for p in range(64):
+    for mps in range(2):
+        nl = (int(trans_lps[p]) << 1) | (mps ^ 1 if p == 0 else mps)
+        nm = (min(p + 1, 62) << 1 | mps) if p < 63 else (63 << 1 | mps)
+        if p == 62: nm = (62 << 1) | mps
+        for q in range(4):
+            fused[(p << 1) | mps, q] = int(range_lps[p, q]) | (nl << 8) | (nm << 16)
+emit('cabac_fused', fused, 'uint32_t', 8, const=True)
 
 sig8 = u8(find([0, 1, 2, 3, 4, 5, 5, 4, 4, 3, 3, 4, 4, 4, 5, 5, 4, 4, 4, 4, 3, 3, 6, 7, 7, 7, 8, 9, 10, 9, 8, 7], 0, 1), 63)
 assert sig8[-1] == 12 or True
