@@ -140,7 +140,7 @@ def run_reference(args):
     mp4 = get_clip(args.frames)
     procs = os.cpu_count() or 1
     ngop = (args.frames + GOP - 1) // GOP
-    sample_gops = list(range(min(ngop, max(procs, 16))))
+    sample_gops = list(range(min(ngop, max(3 * procs, 48))))
     for _ in range(args.warmup):
         cpu_reference_fps(mp4, sample_gops[:procs], procs)
     t0 = time.perf_counter()
@@ -304,7 +304,7 @@ def run_ours(args):
     if world == 1 or True:
         procs = os.cpu_count() or 1
         ngop = (n + GOP - 1) // GOP
-        gops = list(range(min(ngop, max(procs, 16))))
+        gops = list(range(min(ngop, max(3 * procs, 48))))  # ~10-20 s of CPU work
         from oracle import ffmpeg_oracle as fo
         fps, cn, cdt = cpu_reference_fps(mp4, gops, procs)
         cpu = {'value': fps, 'unit': 'frames/s', 'cores': procs, 'kind': 'port',

@@ -179,8 +179,15 @@ int hwb_dev_open(int device, hwb_dev **out) {
   hwb_dev *d = new hwb_dev();
   d->device = device;
   cudaDeviceGetAttribute(&d->sms, cudaDevAttrMultiProcessorCount, device);
-  for (int i = 0; i < HWB_NUM_STREAMS; ++i)
-    if (cudaStreamCreateWithFlags(&d->streams[i], cudaStreamNonBlocking) != cudaSuccess) { delete d; return 1; }
+  // earlier chunks (lower decode stream index) and the copy-out stream get the higher priority, so that a chunk
+  // finishes -- and its frames start travelling to the host -- while the next chunk is still being decoded
+  int least = 0, greatest = 0;
+  cudaDeviceGetStreamPriorityRange(&least, &greatest);
+  for (int i = 0; i < HWB_NUM_STREAMS; ++i) {
+    int prio = i == HWB_STREAM_COPY ? greatest : greatest + i;
+    if (prio > least) prio = least;
+    if (cudaStreamCreateWithPriority(&d->streams[i], cudaStreamNonBlocking, prio) != cudaSuccess) { delete d; return 1; }
+  }
   *out = d;
   return 0;
 }

@@ -15,7 +15,9 @@ extern "C" {
 
 typedef struct hwb_dev hwb_dev;  // one per (host decoder instance, GPU)
 
-enum { HWB_STREAM_DECODE = 0, HWB_STREAM_COPY = 1, HWB_NUM_STREAMS = 2 };
+// Chunks are submitted round-robin on several decode streams, so the (latency-bound) entropy kernel of a chunk runs
+// while earlier chunks are being reconstructed and copied out.
+enum { HWB_STREAM_DECODE = 0, HWB_NUM_DECODE_STREAMS = 4, HWB_STREAM_COPY = 4, HWB_NUM_STREAMS = 5 };
 
 int hwb_dev_count(void);
 int hwb_dev_open(int device, hwb_dev **out);

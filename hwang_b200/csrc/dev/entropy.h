@@ -488,7 +488,7 @@ HWB_FN int cabac_residual(SliceDec &s, int cat, int max_coeff, int start, const 
 }
 
 // ================================================================================ output helpers
-HWB_FN void coef_clear(SliceDec &s, int n) {
+HWB_HD void coef_clear(SliceDec &s, int n) {
 #if HWB_DEVICE_BUILD
   for (int i = 0; i < n; i += 8) *(uint4 *)(s.coef + i) = make_uint4(0, 0, 0, 0);
 #else
@@ -496,7 +496,7 @@ HWB_FN void coef_clear(SliceDec &s, int n) {
 #endif
 }
 // Append s.coef[0..16*nslots) to the arena and mark item bits [bit, bit+nslots).
-HWB_FN void coef_emit(SliceDec &s, int bit, int nslots) {
+HWB_HD void coef_emit(SliceDec &s, int bit, int nslots) {
   int16_t *dst = pic_coefs(*s.c, s.pd->frame) + (uint64_t)s.coef_next * 16;
   for (int i = 0; i < nslots * 2; ++i) cpy16(dst + 8 * i, s.coef + 8 * i);
   s.coef_next += nslots;
@@ -1143,12 +1143,13 @@ HWB_FN void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states
   }
   const int first = sd.first_mb;
   int addr = first;
+  int mbx = first % c.mb_w, mby = first / c.mb_w;
   bool end = false;
   // CAVLC mb_skip_run state: -1 = read a new run before the next macroblock, 0 = the next
   // macroblock is coded, >0 = macroblocks still to skip
   int run = -1;
   while (!end && addr < c.nmb) {
-    s.mbaddr = addr; s.mbx = addr % c.mb_w; s.mby = addr / c.mb_w;
+    s.mbaddr = addr; s.mbx = mbx; s.mby = mby;
     s.availA = s.mbx > 0 && addr - 1 >= first;
     s.availB = addr - c.mb_w >= first;
     s.availC = s.mbx < c.mb_w - 1 && addr - c.mb_w + 1 >= first;
@@ -1177,7 +1178,8 @@ HWB_FN void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states
       if (!br_more_rbsp_data(s.br, s.stop_bitpos)) end = true;
     }
     addr++;
-    if (addr % c.mb_w == 0 || end || addr == c.nmb) {
+    if (++mbx == c.mb_w) { mbx = 0; ++mby; }
+    if (mbx == 0 || end || addr == c.nmb) {
 #if HWB_DEVICE_BUILD
       __threadfence();
       *((volatile int32_t *)(c.entropy_prog + slice_idx)) = (end || addr == c.nmb) ? c.nmb : addr;

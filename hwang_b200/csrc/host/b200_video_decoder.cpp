@@ -1,5 +1,6 @@
 #include "b200_video_decoder.h"
 
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <thread>
@@ -19,6 +20,7 @@ const size_t kLiveBudget = (size_t)96 << 30;  // beyond this much device memory 
 
 B200VideoDecoder::B200VideoDecoder(int device_id, DeviceType, int) : device_id_(device_id) {
   if (hwb_dev_open(device_id, &dev_) != 0) dev_ = nullptr;
+  if (const char *e = getenv("HWB_CHUNK_PICTURES")) { int v = atoi(e); if (v > 0) chunk_target_ = v; }
 }
 
 B200VideoDecoder::~B200VideoDecoder() {
@@ -28,8 +30,7 @@ B200VideoDecoder::~B200VideoDecoder() {
 }
 
 void B200VideoDecoder::release_all() {
-  hwb_dev_stream_sync(dev_, HWB_STREAM_DECODE);
-  hwb_dev_stream_sync(dev_, HWB_STREAM_COPY);
+  for (int i = 0; i < HWB_NUM_STREAMS; ++i) hwb_dev_stream_sync(dev_, i);
   auto drop = [&](std::unique_ptr<Chunk> &c) {
     if (!c) return;
     for (auto e : c->stage_ev) hwb_dev_event_destroy(dev_, e);
@@ -57,22 +58,49 @@ void B200VideoDecoder::release_all() {
   ring_bytes_ = 0;
 }
 
+// Drop every queued / in-flight chunk but keep slabs and staging rings for reuse.
+void B200VideoDecoder::reset_keep_memory() {
+  for (int i = 0; i < HWB_NUM_STREAMS; ++i) hwb_dev_stream_sync(dev_, i);
+  auto recycle = [&](std::unique_ptr<Chunk> &c) {
+    if (!c) return;
+    for (auto e : c->stage_ev) hwb_dev_event_destroy(dev_, e);
+    if (c->ev_begin) hwb_dev_event_destroy(dev_, c->ev_begin);
+    if (c->ev_done) hwb_dev_event_destroy(dev_, c->ev_done);
+    if (c->slab.base) free_slabs_.push_back(c->slab);
+    c.reset();
+  };
+  for (auto &c : queue_) recycle(c);
+  queue_.clear();
+  for (auto &c : retired_) recycle(c);
+  retired_.clear();
+  cur_.reset();
+  pending_.clear();
+  for (auto &e : rgb_ev_) { hwb_dev_event_destroy(dev_, e.first); hwb_dev_event_destroy(dev_, e.second); }
+  rgb_ev_.clear();
+  ring_next_ = 0;
+  // keep the two largest spare slabs
+  std::sort(free_slabs_.begin(), free_slabs_.end(), [](const Slab &a, const Slab &b) { return a.size > b.size; });
+  while (free_slabs_.size() > 2) { live_bytes_ -= free_slabs_.back().size; hwb_dev_free(dev_, free_slabs_.back().base); free_slabs_.pop_back(); }
+}
+
 // reference: SoftwareVideoDecoder::configure, software_video_decoder.cpp:103-165
 Result B200VideoDecoder::configure(const FrameInfo &metadata, const std::vector<uint8_t> &extradata) {
   std::lock_guard<std::mutex> lk(mu_);
   if (!dev_) return Result(false, "B200 decoder: CUDA device unavailable");
   if (!(metadata.format == "h264" || metadata.format == "avc1"))
     return Result(false, "Unsupported video codec: " + metadata.format + " (supports h264 only)");
-  release_all();
+  // hwang re-configures per interval (python/hwang/decoder.py:65): keep the device memory when the geometry is unchanged
+  const bool same_geometry = configured_ && width_ == metadata.width && height_ == metadata.height;
+  if (same_geometry) reset_keep_memory(); else release_all();
   sticky_error_.clear();
   std::string err = stream_.configure(extradata.data(), extradata.size());
-  if (!err.empty()) return Result(false, "B200 decoder: " + err);
+  if (!err.empty()) { configured_ = false; return Result(false, "B200 decoder: " + err); }
   if ((uint32_t)stream_.width() != metadata.width || (uint32_t)stream_.height() != metadata.height)
     return Result(false, "B200 decoder: container size " + std::to_string(metadata.width) + "x" + std::to_string(metadata.height) +
                              " does not match the SPS (" + std::to_string(stream_.width()) + "x" + std::to_string(stream_.height()) + ")");
   width_ = metadata.width; height_ = metadata.height;
   ring_bytes_ = (size_t)width_ * height_ * 3;
-  for (int i = 0; i < kRing; ++i) {
+  for (int i = 0; i < kRing && !rgb_dev_[i]; ++i) {
     rgb_dev_[i] = (uint8_t *)hwb_dev_malloc(dev_, ring_bytes_);
     rgb_pinned_[i] = (uint8_t *)hwb_dev_malloc_host(dev_, ring_bytes_);
     if (!rgb_dev_[i] || !rgb_pinned_[i]) return Result(false, std::string("B200 decoder: out of memory: ") + hwb_dev_error(dev_));
@@ -106,6 +134,7 @@ Result B200VideoDecoder::feed(const uint8_t *encoded_buffer, size_t encoded_size
   if (!cur_) {
     if (!idr) return Result(false, "B200 decoder: interval does not start with an IDR picture");
     cur_.reset(new Chunk());
+    cur_->bitstream.reserve(last_chunk_bytes_ + (last_chunk_bytes_ >> 2) + (1 << 20));
     stream_.reset_dpb();
   }
   hwb::PlannedPic pp;
@@ -165,10 +194,11 @@ Result B200VideoDecoder::submit_current() {
   c.error_flag = c.dbl_prog + (size_t)P * mb_h;
   ch->error_dev = c.error_flag;
 
-  const int st = HWB_STREAM_DECODE;
+  const int st = HWB_STREAM_DECODE + (int)(stats_.chunks % HWB_NUM_DECODE_STREAMS);
   ch->ev_begin = hwb_dev_event_create(dev_);
   ch->ev_done = hwb_dev_event_create(dev_);
   int rc = 0;
+  last_chunk_bytes_ = ch->bitstream.size();
   ch->bitstream.resize(ch->bitstream.size() + 64, 0);  // read-ahead padding for the bit readers
   rc |= hwb_dev_h2d(dev_, st, b + o_bits, ch->bitstream.data(), ch->bitstream.size());
   rc |= hwb_dev_h2d(dev_, st, b + o_pics, ch->pics.data(), (size_t)P * sizeof(PicDesc));

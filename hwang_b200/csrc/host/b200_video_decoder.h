@@ -80,6 +80,7 @@ class B200VideoDecoder : public VideoDecoderInterface {
   void drain_copies();
   Slab take_slab(size_t n);
   void release_all();
+  void reset_keep_memory();
 
   hwb_dev *dev_ = nullptr;
   int device_id_;
@@ -87,12 +88,16 @@ class B200VideoDecoder : public VideoDecoderInterface {
   hwb::H264Stream stream_;
   bool configured_ = false;
   uint32_t width_ = 0, height_ = 0;
-  int chunk_target_ = 4096;  // pictures per GPU batch: the entropy stage is latency-bound per slice, so bigger batches are better
+  // pictures per GPU batch (cut at IDR pictures).  The entropy stage is latency-bound per slice, so batches must be
+  // large; several batches are in flight at once on different streams, which overlaps host parsing, the entropy
+  // stage of the next batch, reconstruction of the previous one and the copies to the host.
+  int chunk_target_ = 4096;
   std::unique_ptr<Chunk> cur_;
   std::deque<std::unique_ptr<Chunk>> queue_;    // submitted chunks, oldest first
   std::vector<std::unique_ptr<Chunk>> retired_;  // fully popped, slab reusable after the next copy-stream sync
   std::vector<Slab> free_slabs_;
   size_t live_bytes_ = 0;
+  size_t last_chunk_bytes_ = 0;
   // output staging
   static const int kRing = 8;
   uint8_t *rgb_dev_[kRing] = {nullptr};

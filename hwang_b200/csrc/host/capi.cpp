@@ -154,7 +154,7 @@ int hwb_automata_initialize(hwb_automata *a, const hwb_encoded_data *iv, size_t 
     d.keyframes.assign(iv[i].keyframes, iv[i].keyframes + iv[i].num_keyframes);
     d.valid_frames.assign(iv[i].valid_frames, iv[i].valid_frames + iv[i].num_valid_frames);
   }
-  return ret(a, a->a->initialize(v, std::vector<uint8_t>(extra, extra + nextra)));
+  return ret(a, a->a->initialize(std::move(v), std::vector<uint8_t>(extra, extra + nextra)));
 }
 int hwb_automata_get_frames(hwb_automata *a, uint8_t *buffer, int32_t n) { return ret(a, a->a->get_frames(buffer, n)); }
 const char *hwb_automata_last_error(hwb_automata *a) { return a->err.c_str(); }

@@ -60,6 +60,10 @@ Result DecoderAutomata::validate(const std::vector<EncodedData> &encoded_data) c
 }
 
 Result DecoderAutomata::initialize(const std::vector<EncodedData> &encoded_data, const std::vector<uint8_t> &extradata) {
+  return initialize(std::vector<EncodedData>(encoded_data), extradata);
+}
+
+Result DecoderAutomata::initialize(std::vector<EncodedData> &&encoded_data, const std::vector<uint8_t> &extradata) {
   // reference: decoder_automata.cpp:80-118
   stop_feeder();
   decoder_->flush();
@@ -71,7 +75,7 @@ Result DecoderAutomata::initialize(const std::vector<EncodedData> &encoded_data,
   interval_ = 0; popped_ = 0; valid_idx_ = 0;
   if (encoded_data.empty()) return Result();
   HWANG_RETURN_ON_ERROR(validate(encoded_data));
-  encoded_data_ = encoded_data;
+  encoded_data_ = std::move(encoded_data);
   info_.width = encoded_data_[0].width; info_.height = encoded_data_[0].height; info_.format = encoded_data_[0].format;
   frame_size_ = (size_t)info_.width * info_.height * 3;
   HWANG_RETURN_ON_ERROR(decoder_->configure(info_, extradata));

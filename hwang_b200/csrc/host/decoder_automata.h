@@ -53,6 +53,8 @@ class DecoderAutomata {
   };
 
   Result initialize(const std::vector<EncodedData> &encoded_data, const std::vector<uint8_t> &extradata);
+  // same, taking ownership of the interval list (no copy of encoded_video)
+  Result initialize(std::vector<EncodedData> &&encoded_data, const std::vector<uint8_t> &extradata);
   Result get_frames(uint8_t *buffer, int32_t num_frames);
   VideoDecoderInterface *decoder() { return decoder_.get(); }
 
