@@ -33,7 +33,7 @@ HWB_HD void idct4_1d(int &d0, int &d1, int &d2, int &d3) {
 }
 
 // coef: 16 raw levels (raster) or nullptr (all AC zero).  dc_override: replaces d[0] after scaling.
-HWB_HD void residual4x4(const int16_t *coef, bool use_dc, int dc, const uint8_t *scaling, int qp, int16_t *out) {
+HWB_FN void residual4x4(const int16_t *coef, bool use_dc, int dc, const uint8_t *scaling, int qp, int16_t *out) {
   int d[16];
   const int qm = qp % 6, qs = qp / 6;
   if (coef) {
@@ -69,22 +69,26 @@ HWB_HD void idct8_1d(int *d, int s) {
   d[4 * s] = b6 - b1; d[5 * s] = b4 - b3; d[6 * s] = b2 - b5; d[7 * s] = b0 - b7;
 }
 
-HWB_HD void residual8x8(const int16_t *coef, const uint8_t *scaling, int qp, int16_t *out) {
+HWB_FN void residual8x8(const int16_t *coef, const uint8_t *scaling, int qp, int16_t *out) {
   int d[64];
   const int qm = qp % 6, qs = qp / 6;
+#pragma unroll 1
   for (int i = 0; i < 64; ++i) {
     int c = coef[i];
     int ls = (int)scaling[i] * dequant8_v[qm * 64 + i];
     d[i] = qs >= 6 ? (c * ls) << (qs - 6) : (c * ls + (1 << (5 - qs))) >> (6 - qs);
   }
+#pragma unroll 1
   for (int r = 0; r < 8; ++r) idct8_1d(d + 8 * r, 1);
+#pragma unroll 1
   for (int c = 0; c < 8; ++c) idct8_1d(d + c, 8);
+#pragma unroll 1
   for (int i = 0; i < 64; ++i) out[i] = (int16_t)((d[i] + 32) >> 6);
 }
 
 // Intra16x16 luma DC: 16 levels in raster order of the 4x4 DC matrix -> dequantised DC per block
 // (written to dc[z] for the block at that raster position).
-HWB_HD void luma_dc_transform(const int16_t *c, int ls00, int qp, int32_t *dc_by_z) {
+HWB_FN void luma_dc_transform(const int16_t *c, int ls00, int qp, int32_t *dc_by_z) {
   int f[16];
   for (int i = 0; i < 16; ++i) f[i] = c[i];
   for (int r = 0; r < 4; ++r) {
@@ -102,7 +106,7 @@ HWB_HD void luma_dc_transform(const int16_t *c, int ls00, int qp, int32_t *dc_by
   }
 }
 
-HWB_HD void chroma_dc_transform(const int16_t *c, int ls00, int qpc, int32_t *dc4) {
+HWB_FN void chroma_dc_transform(const int16_t *c, int ls00, int qpc, int32_t *dc4) {
   int f0 = c[0] + c[1] + c[2] + c[3], f1 = c[0] - c[1] + c[2] - c[3];
   int f2 = c[0] + c[1] - c[2] - c[3], f3 = c[0] - c[1] - c[2] + c[3];
   const int qs = qpc / 6;
@@ -169,10 +173,11 @@ HWB_HD int tap6(int a, int b, int c, int d, int e, int f) { return a - 5 * b + 2
 
 // Luma prediction of a 4 (wide) x 2 (high) region whose top-left integer position (already
 // displaced by mv>>2) is (px,py); fx,fy = mv&3.  ref is a coded luma plane (w x h, pitch w).
-HWB_HD void mc_luma_4x2(const uint8_t *ref, int w, int h, int px, int py, int fx, int fy, int *out) {
+HWB_FN void mc_luma_4x2(const uint8_t *ref, int w, int h, int px, int py, int fx, int fy, int *out) {
   uint8_t win[7][9];  // rows py-2..py+4, cols px-2..px+6
   const bool inside = (px >= 2) && (px + 6 < w) && (py >= 2) && (py + 4 < h);
   if (fx == 0 && fy == 0) {
+#pragma unroll 1
     for (int r = 0; r < 2; ++r) {
       int yy = clip3(0, h - 1, py + r);
       for (int c = 0; c < 4; ++c) out[r * 4 + c] = ref[yy * w + clip3(0, w - 1, px + c)];
@@ -195,12 +200,14 @@ HWB_HD void mc_luma_4x2(const uint8_t *ref, int w, int h, int px, int py, int fx
       win[r][8] = (uint8_t)x2;
     }
 #else
+#pragma unroll 1
     for (int r = 0; r < 7; ++r) {
       const uint8_t *p = ref + (py - 2 + r) * w + px - 2;
       for (int c = 0; c < 9; ++c) win[r][c] = p[c];
     }
 #endif
   } else {
+#pragma unroll 1
     for (int r = 0; r < 7; ++r) {
       int yy = clip3(0, h - 1, py - 2 + r);
 #pragma unroll
@@ -211,12 +218,14 @@ HWB_HD void mc_luma_4x2(const uint8_t *ref, int w, int h, int px, int py, int fx
 #define HWB_V1(r, c) tap6(win[(r)][c], win[(r) + 1][c], win[(r) + 2][c], win[(r) + 3][c], win[(r) + 4][c], win[(r) + 5][c])
   // pixel (r,c) of the region is win[r+2][c+2]
   if (fy == 0) {
+#pragma unroll 1
     for (int r = 0; r < 2; ++r)
       for (int c = 0; c < 4; ++c) {
         int b = clip8((HWB_H1(r + 2, c) + 16) >> 5);
         out[r * 4 + c] = fx == 2 ? b : (b + win[r + 2][c + 2 + (fx == 3)] + 1) >> 1;
       }
   } else if (fx == 0) {
+#pragma unroll 1
     for (int r = 0; r < 2; ++r)
       for (int c = 0; c < 4; ++c) {
         int hh = clip8((HWB_V1(r, c + 2) + 16) >> 5);
@@ -225,7 +234,9 @@ HWB_HD void mc_luma_4x2(const uint8_t *ref, int w, int h, int px, int py, int fx
   } else if (fx == 2 || fy == 2) {
     for (int c = 0; c < 4; ++c) {
       int b1[7];
+#pragma unroll 1
       for (int r = 0; r < 7; ++r) b1[r] = HWB_H1(r, c);
+#pragma unroll 1
       for (int r = 0; r < 2; ++r) {
         int j = clip8((tap6(b1[r], b1[r + 1], b1[r + 2], b1[r + 3], b1[r + 4], b1[r + 5]) + 512) >> 10);
         int v;
@@ -236,6 +247,7 @@ HWB_HD void mc_luma_4x2(const uint8_t *ref, int w, int h, int px, int py, int fx
       }
     }
   } else {
+#pragma unroll 1
     for (int r = 0; r < 2; ++r)
       for (int c = 0; c < 4; ++c) {
         int b = clip8((HWB_H1(r + 2 + (fy == 3), c) + 16) >> 5);
@@ -249,7 +261,7 @@ HWB_HD void mc_luma_4x2(const uint8_t *ref, int w, int h, int px, int py, int fx
 
 // Chroma prediction of a 2x2 region at chroma position (cx,cy) (block origin, before mv); mv in
 // quarter luma samples = eighth chroma samples.  ref: chroma plane (w x h).
-HWB_HD void mc_chroma_2x2(const uint8_t *ref, int w, int h, int cx, int cy, int mvx, int mvy, int *out) {
+HWB_FN void mc_chroma_2x2(const uint8_t *ref, int w, int h, int cx, int cy, int mvx, int mvy, int *out) {
   int x0 = cx + (mvx >> 3), y0 = cy + (mvy >> 3);
   int fx = mvx & 7, fy = mvy & 7;
   int v[3][3];
@@ -291,7 +303,7 @@ HWB_HD int weight_bi(const WeightSel &ws, int p0, int p1) {
 }
 
 // plane: 0 luma, 1 Cb, 2 Cr.  r0/r1: reference indices (or -1).
-HWB_HD WeightSel select_weights(const PicDesc &pd, const SliceDesc &sd, int plane, int r0, int r1) {
+HWB_FN WeightSel select_weights(const PicDesc &pd, const SliceDesc &sd, int plane, int r0, int r1) {
   WeightSel ws;
   ws.mode = 0; ws.logwd = 0; ws.w0 = ws.w1 = 1; ws.o0 = ws.o1 = 0;
   if (sd.use_weights == 1) {
@@ -339,6 +351,7 @@ HWB_FN void recon_mb(const ChunkCtx &c, int pic, int mbx, int mby, ReconScratch 
   if (mb.mbtype == MB_IPCM) {
     const uint8_t *s = (const uint8_t *)coefs;
     HWB_LANES(l)
+#pragma unroll 1
       for (int i = l; i < 384; i += 32) {
         if (i < 256) sm->luma[((i >> 4) + 1) * LT_STRIDE + LT_OFF + (i & 15)] = s[i];
         else { int k = i - 256; sm->chroma[k >> 6][(((k & 63) >> 3) + 1) * CT_STRIDE + CT_OFF + (k & 7)] = s[i]; }
@@ -375,6 +388,7 @@ HWB_FN void recon_mb(const ChunkCtx &c, int pic, int mbx, int mby, ReconScratch 
         sm->has_res = 0;
         if (mb.mbtype == MB_I16x16) {
           if (nz & (1u << NZ_LUMA_DC)) luma_dc_transform(coefs, (int)pd.scaling4[0][0] * dequant4_v[(mb.qp % 6) * 16], mb.qp, sm->dc);
+#pragma unroll 1
           else for (int i = 0; i < 16; ++i) sm->dc[i] = 0;
         }
       } else if (l == 1 || l == 2) {
@@ -383,6 +397,7 @@ HWB_FN void recon_mb(const ChunkCtx &c, int pic, int mbx, int mby, ReconScratch 
         int q = pl ? qpc1 : qpc0;
         if (nz & (1u << bit))
           chroma_dc_transform(coefs + 16 * popc32(nz & ((1u << bit) - 1)), (int)pd.scaling4[sl + 1 + pl][0] * dequant4_v[(q % 6) * 16], q, sm->dc + 16 + 4 * pl);
+#pragma unroll 1
         else for (int i = 0; i < 4; ++i) sm->dc[16 + 4 * pl + i] = 0;
       }
     HWB_LANES_END
@@ -440,6 +455,7 @@ HWB_FN void recon_mb(const ChunkCtx &c, int pic, int mbx, int mby, ReconScratch 
           }
           WeightSel ws = select_weights(pd, sd, 0, r0, r1);
           uint8_t *t = sm->luma + (by * 4 + (l & 1) * 2 + 1) * LT_STRIDE + LT_OFF + bx * 4;
+#pragma unroll 1
           for (int i = 0; i < 8; ++i) {
             int v = (r0 >= 0 && r1 >= 0) ? weight_bi(ws, p0[i], p1[i]) : (r0 >= 0 ? weight_uni(ws, p0[i], ws.w0, ws.o0) : weight_uni(ws, p1[i], ws.w1, ws.o1));
             t[(i >> 2) * LT_STRIDE + (i & 3)] = (uint8_t)v;
@@ -460,6 +476,7 @@ HWB_FN void recon_mb(const ChunkCtx &c, int pic, int mbx, int mby, ReconScratch 
           }
           WeightSel ws = select_weights(pd, sd, 1 + pl, r0, r1);
           uint8_t *t = sm->chroma[pl] + (by * 2 + 1) * CT_STRIDE + CT_OFF + bx * 2;
+#pragma unroll 1
           for (int i = 0; i < 4; ++i) {
             int v = (r0 >= 0 && r1 >= 0) ? weight_bi(ws, p0[i], p1[i]) : (r0 >= 0 ? weight_uni(ws, p0[i], ws.w0, ws.o0) : weight_uni(ws, p1[i], ws.w1, ws.o1));
             t[(i >> 1) * CT_STRIDE + (i & 1)] = (uint8_t)v;
@@ -481,12 +498,14 @@ HWB_FN void recon_mb(const ChunkCtx &c, int pic, int mbx, int mby, ReconScratch 
             dcv = (av.top && av.left) ? (s + 16) >> 5 : ((av.top || av.left) ? (s + 8) >> 4 : 128);
           } else if (mode == 3) {
             int H = 0, V = 0;
+#pragma unroll 1
             for (int i = 0; i < 8; ++i) {
               H += (i + 1) * (T[8 + i] - T[6 - i]);
               V += (i + 1) * (L[(8 + i) * LT_STRIDE] - (i == 7 ? T[-1] : L[(6 - i) * LT_STRIDE]));
             }
             a = 16 * (L[15 * LT_STRIDE] + T[15]); b = (5 * H + 32) >> 6; cc = (5 * V + 32) >> 6;
           }
+#pragma unroll 1
           for (int i = 0; i < 8; ++i) {
             int p = l * 8 + i, x = p & 15, y = p >> 4;
             int v = mode == 0 ? T[x] : mode == 1 ? L[y * LT_STRIDE] : mode == 2 ? dcv : clip8((a + b * (x - 7) + cc * (y - 7) + 16) >> 5);
@@ -497,6 +516,7 @@ HWB_FN void recon_mb(const ChunkCtx &c, int pic, int mbx, int mby, ReconScratch 
         // Intra4x4 / Intra8x8: blocks are serially dependent; residual is added per block here.
         const int N = mb.mbtype == MB_I8x8 ? 8 : 4;
         const int nblk = N == 8 ? 4 : 16;
+#pragma unroll 1
         for (int blk = 0; blk < nblk; ++blk) {
           const int bx = N == 8 ? (blk & 1) * 8 : z2x(blk) * 4, by = N == 8 ? (blk >> 1) * 8 : z2y(blk) * 4;
           const bool aL = bx > 0 || av.left, aT = by > 0 || av.top;
@@ -510,8 +530,11 @@ HWB_FN void recon_mb(const ChunkCtx &c, int pic, int mbx, int mby, ReconScratch 
             // each lane builds the (tiny) edge array itself; 2N+... reads from shared
             uint8_t E[26];
             const uint8_t *org = sm->luma + (by + 1) * LT_STRIDE + LT_OFF + bx;  // pixel (0,0) of block
+#pragma unroll 1
             for (int i = 0; i < N; ++i) E[N - 1 - i] = aL ? org[i * LT_STRIDE - 1] : 128;
+#pragma unroll 1
             for (int i = 0; i < N; ++i) E[N + 1 + i] = aT ? org[-LT_STRIDE + i] : 128;
+#pragma unroll 1
             for (int i = 0; i < N; ++i) E[2 * N + 1 + i] = aC ? org[-LT_STRIDE + N + i] : E[2 * N];
             E[N] = aD ? org[-LT_STRIDE - 1] : 128;
             E[3 * N + 1] = E[3 * N];
@@ -519,6 +542,7 @@ HWB_FN void recon_mb(const ChunkCtx &c, int pic, int mbx, int mby, ReconScratch 
               uint8_t F[26];
               if (aT) {
                 F[9] = aD ? (E[8] + 2 * E[9] + E[10] + 2) >> 2 : (3 * E[9] + E[10] + 2) >> 2;
+#pragma unroll 1
                 for (int i = 1; i < 15; ++i) F[9 + i] = (E[8 + i] + 2 * E[9 + i] + E[10 + i] + 2) >> 2;
                 F[24] = (E[23] + 3 * E[24] + 2) >> 2;
               } else for (int i = 9; i < 25; ++i) F[i] = E[i];
@@ -530,10 +554,12 @@ HWB_FN void recon_mb(const ChunkCtx &c, int pic, int mbx, int mby, ReconScratch 
               } else F[8] = E[8];
               if (aL) {
                 F[7] = aD ? (E[8] + 2 * E[7] + E[6] + 2) >> 2 : (3 * E[7] + E[6] + 2) >> 2;
+#pragma unroll 1
                 for (int i = 1; i < 7; ++i) F[7 - i] = (E[8 - i] + 2 * E[7 - i] + E[6 - i] + 2) >> 2;
                 F[0] = (E[1] + 3 * E[0] + 2) >> 2;
               } else for (int i = 0; i < 8; ++i) F[i] = E[i];
               F[25] = F[24];
+#pragma unroll 1
               for (int i = 0; i < 26; ++i) E[i] = F[i];
             }
             int dcv = 128;
@@ -548,6 +574,7 @@ HWB_FN void recon_mb(const ChunkCtx &c, int pic, int mbx, int mby, ReconScratch 
             const int zb = N == 8 ? blk * 4 : blk;
             const bool hr = (sm->has_res >> zb) & 1;
             if (N == 8) {
+#pragma unroll 1
               for (int k = 0; k < 2; ++k) {
                 int p = l * 2 + k, x = p & 7, y = p >> 3;
                 int v = mode == 2 ? dcv : intra_dir_pred(mode, 8, E, x, y);
@@ -574,6 +601,7 @@ HWB_FN void recon_mb(const ChunkCtx &c, int pic, int mbx, int mby, ReconScratch 
         if (mode == 0) {
           int xo = x0 & 4, yo = y & 4;
           int st = 0, sl2 = 0;
+#pragma unroll 1
           for (int i = 0; i < 4; ++i) { st += T[xo + i]; sl2 += L[(yo + i) * CT_STRIDE]; }
           bool useT = av.top, useL = av.left;
           if (xo > 0 && yo == 0) { if (useT) useL = false; }
@@ -583,6 +611,7 @@ HWB_FN void recon_mb(const ChunkCtx &c, int pic, int mbx, int mby, ReconScratch 
           else if (useL) dcv = (sl2 + 2) >> 2;
         } else if (mode == 3) {
           int H = 0, V = 0;
+#pragma unroll 1
           for (int i = 0; i < 4; ++i) {
             H += (i + 1) * (T[4 + i] - T[2 - i]);
             V += (i + 1) * (L[(4 + i) * CT_STRIDE] - (i == 3 ? T[-1] : L[(2 - i) * CT_STRIDE]));
@@ -590,10 +619,12 @@ HWB_FN void recon_mb(const ChunkCtx &c, int pic, int mbx, int mby, ReconScratch 
           a = 16 * (L[7 * CT_STRIDE] + T[7]); b = (34 * H + 32) >> 6; cc = (34 * V + 32) >> 6;
         }
         int vals[4];
+#pragma unroll 1
         for (int i = 0; i < 4; ++i) {
           int x = x0 + i;
           vals[i] = mode == 0 ? dcv : mode == 1 ? L[y * CT_STRIDE] : mode == 2 ? T[x] : clip8((a + b * (x - 3) + cc * (y - 3) + 16) >> 5);
         }
+#pragma unroll 1
         for (int i = 0; i < 4; ++i) sm->chroma[pl][(y + 1) * CT_STRIDE + CT_OFF + x0 + i] = (uint8_t)vals[i];
       HWB_LANES_END
     }
@@ -602,6 +633,7 @@ HWB_FN void recon_mb(const ChunkCtx &c, int pic, int mbx, int mby, ReconScratch 
     const uint32_t hr = sm->has_res;
     HWB_LANES(l)
       if (!luma_done && (hr & 0xFFFFu)) {
+#pragma unroll 1
         for (int i = 0; i < 8; ++i) {
           int p = l * 8 + i, x = p & 15, y = p >> 4;
           int zb = xy2z(x >> 2, y >> 2);
@@ -616,6 +648,7 @@ HWB_FN void recon_mb(const ChunkCtx &c, int pic, int mbx, int mby, ReconScratch 
         const int pl = l >> 4, p0 = (l & 15) * 4, y = p0 >> 3, x0 = p0 & 7;
         int cbk = 16 + pl * 4 + (y >> 2) * 2 + (x0 >> 2);
         if ((hr >> cbk) & 1) {
+#pragma unroll 1
           for (int i = 0; i < 4; ++i) {
             uint8_t *t = sm->chroma[pl] + (y + 1) * CT_STRIDE + CT_OFF + x0 + i;
             *t = (uint8_t)clip8(*t + sm->res[cbk][(y & 3) * 4 + ((x0 + i) & 3)]);
