@@ -139,18 +139,21 @@ HWB_FN void deblock_mb(const ChunkCtx &c, int pic, int mbx, int mby, DeblockScra
 #if HWB_DEVICE_BUILD
   any = __ballot_sync(0xffffffffu, sm->bs[threadIdx.x & 31] != 0);
 #else
+#pragma unroll 1
   for (int i = 0; i < 32; ++i) any |= sm->bs[i] ? (1u << i) : 0;
 #endif
   if (!any) return;
 
   // ---- load tile (coherent loads: neighbours were written by other warps of this launch)
   HWB_LANES(l)
+#pragma unroll 1
     for (int i = l; i < 100; i += 32) {
       int r = i / 5 - 4, cq = i % 5 - 1;  // row -4..15, column quad -1..3
       if ((r < 0 && mby == 0) || (cq < 0 && mbx == 0)) continue;
       *(uint32_t *)(sm->luma + (r + 4) * DL_STRIDE + DL_OFF + cq * 4) =
           ld_u32_cg((const uint32_t *)(Y + (int64_t)(mby * 16 + r) * wc + mbx * 16 + cq * 4));
     }
+#pragma unroll 1
     for (int i = l; i < 72; i += 32) {
       int pl = i / 36, k = i % 36, r = k / 3 - 4, cq = k % 3 - 1;  // row -4..7, quads -1..1
       if ((r < 0 && mby == 0) || (cq < 0 && mbx == 0)) continue;
@@ -162,10 +165,12 @@ HWB_FN void deblock_mb(const ChunkCtx &c, int pic, int mbx, int mby, DeblockScra
   const int qp_q = mb.qp;
   const int qp_l = have_left ? mbs[mbaddr - 1].qp : 0, qp_t = have_top ? mbs[mbaddr - c.mb_w].qp : 0;
   // ---- vertical edges then horizontal edges
+#pragma unroll 1
   for (int dir = 0; dir < 2; ++dir) {
     const int qp_p_edge = dir ? qp_t : qp_l;
     HWB_LANES(l)
       if (l < 16) {
+#pragma unroll 1
         for (int e = 0; e < 4; ++e) {
           int bS = sm->bs[dir * 16 + e * 4 + (l >> 2)];
           if (!bS) continue;
@@ -180,6 +185,7 @@ HWB_FN void deblock_mb(const ChunkCtx &c, int pic, int mbx, int mby, DeblockScra
       } else {
         const int pl = (l - 16) >> 3, k = l & 7;
         const int off = pd.chroma_qp_offset[pl];
+#pragma unroll 1
         for (int e = 0; e < 4; e += 2) {
           int bS = sm->bs[dir * 16 + e * 4 + (k >> 1)];
           if (!bS) continue;
@@ -199,12 +205,14 @@ HWB_FN void deblock_mb(const ChunkCtx &c, int pic, int mbx, int mby, DeblockScra
   // ---- store rows -3..15 x columns -4..15 (the untouched corner is rewritten with its own value
   //      only where this macroblock has exclusive access, see DESIGN.md "deblock wavefront")
   HWB_LANES(l)
+#pragma unroll 1
     for (int i = l; i < 95; i += 32) {
       int r = i / 5 - 3, cq = i % 5 - 1;
       if ((r < 0 && (mby == 0 || cq < 0)) || (cq < 0 && mbx == 0)) continue;
       *(uint32_t *)(Y + (int64_t)(mby * 16 + r) * wc + mbx * 16 + cq * 4) =
           *(const uint32_t *)(sm->luma + (r + 4) * DL_STRIDE + DL_OFF + cq * 4);
     }
+#pragma unroll 1
     for (int i = l; i < 60; i += 32) {
       int pl = i / 30, k = i % 30, r = k / 3 - 2, cq = k % 3 - 1;
       if ((r < 0 && (mby == 0 || cq < 0)) || (cq < 0 && mbx == 0)) continue;

@@ -233,7 +233,9 @@ HWB_FN void pred_mv(const SliceDec &s, int l, int bx, int by, int w, int ref, in
   }
 }
 HWB_FN void set_motion(SliceDec &s, int l, int bx, int by, int w, int h, int ref, int mx, int my, int amvdx, int amvdy) {
+#pragma unroll 1
   for (int y = by; y < by + h; ++y)
+#pragma unroll 1
     for (int x = bx; x < bx + w; ++x) {
       int ci = HWB_CI(x, y);
       s.ref_cache[l][ci] = (int8_t)ref;
@@ -700,6 +702,7 @@ HWB_FN int cabac_cbp(SliceDec &s) {
   int cbpa = s.availA ? ((L.flags & NBF_IPCM) ? 0x2F : L.cbp) : 0x0F;
   int cbpb = s.availB ? ((T.flags & NBF_IPCM) ? 0x2F : T.cbp) : 0x0F;
   int cbp = 0;
+#pragma unroll 1
   for (int b8 = 0; b8 < 4; ++b8) {
     int a = (b8 & 1) ? !((cbp >> (b8 - 1)) & 1) : !((cbpa >> (b8 + 1)) & 1);
     int bq = (b8 & 2) ? !((cbp >> (b8 - 2)) & 1) : !((cbpb >> (b8 + 2)) & 1);
