@@ -298,6 +298,14 @@ def run_ours(args):
         pass
     peak = float(peaks.get('hbm_gbs', 6650.0))
     alg = algorithmic_bytes(n) * args.steps
+    # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture of the same workload
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'r1_dominant_kernel_traffic.json')))
+        if dom in tr.get('kernel', '') and n == 3000:
+            traffic = tr['dram_bytes_per_launch']
+    except Exception:
+        pass
     # achieved = algorithmic bytes handled per launch of the dominant kernel / its average launch duration
     achieved = (alg / max(1, dom_launches)) / (dom_ms / max(1, dom_launches) / 1000.0) / 1e9 if dom_ms > 0 else 0.0
     cpu = None
@@ -319,7 +327,7 @@ def run_ours(args):
                 'd2h_bytes_per_step': (a1['d2h_bytes'] - a0['d2h_bytes']) // args.steps, 'ms_per_step': 1000.0 * e2e_s / args.steps},
         'gpu_launches': int(d['kernel_launches'] + (a1['kernel_launches'] - a0['kernel_launches'])),
         'roofline': {'bound': 'hbm', 'kernel': dom + '_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                     'frac': achieved / peak, 'traffic': None, 'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback',
+                     'frac': achieved / peak, 'traffic': traffic, 'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback',
                      'whole_pipeline_frac': (alg / dev_s / 1e9) / peak,
                      'stage_ms_per_step': {k: v[0] / args.steps for k, v in stage.items()}},
         'cpu_baseline': cpu,
