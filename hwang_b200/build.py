@@ -17,7 +17,7 @@ HOST_SRCS = ['b200_video_decoder.cpp', 'capi.cpp', 'decoder_automata.cpp', 'h264
 PRODUCT = os.path.join(ROOT, 'hwang_b200', 'libhwang_b200.so')
 GEN = os.path.join(ROOT, 'build', 'libh264gen.so')
 EMU = os.path.join(ROOT, 'tests', 'emu', 'libhwb_emu.so')
-CXXFLAGS = ['-std=c++17', '-O2', '-g', '-fPIC', '-Wall', '-Wno-unused', '-Wno-unknown-pragmas', '-pthread']
+CXXFLAGS = ['-std=c++17', '-O2', '-g', '-fPIC', '-Wall', '-Wno-unused', '-Wno-unknown-pragmas', '-fno-strict-aliasing', '-pthread']
 
 
 def _run(cmd):

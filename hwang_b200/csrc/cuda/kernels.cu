@@ -15,6 +15,11 @@
 #include <atomic>
 #include <string>
 
+// The CABAC engine's fused transition table is read once per bin by the single active lane of every warp: a
+// shared-memory copy (2 KB per CTA, filled at kernel start) keeps that load off the global / constant path.
+__shared__ uint32_t hwb_fused_sm[512];
+#define HWB_CABAC_FUSED hwb_fused_sm
+
 #include "../dev/deblock.h"
 #include "../dev/devapi.h"
 #include "../dev/entropy.h"  // generic (runtime entropy_coding_mode): namespace hwb::ent
@@ -50,16 +55,16 @@ __device__ __forceinline__ int warp_ticket(int32_t *ticket) {
 // line per word and thrash L1 (measured: ~4000 cycles per CABAC bin before this change).
 #define HWB_ENTROPY_KERNEL(NAME, NS)                                                                  \
   __global__ void __launch_bounds__(kThreads) NAME(ChunkCtx cparam, int32_t *ticket) {                \
-    __shared__ uint8_t states[kWarpsPerBlock][464];                                                   \
     __shared__ NS::SliceDec sdec[kWarpsPerBlock];                                                     \
     __shared__ ChunkCtx c;                                                                            \
     if (threadIdx.x == 0) c = cparam;                                                                 \
+    for (int i = threadIdx.x; i < 512; i += kThreads) hwb_fused_sm[i] = cabac_fused[i];               \
     __syncthreads();                                                                                  \
     const int w = threadIdx.x >> 5;                                                                   \
     for (;;) {                                                                                        \
       const int s = warp_ticket(ticket);                                                              \
       if (s >= c.num_slices) return;                                                                  \
-      if ((threadIdx.x & 31) == 0) NS::decode_slice(c, s, states[w], &sdec[w]);                       \
+      NS::decode_slice(c, s, nullptr, &sdec[w]);                                                      \
       __syncwarp();                                                                                   \
     }                                                                                                 \
   }

@@ -80,14 +80,66 @@ HWB_HD void br_align(BitReader &b) { br_skip(b, b.avail & 7); }
 HWB_HD bool br_more_rbsp_data(BitReader &b, uint32_t last_one_bitpos) { return br_bitpos(b) < last_one_bitpos; }
 
 // ------------------------------------------------------------------------------------ CABAC
-struct Cabac {
-  uint32_t range;   // codIRange (9 bits)
-  uint32_t offset;  // codIOffset (9 bits)
+// Arithmetic decoding engine (9.3.3.2) on 32-bit registers only, everything scaled by 2^23: `range` holds
+// codIRange << 23 (normalised <=> bit 31 set, so the renormalisation shift is a plain count-leading-zeros), `low`
+// holds codIOffset << 23 with the next `nb` (<= 16) bits of the stream left-aligned below bit 23, and the fused
+// table's rangeLPS field is pre-shifted too: a decision is  load state, load entry, mask, subtract, compare,
+// select, clz, shift.  Every ~16 consumed bits two more bytes are patched in.  (64-bit shifts cost 2-3
+// instructions each on the GPU: the first engine, built on the generic 64-bit bit reader, spent 46 instructions per
+// decision.)  The engine reads the slice RBSP directly: `base` is the slice's first byte (16-byte aligned on the
+// device), `pos` the byte offset of the next refill (always even).
+#ifndef HWB_CABAC_FUSED
+#define HWB_CABAC_FUSED cabac_fused
+#endif
+enum { CABAC_SCALE = 23 };
+struct alignas(16) Cabac {
+  uint32_t low;
+  uint32_t range;
+  int32_t nb;      // valid stream bits below bit 23 of `low`
+  uint32_t pos;
 };
 
-HWB_HD void cabac_start(Cabac &c, BitReader &b) {
-  c.range = 510;
-  c.offset = br_get(b, 9);
+HWB_HD uint32_t cabac_load16(const uint8_t *base, uint32_t pos) {
+#if HWB_DEVICE_BUILD
+  return __byte_perm((uint32_t)__ldg((const unsigned short *)(base + pos)), 0, 0x4401);
+#else
+  return ((uint32_t)base[pos] << 8) | base[pos + 1];
+#endif
+}
+// count of leading zeros of a non-zero word in one instruction (bfind.shiftamt)
+HWB_HD int cabac_norm_shift(uint32_t r) {
+#if HWB_DEVICE_BUILD
+  int sh;
+  asm("bfind.shiftamt.u32 %0, %1;" : "=r"(sh) : "r"(r));
+  return sh;
+#else
+  return __builtin_clz(r);
+#endif
+}
+// Start (or restart, after I_PCM samples) the engine at byte `p` of the RBSP: codIOffset = the next 9 bits.
+HWB_HD void cabac_start(Cabac &c, const uint8_t *base, uint32_t p) {
+  c.range = 510u << CABAC_SCALE;
+  if (p & 1) {  // 3 bytes: 9 offset bits + 15 pending
+    const uint32_t b0 = base[p];
+    c.low = ((b0 << 16) | cabac_load16(base, p + 1)) << 8;
+    c.nb = 15; c.pos = p + 3;
+  } else {      // 2 bytes: 9 offset bits + 7 pending
+    c.low = cabac_load16(base, p) << 16;
+    c.nb = 7; c.pos = p + 2;
+  }
+}
+// Bits of the RBSP consumed by the arithmetic decoder so far (9 at start + one per renormalisation shift).
+HWB_HD uint32_t cabac_bitpos(const Cabac &c) { return c.pos * 8 - (uint32_t)c.nb; }
+// Invariant between operations: nb >= 1 (a bypass decision compares before it shifts, so the next stream bit must
+// already be in `low`).  nb <= 0: -nb zero bits were shifted into the offset; the top bits of the next 16 belong
+// there.  Written as a loop (it runs once) so that ptxas keeps it a rarely taken branch instead of ten predicated
+// instructions per bin.
+HWB_HD void cabac_refill(Cabac &c, const uint8_t *base) {
+#pragma unroll 1
+  while (c.nb <= 0) {
+    c.low |= cabac_load16(base, c.pos) << (7 - c.nb);
+    c.nb += 16; c.pos += 2;
+  }
 }
 
 HWB_HD void cabac_init_states(uint8_t *st, int table, int slice_qp) {
@@ -99,37 +151,39 @@ HWB_HD void cabac_init_states(uint8_t *st, int table, int slice_qp) {
   }
 }
 
-// Branch-free binary decision (9.3.3.2.1): one fused table entry gives rangeLPS and both successor states.
-HWB_HD int cabac_decision(Cabac &c, BitReader &b, uint8_t *state) {
-  if (b.avail < 16) br_refill(b);
+// Binary decision (9.3.3.2.1).  Fused table entry: rangeLPS << 23 | state after an LPS << 8 | state after an MPS.
+HWB_HD int cabac_decision(Cabac &c, const uint8_t *base, uint8_t *state) {
   const uint32_t s = *state;
-  const uint32_t e = cabac_fused[s * 4 + ((c.range >> 6) & 3)];
-  const uint32_t rlps = e & 0xff;
+  const uint32_t e = HWB_CABAC_FUSED[s * 4 + ((c.range >> 29) & 3)];
+  const uint32_t rlps = e & 0x7F800000u;
   const uint32_t rmps = c.range - rlps;
-  const bool lps = c.offset >= rmps;
-  c.offset = lps ? c.offset - rmps : c.offset;
-  c.range = lps ? rlps : rmps;
-  *state = (uint8_t)(lps ? (e >> 8) : (e >> 16));
-  const int sh = clz32(c.range) - 23;  // renormalisation shift, 0 when range >= 256
-  c.range <<= sh;
-  c.offset = (c.offset << sh) | (uint32_t)((b.cache >> 1) >> (63 - sh));
-  b.cache <<= sh; b.avail -= sh;
+  const bool lps = c.low >= rmps;
+  c.low = lps ? c.low - rmps : c.low;
+  const uint32_t r = lps ? rlps : rmps;
+  *state = (uint8_t)(lps ? (e >> 8) : e);
+  const int sh = cabac_norm_shift(r);
+  c.range = r << sh;
+  c.low <<= sh;
+  c.nb -= sh;
+  cabac_refill(c, base);
   return (int)((s & 1) ^ (lps ? 1u : 0u));
 }
-HWB_HD int cabac_bypass(Cabac &c, BitReader &b) {
-  if (b.avail < 16) br_refill(b);
-  c.offset = (c.offset << 1) | (uint32_t)(b.cache >> 63);
-  b.cache <<= 1; b.avail -= 1;
-  const bool one = c.offset >= c.range;
-  c.offset -= one ? c.range : 0u;
+HWB_HD int cabac_bypass(Cabac &c, const uint8_t *base) {
+  // compare before shifting: 2 * offset + next bit >= range  <=>  low >= range / 2 (exact: range << 22)
+  const uint32_t half = c.range >> 1;
+  const bool one = c.low >= half;
+  c.low = (c.low - (one ? half : 0u)) << 1;
+  --c.nb;
+  cabac_refill(c, base);
   return one ? 1 : 0;
 }
-HWB_HD int cabac_terminate(Cabac &c, BitReader &b) {
-  c.range -= 2;
-  if (c.offset >= c.range) return 1;
-  if (c.range < 256) {
-    c.range <<= 1;
-    c.offset = (c.offset << 1) | br_get(b, 1);
+HWB_HD int cabac_terminate(Cabac &c, const uint8_t *base) {
+  c.range -= 2u << CABAC_SCALE;
+  if (c.low >= c.range) return 1;
+  if (!(c.range >> 31)) {
+    c.range <<= 1; c.low <<= 1;
+    --c.nb;
+    cabac_refill(c, base);
   }
   return 0;
 }

@@ -1,7 +1,8 @@
 // Slice-data entropy decoding (H.264 clauses 7.3.4-7.3.5, 9.1 Exp-Golomb, 9.2 CAVLC, 9.3 CABAC)
 // and motion-vector derivation (8.4.1, including P_Skip and B direct prediction).
-// One lane owns one slice and walks its macroblocks in raster order; slices of every picture of
-// the chunk are decoded concurrently (entropy decoding needs no pixels).  Output: MbInfo records,
+// One warp owns one slice and walks its macroblocks in raster order (the serial syntax decoding runs identically on
+// all 32 lanes, bulk data movement is spread over the lanes: see "warp-cooperative execution model" below); slices of
+// every picture of the chunk are decoded concurrently (entropy decoding needs no pixels).  Output: MbInfo records,
 // coefficient slots, final motion vectors / reference indices per 4x4 / 8x8 block.
 // The file may be included several times with different (HWB_ENT_NS, HWB_ENT_MODE) pairs: the CUDA side compiles a
 // CABAC-only and a CAVLC-only copy of the slice decoder (each a fraction of the code, which matters because this kernel
@@ -58,12 +59,13 @@ struct SliceDec {
   int slice_num;  // inside picture
   BitReader br;
   Cabac cab;
-  uint8_t *st;  // CABAC context states
+  uint8_t *st;  // CABAC context states (== states on the decoder; the stream generator points it at a dummy)
   bool cabac;
   uint32_t stop_bitpos;
   int qp;
   int last_dqp;
   LeftCtx left;
+  uint32_t top_words[4];   // words 0..3 of the top neighbour's line-buffer entry (flags/cbp/cmode/dirmask, cbf, chroma nnz)
   int8_t tl_ref[2];        // top-left macroblock's bottom-right block (saved before its line entry is overwritten)
   alignas(4) int16_t tl_mv[2][2];  // copied as 32-bit words
   NbCtx *line;  // [mb_w] top context
@@ -90,16 +92,19 @@ struct SliceDec {
   uint8_t index[64];
   int8_t refs[2][4];
   int8_t sub[4], shape[4], pf[4];
+  // CABAC context states live inside the slice state (shared memory on the GPU), so that the decoder addresses
+  // them as shared-memory offsets instead of through a generic pointer
+  alignas(16) uint8_t states[464];
 };
 
 HWB_HD void sd_fail(SliceDec &s, int code) { if (!s.error) s.error = code; }
+HWB_HD uint32_t top_flags(const SliceDec &s) { return s.top_words[0] & 0xff; }  // valid when availB
 
 // Out-of-line engine access for the macroblock-layer syntax (tens of call sites): keeps the kernel small enough for
 // the instruction cache.  The residual loops use the inlined, register-resident versions instead.
-HWB_FN int cabac_bin_p(SliceDec &s, uint8_t *st) { return cabac_decision(s.cab, s.br, st); }
-HWB_HD int cabac_bin(SliceDec &s, int ctx) { return cabac_bin_p(s, s.st + ctx); }
-HWB_FN int cabac_byp(SliceDec &s) { return cabac_bypass(s.cab, s.br); }
-HWB_FN int cabac_term(SliceDec &s) { return cabac_terminate(s.cab, s.br); }
+HWB_FN int cabac_bin(SliceDec &s, int ctx) { Cabac c = s.cab; const int b = cabac_decision(c, s.br.base, s.states + ctx); s.cab = c; return b; }
+HWB_FN int cabac_byp(SliceDec &s) { Cabac c = s.cab; const int b = cabac_bypass(c, s.br.base); s.cab = c; return b; }
+HWB_FN int cabac_term(SliceDec &s) { Cabac c = s.cab; const int b = cabac_terminate(c, s.br.base); s.cab = c; return b; }
 HWB_FN uint32_t s_ue(SliceDec &s) { return br_ue(s.br); }
 HWB_FN int32_t s_se(SliceDec &s) { return br_se(s.br); }
 HWB_FN uint32_t s_get(SliceDec &s, int n) { return br_get(s.br, n); }
@@ -116,16 +121,26 @@ HWB_HD void cpy16(void *d, const void *s) {
 #endif
 }
 
+// ---- warp-cooperative execution model of this file
+// All 32 lanes of the warp that owns a slice execute the slice decoder with identical values ("uniform" code: every
+// lane reads the same shared/global addresses and writes the same values, which costs exactly what one lane would).
+// Bulk data movement (neighbour caches, line buffer, outputs) is done in HWB_LANES blocks where lane l moves item l;
+// a block ends with __syncwarp().  Rules: inside a block a lane touches only its own items; uniform code may follow
+// a block immediately (the barrier orders it), and a block may follow uniform code immediately (every lane has
+// itself written whatever uniform code wrote).  Host builds run the lanes as a loop.
+
+// Word w (0..19) of a line-buffer entry (NbCtx) <-> where it lives in the slice state while its macroblock row
+// neighbour is being decoded: the 4-byte word at this byte offset of SliceDec.
+#define HWB_SD_OFF(member) ((uint16_t)offsetof(SliceDec, member))
 // Called once per slice before the first macroblock: entries that never change.
 HWB_FN void init_caches(SliceDec &s) {
-#pragma unroll 1
-  for (int l = 0; l < 2; ++l)
-#pragma unroll 1
-    for (int i = 0; i < HWB_CACHE_N; ++i) { s.ref_cache[l][i] = REF_UNAVAIL; s.mv_cache[l][i][0] = s.mv_cache[l][i][1] = 0; s.mvd_cache[l][i][0] = s.mvd_cache[l][i][1] = 0; }
-#pragma unroll 1
-  for (int i = 0; i < HWB_CACHE_N; ++i) { s.nz_cache[i] = 0x80; s.im_cache[i] = -1; s.dir_cache[i] = 0; }
-#pragma unroll 1
-  for (int p = 0; p < 2; ++p) for (int i = 0; i < 12; ++i) s.cnz_cache[p][i] = 0x80;
+  HWB_LANES(l)
+  for (int i = l; i < HWB_CACHE_N; i += 32) {
+    for (int k = 0; k < 2; ++k) { s.ref_cache[k][i] = REF_UNAVAIL; set4(s.mv_cache[k][i], 0); s.mvd_cache[k][i][0] = s.mvd_cache[k][i][1] = 0; }
+    s.nz_cache[i] = 0x80; s.im_cache[i] = -1; s.dir_cache[i] = 0;
+  }
+  if (l < 24) s.cnz_cache[l / 12][l % 12] = 0x80;
+  HWB_LANES_END
 }
 
 // Per macroblock: the left column is the previous macroblock's right column (still in the caches), the top row
@@ -133,77 +148,72 @@ HWB_FN void init_caches(SliceDec &s) {
 HWB_FN void fill_caches(SliceDec &s, bool unused) {
   (void)unused;
   const int nl = s.sd->slice_type == SLICE_B ? 2 : (s.sd->slice_type == SLICE_P ? 1 : 0);
-  if (s.availA) {
-#pragma unroll 1
-    for (int y = 0; y < 4; ++y) {
-      const int d = HWB_CI(-1, y), f = HWB_CI(3, y);
-      s.nz_cache[d] = s.nz_cache[f]; s.im_cache[d] = s.im_cache[f]; s.dir_cache[d] = s.dir_cache[f];
-#pragma unroll 1
-      for (int l = 0; l < nl; ++l) {
-        s.ref_cache[l][d] = s.ref_cache[l][f];
-        cpy4(s.mv_cache[l][d], s.mv_cache[l][f]);
-        *(uint16_t *)s.mvd_cache[l][d] = *(const uint16_t *)s.mvd_cache[l][f];
+  const int top = HWB_CI(0, -1);
+  const bool availA = s.availA, availB = s.availB, availC = s.availC, availD = s.availD;
+  const NbCtx *T = s.line + s.mbx;
+  // ---- phase 1: top row (one line-buffer word per lane), left column, corners
+  HWB_LANES(l)
+  if (l < 20) {
+    // words 0..2 (flags/cbp/cmode/dirmask, cbf, chroma nnz) go to s.top; 3 is padding; 4.. are cache rows
+    uint32_t v = 0;
+    if (availB) v = ((const uint32_t *)T)[l];
+    else if (l == 4) v = 0x80808080u;       // nnz: unavailable
+    else if (l == 5) v = 0xFFFFFFFFu;       // intra modes: unusable
+    else if (l == 6 || l == 7) v = 0xFEFEFEFEu;  // references: unavailable
+    else if (l == 2) v = 0x80808080u;
+    if (l < 4) s.top_words[l] = v;
+    else if (l == 4) set4(s.nz_cache + top, v);
+    else if (l == 5) set4(s.im_cache + top, v);
+    else if (l < 8) set4(s.ref_cache[l - 6] + top, v);
+    else if (l < 16) set4(s.mv_cache[(l - 8) >> 2][top + (l & 3)], v);
+    else set4(s.mvd_cache[(l - 16) >> 1][top + 2 * (l & 1)], v);
+  } else if (l < 24) {
+    // left column, row y: the previous macroblock's column 3 (or "unavailable")
+    const int y = l - 20, d = HWB_CI(-1, y), f = HWB_CI(3, y);
+    s.nz_cache[d] = availA ? s.nz_cache[f] : (uint8_t)0x80;
+    s.im_cache[d] = availA ? s.im_cache[f] : (int8_t)-1;
+    s.dir_cache[d] = availA ? s.dir_cache[f] : (uint8_t)0;
+    for (int k = 0; k < nl; ++k) {
+      s.ref_cache[k][d] = availA ? s.ref_cache[k][f] : (int8_t)REF_UNAVAIL;
+      set4(s.mv_cache[k][d], availA ? *(const uint32_t *)s.mv_cache[k][f] : 0u);
+      *(uint16_t *)s.mvd_cache[k][d] = availA ? *(const uint16_t *)s.mvd_cache[k][f] : (uint16_t)0;
+    }
+  } else if (l < 28) {
+    // chroma nnz left column: plane p, row r
+    const int pl = (l - 24) >> 1, r = (l - 24) & 1;
+    s.cnz_cache[pl][4 + 4 * r] = availA ? s.cnz_cache[pl][6 + 4 * r] : (uint8_t)0x80;
+  } else {
+    // corners: lanes 28,29 = top-right of list 0,1; lanes 30,31 = top-left
+    const int k = l & 1;
+    if (k < nl) {
+      if (l < 30) {
+        const int tr = HWB_CI(4, -1);
+        if (availC) { const NbCtx &R = T[1]; s.ref_cache[k][tr] = R.ref_b[k][0]; cpy4(s.mv_cache[k][tr], R.mv_b[k][0]); }
+        else { s.ref_cache[k][tr] = REF_UNAVAIL; set4(s.mv_cache[k][tr], 0); }
+      } else {
+        const int tl = HWB_CI(-1, -1);
+        if (availD) { s.ref_cache[k][tl] = s.tl_ref[k]; cpy4(s.mv_cache[k][tl], s.tl_mv[k]); }
+        else { s.ref_cache[k][tl] = REF_UNAVAIL; set4(s.mv_cache[k][tl], 0); }
       }
     }
-#pragma unroll 1
-    for (int p = 0; p < 2; ++p) { s.cnz_cache[p][4] = s.cnz_cache[p][6]; s.cnz_cache[p][8] = s.cnz_cache[p][10]; }
-  } else {
-#pragma unroll 1
-    for (int y = 0; y < 4; ++y) {
-      const int d = HWB_CI(-1, y);
-      s.nz_cache[d] = 0x80; s.im_cache[d] = -1; s.dir_cache[d] = 0;
-#pragma unroll 1
-      for (int l = 0; l < nl; ++l) { s.ref_cache[l][d] = REF_UNAVAIL; set4(s.mv_cache[l][d], 0); *(uint16_t *)s.mvd_cache[l][d] = 0; }
-    }
-#pragma unroll 1
-    for (int p = 0; p < 2; ++p) { s.cnz_cache[p][4] = 0x80; s.cnz_cache[p][8] = 0x80; }
   }
-  const int top = HWB_CI(0, -1);
-  if (s.availB) {
-    const NbCtx &T = s.line[s.mbx];
-    cpy4(s.nz_cache + top, T.nnz_b);
-    cpy4(s.im_cache + top, T.imode_b);
-    const uint32_t dm = T.dirmask;
-    set4(s.dir_cache + top, (dm & 1) | ((dm & 2) << 7) | ((dm & 4) << 14) | ((dm & 8) << 21));
-#pragma unroll 1
-    for (int l = 0; l < nl; ++l) {
-      cpy4(s.ref_cache[l] + top, T.ref_b[l]);
-      cpy16(s.mv_cache[l][top], T.mv_b[l]);
-      cpy8(s.mvd_cache[l][top], T.mvd_b[l]);
-    }
-#pragma unroll 1
-    for (int p = 0; p < 2; ++p) { s.cnz_cache[p][1] = T.cnnz_b[p][0]; s.cnz_cache[p][2] = T.cnnz_b[p][1]; }
-  } else {
-    set4(s.nz_cache + top, 0x80808080u); set4(s.im_cache + top, 0xFFFFFFFFu); set4(s.dir_cache + top, 0);
-#pragma unroll 1
-    for (int l = 0; l < nl; ++l) {
-      set4(s.ref_cache[l] + top, 0xFEFEFEFEu);
-#pragma unroll 1
-      for (int x = 0; x < 4; ++x) set4(s.mv_cache[l][top + x], 0);
-#pragma unroll 1
-      for (int x = 0; x < 4; ++x) *(uint16_t *)s.mvd_cache[l][top + x] = 0;
-    }
-#pragma unroll 1
-    for (int p = 0; p < 2; ++p) { s.cnz_cache[p][1] = 0x80; s.cnz_cache[p][2] = 0x80; }
-  }
-#pragma unroll 1
-  for (int l = 0; l < nl; ++l) {
-    const int tr = HWB_CI(4, -1), tl = HWB_CI(-1, -1);
-    if (s.availC) { const NbCtx &R = s.line[s.mbx + 1]; s.ref_cache[l][tr] = R.ref_b[l][0]; cpy4(s.mv_cache[l][tr], R.mv_b[l][0]); }
-    else { s.ref_cache[l][tr] = REF_UNAVAIL; set4(s.mv_cache[l][tr], 0); }
-    if (s.availD) { s.ref_cache[l][tl] = s.tl_ref[l]; cpy4(s.mv_cache[l][tl], s.tl_mv[l]); }
-    else { s.ref_cache[l][tl] = REF_UNAVAIL; set4(s.mv_cache[l][tl], 0); }
-  }
-  // interior: nothing coded yet, nothing direct, references "not decoded yet"
-#pragma unroll 1
-  for (int y = 0; y < 4; ++y) {
-    const int r = HWB_CI(0, y);
+  HWB_LANES_END
+  // ---- phase 2: interior (nothing coded yet, nothing direct, references "not decoded yet") and what derives from s.top
+  HWB_LANES(l)
+  if (l < 4) {
+    const int r = HWB_CI(0, l);
     set4(s.nz_cache + r, 0); set4(s.dir_cache + r, 0);
-#pragma unroll 1
-    for (int l = 0; l < nl; ++l) set4(s.ref_cache[l] + r, 0xFEFEFEFEu);
+    for (int k = 0; k < nl; ++k) set4(s.ref_cache[k] + r, 0xFEFEFEFEu);
+  } else if (l < 8) {
+    const int pl = (l - 4) >> 1, r = (l - 4) & 1;
+    s.cnz_cache[pl][5 + 4 * r] = 0; s.cnz_cache[pl][6 + 4 * r] = 0;
+    // top chroma nnz of plane pl, column r: byte (2 * pl + r) of s.top word 2
+    s.cnz_cache[pl][1 + r] = (uint8_t)(s.top_words[2] >> (8 * (2 * pl + r)));
+  } else if (l == 8) {
+    const uint32_t dm = s.top_words[0] >> 24;  // dirmask
+    set4(s.dir_cache + top, (dm & 1) | ((dm & 2) << 7) | ((dm & 4) << 14) | ((dm & 8) << 21));
   }
-#pragma unroll 1
-  for (int p = 0; p < 2; ++p) { s.cnz_cache[p][5] = s.cnz_cache[p][6] = s.cnz_cache[p][9] = s.cnz_cache[p][10] = 0; }
+  HWB_LANES_END
 }
 
 // ================================================================================ MV prediction
@@ -233,15 +243,24 @@ HWB_FN void pred_mv(const SliceDec &s, int l, int bx, int by, int w, int ref, in
   }
 }
 HWB_FN void set_motion(SliceDec &s, int l, int bx, int by, int w, int h, int ref, int mx, int my, int amvdx, int amvdy) {
-#pragma unroll 1
-  for (int y = by; y < by + h; ++y)
-#pragma unroll 1
-    for (int x = bx; x < bx + w; ++x) {
-      int ci = HWB_CI(x, y);
-      s.ref_cache[l][ci] = (int8_t)ref;
-      s.mv_cache[l][ci][0] = (int16_t)mx; s.mv_cache[l][ci][1] = (int16_t)my;
-      s.mvd_cache[l][ci][0] = (uint8_t)amvdx; s.mvd_cache[l][ci][1] = (uint8_t)amvdy;
-    }
+  const uint32_t mv = (uint32_t)(uint16_t)mx | ((uint32_t)(uint16_t)my << 16);
+  const uint16_t mvd = (uint16_t)((amvdx & 0xff) | ((amvdy & 0xff) << 8));
+  HWB_LANES(i)
+  const int x = i & 3, y = (i >> 2) & 3;
+  if (i < 16 && x >= bx && x < bx + w && y >= by && y < by + h) {
+    const int ci = HWB_CI(x, y);
+    s.ref_cache[l][ci] = (int8_t)ref;
+    set4(s.mv_cache[l][ci], mv);
+    *(uint16_t *)s.mvd_cache[l][ci] = mvd;
+  }
+  HWB_LANES_END
+}
+// references only (made visible for the ref_idx contexts before the motion vectors are known)
+HWB_FN void set_refs(SliceDec &s, int l, int bx, int by, int w, int h, int ref) {
+  HWB_LANES(i)
+  const int x = i & 3, y = (i >> 2) & 3;
+  if (i < 16 && x >= bx && x < bx + w && y >= by && y < by + h) s.ref_cache[l][HWB_CI(x, y)] = (int8_t)ref;
+  HWB_LANES_END
 }
 
 // ================================================================================ B direct prediction
@@ -254,8 +273,11 @@ HWB_HD void wait_col_mb(const SliceDec &s, int colpic, int mbaddr) {
   int k = cp.first_slice;
   for (int i = 1; i < cp.num_slices; ++i) if (s.c->slices[cp.first_slice + i].first_mb <= mbaddr) k = cp.first_slice + i;
   volatile int32_t *p = s.c->entropy_prog + k;
-  while (*p <= mbaddr) { __nanosleep(200); }
-  __threadfence();
+  if ((threadIdx.x & 31) == 0) {
+    while (*p <= mbaddr) { __nanosleep(200); }
+    __threadfence();
+  }
+  __syncwarp();
 #else
   (void)s; (void)colpic; (void)mbaddr;
 #endif
@@ -335,11 +357,15 @@ HWB_FN void direct_predict(SliceDec &s, int qmask, int8_t dref[2][4], int16_t dm
 }
 
 HWB_FN void apply_direct(SliceDec &s, int l, int q, const int8_t dref[2][4], const int16_t dmv[2][16][2]) {
-  for (int k = 0; k < 4; ++k) {
-    int bx = (q & 1) * 2 + (k & 1), by = (q >> 1) * 2 + (k >> 1), br = by * 4 + bx;
-    set_motion(s, l, bx, by, 1, 1, dref[l][q], dmv[l][br][0], dmv[l][br][1], 0, 0);
-    s.dir_cache[HWB_CI(bx, by)] = 1;
+  HWB_LANES(k)
+  if (k < 4) {
+    const int bx = (q & 1) * 2 + (k & 1), by = (q >> 1) * 2 + (k >> 1), br = by * 4 + bx, ci = HWB_CI(bx, by);
+    s.ref_cache[l][ci] = dref[l][q];
+    s.mv_cache[l][ci][0] = dmv[l][br][0]; s.mv_cache[l][ci][1] = dmv[l][br][1];
+    *(uint16_t *)s.mvd_cache[l][ci] = 0;
+    s.dir_cache[ci] = 1;
   }
+  HWB_LANES_END
 }
 
 // ================================================================================ CAVLC residual
@@ -435,72 +461,100 @@ HWB_FN int cavlc_residual(SliceDec &s, int nC, int max_coeff, int start, const u
 }
 
 // ================================================================================ CABAC residual
-HWB_TABLE uint8_t ctx_inc_identity[16] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15};
 HWB_TABLE uint8_t ctx_inc_chroma_dc[4] = {0, 1, 2, 2};
-HWB_HD int cabac_residual_impl(SliceDec &s, Cabac &cab, BitReader &br, uint8_t *st, int cat, int max_coeff, int start, const uint8_t *scan) {
-  // cat: 0 I16 DC, 1 I16 AC, 2 luma 4x4, 3 chroma DC, 4 chroma AC, 5 luma 8x8
-  const int sig_off = cat == 0 ? 105 : cat == 1 ? 120 : cat == 2 ? 134 : cat == 3 ? 149 : cat == 4 ? 152 : 402;
-  const int last_off = cat == 0 ? 166 : cat == 1 ? 181 : cat == 2 ? 195 : cat == 3 ? 210 : cat == 4 ? 213 : 417;
-  const int abs_off = cat == 0 ? 227 : cat == 1 ? 237 : cat == 2 ? 247 : cat == 3 ? 257 : cat == 4 ? 266 : 426;
-  uint8_t *index = s.index;
-  const uint8_t *sig_tab = cat == 5 ? cabac_sig8x8_ctx : (cat == 3 ? ctx_inc_chroma_dc : ctx_inc_identity);
-  const uint8_t *last_tab = cat == 5 ? cabac_last8x8_ctx : (cat == 3 ? ctx_inc_chroma_dc : ctx_inc_identity);
-  uint8_t *sig_st = st + sig_off, *last_st = st + last_off;
-  int n = 0;
-  int i = 0;
+// 4x4 zig-zag (and the identity order of the 4 chroma DC coefficients) packed 4 bits per scan position: no table load
+#define HWB_ZZ4_PACKED 0xFEB7ADC963258410ull
+#define HWB_IDENT_PACKED 0xFEDCBA9876543210ull
+
+// Levels of the coefficients flagged in `mask` (bit k = scan position bitbase + k), highest frequency first.
+HWB_HD void cabac_levels(SliceDec &s, Cabac &cab, const uint8_t *base, uint8_t *abs_st, uint32_t mask, int bitbase, int cmax,
+                         uint64_t scan_packed, const uint8_t *scan8, int start, int &eq1, int &gt1) {
 #pragma unroll 1
-  for (; i < max_coeff - 1; ++i) {
-    if (cabac_decision(cab, br, sig_st + sig_tab[i])) {
-      index[n++] = (uint8_t)i;
-      if (cabac_decision(cab, br, last_st + last_tab[i])) break;
-    }
-  }
-  if (i == max_coeff - 1) index[n++] = (uint8_t)i;
-  int eq1 = 0, gt1 = 0;
-#pragma unroll 1
-  for (int k = n - 1; k >= 0; --k) {
-    int ctx0 = gt1 ? 0 : (eq1 < 3 ? 1 + eq1 : 4);
+  while (mask) {
+    const int k = 31 - clz32(mask);
+    mask ^= 1u << k;
+    // raster position first: the load (8x8) / shift is off the arithmetic decoder's dependency chain
+    const int pos = scan8 ? scan8[bitbase + k] : (int)((scan_packed >> (4 * (start + k))) & 15);
+    const int ctx0 = gt1 ? 0 : (eq1 < 3 ? 1 + eq1 : 4);
     int absv;
-    if (!cabac_decision(cab, br, st + abs_off + ctx0)) {
+    if (!cabac_decision(cab, base, abs_st + ctx0)) {
       absv = 1; eq1++;
     } else {
-      int cmax = cat == 3 ? 3 : 4;
-      int ctx1 = 5 + (gt1 < cmax ? gt1 : cmax);
+      uint8_t *st1 = abs_st + 5 + (gt1 < cmax ? gt1 : cmax);
       absv = 2;
 #pragma unroll 1
-      while (absv < 15 && cabac_decision(cab, br, st + abs_off + ctx1)) absv++;
+      while (absv < 15 && cabac_decision(cab, base, st1)) absv++;
       if (absv >= 15) {
         int kk = 0;
-        while (cabac_bypass(cab, br)) { absv += 1 << kk; kk++; if (kk > 20) { sd_fail(s, 30); return n; } }
-        while (kk--) absv += cabac_bypass(cab, br) << kk;
+        while (cabac_bypass(cab, base)) { absv += 1 << kk; kk++; if (kk > 20) { sd_fail(s, 30); return; } }
+        while (kk--) absv += cabac_bypass(cab, base) << kk;
       }
       gt1++;
     }
-    int sign = cabac_bypass(cab, br);
-    s.coef[scan[start + index[k]]] = (int16_t)(sign ? -absv : absv);
+    const int sign = cabac_bypass(cab, base);
+    s.coef[pos] = (int16_t)(sign ? -absv : absv);
   }
-  return n;
 }
-HWB_FN int cabac_residual(SliceDec &s, int cat, int max_coeff, int start, const uint8_t *scan) {
+
+// cat: 0 I16 DC, 1 I16 AC, 2 luma 4x4, 3 chroma DC, 4 chroma AC, 5 luma 8x8.  The significance map is kept in
+// registers (one bit per scan position).  Returns the number of non-zero coefficients.
+HWB_HD int cabac_residual_impl(SliceDec &s, Cabac &cab, const uint8_t *base, uint8_t *st, int cat, int max_coeff, int start) {
+  const int sig_off = cat == 0 ? 105 : cat == 1 ? 120 : cat == 2 ? 134 : cat == 3 ? 149 : cat == 4 ? 152 : 402;
+  const int last_off = cat == 0 ? 166 : cat == 1 ? 181 : cat == 2 ? 195 : cat == 3 ? 210 : cat == 4 ? 213 : 417;
+  const int abs_off = cat == 0 ? 227 : cat == 1 ? 237 : cat == 2 ? 247 : cat == 3 ? 257 : cat == 4 ? 266 : 426;
+  uint8_t *sig_st = st + sig_off, *last_st = st + last_off;
+  uint32_t m0 = 0, m1 = 0;
+  const int lastc = max_coeff - 1;
+  int i = 0;
+  if (cat == 5 || cat == 3) {
+    const uint8_t *sig_tab = cat == 5 ? cabac_sig8x8_ctx : ctx_inc_chroma_dc;
+    const uint8_t *last_tab = cat == 5 ? cabac_last8x8_ctx : ctx_inc_chroma_dc;
+#pragma unroll 1
+    for (; i < lastc; ++i) {
+      if (cabac_decision(cab, base, sig_st + sig_tab[i])) {
+        if (i < 32) m0 |= 1u << i; else m1 |= 1u << (i - 32);
+        if (cabac_decision(cab, base, last_st + last_tab[i])) break;
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (; i < lastc; ++i) {
+      if (cabac_decision(cab, base, sig_st + i)) {
+        m0 |= 1u << i;
+        if (cabac_decision(cab, base, last_st + i)) break;
+      }
+    }
+  }
+  if (i == lastc) { if (i < 32) m0 |= 1u << i; else m1 |= 1u << (i - 32); }
+  int eq1 = 0, gt1 = 0;
+  const int cmax = cat == 3 ? 3 : 4;
+  if (cat == 5) {
+    cabac_levels(s, cab, base, st + abs_off, m1, 32, cmax, 0, zigzag8x8, 0, eq1, gt1);
+    cabac_levels(s, cab, base, st + abs_off, m0, 0, cmax, 0, zigzag8x8, 0, eq1, gt1);
+  } else {
+    cabac_levels(s, cab, base, st + abs_off, m0, 0, cmax, cat == 3 ? HWB_IDENT_PACKED : HWB_ZZ4_PACKED, nullptr, start, eq1, gt1);
+  }
+  return popc32(m0) + popc32(m1);
+}
+HWB_FN int cabac_residual(SliceDec &s, int cat, int max_coeff, int start) {
   Cabac cab = s.cab;
-  BitReader br = s.br;
-  int n = cabac_residual_impl(s, cab, br, s.st, cat, max_coeff, start, scan);
-  s.cab = cab; s.br = br;
+  const int n = cabac_residual_impl(s, cab, s.br.base, s.states, cat, max_coeff, start);
+  s.cab = cab;
   return n;
 }
 
 // ================================================================================ output helpers
 HWB_HD void coef_clear(SliceDec &s, int n) {
-#if HWB_DEVICE_BUILD
-  for (int i = 0; i < n; i += 8) *(uint4 *)(s.coef + i) = make_uint4(0, 0, 0, 0);
-#else
-  for (int i = 0; i < n; ++i) s.coef[i] = 0;
-#endif
+  HWB_LANES(l)
+  if (2 * l < n) ((uint32_t *)s.coef)[l] = 0;
+  HWB_LANES_END
 }
 // Append s.coef[0..16*nslots) to the arena and mark item bits [bit, bit+nslots).
 HWB_HD void coef_emit(SliceDec &s, int bit, int nslots) {
-  int16_t *dst = pic_coefs(*s.c, s.pd->frame) + (uint64_t)s.coef_next * 16;
-  for (int i = 0; i < nslots * 2; ++i) cpy16(dst + 8 * i, s.coef + 8 * i);
+  uint32_t *dst = (uint32_t *)(pic_coefs(*s.c, s.pd->frame) + (uint64_t)s.coef_next * 16);
+  HWB_LANES(l)
+  if (l < nslots * 8) dst[l] = ((const uint32_t *)s.coef)[l];
+  HWB_LANES_END
   s.coef_next += nslots;
   s.out.nzmask |= ((1u << nslots) - 1u) << bit;
 }
@@ -518,12 +572,12 @@ HWB_FN void decode_residual(SliceDec &s, bool i16, int cbp, bool t8) {
     int coded = 1;
     if (cabac) {
       int a = s.availA ? ((s.left.flags & NBF_IPCM) ? 1 : (s.left.cbf >> NZ_LUMA_DC) & 1) : cbf_unavail;
-      int bq = s.availB ? ((s.line[s.mbx].flags & NBF_IPCM) ? 1 : (s.line[s.mbx].cbf >> NZ_LUMA_DC) & 1) : cbf_unavail;
+      int bq = s.availB ? ((top_flags(s) & NBF_IPCM) ? 1 : (s.top_words[1] >> NZ_LUMA_DC) & 1) : cbf_unavail;
       coded = cabac_bin(s, 85 + 0 + a + 2 * bq);
     }
     if (coded) {
       coef_clear(s, 16);
-      int n = cabac ? cabac_residual(s, 0, 16, 0, zigzag4x4)
+      int n = cabac ? cabac_residual(s, 0, 16, 0)
                     : cavlc_residual(s, cavlc_nc(s.nz_cache[HWB_CI(-1, 0)], s.nz_cache[HWB_CI(0, -1)]), 16, 0, zigzag4x4, nullptr, 0);
       if (n) coef_emit(s, NZ_LUMA_DC, 1);
     }
@@ -535,7 +589,7 @@ HWB_FN void decode_residual(SliceDec &s, bool i16, int cbp, bool t8) {
       int n = 0;
       coef_clear(s, 64);
       if (cabac) {
-        n = cabac_residual(s, 5, 64, 0, zigzag8x8);
+        n = cabac_residual(s, 5, 64, 0);
 #pragma unroll 1
         for (int k = 0; k < 4; ++k) {
           int bx = (q & 1) * 2 + (k & 1), by = (q >> 1) * 2 + (k >> 1);
@@ -564,7 +618,7 @@ HWB_FN void decode_residual(SliceDec &s, bool i16, int cbp, bool t8) {
         }
         if (coded) {
           coef_clear(s, 16);
-          if (cabac) n = cabac_residual(s, i16 ? 1 : 2, i16 ? 15 : 16, i16 ? 1 : 0, zigzag4x4);
+          if (cabac) n = cabac_residual(s, i16 ? 1 : 2, i16 ? 15 : 16, i16 ? 1 : 0);
           else n = cavlc_residual(s, cavlc_nc(na, nb), i16 ? 15 : 16, i16 ? 1 : 0, zigzag4x4, nullptr, 0);
           if (n) coef_emit(s, NZ_LUMA0 + z, 1);
         }
@@ -579,12 +633,12 @@ HWB_FN void decode_residual(SliceDec &s, bool i16, int cbp, bool t8) {
       int bit = p ? NZ_CR_DC : NZ_CB_DC;
       if (cabac) {
         int a = s.availA ? ((s.left.flags & NBF_IPCM) ? 1 : (s.left.cbf >> bit) & 1) : cbf_unavail;
-        int bq = s.availB ? ((s.line[s.mbx].flags & NBF_IPCM) ? 1 : (s.line[s.mbx].cbf >> bit) & 1) : cbf_unavail;
+        int bq = s.availB ? ((top_flags(s) & NBF_IPCM) ? 1 : (s.top_words[1] >> bit) & 1) : cbf_unavail;
         coded = cabac_bin(s, 85 + 12 + a + 2 * bq);
       }
       if (coded) {
         coef_clear(s, 16);
-        int n = cabac ? cabac_residual(s, 3, 4, 0, scan_ident4) : cavlc_residual(s, -1, 4, 0, scan_ident4, nullptr, 0);
+        int n = cabac ? cabac_residual(s, 3, 4, 0) : cavlc_residual(s, -1, 4, 0, scan_ident4, nullptr, 0);
         if (n) coef_emit(s, bit, 1);
       }
     }
@@ -603,7 +657,7 @@ HWB_FN void decode_residual(SliceDec &s, bool i16, int cbp, bool t8) {
         }
         if (coded) {
           coef_clear(s, 16);
-          n = cabac ? cabac_residual(s, 4, 15, 1, zigzag4x4) : cavlc_residual(s, cavlc_nc(na, nb), 15, 1, zigzag4x4, nullptr, 0);
+          n = cabac ? cabac_residual(s, 4, 15, 1) : cavlc_residual(s, cavlc_nc(na, nb), 15, 1, zigzag4x4, nullptr, 0);
           if (n) coef_emit(s, (p ? NZ_CR0 : NZ_CB0) + k, 1);
         }
         s.cnz_cache[p][(by + 1) * 4 + bx + 1] = (uint8_t)n;
@@ -613,55 +667,55 @@ HWB_FN void decode_residual(SliceDec &s, bool i16, int cbp, bool t8) {
 
 // ================================================================================ CABAC syntax elements
 HWB_FN int cabac_intra_mb_type(SliceDec &s, int base, bool islice) {
-  uint8_t *st = s.st + base;
+  int st = base;
   if (islice) {
     int ctx = 0;
     if (s.availA && !(s.left.flags & NBF_INXN)) ctx++;
-    if (s.availB && !(s.line[s.mbx].flags & NBF_INXN)) ctx++;
-    if (!cabac_bin_p(s, st + ctx)) return 0;
+    if (s.availB && !(top_flags(s) & NBF_INXN)) ctx++;
+    if (!cabac_bin(s, st + ctx)) return 0;
     st += 2;
   } else {
-    if (!cabac_bin_p(s, st)) return 0;
+    if (!cabac_bin(s, st)) return 0;
   }
   if (cabac_term(s)) return 25;
   int t = 1;
-  t += 12 * cabac_bin_p(s, st + 1);
-  if (cabac_bin_p(s, st + 2)) t += 4 + 4 * cabac_bin_p(s, st + 2 + (islice ? 1 : 0));
-  t += 2 * cabac_bin_p(s, st + 3 + (islice ? 1 : 0));
-  t += cabac_bin_p(s, st + 3 + (islice ? 2 : 0));
+  t += 12 * cabac_bin(s, st + 1);
+  if (cabac_bin(s, st + 2)) t += 4 + 4 * cabac_bin(s, st + 2 + (islice ? 1 : 0));
+  t += 2 * cabac_bin(s, st + 3 + (islice ? 1 : 0));
+  t += cabac_bin(s, st + 3 + (islice ? 2 : 0));
   return t;
 }
 
 HWB_FN int cabac_b_mb_type(SliceDec &s) {
   int ctx = 0;
   if (s.availA && !(s.left.flags & NBF_DIRECT16)) ctx++;
-  if (s.availB && !(s.line[s.mbx].flags & NBF_DIRECT16)) ctx++;
-  uint8_t *st = s.st + 27;
-  if (!cabac_bin_p(s, st + ctx)) return 0;
-  if (!cabac_bin_p(s, st + 3)) return 1 + cabac_bin_p(s, st + 5);
-  int bits = cabac_bin_p(s, st + 4) << 3;
-  bits |= cabac_bin_p(s, st + 5) << 2;
-  bits |= cabac_bin_p(s, st + 5) << 1;
-  bits |= cabac_bin_p(s, st + 5);
+  if (s.availB && !(top_flags(s) & NBF_DIRECT16)) ctx++;
+  const int st = 27;
+  if (!cabac_bin(s, st + ctx)) return 0;
+  if (!cabac_bin(s, st + 3)) return 1 + cabac_bin(s, st + 5);
+  int bits = cabac_bin(s, st + 4) << 3;
+  bits |= cabac_bin(s, st + 5) << 2;
+  bits |= cabac_bin(s, st + 5) << 1;
+  bits |= cabac_bin(s, st + 5);
   if (bits < 8) return bits + 3;
   if (bits == 13) return 23 + cabac_intra_mb_type(s, 32, false);
   if (bits == 14) return 11;
   if (bits == 15) return 22;
-  bits = (bits << 1) | cabac_bin_p(s, st + 5);
+  bits = (bits << 1) | cabac_bin(s, st + 5);
   return bits - 4;
 }
 
 HWB_FN int cabac_b_sub_type(SliceDec &s) {
-  uint8_t *st = s.st + 36;
-  if (!cabac_bin_p(s, st)) return 0;
-  if (!cabac_bin_p(s, st + 1)) return 1 + cabac_bin_p(s, st + 3);
+  const int st = 36;
+  if (!cabac_bin(s, st)) return 0;
+  if (!cabac_bin(s, st + 1)) return 1 + cabac_bin(s, st + 3);
   int t = 3;
-  if (cabac_bin_p(s, st + 2)) {
-    if (cabac_bin_p(s, st + 3)) return 11 + cabac_bin_p(s, st + 3);
+  if (cabac_bin(s, st + 2)) {
+    if (cabac_bin(s, st + 3)) return 11 + cabac_bin(s, st + 3);
     t += 4;
   }
-  t += 2 * cabac_bin_p(s, st + 3);
-  t += cabac_bin_p(s, st + 3);
+  t += 2 * cabac_bin(s, st + 3);
+  t += cabac_bin(s, st + 3);
   return t;
 }
 
@@ -697,10 +751,9 @@ HWB_FN int cabac_mvd(SliceDec &s, int base, int amvd, int &absout) {
 
 HWB_FN int cabac_cbp(SliceDec &s) {
   const LeftCtx &L = s.left;
-  const NbCtx &T = s.line[s.mbx];
   // luma: cbp bits of neighbours; unavailable / I_PCM behave as "all coded"
   int cbpa = s.availA ? ((L.flags & NBF_IPCM) ? 0x2F : L.cbp) : 0x0F;
-  int cbpb = s.availB ? ((T.flags & NBF_IPCM) ? 0x2F : T.cbp) : 0x0F;
+  int cbpb = s.availB ? ((top_flags(s) & NBF_IPCM) ? 0x2F : (int)((s.top_words[0] >> 8) & 0xff)) : 0x0F;
   int cbp = 0;
 #pragma unroll 1
   for (int b8 = 0; b8 < 4; ++b8) {
@@ -730,7 +783,7 @@ HWB_FN int cabac_dqp(SliceDec &s) {
 HWB_FN int cabac_chroma_mode(SliceDec &s) {
   int ctx = 0;
   if (s.availA && s.left.cmode != 0) ctx++;
-  if (s.availB && s.line[s.mbx].cmode != 0) ctx++;
+  if (s.availB && ((s.top_words[0] >> 16) & 0xff) != 0) ctx++;
   if (!cabac_bin(s, 64 + ctx)) return 0;
   if (!cabac_bin(s, 64 + 3)) return 1;
   return 2 + cabac_bin(s, 64 + 3);
@@ -748,72 +801,63 @@ HWB_FN void finish_mb(SliceDec &s, bool skipped, bool direct16, bool is_pcm) {
   const int f = s.pd->frame;
   const bool inter = o.mbtype == MB_INTER;
   const bool inxn = o.mbtype == MB_I4x4 || o.mbtype == MB_I8x8;
-  // ---- normalise the interior so that the right column / bottom row say what neighbours must see
-  if (!inter) {
-#pragma unroll 1
-    for (int l = 0; l < nl; ++l)
-#pragma unroll 1
-      for (int y = 0; y < 4; ++y) {
-        const int r = HWB_CI(0, y);
-        set4(s.ref_cache[l] + r, 0xFFFFFFFFu);
-#pragma unroll 1
-        for (int x = 0; x < 4; ++x) { set4(s.mv_cache[l][r + x], 0); *(uint16_t *)s.mvd_cache[l][r + x] = 0; }
-      }
-  }
-  if (!inxn) {
-    const uint32_t v = (inter && s.pd->constrained_intra_pred) ? 0xFFFFFFFFu : 0x02020202u;
-#pragma unroll 1
-    for (int y = 0; y < 4; ++y) set4(s.im_cache + HWB_CI(0, y), v);
-  }
-  // ---- outputs
-  {
-    MbInfo *dst = pic_mbinfo(c, f) + s.mbaddr;
-    cpy16(dst, &o); cpy16((uint8_t *)dst + 16, (const uint8_t *)&o + 16);
-  }
-  if (inter) {
-#pragma unroll 1
-    for (int l = 0; l < nl; ++l) {
-      int16_t *mvo = pic_mv(c, f, l) + (uint64_t)s.mbaddr * 32;
-#pragma unroll 1
-      for (int y = 0; y < 4; ++y) cpy16(mvo + 8 * y, s.mv_cache[l][HWB_CI(0, y)]);
-      int8_t *ro = pic_refidx(c, f, l) + (uint64_t)s.mbaddr * 4;
-      int16_t *po = pic_refpic(c, f, l) + (uint64_t)s.mbaddr * 4;
-#pragma unroll 1
-      for (int q = 0; q < 4; ++q) {
-        int r = s.ref_cache[l][HWB_CI((q & 1) * 2, (q >> 1) * 2)];
-        ro[q] = (int8_t)r;
-        po[q] = r >= 0 ? sd.ref_frame[l][r] : (int16_t)-1;
-      }
-    }
-    if (!B && s.pd->has_inter == 2) {
-      set4(pic_refidx(c, f, 1) + (uint64_t)s.mbaddr * 4, 0xFFFFFFFFu);
-      int16_t *po = pic_refpic(c, f, 1) + (uint64_t)s.mbaddr * 4;
-#pragma unroll 1
-      for (int q = 0; q < 4; ++q) po[q] = -1;
-    }
-  }
-  // ---- neighbour context: bottom edge to the line buffer (after saving what the next macroblock's top-left needs)
-  NbCtx &n = s.line[s.mbx];
-#pragma unroll 1
-  for (int l = 0; l < nl; ++l) { s.tl_ref[l] = n.ref_b[l][3]; cpy4(s.tl_mv[l], n.mv_b[l][3]); }
+  const bool l1_none = inter && !B && s.pd->has_inter == 2;  // P macroblock of a picture that also has B slices
+  const uint32_t imv = (inter && s.pd->constrained_intra_pred) ? 0xFFFFFFFFu : 0x02020202u;
   const uint8_t flags = (uint8_t)((inter ? 0 : NBF_INTRA) | (is_pcm ? NBF_IPCM : 0) | (skipped ? NBF_SKIP : 0) | (direct16 ? NBF_DIRECT16 : 0) |
                                   ((o.flags & MBF_T8x8) ? NBF_T8 : 0) | (o.mbtype == MB_I16x16 ? NBF_I16 : 0) | (inxn ? NBF_INXN : 0));
-  const int bot = HWB_CI(0, 3);
-  uint32_t dm = 0;
-#pragma unroll 1
-  for (int x = 0; x < 4; ++x) if (s.dir_cache[bot + x]) dm |= 1u << x;
   const uint32_t cbf = is_pcm ? 0x7FFFFFFu : o.nzmask;
-  n.flags = flags; n.cbp = o.cbp; n.cmode = o.cmode; n.dirmask = (uint8_t)dm; n.cbf = cbf;
-#pragma unroll 1
-  for (int p = 0; p < 2; ++p) { n.cnnz_b[p][0] = s.cnz_cache[p][9]; n.cnnz_b[p][1] = s.cnz_cache[p][10]; }
-  cpy4(n.nnz_b, s.nz_cache + bot);
-  cpy4(n.imode_b, s.im_cache + bot);
-#pragma unroll 1
-  for (int l = 0; l < nl; ++l) {
-    cpy4(n.ref_b[l], s.ref_cache[l] + bot);
-    cpy16(n.mv_b[l], s.mv_cache[l][bot]);
-    cpy8(n.mvd_b[l], s.mvd_cache[l][bot]);
+  const int bot = HWB_CI(0, 3);
+  NbCtx *n = s.line + s.mbx;
+  MbInfo *dst = pic_mbinfo(c, f) + s.mbaddr;
+  // ---- phase 1: normalise the interior so that the right column / bottom row say what neighbours must see; save
+  // what the next macroblock's top-left needs from the line entry that is about to be overwritten; MbInfo out
+  HWB_LANES(l)
+  if (l < 16) {
+    const int ci = HWB_CI(l & 3, l >> 2);
+    if (!inter)
+      for (int k = 0; k < nl; ++k) { s.ref_cache[k][ci] = REF_NONE; set4(s.mv_cache[k][ci], 0); *(uint16_t *)s.mvd_cache[k][ci] = 0; }
+    if (!inxn) s.im_cache[ci] = (int8_t)imv;
+  } else if (l < 24) {
+    ((uint32_t *)dst)[l - 16] = ((const uint32_t *)&o)[l - 16];
+  } else if (l < 26) {
+    const int k = l - 24;
+    if (k < nl) { s.tl_ref[k] = n->ref_b[k][3]; cpy4(s.tl_mv[k], n->mv_b[k][3]); }
   }
+  HWB_LANES_END
+  // ---- phase 2: motion out (lane = 4x4 block, lanes 0..15 list 0, 16..31 list 1), line entry (lane = word), left context
+  uint32_t dm = 0;
+  for (int x = 0; x < 4; ++x) if (s.dir_cache[bot + x]) dm |= 1u << x;
+  const uint32_t w0 = flags | ((uint32_t)o.cbp << 8) | ((uint32_t)o.cmode << 16) | (dm << 24);
+  const uint32_t w2 = s.cnz_cache[0][9] | ((uint32_t)s.cnz_cache[0][10] << 8) | ((uint32_t)s.cnz_cache[1][9] << 16) | ((uint32_t)s.cnz_cache[1][10] << 24);
+  HWB_LANES(l)
+  if (inter) {
+    const int k = l >> 4, i = l & 15;
+    if (k < nl) {
+      ((uint32_t *)(pic_mv(c, f, k) + (uint64_t)s.mbaddr * 32))[i] = *(const uint32_t *)s.mv_cache[k][HWB_CI(i & 3, i >> 2)];
+      if (i < 4) {
+        const int r = s.ref_cache[k][HWB_CI((i & 1) * 2, (i >> 1) * 2)];
+        pic_refidx(c, f, k)[(uint64_t)s.mbaddr * 4 + i] = (int8_t)r;
+        pic_refpic(c, f, k)[(uint64_t)s.mbaddr * 4 + i] = r >= 0 ? sd.ref_frame[k][r] : (int16_t)-1;
+      }
+    } else if (l1_none && i < 4) {
+      pic_refidx(c, f, 1)[(uint64_t)s.mbaddr * 4 + i] = -1;
+      pic_refpic(c, f, 1)[(uint64_t)s.mbaddr * 4 + i] = -1;
+    }
+  }
+  if (l < 20) {
+    uint32_t v;
+    if (l == 0) v = w0;
+    else if (l == 1) v = cbf;
+    else if (l == 2) v = w2;
+    else if (l == 3) v = 0;
+    else if (l == 4) v = *(const uint32_t *)(s.nz_cache + bot);
+    else if (l == 5) v = *(const uint32_t *)(s.im_cache + bot);
+    else if (l < 8) v = *(const uint32_t *)(s.ref_cache[l - 6] + bot);
+    else if (l < 16) v = *(const uint32_t *)s.mv_cache[(l - 8) >> 2][bot + (l & 3)];
+    else v = *(const uint32_t *)s.mvd_cache[(l - 16) >> 1][bot + 2 * (l & 1)];
+    ((uint32_t *)n)[l] = v;
+  }
+  HWB_LANES_END
   s.left.flags = flags; s.left.cbp = o.cbp; s.left.cmode = o.cmode; s.left.cbf = cbf;
 }
 
@@ -844,19 +888,17 @@ HWB_FN void read_mvd_and_set(SliceDec &s, int l, int bx, int by, int w, int h, i
   set_motion(s, l, bx, by, w, h, ref, px + dx, py + dy, ax, ay);
 }
 
-// Decode one macroblock; s.mbx/mby/mbaddr and availability set by caller.  `skipped`: P_Skip/B_Skip.
+// Decode one macroblock; s.mbx/mby/mbaddr and availability set by the caller, which has also called fill_caches.  `skipped`: P_Skip/B_Skip.
 HWB_FN void decode_mb(SliceDec &s, bool skipped) {
   const ChunkCtx &c = *s.c;
   const SliceDesc &sd = *s.sd;
   const int st = sd.slice_type;
   const bool B = st == SLICE_B;
   const int nl = B ? 2 : 1;
-  fill_caches(s, false);
   MbInfo &o = s.out;
   o.mbtype = MB_INTER; o.qp = (uint8_t)s.qp; o.cbp = 0; o.flags = 0; o.imode = 0; o.cmode = 0;
   o.slice = (uint16_t)s.slice_num; o.nzmask = 0; o.coef_off = s.coef_next;
-#pragma unroll 1
-  for (int i = 0; i < 16; ++i) o.i4modes[i] = 2;
+  for (int i = 0; i < 4; ++i) set4(o.i4modes + 4 * i, 0x02020202u);
   bool direct16 = false;
   uint32_t dirq = 0;  // quadrants predicted in direct mode
   int8_t (*dref)[4] = s.dref;
@@ -900,15 +942,21 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
       // ---------------- I_PCM
       is_pcm = true;
       o.mbtype = MB_IPCM; o.qp = 0; o.cbp = 0x2F;
-      br_align(s.br);
       uint8_t *dst = (uint8_t *)(pic_coefs(c, s.pd->frame) + (uint64_t)s.coef_next * 16);
+      if (HWB_IS_CABAC(s)) {
+        // pcm_alignment_zero_bits, 384 raw bytes, then the arithmetic decoder restarts (9.3.1.2)
+        const uint32_t p = (cabac_bitpos(s.cab) + 7) >> 3;
+        HWB_LANES(l)
+        for (int i = l; i < 384; i += 32) dst[i] = s.br.base[p + i];
+        HWB_LANES_END
+        cabac_start(s.cab, s.br.base, p + 384);
+      } else {
+        br_align(s.br);
 #pragma unroll 1
-      for (int i = 0; i < 384; ++i) dst[i] = (uint8_t)s_get(s, 8);
+        for (int i = 0; i < 384; ++i) dst[i] = (uint8_t)s_get(s, 8);
+      }
       s.coef_next += 12; o.nzmask = 0xFFF;
-      if (HWB_IS_CABAC(s)) cabac_start(s.cab, s.br);
-#pragma unroll 1
       for (int y = 0; y < 4; ++y) set4(s.nz_cache + HWB_CI(0, y), 0x10101010u);
-#pragma unroll 1
       for (int p = 0; p < 2; ++p) { s.cnz_cache[p][5] = s.cnz_cache[p][6] = s.cnz_cache[p][9] = s.cnz_cache[p][10] = 16; }
       s.last_dqp = 0;
     } else if (imbt >= 0) {
@@ -918,7 +966,7 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
       if (imbt == 0) {
         if (s.pd->transform8x8_mode) {
           if (HWB_IS_CABAC(s)) {
-            int ctx = (s.availA && (s.left.flags & NBF_T8)) + (s.availB && (s.line[s.mbx].flags & NBF_T8));
+            int ctx = (s.availA && (s.left.flags & NBF_T8)) + (s.availB && (top_flags(s) & NBF_T8));
             t8 = cabac_bin(s, 399 + ctx) != 0;
           } else t8 = s_get(s, 1) != 0;
         }
@@ -1019,19 +1067,12 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
               if (refs[l][q] >= sd.num_ref[l]) { sd_fail(s, 54); return; }
             }
             // make the reference visible for later ref_idx contexts of this list
-            int bx = (q & 1) * 2, by = (q >> 1) * 2;
-#pragma unroll 1
-            for (int y = by; y < by + 2; ++y) for (int x = bx; x < bx + 2; ++x) s.ref_cache[l][HWB_CI(x, y)] = (int8_t)(refs[l][q] >= 0 ? refs[l][q] : REF_NONE);
+            set_refs(s, l, (q & 1) * 2, (q >> 1) * 2, 2, 2, refs[l][q] >= 0 ? refs[l][q] : REF_NONE);
           }
         // references of not-yet-decoded quadrants must look unavailable for C-neighbour lookups
 #pragma unroll 1
         for (int l = 0; l < nl; ++l) {
-#pragma unroll 1
-          for (int q = 0; q < 4; ++q) {
-            int bx = (q & 1) * 2, by = (q >> 1) * 2;
-#pragma unroll 1
-            for (int y = by; y < by + 2; ++y) for (int x = bx; x < bx + 2; ++x) s.ref_cache[l][HWB_CI(x, y)] = REF_UNAVAIL;
-          }
+          set_refs(s, l, 0, 0, 4, 4, REF_UNAVAIL);
 #pragma unroll 1
           for (int q = 0; q < 4; ++q) {
             int bx = (q & 1) * 2, by = (q >> 1) * 2;
@@ -1072,13 +1113,11 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
               refs[l][p] = (int8_t)read_ref(s, l, bx, by);
               if (refs[l][p] >= sd.num_ref[l]) { sd_fail(s, 55); return; }
             }
-#pragma unroll 1
-            for (int y = by; y < by + h; ++y) for (int x = bx; x < bx + w; ++x) s.ref_cache[l][HWB_CI(x, y)] = (int8_t)(refs[l][p] >= 0 ? refs[l][p] : REF_NONE);
+            set_refs(s, l, bx, by, w, h, refs[l][p] >= 0 ? refs[l][p] : REF_NONE);
           }
 #pragma unroll 1
         for (int l = 0; l < nl; ++l) {
-#pragma unroll 1
-          for (int i = 0; i < 16; ++i) s.ref_cache[l][HWB_CI(i & 3, i >> 2)] = REF_UNAVAIL;
+          set_refs(s, l, 0, 0, 4, 4, REF_UNAVAIL);
 #pragma unroll 1
           for (int p = 0; p < np; ++p) {
             int bx = (shape == 2 && p) ? 2 : 0, by = (shape == 1 && p) ? 2 : 0;
@@ -1096,7 +1135,7 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
       bool t8 = false;
       if ((cbp & 15) && s.pd->transform8x8_mode && t8_allowed) {
         if (HWB_IS_CABAC(s)) {
-          int ctx = (s.availA && (s.left.flags & NBF_T8)) + (s.availB && (s.line[s.mbx].flags & NBF_T8));
+          int ctx = (s.availA && (s.left.flags & NBF_T8)) + (s.availB && (top_flags(s) & NBF_T8));
           t8 = cabac_bin(s, 399 + ctx) != 0;
         } else t8 = s_get(s, 1) != 0;
       }
@@ -1120,7 +1159,8 @@ HWB_FN void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states
   s.c = &c; s.sd = &c.slices[slice_idx]; s.pd = &c.pics[s.sd->pic];
   s.slice_num = slice_idx - s.pd->first_slice;
   s.cabac = s.pd->cabac != 0;
-  s.st = cabac_states;
+  (void)cabac_states;
+  s.st = s.states;
   s.error = 0;
   const SliceDesc &sd = *s.sd;
   const uint8_t *data = c.bitstream + sd.data_off;
@@ -1140,9 +1180,8 @@ HWB_FN void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states
   // the arena region of a slice starts at its first macroblock's worst-case offset
   s.coef_next = (uint32_t)sd.first_mb * SLOTS_PER_MB;
   if (HWB_IS_CABAC(s)) {
-    br_align(s.br);
-    cabac_init_states(s.st, sd.slice_type == SLICE_I ? 0 : 1 + sd.cabac_init_idc, sd.qp);
-    cabac_start(s.cab, s.br);
+    cabac_init_states(s.states, sd.slice_type == SLICE_I ? 0 : 1 + sd.cabac_init_idc, sd.qp);
+    cabac_start(s.cab, data, (sd.bit_off + 7) >> 3);  // cabac_alignment_one_bits, then 9 bits of codIOffset
   }
   const int first = sd.first_mb;
   int addr = first;
@@ -1157,10 +1196,11 @@ HWB_FN void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states
     s.availB = addr - c.mb_w >= first;
     s.availC = s.mbx < c.mb_w - 1 && addr - c.mb_w + 1 >= first;
     s.availD = s.mbx > 0 && addr - c.mb_w - 1 >= first;
+    fill_caches(s, false);  // also brings the top neighbour's flags into the slice state (mb_skip_flag context)
     bool skipped = false;
     if (sd.slice_type != SLICE_I) {
       if (HWB_IS_CABAC(s)) {
-        int ctx = (s.availA && !(s.left.flags & NBF_SKIP)) + (s.availB && !(s.line[s.mbx].flags & NBF_SKIP));
+        int ctx = (s.availA && !(s.left.flags & NBF_SKIP)) + (s.availB && !(top_flags(s) & NBF_SKIP));
         skipped = cabac_bin(s, (sd.slice_type == SLICE_B ? 24 : 11) + ctx) != 0;
       } else {
         if (run < 0) {
@@ -1171,6 +1211,7 @@ HWB_FN void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states
       }
     }
     decode_mb(s, skipped);
+    if (HWB_IS_CABAC(s) && s.cab.pos > sd.data_size + 8) s.br.overrun = true;  // the engine legitimately reads a few bytes ahead
     if (s.error || s.br.overrun) break;
     if (HWB_IS_CABAC(s)) {
       end = cabac_term(s) != 0;
@@ -1184,8 +1225,11 @@ HWB_FN void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states
     if (++mbx == c.mb_w) { mbx = 0; ++mby; }
     if (mbx == 0 || end || addr == c.nmb) {
 #if HWB_DEVICE_BUILD
-      __threadfence();
-      *((volatile int32_t *)(c.entropy_prog + slice_idx)) = (end || addr == c.nmb) ? c.nmb : addr;
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) {
+        __threadfence();
+        *((volatile int32_t *)(c.entropy_prog + slice_idx)) = (end || addr == c.nmb) ? c.nmb : addr;
+      }
 #else
       c.entropy_prog[slice_idx] = (end || addr == c.nmb) ? c.nmb : addr;
 #endif
@@ -1193,9 +1237,12 @@ HWB_FN void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states
   }
   if (s.error || s.br.overrun) {
 #if HWB_DEVICE_BUILD
-    atomicExch(c.error_flag, s.error ? s.error : 99);
-    __threadfence();
-    *((volatile int32_t *)(c.entropy_prog + slice_idx)) = c.nmb;  // never leave consumers spinning
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+      atomicExch(c.error_flag, s.error ? s.error : 99);
+      __threadfence();
+      *((volatile int32_t *)(c.entropy_prog + slice_idx)) = c.nmb;  // never leave consumers spinning
+    }
 #else
     *c.error_flag = s.error ? s.error : 99;
     c.entropy_prog[slice_idx] = c.nmb;

@@ -96,7 +96,8 @@ assert trans_lps.tolist() == spec_lps
 assert trans_mps.tolist() == [min(p + 1, 62) for p in range(63)] + [63]
 emit('cabac_trans_lps', trans_lps, const=True)
 # fused table for the branch-free decoder: index = (pStateIdx << 1 | valMPS) * 4 + qCodIRangeIdx,
-# entry = rangeLPS | next state after an LPS << 8 | next state after an MPS << 16   (state = pStateIdx << 1 | valMPS)
+# entry = rangeLPS << 23 | next state after an LPS << 8 | next state after an MPS   (state = pStateIdx << 1 | valMPS);
+# rangeLPS sits where the decoder keeps codIRange (scaled by 2^23, see csrc/dev/bits.h)
 fused = np.zeros((128, 4), np.uint32)
 for p in range(64):
     for mps in range(2):
@@ -104,7 +105,7 @@ for p in range(64):
         nm = (min(p + 1, 62) << 1 | mps) if p < 63 else (63 << 1 | mps)
         if p == 62: nm = (62 << 1) | mps
         for q in range(4):
-            fused[(p << 1) | mps, q] = int(range_lps[p, q]) | (nl << 8) | (nm << 16)
+            fused[(p << 1) | mps, q] = (int(range_lps[p, q]) << 23) | (nl << 8) | nm
 emit('cabac_fused', fused, 'uint32_t', 8, const=True)
 
 sig8 = u8(find([0, 1, 2, 3, 4, 5, 5, 4, 4, 3, 3, 4, 4, 4, 5, 5, 4, 4, 4, 4, 3, 3, 6, 7, 7, 7, 8, 9, 10, 9, 8, 7], 0, 1), 63)
