@@ -10,14 +10,15 @@
 //        level of the chunk) per launch so the wavefronts of different pictures fill the 148 SMs.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
 #include <string>
 
 // The CABAC engine's fused transition table is read once per bin by the single active lane of every warp: a
-// shared-memory copy (2 KB per CTA, filled at kernel start) keeps that load off the global / constant path.
-__shared__ uint32_t hwb_fused_sm[512];
+// shared-memory copy (1 KB per CTA, filled at kernel start) keeps that load off the global / constant path.
+__shared__ __align__(8) uint32_t hwb_fused_sm[256];
 #define HWB_CABAC_FUSED hwb_fused_sm
 
 #include "../dev/deblock.h"
@@ -58,12 +59,13 @@ __device__ __forceinline__ int warp_ticket(int32_t *ticket) {
     __shared__ NS::SliceDec sdec[kWarpsPerBlock];                                                     \
     __shared__ ChunkCtx c;                                                                            \
     if (threadIdx.x == 0) c = cparam;                                                                 \
-    for (int i = threadIdx.x; i < 512; i += kThreads) hwb_fused_sm[i] = cabac_fused[i];               \
+    for (int i = threadIdx.x; i < 256; i += kThreads) hwb_fused_sm[i] = cabac_fused[i];               \
     __syncthreads();                                                                                  \
     const int w = threadIdx.x >> 5;                                                                   \
     for (;;) {                                                                                        \
-      const int s = warp_ticket(ticket);                                                              \
-      if (s >= c.num_slices) return;                                                                  \
+      const int t = warp_ticket(ticket);                                                              \
+      if (t >= c.num_slices) return;                                                                  \
+      const int s = c.entropy_order[t];                                                               \
       NS::decode_slice(c, s, nullptr, &sdec[w]);                                                      \
       __syncwarp();                                                                                   \
     }                                                                                                 \
@@ -251,7 +253,11 @@ static int grid_for(hwb_dev *d, int work_warps, int blocks_per_sm) {
 
 int hwb_dev_entropy(hwb_dev *d, int s, const ChunkCtx *c, int32_t *ticket, int mode) {
   cudaSetDevice(d->device);
-  const int grid = grid_for(d, c->num_slices, 8);
+  // Resident warps per SM are capped: the slice decoder is branchy code far larger than the instruction caches, and
+  // every extra warp wandering through a different part of it costs all of them fetch misses (measured: 67% of the
+  // stall cycles at 20 warps per SM).  HWB_ENTROPY_BLOCKS_PER_SM overrides the cap (4 warps per block).
+  static int bpsm = [] { const char *e = getenv("HWB_ENTROPY_BLOCKS_PER_SM"); int v = e ? atoi(e) : 0; return v > 0 ? v : 8; }();
+  const int grid = grid_for(d, c->num_slices, bpsm);
   if (mode == 1) entropy_cabac_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);
   else if (mode == 0) entropy_cavlc_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);
   else entropy_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);

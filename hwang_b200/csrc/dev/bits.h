@@ -83,8 +83,8 @@ HWB_HD bool br_more_rbsp_data(BitReader &b, uint32_t last_one_bitpos) { return b
 // Arithmetic decoding engine (9.3.3.2) on 32-bit registers only, everything scaled by 2^23: `range` holds
 // codIRange << 23 (normalised <=> bit 31 set, so the renormalisation shift is a plain count-leading-zeros), `low`
 // holds codIOffset << 23 with the next `nb` (<= 16) bits of the stream left-aligned below bit 23, and the fused
-// table's rangeLPS field is pre-shifted too: a decision is  load state, load entry, mask, subtract, compare,
-// select, clz, shift.  Every ~16 consumed bits two more bytes are patched in.  (64-bit shifts cost 2-3
+// table is indexed by the context state alone (see CtxPre): a decision is  load state, load entry, pick the rangeLPS
+// byte, subtract, compare, select, clz, shift.  Every ~16 consumed bits two more bytes are patched in.  (64-bit shifts cost 2-3
 // instructions each on the GPU: the first engine, built on the generic 64-bit bit reader, spent 46 instructions per
 // decision.)  The engine reads the slice RBSP directly: `base` is the slice's first byte (16-byte aligned on the
 // device), `pos` the byte offset of the next refill (always even).
@@ -151,22 +151,44 @@ HWB_HD void cabac_init_states(uint8_t *st, int table, int slice_qp) {
   }
 }
 
-// Binary decision (9.3.3.2.1).  Fused table entry: rangeLPS << 23 | state after an LPS << 8 | state after an MPS.
-HWB_HD int cabac_decision(Cabac &c, const uint8_t *base, uint8_t *state) {
-  const uint32_t s = *state;
-  const uint32_t e = HWB_CABAC_FUSED[s * 4 + ((c.range >> 29) & 3)];
-  const uint32_t rlps = e & 0x7F800000u;
+// A context as the decision uses it: the state byte and the two table words that depend on it alone (rangeLPS for
+// the four codIRange quantiser values, and both successor states), so both loads issue before codIRange is needed.
+// (Fetching the *next* contexts ahead of time was tried and lost: on this latency-bound single-warp code the extra
+// instructions cost more than the shared-memory round trips they hid.)
+struct CtxPre { uint32_t s, rl4, ns; };
+HWB_HD CtxPre cabac_prefetch(const uint8_t *state) {
+  CtxPre p;
+  p.s = *state;
+#if HWB_DEVICE_BUILD
+  const uint2 e = *(const uint2 *)(HWB_CABAC_FUSED + 2 * p.s);
+  p.rl4 = e.x; p.ns = e.y;
+#else
+  p.rl4 = HWB_CABAC_FUSED[2 * p.s]; p.ns = HWB_CABAC_FUSED[2 * p.s + 1];
+#endif
+  return p;
+}
+// Binary decision (9.3.3.2.1) with a prefetched context.  On the chain from codIRange to the decision: pick the
+// rangeLPS byte (quantiser bits 30:29 of the scaled range -> byte selector), subtract, compare.
+HWB_HD int cabac_decide(Cabac &c, const uint8_t *base, const CtxPre p, uint8_t *state) {
+#if HWB_DEVICE_BUILD
+  const uint32_t rlps = __byte_perm(p.rl4, 0, ((c.range >> 17) & 0x3000u) | 0x0444u) >> 1;  // byte q -> bits 30:23
+#else
+  const uint32_t rlps = ((p.rl4 >> (8 * ((c.range >> 29) & 3))) & 0xffu) << CABAC_SCALE;
+#endif
   const uint32_t rmps = c.range - rlps;
   const bool lps = c.low >= rmps;
   c.low = lps ? c.low - rmps : c.low;
   const uint32_t r = lps ? rlps : rmps;
-  *state = (uint8_t)(lps ? (e >> 8) : e);
+  *state = (uint8_t)(lps ? (p.ns >> 8) : p.ns);
   const int sh = cabac_norm_shift(r);
   c.range = r << sh;
   c.low <<= sh;
   c.nb -= sh;
   cabac_refill(c, base);
-  return (int)((s & 1) ^ (lps ? 1u : 0u));
+  return (int)((p.s & 1) ^ (lps ? 1u : 0u));
+}
+HWB_HD int cabac_decision(Cabac &c, const uint8_t *base, uint8_t *state) {
+  return cabac_decide(c, base, cabac_prefetch(state), state);
 }
 HWB_HD int cabac_bypass(Cabac &c, const uint8_t *base) {
   // compare before shifting: 2 * offset + next bit >= range  <=>  low >= range / 2 (exact: range << 22)

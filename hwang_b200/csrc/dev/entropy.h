@@ -92,6 +92,7 @@ struct SliceDec {
   uint8_t index[64];
   int8_t refs[2][4];
   int8_t sub[4], shape[4], pf[4];
+  uint16_t grp[4];  // inter macroblock: reference groups (see decode_mb)
   // CABAC context states live inside the slice state (shared memory on the GPU), so that the decoder addresses
   // them as shared-memory offsets instead of through a generic pointer
   alignas(16) uint8_t states[464];
@@ -129,9 +130,16 @@ HWB_HD void cpy16(void *d, const void *s) {
 // a block immediately (the barrier orders it), and a block may follow uniform code immediately (every lane has
 // itself written whatever uniform code wrote).  Host builds run the lanes as a loop.
 
-// Word w (0..19) of a line-buffer entry (NbCtx) <-> where it lives in the slice state while its macroblock row
-// neighbour is being decoded: the 4-byte word at this byte offset of SliceDec.
-#define HWB_SD_OFF(member) ((uint16_t)offsetof(SliceDec, member))
+// Move tables for the per-macroblock cache maintenance: lane l moves item l.  Entries are byte offsets into SliceDec,
+// destination << 16 | source.  Table-driven because the hand-written version was several KB of divergent address
+// arithmetic in a kernel that is bound by instruction fetch.
+#define HWB_O(member) ((uint32_t)offsetof(SliceDec, member))
+#define HWB_MV(dst, src) (((dst) << 16) | (src))
+#define HWB_LEFT_D(y) (((y) + 1) * 8 + 3)   /* HWB_CI(-1, y) */
+#define HWB_LEFT_F(y) (((y) + 1) * 8 + 7)   /* HWB_CI(3, y)  */
+#define HWB_ROWS4(base, elem) \
+  HWB_MV((base) + HWB_LEFT_D(0) * (elem), (base) + HWB_LEFT_F(0) * (elem)), HWB_MV((base) + HWB_LEFT_D(1) * (elem), (base) + HWB_LEFT_F(1) * (elem)), \
+  HWB_MV((base) + HWB_LEFT_D(2) * (elem), (base) + HWB_LEFT_F(2) * (elem)), HWB_MV((base) + HWB_LEFT_D(3) * (elem), (base) + HWB_LEFT_F(3) * (elem))
 // Called once per slice before the first macroblock: entries that never change.
 HWB_FN void init_caches(SliceDec &s) {
   HWB_LANES(l)
@@ -143,6 +151,32 @@ HWB_FN void init_caches(SliceDec &s) {
   HWB_LANES_END
 }
 
+// Left column, pass A: lanes 0..19 byte items (nz, intra mode, direct flag, ref list 0 / 1, rows 0..3), lanes 20..23
+// chroma nnz bytes, lanes 24..31 mvd pairs (16 bits) of list 0 / 1.
+HWB_TABLE uint32_t fill_tab_a[32] = {
+  HWB_ROWS4(HWB_O(nz_cache), 1), HWB_ROWS4(HWB_O(im_cache), 1), HWB_ROWS4(HWB_O(dir_cache), 1),
+  HWB_ROWS4(HWB_O(ref_cache[0]), 1), HWB_ROWS4(HWB_O(ref_cache[1]), 1),
+  HWB_MV(HWB_O(cnz_cache[0]) + 4, HWB_O(cnz_cache[0]) + 6), HWB_MV(HWB_O(cnz_cache[0]) + 8, HWB_O(cnz_cache[0]) + 10),
+  HWB_MV(HWB_O(cnz_cache[1]) + 4, HWB_O(cnz_cache[1]) + 6), HWB_MV(HWB_O(cnz_cache[1]) + 8, HWB_O(cnz_cache[1]) + 10),
+  HWB_ROWS4(HWB_O(mvd_cache[0]), 2), HWB_ROWS4(HWB_O(mvd_cache[1]), 2)};
+HWB_TABLE uint8_t fill_dflt_a[24] = {0x80, 0x80, 0x80, 0x80, 0xFF, 0xFF, 0xFF, 0xFF, 0, 0, 0, 0, 0xFE, 0xFE, 0xFE, 0xFE, 0xFE, 0xFE, 0xFE, 0xFE,
+                                     0x80, 0x80, 0x80, 0x80};
+// Pass B: lanes 0..19 = destination of word l of the top neighbour's line-buffer entry (words 0..3 -> s.top_words),
+// lanes 20..27 = mv words of the left column, list 0 / 1.
+#define HWB_TOPROW 4 /* HWB_CI(0, -1) */
+#define HWB_BOTROW 36 /* HWB_CI(0, 3) */
+#define HWB_LINE_WORDS(row) \
+  HWB_O(top_words[0]), HWB_O(top_words[1]), HWB_O(top_words[2]), HWB_O(top_words[3]), HWB_O(nz_cache) + (row), HWB_O(im_cache) + (row), \
+  HWB_O(ref_cache[0]) + (row), HWB_O(ref_cache[1]) + (row), \
+  HWB_O(mv_cache[0]) + 4 * (row), HWB_O(mv_cache[0]) + 4 * (row) + 4, HWB_O(mv_cache[0]) + 4 * (row) + 8, HWB_O(mv_cache[0]) + 4 * (row) + 12, \
+  HWB_O(mv_cache[1]) + 4 * (row), HWB_O(mv_cache[1]) + 4 * (row) + 4, HWB_O(mv_cache[1]) + 4 * (row) + 8, HWB_O(mv_cache[1]) + 4 * (row) + 12, \
+  HWB_O(mvd_cache[0]) + 2 * (row), HWB_O(mvd_cache[0]) + 2 * (row) + 4, HWB_O(mvd_cache[1]) + 2 * (row), HWB_O(mvd_cache[1]) + 2 * (row) + 4
+HWB_TABLE uint32_t fill_tab_b[28] = {HWB_LINE_WORDS(HWB_TOPROW), HWB_ROWS4(HWB_O(mv_cache[0]), 4), HWB_ROWS4(HWB_O(mv_cache[1]), 4)};
+// what an unavailable top neighbour looks like, word by word
+HWB_TABLE uint32_t top_dflt[20] = {0, 0, 0x80808080u, 0, 0x80808080u, 0xFFFFFFFFu, 0xFEFEFEFEu, 0xFEFEFEFEu, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+// finish_mb: source of word l of the line-buffer entry (the bottom row of the caches; words 0..3 staged in s.top_words)
+HWB_TABLE uint32_t line_tab[20] = {HWB_LINE_WORDS(HWB_BOTROW)};
+
 // Per macroblock: the left column is the previous macroblock's right column (still in the caches), the top row
 // comes from the slice's line buffer, the interior is reset.
 HWB_FN void fill_caches(SliceDec &s, bool unused) {
@@ -151,37 +185,21 @@ HWB_FN void fill_caches(SliceDec &s, bool unused) {
   const int top = HWB_CI(0, -1);
   const bool availA = s.availA, availB = s.availB, availC = s.availC, availD = s.availD;
   const NbCtx *T = s.line + s.mbx;
-  // ---- phase 1: top row (one line-buffer word per lane), left column, corners
+  uint8_t *sb = (uint8_t *)&s;
+  // ---- phase 1: left column, top row (one line-buffer word per lane), corners
   HWB_LANES(l)
+  {
+    const uint32_t e = fill_tab_a[l];
+    uint8_t *d = sb + (e >> 16);
+    const uint8_t *f = sb + (e & 0xffff);
+    if (l < 24) *d = availA ? *f : fill_dflt_a[l];
+    else *(uint16_t *)d = availA ? *(const uint16_t *)f : (uint16_t)0;
+  }
   if (l < 20) {
-    // words 0..2 (flags/cbp/cmode/dirmask, cbf, chroma nnz) go to s.top; 3 is padding; 4.. are cache rows
-    uint32_t v = 0;
-    if (availB) v = ((const uint32_t *)T)[l];
-    else if (l == 4) v = 0x80808080u;       // nnz: unavailable
-    else if (l == 5) v = 0xFFFFFFFFu;       // intra modes: unusable
-    else if (l == 6 || l == 7) v = 0xFEFEFEFEu;  // references: unavailable
-    else if (l == 2) v = 0x80808080u;
-    if (l < 4) s.top_words[l] = v;
-    else if (l == 4) set4(s.nz_cache + top, v);
-    else if (l == 5) set4(s.im_cache + top, v);
-    else if (l < 8) set4(s.ref_cache[l - 6] + top, v);
-    else if (l < 16) set4(s.mv_cache[(l - 8) >> 2][top + (l & 3)], v);
-    else set4(s.mvd_cache[(l - 16) >> 1][top + 2 * (l & 1)], v);
-  } else if (l < 24) {
-    // left column, row y: the previous macroblock's column 3 (or "unavailable")
-    const int y = l - 20, d = HWB_CI(-1, y), f = HWB_CI(3, y);
-    s.nz_cache[d] = availA ? s.nz_cache[f] : (uint8_t)0x80;
-    s.im_cache[d] = availA ? s.im_cache[f] : (int8_t)-1;
-    s.dir_cache[d] = availA ? s.dir_cache[f] : (uint8_t)0;
-    for (int k = 0; k < nl; ++k) {
-      s.ref_cache[k][d] = availA ? s.ref_cache[k][f] : (int8_t)REF_UNAVAIL;
-      set4(s.mv_cache[k][d], availA ? *(const uint32_t *)s.mv_cache[k][f] : 0u);
-      *(uint16_t *)s.mvd_cache[k][d] = availA ? *(const uint16_t *)s.mvd_cache[k][f] : (uint16_t)0;
-    }
+    *(uint32_t *)(sb + fill_tab_b[l]) = availB ? ((const uint32_t *)T)[l] : top_dflt[l];
   } else if (l < 28) {
-    // chroma nnz left column: plane p, row r
-    const int pl = (l - 24) >> 1, r = (l - 24) & 1;
-    s.cnz_cache[pl][4 + 4 * r] = availA ? s.cnz_cache[pl][6 + 4 * r] : (uint8_t)0x80;
+    const uint32_t e = fill_tab_b[l];
+    *(uint32_t *)(sb + (e >> 16)) = availA ? *(const uint32_t *)(sb + (e & 0xffff)) : 0u;
   } else {
     // corners: lanes 28,29 = top-right of list 0,1; lanes 30,31 = top-left
     const int k = l & 1;
@@ -203,7 +221,8 @@ HWB_FN void fill_caches(SliceDec &s, bool unused) {
   if (l < 4) {
     const int r = HWB_CI(0, l);
     set4(s.nz_cache + r, 0); set4(s.dir_cache + r, 0);
-    for (int k = 0; k < nl; ++k) set4(s.ref_cache[k] + r, 0xFEFEFEFEu);
+    if (nl > 0) set4(s.ref_cache[0] + r, 0xFEFEFEFEu);
+    if (nl > 1) set4(s.ref_cache[1] + r, 0xFEFEFEFEu);
   } else if (l < 8) {
     const int pl = (l - 4) >> 1, r = (l - 4) & 1;
     s.cnz_cache[pl][5 + 4 * r] = 0; s.cnz_cache[pl][6 + 4 * r] = 0;
@@ -219,28 +238,30 @@ HWB_FN void fill_caches(SliceDec &s, bool unused) {
 // ================================================================================ MV prediction
 struct MvRef { int ref; int mx, my; };
 HWB_HD MvRef mv_at(const SliceDec &s, int l, int bx, int by) {
-  int ci = HWB_CI(bx, by);
-  MvRef r; r.ref = s.ref_cache[l][ci]; r.mx = s.mv_cache[l][ci][0]; r.my = s.mv_cache[l][ci][1];
+  const int ci = HWB_CI(bx, by);
+  const uint32_t w = *(const uint32_t *)s.mv_cache[l][ci];
+  MvRef r; r.ref = s.ref_cache[l][ci]; r.mx = (int16_t)(w & 0xffff); r.my = (int16_t)(w >> 16);
   return r;
 }
 // Median / directional prediction for the partition whose top-left 4x4 block is (bx,by), width w
 // (in 4x4 units).  shape: 0 = general (median), 1 = 16x8 upper, 2 = 16x8 lower, 3 = 8x16 left, 4 = 8x16 right.
 HWB_FN void pred_mv(const SliceDec &s, int l, int bx, int by, int w, int ref, int shape, int &px, int &py) {
-  MvRef A = mv_at(s, l, bx - 1, by), Bn = mv_at(s, l, bx, by - 1), C = mv_at(s, l, bx + w, by - 1);
+  const MvRef A = mv_at(s, l, bx - 1, by), Bn = mv_at(s, l, bx, by - 1);
+  MvRef C = mv_at(s, l, bx + w, by - 1);
   if (C.ref == REF_UNAVAIL) C = mv_at(s, l, bx - 1, by - 1);
-  if (shape == 1 && Bn.ref == ref) { px = Bn.mx; py = Bn.my; return; }
-  if (shape == 2 && A.ref == ref) { px = A.mx; py = A.my; return; }
-  if (shape == 3 && A.ref == ref) { px = A.mx; py = A.my; return; }
-  if (shape == 4 && C.ref == ref) { px = C.mx; py = C.my; return; }
-  int n = (A.ref == ref) + (Bn.ref == ref) + (C.ref == ref);
-  if (n == 1) {
-    const MvRef &m = A.ref == ref ? A : (Bn.ref == ref ? Bn : C);
-    px = m.mx; py = m.my;
-  } else if (n == 0 && Bn.ref == REF_UNAVAIL && C.ref == REF_UNAVAIL && A.ref != REF_UNAVAIL) {
-    px = A.mx; py = A.my;
-  } else {
-    px = median3(A.mx, Bn.mx, C.mx); py = median3(A.my, Bn.my, C.my);
+  const bool ea = A.ref == ref, eb = Bn.ref == ref, ec = C.ref == ref;
+  // directional rules first, then "exactly one neighbour uses this reference", then the median
+  int pick = -1;  // 0 A, 1 B, 2 C
+  if (shape == 1 && eb) pick = 1;
+  else if ((shape == 2 || shape == 3) && ea) pick = 0;
+  else if (shape == 4 && ec) pick = 2;
+  else {
+    const int n = (int)ea + (int)eb + (int)ec;
+    if (n == 1) pick = ea ? 0 : (eb ? 1 : 2);
+    else if (n == 0 && Bn.ref == REF_UNAVAIL && C.ref == REF_UNAVAIL && A.ref != REF_UNAVAIL) pick = 0;
   }
+  if (pick < 0) { px = median3(A.mx, Bn.mx, C.mx); py = median3(A.my, Bn.my, C.my); }
+  else { px = pick == 0 ? A.mx : (pick == 1 ? Bn.mx : C.mx); py = pick == 0 ? A.my : (pick == 1 ? Bn.my : C.my); }
 }
 HWB_FN void set_motion(SliceDec &s, int l, int bx, int by, int w, int h, int ref, int mx, int my, int amvdx, int amvdy) {
   const uint32_t mv = (uint32_t)(uint16_t)mx | ((uint32_t)(uint16_t)my << 16);
@@ -466,83 +487,69 @@ HWB_TABLE uint8_t ctx_inc_chroma_dc[4] = {0, 1, 2, 2};
 #define HWB_ZZ4_PACKED 0xFEB7ADC963258410ull
 #define HWB_IDENT_PACKED 0xFEDCBA9876543210ull
 
-// Levels of the coefficients flagged in `mask` (bit k = scan position bitbase + k), highest frequency first.
-HWB_HD void cabac_levels(SliceDec &s, Cabac &cab, const uint8_t *base, uint8_t *abs_st, uint32_t mask, int bitbase, int cmax,
-                         uint64_t scan_packed, const uint8_t *scan8, int start, int &eq1, int &gt1) {
-#pragma unroll 1
-  while (mask) {
-    const int k = 31 - clz32(mask);
-    mask ^= 1u << k;
-    // raster position first: the load (8x8) / shift is off the arithmetic decoder's dependency chain
-    const int pos = scan8 ? scan8[bitbase + k] : (int)((scan_packed >> (4 * (start + k))) & 15);
-    const int ctx0 = gt1 ? 0 : (eq1 < 3 ? 1 + eq1 : 4);
-    int absv;
-    if (!cabac_decision(cab, base, abs_st + ctx0)) {
-      absv = 1; eq1++;
-    } else {
-      uint8_t *st1 = abs_st + 5 + (gt1 < cmax ? gt1 : cmax);
-      absv = 2;
-#pragma unroll 1
-      while (absv < 15 && cabac_decision(cab, base, st1)) absv++;
-      if (absv >= 15) {
-        int kk = 0;
-        while (cabac_bypass(cab, base)) { absv += 1 << kk; kk++; if (kk > 20) { sd_fail(s, 30); return; } }
-        while (kk--) absv += cabac_bypass(cab, base) << kk;
-      }
-      gt1++;
-    }
-    const int sign = cabac_bypass(cab, base);
-    s.coef[pos] = (int16_t)(sign ? -absv : absv);
-  }
-}
-
 // cat: 0 I16 DC, 1 I16 AC, 2 luma 4x4, 3 chroma DC, 4 chroma AC, 5 luma 8x8.  The significance map is kept in
-// registers (one bit per scan position).  Returns the number of non-zero coefficients.
+// registers (one bit per scan position).  Returns the number of non-zero coefficients.  Written for a small code
+// footprint (one loop for the map, one for the levels, shared by all categories): with many warps per SM inside
+// different parts of the slice decoder, instruction fetch misses cost more than the few extra selects.
 HWB_HD int cabac_residual_impl(SliceDec &s, Cabac &cab, const uint8_t *base, uint8_t *st, int cat, int max_coeff, int start) {
   const int sig_off = cat == 0 ? 105 : cat == 1 ? 120 : cat == 2 ? 134 : cat == 3 ? 149 : cat == 4 ? 152 : 402;
   const int last_off = cat == 0 ? 166 : cat == 1 ? 181 : cat == 2 ? 195 : cat == 3 ? 210 : cat == 4 ? 213 : 417;
   const int abs_off = cat == 0 ? 227 : cat == 1 ? 237 : cat == 2 ? 247 : cat == 3 ? 257 : cat == 4 ? 266 : 426;
-  uint8_t *sig_st = st + sig_off, *last_st = st + last_off;
-  uint32_t m0 = 0, m1 = 0;
+  uint8_t *sig_st = st + sig_off, *last_st = st + last_off, *abs_st = st + abs_off;
+  // ---- significance map: one loop for all categories (8x8 and chroma DC map scan positions to contexts by table)
+  const bool tab = cat == 5 || cat == 3;
+  const uint8_t *sig_tab = cat == 5 ? cabac_sig8x8_ctx : ctx_inc_chroma_dc;
+  const uint8_t *last_tab = cat == 5 ? cabac_last8x8_ctx : ctx_inc_chroma_dc;
+  uint32_t m[2] = {0, 0};
   const int lastc = max_coeff - 1;
   int i = 0;
-  if (cat == 5 || cat == 3) {
-    const uint8_t *sig_tab = cat == 5 ? cabac_sig8x8_ctx : ctx_inc_chroma_dc;
-    const uint8_t *last_tab = cat == 5 ? cabac_last8x8_ctx : ctx_inc_chroma_dc;
 #pragma unroll 1
-    for (; i < lastc; ++i) {
-      if (cabac_decision(cab, base, sig_st + sig_tab[i])) {
-        if (i < 32) m0 |= 1u << i; else m1 |= 1u << (i - 32);
-        if (cabac_decision(cab, base, last_st + last_tab[i])) break;
-      }
-    }
-  } else {
-#pragma unroll 1
-    for (; i < lastc; ++i) {
-      if (cabac_decision(cab, base, sig_st + i)) {
-        m0 |= 1u << i;
-        if (cabac_decision(cab, base, last_st + i)) break;
-      }
+  for (; i < lastc; ++i) {
+    int si = i, li = i;
+    if (tab) { si = sig_tab[i]; li = last_tab[i]; }
+    if (cabac_decision(cab, base, sig_st + si)) {
+      m[i >> 5] |= 1u << (i & 31);
+      if (cabac_decision(cab, base, last_st + li)) break;
     }
   }
-  if (i == lastc) { if (i < 32) m0 |= 1u << i; else m1 |= 1u << (i - 32); }
+  if (i == lastc) m[i >> 5] |= 1u << (i & 31);
+  // ---- levels, highest frequency first
   int eq1 = 0, gt1 = 0;
   const int cmax = cat == 3 ? 3 : 4;
-  if (cat == 5) {
-    cabac_levels(s, cab, base, st + abs_off, m1, 32, cmax, 0, zigzag8x8, 0, eq1, gt1);
-    cabac_levels(s, cab, base, st + abs_off, m0, 0, cmax, 0, zigzag8x8, 0, eq1, gt1);
-  } else {
-    cabac_levels(s, cab, base, st + abs_off, m0, 0, cmax, cat == 3 ? HWB_IDENT_PACKED : HWB_ZZ4_PACKED, nullptr, start, eq1, gt1);
+  const uint64_t scan_packed = cat == 3 ? HWB_IDENT_PACKED : HWB_ZZ4_PACKED;
+#pragma unroll 1
+  for (int half = cat == 5 ? 1 : 0; half >= 0; --half) {
+    uint32_t mask = m[half];
+#pragma unroll 1
+    while (mask) {
+      const int k = 31 - clz32(mask);
+      mask ^= 1u << k;
+      // raster position first: the load (8x8) / shift is off the arithmetic decoder's dependency chain
+      const int pos = cat == 5 ? zigzag8x8[32 * half + k] : (int)((scan_packed >> (4 * (start + k))) & 15);
+      const int ctx0 = gt1 ? 0 : (eq1 < 3 ? 1 + eq1 : 4);
+      int absv;
+      if (!cabac_decision(cab, base, abs_st + ctx0)) {
+        absv = 1; eq1++;
+      } else {
+        uint8_t *st1 = abs_st + 5 + (gt1 < cmax ? gt1 : cmax);
+        absv = 2;
+#pragma unroll 1
+        while (absv < 15 && cabac_decision(cab, base, st1)) absv++;
+        if (absv >= 15) {
+          int kk = 0;
+#pragma unroll 1
+          while (cabac_bypass(cab, base)) { absv += 1 << kk; kk++; if (kk > 20) { sd_fail(s, 30); return 0; } }
+#pragma unroll 1
+          while (kk--) absv += cabac_bypass(cab, base) << kk;
+        }
+        gt1++;
+      }
+      const int sign = cabac_bypass(cab, base);
+      s.coef[pos] = (int16_t)(sign ? -absv : absv);
+    }
   }
-  return popc32(m0) + popc32(m1);
+  return popc32(m[0]) + popc32(m[1]);
 }
-HWB_FN int cabac_residual(SliceDec &s, int cat, int max_coeff, int start) {
-  Cabac cab = s.cab;
-  const int n = cabac_residual_impl(s, cab, s.br.base, s.states, cat, max_coeff, start);
-  s.cab = cab;
-  return n;
-}
-
 // ================================================================================ output helpers
 HWB_HD void coef_clear(SliceDec &s, int n) {
   HWB_LANES(l)
@@ -559,6 +566,24 @@ HWB_HD void coef_emit(SliceDec &s, int bit, int nslots) {
   s.out.nzmask |= ((1u << nslots) - 1u) << bit;
 }
 
+// One residual block in CABAC mode: coded_block_flag (context increment cbf_inc; < 0: none, the block is coded),
+// levels into s.coef, slot(s) to the arena.  Returns the number of non-zero coefficients.
+HWB_FN int cabac_block(SliceDec &s, int cat, int cbf_inc, int bit) {
+  Cabac cab = s.cab;
+  const uint8_t *base = s.br.base;
+  int n = 0;
+  bool coded = true;
+  if (cbf_inc >= 0) coded = cabac_decision(cab, base, s.states + 85 + 4 * (cat == 5 ? 0 : cat) + cbf_inc) != 0;
+  if (coded) {
+    coef_clear(s, cat == 5 ? 64 : 16);
+    n = cabac_residual_impl(s, cab, base, s.states, cat, cat == 5 ? 64 : (cat == 3 ? 4 : ((cat == 1 || cat == 4) ? 15 : 16)),
+                            (cat == 1 || cat == 4) ? 1 : 0);
+    coef_emit(s, bit, cat == 5 ? 4 : 1);
+  }
+  s.cab = cab;
+  return n;
+}
+
 // identity scan for blocks whose coefficients are already in raster order
 HWB_TABLE uint8_t scan_ident4[4] = {0, 1, 2, 3};
 
@@ -569,16 +594,13 @@ HWB_FN void decode_residual(SliceDec &s, bool i16, int cbp, bool t8) {
   const bool intra = s.out.mbtype != MB_INTER;
   const int cbf_unavail = intra ? 1 : 0;
   if (i16) {
-    int coded = 1;
     if (cabac) {
       int a = s.availA ? ((s.left.flags & NBF_IPCM) ? 1 : (s.left.cbf >> NZ_LUMA_DC) & 1) : cbf_unavail;
       int bq = s.availB ? ((top_flags(s) & NBF_IPCM) ? 1 : (s.top_words[1] >> NZ_LUMA_DC) & 1) : cbf_unavail;
-      coded = cabac_bin(s, 85 + 0 + a + 2 * bq);
-    }
-    if (coded) {
+      cabac_block(s, 0, a + 2 * bq, NZ_LUMA_DC);
+    } else {
       coef_clear(s, 16);
-      int n = cabac ? cabac_residual(s, 0, 16, 0)
-                    : cavlc_residual(s, cavlc_nc(s.nz_cache[HWB_CI(-1, 0)], s.nz_cache[HWB_CI(0, -1)]), 16, 0, zigzag4x4, nullptr, 0);
+      int n = cavlc_residual(s, cavlc_nc(s.nz_cache[HWB_CI(-1, 0)], s.nz_cache[HWB_CI(0, -1)]), 16, 0, zigzag4x4, nullptr, 0);
       if (n) coef_emit(s, NZ_LUMA_DC, 1);
     }
   }
@@ -587,15 +609,13 @@ HWB_FN void decode_residual(SliceDec &s, bool i16, int cbp, bool t8) {
     if (!((cbp >> q) & 1)) continue;
     if (t8) {
       int n = 0;
-      coef_clear(s, 64);
       if (cabac) {
-        n = cabac_residual(s, 5, 64, 0);
-#pragma unroll 1
-        for (int k = 0; k < 4; ++k) {
-          int bx = (q & 1) * 2 + (k & 1), by = (q >> 1) * 2 + (k >> 1);
-          s.nz_cache[HWB_CI(bx, by)] = (uint8_t)(n > 16 ? 16 : n);
-        }
+        n = cabac_block(s, 5, -1, NZ_LUMA0 + q * 4);
+        const uint32_t v = (uint32_t)(n > 16 ? 16 : n) * 0x0101u;
+        const int bx = (q & 1) * 2, by = (q >> 1) * 2;
+        *(uint16_t *)(s.nz_cache + HWB_CI(bx, by)) = (uint16_t)v; *(uint16_t *)(s.nz_cache + HWB_CI(bx, by + 1)) = (uint16_t)v;
       } else {
+        coef_clear(s, 64);
 #pragma unroll 1
         for (int k = 0; k < 4; ++k) {
           int bx = (q & 1) * 2 + (k & 1), by = (q >> 1) * 2 + (k >> 1);
@@ -604,22 +624,20 @@ HWB_FN void decode_residual(SliceDec &s, bool i16, int cbp, bool t8) {
           s.nz_cache[HWB_CI(bx, by)] = (uint8_t)m;
           n += m;
         }
+        if (n) coef_emit(s, NZ_LUMA0 + q * 4, 4);
       }
-      if (n) coef_emit(s, NZ_LUMA0 + q * 4, 4);
     } else {
 #pragma unroll 1
       for (int k = 0; k < 4; ++k) {
         int z = q * 4 + k, bx = z2x(z), by = z2y(z);
         int na = s.nz_cache[HWB_CI(bx - 1, by)], nb = s.nz_cache[HWB_CI(bx, by - 1)];
-        int n = 0, coded = 1;
+        int n = 0;
         if (cabac) {
           int a = na == 0x80 ? cbf_unavail : (na != 0), bq = nb == 0x80 ? cbf_unavail : (nb != 0);
-          coded = cabac_bin(s, 85 + (i16 ? 4 : 8) + a + 2 * bq);
-        }
-        if (coded) {
+          n = cabac_block(s, i16 ? 1 : 2, a + 2 * bq, NZ_LUMA0 + z);
+        } else {
           coef_clear(s, 16);
-          if (cabac) n = cabac_residual(s, i16 ? 1 : 2, i16 ? 15 : 16, i16 ? 1 : 0);
-          else n = cavlc_residual(s, cavlc_nc(na, nb), i16 ? 15 : 16, i16 ? 1 : 0, zigzag4x4, nullptr, 0);
+          n = cavlc_residual(s, cavlc_nc(na, nb), i16 ? 15 : 16, i16 ? 1 : 0, zigzag4x4, nullptr, 0);
           if (n) coef_emit(s, NZ_LUMA0 + z, 1);
         }
         s.nz_cache[HWB_CI(bx, by)] = (uint8_t)n;
@@ -629,16 +647,14 @@ HWB_FN void decode_residual(SliceDec &s, bool i16, int cbp, bool t8) {
   if (cbp & 0x30) {
 #pragma unroll 1
     for (int p = 0; p < 2; ++p) {
-      int coded = 1;
       int bit = p ? NZ_CR_DC : NZ_CB_DC;
       if (cabac) {
         int a = s.availA ? ((s.left.flags & NBF_IPCM) ? 1 : (s.left.cbf >> bit) & 1) : cbf_unavail;
         int bq = s.availB ? ((top_flags(s) & NBF_IPCM) ? 1 : (s.top_words[1] >> bit) & 1) : cbf_unavail;
-        coded = cabac_bin(s, 85 + 12 + a + 2 * bq);
-      }
-      if (coded) {
+        cabac_block(s, 3, a + 2 * bq, bit);
+      } else {
         coef_clear(s, 16);
-        int n = cabac ? cabac_residual(s, 3, 4, 0) : cavlc_residual(s, -1, 4, 0, scan_ident4, nullptr, 0);
+        int n = cavlc_residual(s, -1, 4, 0, scan_ident4, nullptr, 0);
         if (n) coef_emit(s, bit, 1);
       }
     }
@@ -650,14 +666,13 @@ HWB_FN void decode_residual(SliceDec &s, bool i16, int cbp, bool t8) {
       for (int k = 0; k < 4; ++k) {
         int bx = k & 1, by = k >> 1;
         int na = s.cnz_cache[p][(by + 1) * 4 + bx], nb = s.cnz_cache[p][by * 4 + bx + 1];
-        int n = 0, coded = 1;
+        int n = 0;
         if (cabac) {
           int a = na == 0x80 ? cbf_unavail : (na != 0), bq = nb == 0x80 ? cbf_unavail : (nb != 0);
-          coded = cabac_bin(s, 85 + 16 + a + 2 * bq);
-        }
-        if (coded) {
+          n = cabac_block(s, 4, a + 2 * bq, (p ? NZ_CR0 : NZ_CB0) + k);
+        } else {
           coef_clear(s, 16);
-          n = cabac ? cabac_residual(s, 4, 15, 1) : cavlc_residual(s, cavlc_nc(na, nb), 15, 1, zigzag4x4, nullptr, 0);
+          n = cavlc_residual(s, cavlc_nc(na, nb), 15, 1, zigzag4x4, nullptr, 0);
           if (n) coef_emit(s, (p ? NZ_CR0 : NZ_CB0) + k, 1);
         }
         s.cnz_cache[p][(by + 1) * 4 + bx + 1] = (uint8_t)n;
@@ -742,7 +757,9 @@ HWB_FN int cabac_mvd(SliceDec &s, int base, int amvd, int &absout) {
   while (mvd < 9 && cabac_bin(s, ctx)) { if (mvd < 4) ctx++; mvd++; }
   if (mvd >= 9) {
     int k = 3;
+#pragma unroll 1
     while (cabac_byp(s)) { mvd += 1 << k; k++; if (k > 24) { sd_fail(s, 41); return 0; } }
+#pragma unroll 1
     while (k--) mvd += cabac_byp(s) << k;
   }
   absout = mvd < 70 ? mvd : 70;
@@ -814,8 +831,10 @@ HWB_FN void finish_mb(SliceDec &s, bool skipped, bool direct16, bool is_pcm) {
   HWB_LANES(l)
   if (l < 16) {
     const int ci = HWB_CI(l & 3, l >> 2);
-    if (!inter)
-      for (int k = 0; k < nl; ++k) { s.ref_cache[k][ci] = REF_NONE; set4(s.mv_cache[k][ci], 0); *(uint16_t *)s.mvd_cache[k][ci] = 0; }
+    if (!inter) {  // both lists, whatever the slice type (an unused list's cache is never read)
+      s.ref_cache[0][ci] = REF_NONE; set4(s.mv_cache[0][ci], 0); *(uint16_t *)s.mvd_cache[0][ci] = 0;
+      s.ref_cache[1][ci] = REF_NONE; set4(s.mv_cache[1][ci], 0); *(uint16_t *)s.mvd_cache[1][ci] = 0;
+    }
     if (!inxn) s.im_cache[ci] = (int8_t)imv;
   } else if (l < 24) {
     ((uint32_t *)dst)[l - 16] = ((const uint32_t *)&o)[l - 16];
@@ -827,8 +846,11 @@ HWB_FN void finish_mb(SliceDec &s, bool skipped, bool direct16, bool is_pcm) {
   // ---- phase 2: motion out (lane = 4x4 block, lanes 0..15 list 0, 16..31 list 1), line entry (lane = word), left context
   uint32_t dm = 0;
   for (int x = 0; x < 4; ++x) if (s.dir_cache[bot + x]) dm |= 1u << x;
-  const uint32_t w0 = flags | ((uint32_t)o.cbp << 8) | ((uint32_t)o.cmode << 16) | (dm << 24);
-  const uint32_t w2 = s.cnz_cache[0][9] | ((uint32_t)s.cnz_cache[0][10] << 8) | ((uint32_t)s.cnz_cache[1][9] << 16) | ((uint32_t)s.cnz_cache[1][10] << 24);
+  // words 0..3 of the line entry are staged where fill_caches keeps the top neighbour's (no longer needed)
+  s.top_words[0] = flags | ((uint32_t)o.cbp << 8) | ((uint32_t)o.cmode << 16) | (dm << 24);
+  s.top_words[1] = cbf;
+  s.top_words[2] = s.cnz_cache[0][9] | ((uint32_t)s.cnz_cache[0][10] << 8) | ((uint32_t)s.cnz_cache[1][9] << 16) | ((uint32_t)s.cnz_cache[1][10] << 24);
+  s.top_words[3] = 0;
   HWB_LANES(l)
   if (inter) {
     const int k = l >> 4, i = l & 15;
@@ -844,19 +866,7 @@ HWB_FN void finish_mb(SliceDec &s, bool skipped, bool direct16, bool is_pcm) {
       pic_refpic(c, f, 1)[(uint64_t)s.mbaddr * 4 + i] = -1;
     }
   }
-  if (l < 20) {
-    uint32_t v;
-    if (l == 0) v = w0;
-    else if (l == 1) v = cbf;
-    else if (l == 2) v = w2;
-    else if (l == 3) v = 0;
-    else if (l == 4) v = *(const uint32_t *)(s.nz_cache + bot);
-    else if (l == 5) v = *(const uint32_t *)(s.im_cache + bot);
-    else if (l < 8) v = *(const uint32_t *)(s.ref_cache[l - 6] + bot);
-    else if (l < 16) v = *(const uint32_t *)s.mv_cache[(l - 8) >> 2][bot + (l & 3)];
-    else v = *(const uint32_t *)s.mvd_cache[(l - 16) >> 1][bot + 2 * (l & 1)];
-    ((uint32_t *)n)[l] = v;
-  }
+  if (l < 20) ((uint32_t *)n)[l] = *(const uint32_t *)((const uint8_t *)&s + line_tab[l]);
   HWB_LANES_END
   s.left.flags = flags; s.left.cbp = o.cbp; s.left.cmode = o.cmode; s.left.cbf = cbf;
 }
@@ -1018,10 +1028,13 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
       decode_residual(s, imbt > 0, cbp, t8);
     } else {
       // ---------------- inter
+      // One code path for every partitioning: the macroblock is split into `ng` groups that share a reference
+      // (the 16x16 / 16x8 / 8x16 partitions, or the four 8x8 quadrants), each group into 1, 2 or 4 motion
+      // partitions.  s.grp[g] = bx | by << 2 | (w-1) << 4 | (h-1) << 6 | sub-shape << 8 | pred_mv shape << 10.
       int cbp;
       bool t8_allowed = true;
-      int8_t *sub = s.sub;
-      sub[0] = sub[1] = sub[2] = sub[3] = 0;
+      int8_t *sub = s.sub, *pf = s.pf;
+      int ng = 0;
       if (B && mbt == 0) {
         direct16 = true; dirq = 15;
         direct_predict(s, 15, dref, dmv);
@@ -1029,66 +1042,26 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
         for (int l = 0; l < 2; ++l) for (int q = 0; q < 4; ++q) apply_direct(s, l, q, dref, dmv);
         t8_allowed = s.pd->direct_8x8_inference != 0;
       } else if ((!B && mbt >= 3) || (B && mbt == 22)) {
-        // 8x8 with sub-macroblock types
+        // 8x8 with sub-macroblock types.  sub shapes: 0: 8x8, 1: 8x4, 2: 4x8, 3: 4x4; pred flags: 1 L0, 2 L1, 3 Bi
+        ng = 4;
 #pragma unroll 1
         for (int q = 0; q < 4; ++q) {
+          int t;
           if (HWB_IS_CABAC(s)) {
-            if (B) sub[q] = (int8_t)cabac_b_sub_type(s);
-            else sub[q] = (int8_t)(cabac_bin(s, 21) ? 0 : (!cabac_bin(s, 22) ? 1 : (cabac_bin(s, 23) ? 2 : 3)));
-          } else sub[q] = (int8_t)s_ue(s);
-          if (sub[q] > (B ? 12 : 3)) { sd_fail(s, 53); return; }
-          if (B && sub[q] == 0) dirq |= 1u << q;
+            if (B) t = cabac_b_sub_type(s);
+            else t = cabac_bin(s, 21) ? 0 : (!cabac_bin(s, 22) ? 1 : (cabac_bin(s, 23) ? 2 : 3));
+          } else t = (int)s_ue(s);
+          if (t > (B ? 12 : 3)) { sd_fail(s, 53); return; }
+          int shp = t, f = 1;
+          if (B) {
+            if (t == 0) { dirq |= 1u << q; shp = 0; f = 0; if (!s.pd->direct_8x8_inference) t8_allowed = false; }
+            else { shp = t <= 3 ? 0 : (t >= 10 ? 3 : ((t & 1) ? 2 : 1)); f = t <= 3 ? t : (t >= 10 ? t - 9 : ((t - 4) >> 1) + 1); }
+          }
+          if (shp != 0) t8_allowed = false;
+          sub[q] = (int8_t)t; pf[q] = (int8_t)f;
+          s.grp[q] = (uint16_t)(((q & 1) * 2) | ((q >> 1) * 2) << 2 | 1 << 4 | 1 << 6 | shp << 8);
         }
         if (dirq) direct_predict(s, (int)dirq, dref, dmv);
-        // sub shapes: 0: 8x8, 1: 8x4, 2: 4x8, 3: 4x4; pred flags: 1 L0, 2 L1, 3 Bi
-        int8_t *shape = s.shape, *pf = s.pf;
-#pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
-          if (!B) { shape[q] = sub[q]; pf[q] = 1; }
-          else if (sub[q] == 0) { shape[q] = 0; pf[q] = 0; }
-          else {
-            int t = sub[q];
-            shape[q] = (int8_t)(t <= 3 ? 0 : (t >= 10 ? 3 : ((t & 1) ? 2 : 1)));
-            pf[q] = (int8_t)(t <= 3 ? t : (t >= 10 ? t - 9 : ((t - 4) >> 1) + 1));
-          }
-          if (shape[q] != 0) t8_allowed = false;
-          if (B && sub[q] == 0 && !s.pd->direct_8x8_inference) t8_allowed = false;
-        }
-        int8_t (*refs)[4] = s.refs;
-        const bool ref0_only = !B && mbt == 4 && !HWB_IS_CABAC(s);  // P_8x8ref0 (CAVLC only)
-#pragma unroll 1
-        for (int l = 0; l < nl; ++l)
-#pragma unroll 1
-          for (int q = 0; q < 4; ++q) {
-            refs[l][q] = -1;
-            if ((dirq >> q) & 1) continue;
-            if (pf[q] & (1 << l)) {
-              refs[l][q] = (int8_t)(ref0_only ? 0 : read_ref(s, l, (q & 1) * 2, (q >> 1) * 2));
-              if (refs[l][q] >= sd.num_ref[l]) { sd_fail(s, 54); return; }
-            }
-            // make the reference visible for later ref_idx contexts of this list
-            set_refs(s, l, (q & 1) * 2, (q >> 1) * 2, 2, 2, refs[l][q] >= 0 ? refs[l][q] : REF_NONE);
-          }
-        // references of not-yet-decoded quadrants must look unavailable for C-neighbour lookups
-#pragma unroll 1
-        for (int l = 0; l < nl; ++l) {
-          set_refs(s, l, 0, 0, 4, 4, REF_UNAVAIL);
-#pragma unroll 1
-          for (int q = 0; q < 4; ++q) {
-            int bx = (q & 1) * 2, by = (q >> 1) * 2;
-            if ((dirq >> q) & 1) { apply_direct(s, l, q, dref, dmv); continue; }
-            if (refs[l][q] < 0) { set_motion(s, l, bx, by, 2, 2, REF_NONE, 0, 0, 0, 0); continue; }
-            int r = refs[l][q];
-            switch (shape[q]) {
-              case 0: read_mvd_and_set(s, l, bx, by, 2, 2, r, 0); break;
-              case 1: read_mvd_and_set(s, l, bx, by, 2, 1, r, 0); read_mvd_and_set(s, l, bx, by + 1, 2, 1, r, 0); break;
-              case 2: read_mvd_and_set(s, l, bx, by, 1, 2, r, 0); read_mvd_and_set(s, l, bx + 1, by, 1, 2, r, 0); break;
-              default:
-#pragma unroll 1
-                for (int k = 0; k < 4; ++k) read_mvd_and_set(s, l, bx + (k & 1), by + (k >> 1), 1, 1, r, 0);
-            }
-          }
-        }
       } else {
         // 16x16, 16x8, 8x16
         int shape, pf0, pf1;
@@ -1099,32 +1072,48 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
           int k = (mbt - 4) >> 1;
           pf0 = b_part_pred[k * 2]; pf1 = b_part_pred[k * 2 + 1];
         }
-        const int np = shape == 0 ? 1 : 2;
+        ng = shape == 0 ? 1 : 2;
+        pf[0] = (int8_t)pf0; pf[1] = (int8_t)pf1;
+        if (shape == 0) s.grp[0] = (uint16_t)(3 << 4 | 3 << 6);
+        else if (shape == 1) { s.grp[0] = (uint16_t)(3 << 4 | 1 << 6 | 1 << 10); s.grp[1] = (uint16_t)(2 << 2 | 3 << 4 | 1 << 6 | 2 << 10); }
+        else { s.grp[0] = (uint16_t)(1 << 4 | 3 << 6 | 3 << 10); s.grp[1] = (uint16_t)(2 | 1 << 4 | 3 << 6 | 4 << 10); }
+      }
+      if (ng) {
         int8_t (*refs)[4] = s.refs;
+        const bool ref0_only = !B && mbt == 4 && !HWB_IS_CABAC(s);  // P_8x8ref0 (CAVLC only)
+        // reference indices, list by list; each is made visible at once for the ref_idx contexts of the next ones
 #pragma unroll 1
         for (int l = 0; l < nl; ++l)
 #pragma unroll 1
-          for (int p = 0; p < np; ++p) {
-            int pf = p ? pf1 : pf0;
-            int bx = (shape == 2 && p) ? 2 : 0, by = (shape == 1 && p) ? 2 : 0;
-            int w = shape == 2 ? 2 : 4, h = shape == 1 ? 2 : 4;
-            refs[l][p] = -1;
-            if (pf & (1 << l)) {
-              refs[l][p] = (int8_t)read_ref(s, l, bx, by);
-              if (refs[l][p] >= sd.num_ref[l]) { sd_fail(s, 55); return; }
+          for (int g = 0; g < ng; ++g) {
+            const int e = s.grp[g], bx = e & 3, by = (e >> 2) & 3, w = ((e >> 4) & 3) + 1, h = ((e >> 6) & 3) + 1;
+            int r = -1;
+            if (ng == 4 && ((dirq >> g) & 1)) { refs[l][g] = -1; continue; }
+            if (pf[g] & (1 << l)) {
+              r = ref0_only ? 0 : read_ref(s, l, bx, by);
+              if (r >= sd.num_ref[l]) { sd_fail(s, 54); return; }
             }
-            set_refs(s, l, bx, by, w, h, refs[l][p] >= 0 ? refs[l][p] : REF_NONE);
+            refs[l][g] = (int8_t)r;
+            set_refs(s, l, bx, by, w, h, r >= 0 ? r : REF_NONE);
           }
+        // motion vectors; references of not-yet-decoded groups must look unavailable for C-neighbour lookups
 #pragma unroll 1
         for (int l = 0; l < nl; ++l) {
           set_refs(s, l, 0, 0, 4, 4, REF_UNAVAIL);
 #pragma unroll 1
-          for (int p = 0; p < np; ++p) {
-            int bx = (shape == 2 && p) ? 2 : 0, by = (shape == 1 && p) ? 2 : 0;
-            int w = shape == 2 ? 2 : 4, h = shape == 1 ? 2 : 4;
-            if (refs[l][p] < 0) { set_motion(s, l, bx, by, w, h, REF_NONE, 0, 0, 0, 0); continue; }
-            int sh = shape == 0 ? 0 : (shape == 1 ? 1 + p : 3 + p);
-            read_mvd_and_set(s, l, bx, by, w, h, refs[l][p], sh);
+          for (int g = 0; g < ng; ++g) {
+            const int e = s.grp[g], bx = e & 3, by = (e >> 2) & 3, w = ((e >> 4) & 3) + 1, h = ((e >> 6) & 3) + 1;
+            if (ng == 4 && ((dirq >> g) & 1)) { apply_direct(s, l, g, dref, dmv); continue; }
+            const int r = refs[l][g];
+            if (r < 0) { set_motion(s, l, bx, by, w, h, REF_NONE, 0, 0, 0, 0); continue; }
+            const int shp = (e >> 8) & 3, pshape = (e >> 10) & 7;
+            const int pw = (shp & 2) ? 1 : w, ph = (shp & 1) ? 1 : h;  // sub-shapes only occur on 8x8 groups (w == h == 2)
+            const int n = (w * h) / (pw * ph);
+#pragma unroll 1
+            for (int k = 0; k < n; ++k) {
+              const int dx = pw < w ? (k & 1) : 0, dy = ph < h ? (pw < w ? k >> 1 : k) : 0;
+              read_mvd_and_set(s, l, bx + dx, by + dy, pw, ph, r, pshape);
+            }
           }
         }
       }

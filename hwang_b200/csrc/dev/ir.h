@@ -103,6 +103,7 @@ struct ChunkCtx {
   const uint8_t *bitstream;
   const PicDesc *pics;
   const SliceDesc *slices;
+  const int32_t *entropy_order;  // [slice] ticket -> slice index: I slices first (longest, no dependencies), then decode order
   int32_t *entropy_prog;   // [slice] first macroblock address not yet entropy-decoded (B direct col dependency)
   int32_t *recon_prog;     // [pic][mb_h] macroblocks reconstructed per row
   int32_t *dbl_prog;       // [pic][mb_h] macroblocks deblocked per row

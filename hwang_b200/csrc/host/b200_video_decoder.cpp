@@ -173,7 +173,7 @@ Result B200VideoDecoder::submit_current() {
                o_refidx = take((size_t)P * 2 * nmb * 4), o_refpic = take((size_t)P * 2 * nmb * 8),
                o_coefs = take((size_t)P * nmb * hwb::SLOTS_PER_MB * 32), o_ectx = take((size_t)S * mb_w * sizeof(hwb::NbCtx)),
                o_bits = take(ch->bitstream.size() + 64), o_pics = take((size_t)P * sizeof(PicDesc)), o_slices = take((size_t)S * sizeof(SliceDesc)),
-               o_levels = take((size_t)P * 4);
+               o_levels = take((size_t)P * 4), o_order = take((size_t)S * 4);
   const size_t n_sync = (size_t)(2 * nlevels + 1) + S + 2 * (size_t)P * mb_h + 4;
   const size_t o_sync = take(n_sync * 4);
   ch->slab = take_slab(off);
@@ -204,6 +204,14 @@ Result B200VideoDecoder::submit_current() {
   rc |= hwb_dev_h2d(dev_, st, b + o_pics, ch->pics.data(), (size_t)P * sizeof(PicDesc));
   rc |= hwb_dev_h2d(dev_, st, b + o_slices, ch->slices.data(), (size_t)S * sizeof(SliceDesc));
   rc |= hwb_dev_h2d(dev_, st, b + o_levels, level_list.data(), (size_t)P * 4);
+  // Entropy tickets: intra slices carry several times the bits of inter slices and wait on nothing, so they start
+  // first; everything else keeps decode order (a B slice's co-located picture then always holds an earlier ticket).
+  std::vector<int32_t> order;
+  order.reserve(S);
+  for (int i = 0; i < S; ++i) if (ch->slices[i].slice_type == hwb::SLICE_I) order.push_back(i);
+  for (int i = 0; i < S; ++i) if (ch->slices[i].slice_type != hwb::SLICE_I) order.push_back(i);
+  rc |= hwb_dev_h2d(dev_, st, b + o_order, order.data(), (size_t)S * 4);
+  c.entropy_order = (const int32_t *)(b + o_order);
   rc |= hwb_dev_memset(dev_, st, sync, 0, n_sync * 4);
   stats_.h2d_bytes += ch->bitstream.size() + (size_t)P * sizeof(PicDesc) + (size_t)S * sizeof(SliceDesc) + (size_t)P * 4;
   rc |= hwb_dev_event_record(dev_, ch->ev_begin, st);  // inputs are resident in HBM from here on

@@ -95,17 +95,18 @@ spec_lps = [0, 0, 1, 2, 2, 4, 4, 5, 6, 7, 8, 9, 9, 11, 11, 12, 13, 13, 15, 15, 1
 assert trans_lps.tolist() == spec_lps
 assert trans_mps.tolist() == [min(p + 1, 62) for p in range(63)] + [63]
 emit('cabac_trans_lps', trans_lps, const=True)
-# fused table for the branch-free decoder: index = (pStateIdx << 1 | valMPS) * 4 + qCodIRangeIdx,
-# entry = rangeLPS << 23 | next state after an LPS << 8 | next state after an MPS   (state = pStateIdx << 1 | valMPS);
-# rangeLPS sits where the decoder keeps codIRange (scaled by 2^23, see csrc/dev/bits.h)
-fused = np.zeros((128, 4), np.uint32)
+# fused table for the branch-free decoder, two 32-bit words per state (state = pStateIdx << 1 | valMPS):
+#   word 0 = rangeLPS for qCodIRangeIdx 0..3, one byte each (byte q)
+#   word 1 = next state after an MPS | next state after an LPS << 8
+# Both words depend on the context state only, so the decoder can fetch them before codIRange is known.
+fused = np.zeros((128, 2), np.uint32)
 for p in range(64):
     for mps in range(2):
         nl = (int(trans_lps[p]) << 1) | (mps ^ 1 if p == 0 else mps)
         nm = (min(p + 1, 62) << 1 | mps) if p < 63 else (63 << 1 | mps)
         if p == 62: nm = (62 << 1) | mps
-        for q in range(4):
-            fused[(p << 1) | mps, q] = (int(range_lps[p, q]) << 23) | (nl << 8) | nm
+        fused[(p << 1) | mps, 0] = sum(int(range_lps[p, q]) << (8 * q) for q in range(4))
+        fused[(p << 1) | mps, 1] = nm | (nl << 8)
 emit('cabac_fused', fused, 'uint32_t', 8, const=True)
 
 sig8 = u8(find([0, 1, 2, 3, 4, 5, 5, 4, 4, 3, 3, 4, 4, 4, 5, 5, 4, 4, 4, 4, 3, 3, 6, 7, 7, 7, 8, 9, 10, 9, 8, 7], 0, 1), 63)
