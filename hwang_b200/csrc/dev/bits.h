@@ -132,13 +132,19 @@ HWB_HD void cabac_start(Cabac &c, const uint8_t *base, uint32_t p) {
 HWB_HD uint32_t cabac_bitpos(const Cabac &c) { return c.pos * 8 - (uint32_t)c.nb; }
 // Invariant between operations: nb >= 1 (a bypass decision compares before it shifts, so the next stream bit must
 // already be in `low`).  nb <= 0: -nb zero bits were shifted into the offset; the top bits of the next 16 belong
-// there.  Written as a loop (it runs once) so that ptxas keeps it a rarely taken branch instead of ten predicated
-// instructions per bin.
+// there.  The refill itself is one shared out-of-line routine (it runs once per ~20 bins; inlined at every decision
+// site it was a quarter of the residual decoder's code).
+struct CabacFill { uint32_t low; int32_t nb; uint32_t pos; };
+HWB_FN CabacFill cabac_refill_ool(uint32_t low, int32_t nb, uint32_t pos, const uint8_t *base) {
+  CabacFill f;
+  f.low = low | (cabac_load16(base, pos) << (7 - nb));
+  f.nb = nb + 16; f.pos = pos + 2;
+  return f;
+}
 HWB_HD void cabac_refill(Cabac &c, const uint8_t *base) {
-#pragma unroll 1
-  while (c.nb <= 0) {
-    c.low |= cabac_load16(base, c.pos) << (7 - c.nb);
-    c.nb += 16; c.pos += 2;
+  if (c.nb <= 0) {
+    const CabacFill f = cabac_refill_ool(c.low, c.nb, c.pos, base);
+    c.low = f.low; c.nb = f.nb; c.pos = f.pos;
   }
 }
 

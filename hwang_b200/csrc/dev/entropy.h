@@ -93,6 +93,12 @@ struct SliceDec {
   int8_t refs[2][4];
   int8_t sub[4], shape[4], pf[4];
   uint16_t grp[4];  // inter macroblock: reference groups (see decode_mb)
+  // output arrays of this slice's picture (set by init_caches: saves the address arithmetic per macroblock)
+  MbInfo *o_mbinfo;
+  int16_t *o_mv[2];
+  int8_t *o_refidx[2];
+  int16_t *o_refpic[2];
+  int16_t *o_coefs;
   // CABAC context states live inside the slice state (shared memory on the GPU), so that the decoder addresses
   // them as shared-memory offsets instead of through a generic pointer
   alignas(16) uint8_t states[464];
@@ -142,6 +148,12 @@ HWB_HD void cpy16(void *d, const void *s) {
   HWB_MV((base) + HWB_LEFT_D(2) * (elem), (base) + HWB_LEFT_F(2) * (elem)), HWB_MV((base) + HWB_LEFT_D(3) * (elem), (base) + HWB_LEFT_F(3) * (elem))
 // Called once per slice before the first macroblock: entries that never change.
 HWB_FN void init_caches(SliceDec &s) {
+  {
+    const ChunkCtx &c = *s.c;
+    const int f = s.pd->frame;
+    s.o_mbinfo = pic_mbinfo(c, f); s.o_coefs = pic_coefs(c, f);
+    for (int k = 0; k < 2; ++k) { s.o_mv[k] = pic_mv(c, f, k); s.o_refidx[k] = pic_refidx(c, f, k); s.o_refpic[k] = pic_refpic(c, f, k); }
+  }
   HWB_LANES(l)
   for (int i = l; i < HWB_CACHE_N; i += 32) {
     for (int k = 0; k < 2; ++k) { s.ref_cache[k][i] = REF_UNAVAIL; set4(s.mv_cache[k][i], 0); s.mvd_cache[k][i][0] = s.mvd_cache[k][i][1] = 0; }
@@ -483,6 +495,9 @@ HWB_FN int cavlc_residual(SliceDec &s, int nC, int max_coeff, int start, const u
 
 // ================================================================================ CABAC residual
 HWB_TABLE uint8_t ctx_inc_chroma_dc[4] = {0, 1, 2, 2};
+#define HWB_CAT(sig, last, abs) ((sig) | (last) << 10 | (abs) << 20)
+HWB_CTABLE uint32_t cabac_cat_ctx[6] = {HWB_CAT(105, 166, 227), HWB_CAT(120, 181, 237), HWB_CAT(134, 195, 247),
+                                        HWB_CAT(149, 210, 257), HWB_CAT(152, 213, 266), HWB_CAT(402, 417, 426)};
 // 4x4 zig-zag (and the identity order of the 4 chroma DC coefficients) packed 4 bits per scan position: no table load
 #define HWB_ZZ4_PACKED 0xFEB7ADC963258410ull
 #define HWB_IDENT_PACKED 0xFEDCBA9876543210ull
@@ -492,10 +507,8 @@ HWB_TABLE uint8_t ctx_inc_chroma_dc[4] = {0, 1, 2, 2};
 // footprint (one loop for the map, one for the levels, shared by all categories): with many warps per SM inside
 // different parts of the slice decoder, instruction fetch misses cost more than the few extra selects.
 HWB_HD int cabac_residual_impl(SliceDec &s, Cabac &cab, const uint8_t *base, uint8_t *st, int cat, int max_coeff, int start) {
-  const int sig_off = cat == 0 ? 105 : cat == 1 ? 120 : cat == 2 ? 134 : cat == 3 ? 149 : cat == 4 ? 152 : 402;
-  const int last_off = cat == 0 ? 166 : cat == 1 ? 181 : cat == 2 ? 195 : cat == 3 ? 210 : cat == 4 ? 213 : 417;
-  const int abs_off = cat == 0 ? 227 : cat == 1 ? 237 : cat == 2 ? 247 : cat == 3 ? 257 : cat == 4 ? 266 : 426;
-  uint8_t *sig_st = st + sig_off, *last_st = st + last_off, *abs_st = st + abs_off;
+  const uint32_t offs = cabac_cat_ctx[cat];  // ctxIdxOffset of significant_coeff_flag | last_... << 10 | coeff_abs_level_minus1 << 20
+  uint8_t *sig_st = st + (offs & 1023), *last_st = st + ((offs >> 10) & 1023), *abs_st = st + (offs >> 20);
   // ---- significance map: one loop for all categories (8x8 and chroma DC map scan positions to contexts by table)
   const bool tab = cat == 5 || cat == 3;
   const uint8_t *sig_tab = cat == 5 ? cabac_sig8x8_ctx : ctx_inc_chroma_dc;
@@ -558,7 +571,7 @@ HWB_HD void coef_clear(SliceDec &s, int n) {
 }
 // Append s.coef[0..16*nslots) to the arena and mark item bits [bit, bit+nslots).
 HWB_HD void coef_emit(SliceDec &s, int bit, int nslots) {
-  uint32_t *dst = (uint32_t *)(pic_coefs(*s.c, s.pd->frame) + (uint64_t)s.coef_next * 16);
+  uint32_t *dst = (uint32_t *)(s.o_coefs + (uint64_t)s.coef_next * 16);
   HWB_LANES(l)
   if (l < nslots * 8) dst[l] = ((const uint32_t *)s.coef)[l];
   HWB_LANES_END
@@ -825,7 +838,7 @@ HWB_FN void finish_mb(SliceDec &s, bool skipped, bool direct16, bool is_pcm) {
   const uint32_t cbf = is_pcm ? 0x7FFFFFFu : o.nzmask;
   const int bot = HWB_CI(0, 3);
   NbCtx *n = s.line + s.mbx;
-  MbInfo *dst = pic_mbinfo(c, f) + s.mbaddr;
+  MbInfo *dst = s.o_mbinfo + s.mbaddr;
   // ---- phase 1: normalise the interior so that the right column / bottom row say what neighbours must see; save
   // what the next macroblock's top-left needs from the line entry that is about to be overwritten; MbInfo out
   HWB_LANES(l)
@@ -855,15 +868,15 @@ HWB_FN void finish_mb(SliceDec &s, bool skipped, bool direct16, bool is_pcm) {
   if (inter) {
     const int k = l >> 4, i = l & 15;
     if (k < nl) {
-      ((uint32_t *)(pic_mv(c, f, k) + (uint64_t)s.mbaddr * 32))[i] = *(const uint32_t *)s.mv_cache[k][HWB_CI(i & 3, i >> 2)];
+      ((uint32_t *)(s.o_mv[k] + (uint64_t)s.mbaddr * 32))[i] = *(const uint32_t *)s.mv_cache[k][HWB_CI(i & 3, i >> 2)];
       if (i < 4) {
         const int r = s.ref_cache[k][HWB_CI((i & 1) * 2, (i >> 1) * 2)];
-        pic_refidx(c, f, k)[(uint64_t)s.mbaddr * 4 + i] = (int8_t)r;
-        pic_refpic(c, f, k)[(uint64_t)s.mbaddr * 4 + i] = r >= 0 ? sd.ref_frame[k][r] : (int16_t)-1;
+        s.o_refidx[k][(uint64_t)s.mbaddr * 4 + i] = (int8_t)r;
+        s.o_refpic[k][(uint64_t)s.mbaddr * 4 + i] = r >= 0 ? sd.ref_frame[k][r] : (int16_t)-1;
       }
     } else if (l1_none && i < 4) {
-      pic_refidx(c, f, 1)[(uint64_t)s.mbaddr * 4 + i] = -1;
-      pic_refpic(c, f, 1)[(uint64_t)s.mbaddr * 4 + i] = -1;
+      s.o_refidx[1][(uint64_t)s.mbaddr * 4 + i] = -1;
+      s.o_refpic[1][(uint64_t)s.mbaddr * 4 + i] = -1;
     }
   }
   if (l < 20) ((uint32_t *)n)[l] = *(const uint32_t *)((const uint8_t *)&s + line_tab[l]);
@@ -952,7 +965,7 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
       // ---------------- I_PCM
       is_pcm = true;
       o.mbtype = MB_IPCM; o.qp = 0; o.cbp = 0x2F;
-      uint8_t *dst = (uint8_t *)(pic_coefs(c, s.pd->frame) + (uint64_t)s.coef_next * 16);
+      uint8_t *dst = (uint8_t *)(s.o_coefs + (uint64_t)s.coef_next * 16);
       if (HWB_IS_CABAC(s)) {
         // pcm_alignment_zero_bits, 384 raw bytes, then the arithmetic decoder restarts (9.3.1.2)
         const uint32_t p = (cabac_bitpos(s.cab) + 7) >> 3;
