@@ -253,10 +253,12 @@ static int grid_for(hwb_dev *d, int work_warps, int blocks_per_sm) {
 
 int hwb_dev_entropy(hwb_dev *d, int s, const ChunkCtx *c, int32_t *ticket, int mode) {
   cudaSetDevice(d->device);
-  // Resident warps per SM are capped: the slice decoder is branchy code far larger than the instruction caches, and
-  // every extra warp wandering through a different part of it costs all of them fetch misses (measured: 67% of the
-  // stall cycles at 20 warps per SM).  HWB_ENTROPY_BLOCKS_PER_SM overrides the cap (4 warps per block).
-  static int bpsm = [] { const char *e = getenv("HWB_ENTROPY_BLOCKS_PER_SM"); int v = e ? atoi(e) : 0; return v > 0 ? v : 8; }();
+  // Resident warps per SM are capped at 12 (3 blocks of 4 warps): the slice decoder is branchy code larger than the
+  // SM's instruction cache, every extra warp wandering through a different part of it costs all of them fetch
+  // misses, and those misses saturate the GPC-level instruction cache (measured at 20 warps per SM: 67% of the stall
+  // cycles are "no instruction", gcc instruction requests at 67% of peak).  Sweep on the 3000-slice benchmark chunk:
+  // 1 block/SM 561 ms, 2: 411, 3: 394, 4: 402, 5: 409, 8: 430.  HWB_ENTROPY_BLOCKS_PER_SM overrides.
+  static int bpsm = [] { const char *e = getenv("HWB_ENTROPY_BLOCKS_PER_SM"); int v = e ? atoi(e) : 0; return v > 0 ? v : 3; }();
   const int grid = grid_for(d, c->num_slices, bpsm);
   if (mode == 1) entropy_cabac_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);
   else if (mode == 0) entropy_cavlc_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);

@@ -194,7 +194,11 @@ Result B200VideoDecoder::submit_current() {
   c.error_flag = c.dbl_prog + (size_t)P * mb_h;
   ch->error_dev = c.error_flag;
 
-  const int st = HWB_STREAM_DECODE + (int)(stats_.chunks % HWB_NUM_DECODE_STREAMS);
+  // Two decode streams shared by all chunks: inputs + entropy decoding on the first, reconstruction + deblocking on
+  // the second.  Entropy decoding of chunk k+1 (bound by instruction fetch and by the latency of the intra slices)
+  // then overlaps the level-by-level reconstruction of chunk k (bound by the wavefront latency of each level), and
+  // chunk k's frames travel to the host while chunk k+1 is reconstructed.
+  const int st = HWB_STREAM_DECODE, st_recon = HWB_STREAM_DECODE + 1;
   ch->ev_begin = hwb_dev_event_create(dev_);
   ch->ev_done = hwb_dev_event_create(dev_);
   int rc = 0;
@@ -221,17 +225,25 @@ Result B200VideoDecoder::submit_current() {
   for (auto &p : ch->pics) if ((p.cabac ? 1 : 0) != mode) mode = -1;
   rc |= hwb_dev_entropy(dev_, st, &c, tickets, mode);
   mark();
+  {
+    hwb_event *ev_entropy = hwb_dev_event_create(dev_);
+    rc |= hwb_dev_event_record(dev_, ev_entropy, st);
+    rc |= hwb_dev_stream_wait(dev_, st_recon, ev_entropy);
+    hwb_dev_event_destroy(dev_, ev_entropy);  // the wait already enqueued keeps its own reference
+  }
+  auto mark_recon = [&]() { if (profile_) { hwb_event *e = hwb_dev_event_create(dev_); hwb_dev_event_record(dev_, e, st_recon); ch->stage_ev.push_back(e); } };
+  mark_recon();  // stage_ev[2]: reconstruction stream free and entropy done
   size_t lo = 0;
   for (int l = 0; l < nlevels; ++l) {
     const int n = (int)by_level[l].size();
     const int32_t *pl = (const int32_t *)(b + o_levels) + lo;
-    rc |= hwb_dev_recon(dev_, st, &c, pl, n, tickets + 1 + 2 * l);
-    mark();
-    rc |= hwb_dev_deblock(dev_, st, &c, pl, n, tickets + 2 + 2 * l);
-    mark();
+    rc |= hwb_dev_recon(dev_, st_recon, &c, pl, n, tickets + 1 + 2 * l);
+    mark_recon();
+    rc |= hwb_dev_deblock(dev_, st_recon, &c, pl, n, tickets + 2 + 2 * l);
+    mark_recon();
     lo += n;
   }
-  rc |= hwb_dev_event_record(dev_, ch->ev_done, st);
+  rc |= hwb_dev_event_record(dev_, ch->ev_done, st_recon);
   if (rc) { sticky_error_ = std::string("B200 decoder: CUDA launch failed: ") + hwb_dev_error(dev_); return Result(false, sticky_error_); }
   for (auto &p : ch->pics) ch->alg_bytes += fs + (p.has_inter ? fs : 0);
   ch->submitted = true;
@@ -262,7 +274,8 @@ Result B200VideoDecoder::finish_chunk(Chunk &c) {
     float t = 0;
     if (hwb_dev_event_elapsed(dev_, c.stage_ev[i - 1], c.stage_ev[i], &t) != 0) continue;
     if (i == 1) { stats_.entropy_ms += t; stats_.entropy_launches++; }
-    else if (i % 2 == 0) { stats_.recon_ms += t; stats_.recon_launches++; }
+    else if (i == 2) continue;  // waiting for the reconstruction stream (another chunk's levels)
+    else if (i % 2 == 1) { stats_.recon_ms += t; stats_.recon_launches++; }
     else { stats_.deblock_ms += t; stats_.deblock_launches++; }
   }
   for (auto e : c.stage_ev) hwb_dev_event_destroy(dev_, e);

@@ -91,7 +91,7 @@ class B200VideoDecoder : public VideoDecoderInterface {
   // pictures per GPU batch (cut at IDR pictures).  The entropy stage is latency-bound per slice, so batches must be
   // large; several batches are in flight at once on different streams, which overlaps host parsing, the entropy
   // stage of the next batch, reconstruction of the previous one and the copies to the host.
-  int chunk_target_ = 4096;
+  int chunk_target_ = 4096;  // pictures per chunk (cut at IDR pictures); measured: splitting a 3000-picture clip only loses (every stage is bound by instruction fetch, overlapped chunks share that budget)
   std::unique_ptr<Chunk> cur_;
   std::deque<std::unique_ptr<Chunk>> queue_;    // submitted chunks, oldest first
   std::vector<std::unique_ptr<Chunk>> retired_;  // fully popped, slab reusable after the next copy-stream sync

@@ -1,5 +1,7 @@
 #include "decoder_automata.h"
 
+#include <chrono>
+
 namespace hwang {
 
 DecoderAutomata *DecoderAutomata::make_instance(DeviceHandle device_handle, int32_t num_devices, VideoDecoderType decoder_type) {
@@ -139,7 +141,9 @@ Result DecoderAutomata::get_frames(uint8_t *buffer, int32_t num_frames) {
       for (size_t j = interval_ + 1; j < encoded_data_.size(); ++j) more |= !encoded_data_[j].valid_frames.empty();
       if (!more) return Result(false, "get_frames: requested more frames than the intervals contain");
     }
-    if (decoder_->decoded_frames_buffered() <= 0) { std::this_thread::yield(); continue; }
+    // nothing to pop yet: back off instead of spinning (the reference yields in a tight loop, decoder_automata.cpp:242;
+    // here the poll takes the decoder's lock, which the feeder thread needs for every sample it parses)
+    if (decoder_->decoded_frames_buffered() <= 0) { std::this_thread::sleep_for(std::chrono::microseconds(50)); continue; }
     const uint64_t frame = d.start_keyframe + popped_;
     if (valid_idx_ < d.valid_frames.size() && d.valid_frames[valid_idx_] == frame) {
       HWANG_RETURN_ON_ERROR(decoder_->get_frame(buffer + (size_t)got * frame_size_, frame_size_));
