@@ -359,10 +359,19 @@ Result B200VideoDecoder::pop_common(int mode, uint8_t *buf, size_t size, uint8_t
   const int slot = ring_next_++;
   int rc;
   hwb_event *r0 = nullptr, *r1 = nullptr;
-  if (profile_ && mode != 1) { r0 = hwb_dev_event_create(dev_); r1 = hwb_dev_event_create(dev_); hwb_dev_event_record(dev_, r0, HWB_STREAM_COPY); }
-  if (mode == 1) rc = hwb_dev_yuv(dev_, HWB_STREAM_COPY, &c.ctx, frame, stream_.crop_left(), stream_.crop_top(), (int)width_, (int)height_, rgb_dev_[slot]);
-  else rc = hwb_dev_rgb24(dev_, HWB_STREAM_COPY, &c.ctx, frame, stream_.crop_left(), stream_.crop_top(), (int)width_, (int)height_, rgb_dev_[slot]);
-  if (r1) { hwb_dev_event_record(dev_, r1, HWB_STREAM_COPY); rgb_ev_.push_back({r0, r1}); }
+  // colour conversion on its own stream, the copy stream waits for it: the conversion of frame k+1 overlaps the
+  // device-to-host copy of frame k (slots of the ring are recycled only after drain_copies)
+  const int st_rgb = HWB_STREAM_DECODE + 2;
+  if (profile_ && mode != 1) { r0 = hwb_dev_event_create(dev_); r1 = hwb_dev_event_create(dev_); hwb_dev_event_record(dev_, r0, st_rgb); }
+  if (mode == 1) rc = hwb_dev_yuv(dev_, st_rgb, &c.ctx, frame, stream_.crop_left(), stream_.crop_top(), (int)width_, (int)height_, rgb_dev_[slot]);
+  else rc = hwb_dev_rgb24(dev_, st_rgb, &c.ctx, frame, stream_.crop_left(), stream_.crop_top(), (int)width_, (int)height_, rgb_dev_[slot]);
+  if (r1) { hwb_dev_event_record(dev_, r1, st_rgb); rgb_ev_.push_back({r0, r1}); }
+  {
+    hwb_event *conv = hwb_dev_event_create(dev_);
+    rc |= hwb_dev_event_record(dev_, conv, st_rgb);
+    rc |= hwb_dev_stream_wait(dev_, HWB_STREAM_COPY, conv);
+    hwb_dev_event_destroy(dev_, conv);
+  }
   if (mode == 2) {
     *dev_out = rgb_dev_[slot];
     pending_.push_back({nullptr, nullptr, 0});

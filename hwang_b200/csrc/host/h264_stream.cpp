@@ -10,29 +10,41 @@ namespace hwb {
 
 namespace {
 
+// Strip emulation_prevention_three_bytes (00 00 03 -> 00 00) while appending to `out`; returns the RBSP size.
+// One memchr pass over the candidates (bytes equal to 3) and block copies in between: the sample bytes of a chunk
+// go through here once, straight into the buffer that is uploaded to the GPU.
+size_t unescape_append(std::vector<uint8_t> &out, const uint8_t *p, size_t n) {
+  const size_t base = out.size();
+  out.resize(base + n);
+  uint8_t *d = out.data() + base;
+  size_t o = 0, i = 0, scan = 0;  // i: start of the pending copy, scan: where to look for the next 03
+  while (scan < n) {
+    const uint8_t *z = (const uint8_t *)memchr(p + scan, 3, n - scan);
+    if (!z) break;
+    const size_t k = (size_t)(z - p);
+    if (k >= i + 2 && p[k - 1] == 0 && p[k - 2] == 0) {  // the two zeros must follow the previous emulation byte
+      memcpy(d + o, p + i, k - i); o += k - i;
+      i = k + 1;
+    }
+    scan = k + 1;
+  }
+  memcpy(d + o, p + i, n - i); o += n - i;
+  out.resize(base + o);
+  return o;
+}
 std::vector<uint8_t> unescape(const uint8_t *p, size_t n) {
   std::vector<uint8_t> out;
-  out.reserve(n);
-  size_t i = 0;
-  while (i < n) {
-    // fast path: copy up to the next 00 00 03
-    const uint8_t *z = (const uint8_t *)memchr(p + i, 0, n - i);
-    if (!z) { out.insert(out.end(), p + i, p + n); break; }
-    size_t k = (size_t)(z - p);
-    out.insert(out.end(), p + i, p + k);
-    i = k;
-    if (i + 2 < n && p[i + 1] == 0 && p[i + 2] == 3) { out.push_back(0); out.push_back(0); i += 3; }
-    else { out.push_back(0); i += 1; }
-  }
+  unescape_append(out, p, n);
   return out;
 }
 
 struct Rd {
   BitReader b;
   uint32_t stop;  // bit position of the rbsp stop bit
-  explicit Rd(const std::vector<uint8_t> &v) {
-    br_init(b, v.data(), (uint32_t)v.size(), 0);
-    int n = (int)v.size();
+  explicit Rd(const std::vector<uint8_t> &v) : Rd(v.data(), v.size()) {}
+  Rd(const uint8_t *v, size_t size) {
+    br_init(b, v, (uint32_t)size, 0);
+    int n = (int)size;
     while (n > 0 && v[n - 1] == 0) --n;
     stop = 0;
     if (n > 0) { int tz = 0; while (!((v[n - 1] >> tz) & 1)) ++tz; stop = (uint32_t)((n - 1) * 8 + 7 - tz); }
@@ -237,8 +249,8 @@ bool H264Stream::next_is_idr(const uint8_t *data, size_t n) const {
   return false;
 }
 
-std::string H264Stream::parse_slice_header(const std::vector<uint8_t> &rbsp, int nal_type, int nal_ref_idc, SliceHeader &sh) {
-  Rd r(rbsp);
+std::string H264Stream::parse_slice_header(const uint8_t *rbsp, size_t rbsp_size, int nal_type, int nal_ref_idc, SliceHeader &sh) {
+  Rd r(rbsp, rbsp_size);
   sh.nal_type = nal_type; sh.nal_ref_idc = nal_ref_idc;
   sh.first_mb = (int)r.ue();
   uint32_t st = r.ue();
@@ -517,10 +529,13 @@ std::string H264Stream::parse_sample(const uint8_t *data, size_t n, int pic_inde
     if (nal_type == 8) { std::string e = parse_pps(unescape(nal + 1, len - 1)); if (!e.empty()) return e; continue; }
     if (nal_type >= 2 && nal_type <= 4) return "unsupported: data partitioning";
     if (nal_type != 1 && nal_type != 5) continue;
-    std::vector<uint8_t> rbsp = unescape(nal + 1, len - 1);
+    // the slice RBSP goes straight to the chunk bitstream, 16-byte aligned (dropped again if the header is bad)
+    while (bitstream.size() & 15) bitstream.push_back(0);
+    const size_t rbsp_off = bitstream.size();
+    const size_t rbsp_size = unescape_append(bitstream, nal + 1, len - 1);
     SliceHeader sh;
-    std::string e = parse_slice_header(rbsp, nal_type, nal_ref_idc, sh);
-    if (!e.empty()) return e;
+    std::string e = parse_slice_header(bitstream.data() + rbsp_off, rbsp_size, nal_type, nal_ref_idc, sh);
+    if (!e.empty()) { bitstream.resize(rbsp_off); return e; }
     const Pps &pps = pps_[sh.pps_id];
     const Sps &sps = sps_[pps.sps_id];
     if (sps.mb_w != mb_w_ || sps.mb_h != mb_h_) return "unsupported: resolution change inside a stream";
@@ -569,10 +584,7 @@ std::string H264Stream::parse_sample(const uint8_t *data, size_t n, int pic_inde
         }
       }
     }
-    // slice RBSP goes to the chunk bitstream, 16-byte aligned
-    while (bitstream.size() & 15) bitstream.push_back(0);
-    sd.data_off = (uint32_t)bitstream.size(); sd.data_size = (uint32_t)rbsp.size(); sd.bit_off = sh.data_bit_off;
-    bitstream.insert(bitstream.end(), rbsp.begin(), rbsp.end());
+    sd.data_off = (uint32_t)rbsp_off; sd.data_size = (uint32_t)rbsp_size; sd.bit_off = sh.data_bit_off;
     out.slices.push_back(sd);
   }
   if (!have_pic) return "sample contains no slice";

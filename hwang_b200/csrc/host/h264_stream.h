@@ -108,7 +108,7 @@ class H264Stream {
   };
   std::string parse_sps(const std::vector<uint8_t> &rbsp);
   std::string parse_pps(const std::vector<uint8_t> &rbsp);
-  std::string parse_slice_header(const std::vector<uint8_t> &rbsp, int nal_type, int nal_ref_idc, SliceHeader &sh);
+  std::string parse_slice_header(const uint8_t *rbsp, size_t rbsp_size, int nal_type, int nal_ref_idc, SliceHeader &sh);
   int compute_poc(const Sps &sps, const SliceHeader &sh);
   void build_ref_lists(const Sps &sps, const SliceHeader &sh, int cur_poc, std::vector<DpbEntry> lists[2]);
   void mark_references(const Sps &sps, const SliceHeader &sh, int cur_frame, int cur_poc);
