@@ -112,3 +112,72 @@ def test_get_frames_in_batches_of_8_and_reconfigure(gpu):
             got += auto.get_frames(index, 8)
         for r, f in enumerate(got):
             assert np.array_equal(np.asarray(f), fo.yuv420_to_rgb24(*ref[r])), (rep, r)
+
+
+def test_config2_full_size_properties(gpu):
+    """BASELINE configs[1] at full size: the 3000-frame 1080p Main/CABAC GOP-30 clip of bench.py, dense, through
+    DecoderAutomata.get_frames.  The oracle cannot decode 3000 frames in seconds, so full size is covered by
+    (a) bit-exact RGB against libavcodec + the swscale arithmetic on three whole GOPs (first, middle, last),
+    (b) a checksum of per-frame checksums that must not depend on how the clip is cut into chunks (one chunk of
+        3000 pictures against chunks of 10 GOPs), which also makes two independent decodes reproduce each other,
+    (c) seek == sequential at full size: a sparse request for the last frame of a GOP in the middle of the clip
+        returns the bytes the dense pass returned."""
+    import zlib
+    import bench
+    from hwang_b200 import _lib as lib_mod
+    mp4 = bench.get_clip(3000)
+    index = hw.index_video(io.BytesIO(mp4))
+    offs, sizes = index.sample_offsets(), index.sample_sizes()
+    kfs = sorted(index.keyframe_indices())
+    n = len(offs)
+    assert n == 3000 and len(kfs) == 100
+    W, H = bench.W, bench.H
+    fs = W * H * 3
+    L = lib_mod.lib()
+
+    def dense_checksums(chunk_pictures):
+        import os
+        os.environ['HWB_CHUNK_PICTURES'] = str(chunk_pictures)
+        try:
+            auto = hw.DecoderAutomata(hw.DeviceHandle(hw.DeviceType.GPU, 0), 1, hw.VideoDecoderType.B200)
+        finally:
+            del os.environ['HWB_CHUNK_PICTURES']
+        ed = hw.EncodedData()
+        ed.width, ed.height, ed.format = W, H, index.format()
+        ed.start_keyframe, ed.end_keyframe = 0, n
+        ed.sample_offsets = [o - offs[0] for o in offs]
+        ed.sample_sizes = sizes
+        ed.keyframes = kfs
+        ed.valid_frames = list(range(n))
+        ed.encoded_video = mp4[offs[0]:offs[-1] + sizes[-1]]
+        auto.initialize([ed], index.metadata_bytes())
+        batch = 50
+        pinned = hw.api.PinnedBuffer(fs * batch)
+        sums, keep = [], {}
+        done = 0
+        while done < n:
+            k = min(batch, n - done)
+            assert L.hwb_automata_get_frames(auto._h, pinned.ptr, k) == 0, L.hwb_automata_last_error(auto._h).decode()
+            view = pinned.array[:fs * k].reshape(k, fs)
+            for i in range(k):
+                sums.append(zlib.adler32(view[i]))
+                if (done + i) // 30 in (0, 50, 99):
+                    keep[done + i] = view[i].copy()
+            done += k
+        return sums, keep
+
+    sums_one, keep = dense_checksums(1 << 30)
+    sums_cut, _ = dense_checksums(300)
+    assert len(sums_one) == n
+    assert sums_one == sums_cut, 'result depends on the chunking'
+    assert zlib.adler32(np.asarray(sums_one, np.uint32).tobytes()) == zlib.adler32(np.asarray(sums_cut, np.uint32).tobytes())
+    # (a) three whole GOPs against the oracle
+    for g in (0, 50, 99):
+        samples = [mp4[offs[i]:offs[i] + sizes[i]] for i in range(g * 30, g * 30 + 30)]
+        ref = fo.decode_samples(index.metadata_bytes(), samples, [i == 0 for i in range(30)])
+        for i in range(30):
+            exp = fo.yuv420_to_rgb24(*ref[i]).reshape(-1)
+            assert np.array_equal(keep[g * 30 + i], exp), 'frame %d differs from the oracle' % (g * 30 + i)
+    # (c) seek == sequential
+    single = hw.Decoder(io.BytesIO(mp4), video_index=index).retrieve([50 * 30 + 29])
+    assert np.array_equal(np.asarray(single[0]).reshape(-1), keep[50 * 30 + 29])
