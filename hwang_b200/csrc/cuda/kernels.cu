@@ -34,6 +34,13 @@ __shared__ __align__(8) uint32_t hwb_fused_sm[256];
 #include "../dev/entropy.h"
 #undef HWB_ENT_NS
 #undef HWB_ENT_MODE
+#define HWB_ENT_NS ent_cabac_ip
+#define HWB_ENT_MODE 1
+#define HWB_ENT_NO_B 1
+#include "../dev/entropy.h"
+#undef HWB_ENT_NS
+#undef HWB_ENT_MODE
+#undef HWB_ENT_NO_B
 #include "../dev/recon.h"
 #include "../dev/rgb.h"
 
@@ -73,6 +80,7 @@ __device__ __forceinline__ int warp_ticket(int32_t *ticket) {
 HWB_ENTROPY_KERNEL(entropy_kernel, hwb::ent)              // pictures of both entropy modes in one chunk
 HWB_ENTROPY_KERNEL(entropy_cabac_kernel, hwb::ent_cabac)  // every picture of the chunk is CABAC
 HWB_ENTROPY_KERNEL(entropy_cavlc_kernel, hwb::ent_cavlc)  // every picture of the chunk is CAVLC
+HWB_ENTROPY_KERNEL(entropy_cabac_ip_kernel, hwb::ent_cabac_ip)  // CABAC, no B slice in the chunk
 
 // ------------------------------------------------------------------------------------ reconstruction
 __device__ __forceinline__ void wait_progress(const int32_t *p, int need) {
@@ -265,7 +273,8 @@ int hwb_dev_entropy(hwb_dev *d, int s, const ChunkCtx *c, int32_t *ticket, int m
   // 1 block/SM 561 ms, 2: 411, 3: 394, 4: 402, 5: 409, 8: 430.  HWB_ENTROPY_BLOCKS_PER_SM overrides.
   static int bpsm = [] { const char *e = getenv("HWB_ENTROPY_BLOCKS_PER_SM"); int v = e ? atoi(e) : 0; return v > 0 ? v : 3; }();
   const int grid = grid_for(d, c->num_slices, bpsm);
-  if (mode == 1) entropy_cabac_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);
+  if (mode == 3) entropy_cabac_ip_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);
+  else if (mode == 1) entropy_cabac_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);
   else if (mode == 0) entropy_cavlc_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);
   else entropy_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);
   HWB_CUDA(d, cudaGetLastError());

@@ -36,7 +36,7 @@ int hwb_dev_memset(hwb_dev *d, int stream, void *dst, int value, size_t n);
 
 // Decode stages.  `c` is a host copy of the chunk context (its pointers are device pointers).
 // tickets: device int32[4] zeroed by the caller, used for ordered work distribution.
-// mode: 1 = every picture of the chunk is CABAC, 0 = every picture is CAVLC, -1 = mixed (generic kernel)
+// mode: 1 = every picture of the chunk is CABAC, 3 = CABAC and no B slice, 0 = every picture is CAVLC, -1 = mixed (generic kernel)
 int hwb_dev_entropy(hwb_dev *d, int stream, const hwb::ChunkCtx *c, int32_t *ticket, int mode);
 int hwb_dev_recon(hwb_dev *d, int stream, const hwb::ChunkCtx *c, const int32_t *pics_dev, int npics, int32_t *ticket);
 int hwb_dev_deblock(hwb_dev *d, int stream, const hwb::ChunkCtx *c, const int32_t *pics_dev, int npics, int32_t *ticket);

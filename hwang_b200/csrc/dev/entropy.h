@@ -15,6 +15,14 @@
 #define HWB_ENT_NS ent
 #define HWB_ENT_MODE (-1)
 #endif
+// HWB_ENT_NO_B: a copy of the slice decoder for chunks without B slices (no second list, no direct prediction): the
+// per-macroblock path is what the instruction caches have to hold, and B support is a fifth of it.
+#undef HWB_IS_B
+#ifdef HWB_ENT_NO_B
+#define HWB_IS_B(slice_type) false
+#else
+#define HWB_IS_B(slice_type) ((slice_type) == SLICE_B)
+#endif
 #undef HWB_IS_CABAC
 #if HWB_ENT_MODE == 1
 #define HWB_IS_CABAC(s) true
@@ -193,7 +201,7 @@ HWB_TABLE uint32_t line_tab[20] = {HWB_LINE_WORDS(HWB_BOTROW)};
 // comes from the slice's line buffer, the interior is reset.
 HWB_FN void fill_caches(SliceDec &s, bool unused) {
   (void)unused;
-  const int nl = s.sd->slice_type == SLICE_B ? 2 : (s.sd->slice_type == SLICE_P ? 1 : 0);
+  const int nl = HWB_IS_B(s.sd->slice_type) ? 2 : (s.sd->slice_type == SLICE_P ? 1 : 0);
   const int top = HWB_CI(0, -1);
   const bool availA = s.availA, availB = s.availB, availC = s.availC, availD = s.availD;
   const NbCtx *T = s.line + s.mbx;
@@ -825,7 +833,7 @@ HWB_FN int cabac_chroma_mode(SliceDec &s) {
 HWB_FN void finish_mb(SliceDec &s, bool skipped, bool direct16, bool is_pcm) {
   const ChunkCtx &c = *s.c;
   const SliceDesc &sd = *s.sd;
-  const bool B = sd.slice_type == SLICE_B;
+  const bool B = HWB_IS_B(sd.slice_type);
   const int nl = B ? 2 : (sd.slice_type == SLICE_P ? 1 : 0);
   MbInfo &o = s.out;
   const int f = s.pd->frame;
@@ -916,7 +924,7 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
   const ChunkCtx &c = *s.c;
   const SliceDesc &sd = *s.sd;
   const int st = sd.slice_type;
-  const bool B = st == SLICE_B;
+  const bool B = HWB_IS_B(st);
   const int nl = B ? 2 : 1;
   MbInfo &o = s.out;
   o.mbtype = MB_INTER; o.qp = (uint8_t)s.qp; o.cbp = 0; o.flags = 0; o.imode = 0; o.cmode = 0;
@@ -1203,7 +1211,7 @@ HWB_FN void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states
     if (sd.slice_type != SLICE_I) {
       if (HWB_IS_CABAC(s)) {
         int ctx = (s.availA && !(s.left.flags & NBF_SKIP)) + (s.availB && !(top_flags(s) & NBF_SKIP));
-        skipped = cabac_bin(s, (sd.slice_type == SLICE_B ? 24 : 11) + ctx) != 0;
+        skipped = cabac_bin(s, (HWB_IS_B(sd.slice_type) ? 24 : 11) + ctx) != 0;
       } else {
         if (run < 0) {
           run = (int)s_ue(s);

@@ -223,6 +223,11 @@ Result B200VideoDecoder::submit_current() {
   mark();
   int mode = ch->pics[0].cabac ? 1 : 0;
   for (auto &p : ch->pics) if ((p.cabac ? 1 : 0) != mode) mode = -1;
+  if (mode == 1) {  // CABAC throughout: the copy of the kernel without B-slice support when the chunk has none
+    bool has_b = false;
+    for (auto &sl : ch->slices) has_b |= sl.slice_type == hwb::SLICE_B;
+    if (!has_b) mode = 3;
+  }
   rc |= hwb_dev_entropy(dev_, st, &c, tickets, mode);
   mark();
   {
