@@ -22,7 +22,13 @@ struct ReconScratch {
   int16_t res[24][16];  // residual per 4x4 block: 16 luma (z order; 8x8 blocks use 4 slots as 64), 4 Cb, 4 Cr
   int32_t dc[24];       // dequantised DC per block (Intra16x16 luma DC, chroma DC)
   uint32_t has_res;     // bit b: res[b] is non-zero
+  // Per-lane motion-compensation scratch: the 7x9 reference window (63 bytes), the intermediate column b1[7] and
+  // the two prediction arrays.  They are indexed dynamically, so as thread-local arrays they lived in local memory
+  // (measured: 164 M local loads/stores per launch, 1.5 TB/s of L2 traffic, long-scoreboard the second largest
+  // stall); a stride of 41 words keeps the 32 lanes on different banks.
+  uint32_t lane_scratch[32][41];
 };
+enum { LS_WIN = 0, LS_B1 = 16, LS_P0 = 24, LS_P1 = 32 };  // word offsets inside a lane's scratch
 
 // ---------------------------------------------------------------------------------------------
 // transforms
@@ -173,8 +179,9 @@ HWB_HD int tap6(int a, int b, int c, int d, int e, int f) { return a - 5 * b + 2
 
 // Luma prediction of a 4 (wide) x 2 (high) region whose top-left integer position (already
 // displaced by mv>>2) is (px,py); fx,fy = mv&3.  ref is a coded luma plane (w x h, pitch w).
-HWB_FN void mc_luma_4x2(const uint8_t *ref, int w, int h, int px, int py, int fx, int fy, int *out) {
-  uint8_t win[7][9];  // rows py-2..py+4, cols px-2..px+6
+HWB_FN void mc_luma_4x2(const uint8_t *ref, int w, int h, int px, int py, int fx, int fy, int *out, uint32_t *scratch) {
+  uint8_t (*win)[9] = (uint8_t (*)[9])(scratch + LS_WIN);  // rows py-2..py+4, cols px-2..px+6
+  int *b1 = (int *)(scratch + LS_B1);
   const bool inside = (px >= 2) && (px + 6 < w) && (py >= 2) && (py + 4 < h);
   if (fx == 0 && fy == 0) {
 #pragma unroll 1
@@ -233,7 +240,6 @@ HWB_FN void mc_luma_4x2(const uint8_t *ref, int w, int h, int px, int py, int fx
       }
   } else if (fx == 2 || fy == 2) {
     for (int c = 0; c < 4; ++c) {
-      int b1[7];
 #pragma unroll 1
       for (int r = 0; r < 7; ++r) b1[r] = HWB_H1(r, c);
 #pragma unroll 1
@@ -443,15 +449,16 @@ HWB_FN void recon_mb(const ChunkCtx &c, int pic, int mbx, int mby, ReconScratch 
         {  // luma: raster 4x4 block l>>1, rows (l&1)*2..+1
           int br = l >> 1, bx = br & 3, by = br >> 2, q = (by >> 1) * 2 + (bx >> 1);
           int r0 = ri0[q], r1 = bslice ? ri1[q] : -1;
-          int p0[8], p1[8];
+          uint32_t *ls = sm->lane_scratch[l];
+          int *p0 = (int *)(ls + LS_P0), *p1 = (int *)(ls + LS_P1);
           int x = mbx * 16 + bx * 4, y = mby * 16 + by * 4 + (l & 1) * 2;
           if (r0 >= 0) {
             int mx = mv0[br * 2], my = mv0[br * 2 + 1];
-            mc_luma_4x2(frame_y(c, sd.ref_frame[0][r0]), c.wc, c.hc, x + (mx >> 2), y + (my >> 2), mx & 3, my & 3, p0);
+            mc_luma_4x2(frame_y(c, sd.ref_frame[0][r0]), c.wc, c.hc, x + (mx >> 2), y + (my >> 2), mx & 3, my & 3, p0, ls);
           }
           if (r1 >= 0) {
             int mx = mv1[br * 2], my = mv1[br * 2 + 1];
-            mc_luma_4x2(frame_y(c, sd.ref_frame[1][r1]), c.wc, c.hc, x + (mx >> 2), y + (my >> 2), mx & 3, my & 3, p1);
+            mc_luma_4x2(frame_y(c, sd.ref_frame[1][r1]), c.wc, c.hc, x + (mx >> 2), y + (my >> 2), mx & 3, my & 3, p1, ls);
           }
           WeightSel ws = select_weights(pd, sd, 0, r0, r1);
           uint8_t *t = sm->luma + (by * 4 + (l & 1) * 2 + 1) * LT_STRIDE + LT_OFF + bx * 4;
@@ -464,7 +471,7 @@ HWB_FN void recon_mb(const ChunkCtx &c, int pic, int mbx, int mby, ReconScratch 
         {  // chroma: plane l>>4, luma block l&15 -> 2x2 chroma samples
           int pl = l >> 4, br = l & 15, bx = br & 3, by = br >> 2, q = (by >> 1) * 2 + (bx >> 1);
           int r0 = ri0[q], r1 = bslice ? ri1[q] : -1;
-          int p0[4], p1[4];
+          int *p0 = (int *)(sm->lane_scratch[l] + LS_P0), *p1 = (int *)(sm->lane_scratch[l] + LS_P1);
           int cx = mbx * 8 + bx * 2, cy = mby * 8 + by * 2;
           if (r0 >= 0) {
             const uint8_t *rp = pl ? frame_cr(c, sd.ref_frame[0][r0]) : frame_cb(c, sd.ref_frame[0][r0]);
