@@ -85,7 +85,7 @@ HWB_ENTROPY_KERNEL(entropy_cabac_ip_kernel, hwb::ent_cabac_ip)  // CABAC, no B s
 // ------------------------------------------------------------------------------------ reconstruction
 __device__ __forceinline__ void wait_progress(const int32_t *p, int need) {
   if ((threadIdx.x & 31) == 0) {
-    while (*((volatile const int32_t *)p) < need) __nanosleep(200);
+    while (*((volatile const int32_t *)p) < need) __nanosleep(40);
   }
   __syncwarp();
 }
@@ -99,7 +99,7 @@ __device__ __forceinline__ void publish_progress(int32_t *p, int v) {
 
 // 6 blocks (24 warps) per SM: 80 registers.  Measured on the benchmark clip: 4 blocks/SM (128 registers) 173 ms,
 // 6: 156 ms, 8 (64 registers): 163 ms per 3000 pictures.
-__global__ void __launch_bounds__(kThreads, 6) recon_kernel(ChunkCtx c, const int32_t *pics, int npics, int32_t *ticket) {
+__global__ void __launch_bounds__(kThreads, 6) recon_kernel(const __grid_constant__ ChunkCtx c, const int32_t *pics, int npics, int32_t *ticket) {
   __shared__ ReconScratch sm[kWarpsPerBlock];
   ReconScratch *my = &sm[threadIdx.x >> 5];
   const int total = npics * c.mb_h;
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kThreads, 6) recon_kernel(ChunkCtx c, const in
 
 // 64 registers, 8 blocks (32 warps) per SM; squeezing it to 40 / 32 registers for 48 / 64 warps measured slower
 // (118 / 124 ms against 103 ms per 3000 pictures).
-__global__ void __launch_bounds__(kThreads, 8) deblock_kernel(ChunkCtx c, const int32_t *pics, int npics, int32_t *ticket) {
+__global__ void __launch_bounds__(kThreads, 8) deblock_kernel(const __grid_constant__ ChunkCtx c, const int32_t *pics, int npics, int32_t *ticket) {
   __shared__ DeblockScratch sm[kWarpsPerBlock];
   DeblockScratch *my = &sm[threadIdx.x >> 5];
   const int total = npics * c.mb_h;

@@ -14,6 +14,9 @@ struct DeblockScratch {
   uint8_t luma[20 * DL_STRIDE];       // rows -4..15 (row r at (r+4)), col c at DL_OFF + c (c = -4..15)
   uint8_t chroma[2][12 * DC_STRIDE];  // rows -4..7, col c at DC_OFF + c (c = -4..7)
   uint8_t bs[32];                     // [dir][edge][segment]
+#if !HWB_DEVICE_BUILD
+  uint32_t pre_l[32][4], pre_c[32][3];  // host emulation only: per-lane registers that live across lane blocks
+#endif
 };
 
 HWB_HD bool mv_far(const int16_t *a, const int16_t *b) {
@@ -118,6 +121,29 @@ HWB_FN void deblock_mb(const ChunkCtx &c, int pic, int mbx, int mby, DeblockScra
   uint8_t *Y = frame_y(c, pd.frame), *Cb = frame_cb(c, pd.frame), *Cr = frame_cr(c, pd.frame);
   const bool two_lists = pd.has_inter == 2;  // picture contains B slices
 
+  // ---- tile loads first (coherent loads: neighbours were written by other warps of this launch): 4 + 3 words per
+  // lane, all issued before anything waits on them, so that their L2 round trips overlap each other and the
+  // boundary-strength phase below (this stage is bound by load latency on the wavefront's critical path)
+  uint32_t tl[4], tc[3];
+  HWB_LANES(l)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = l + 32 * k, r = i / 5 - 4, cq = i % 5 - 1;  // row -4..15, column quad -1..3
+      const bool ok = i < 100 && !((r < 0 && mby == 0) || (cq < 0 && mbx == 0));
+      tl[k] = ok ? ld_u32_cg((const uint32_t *)(Y + (int64_t)(mby * 16 + r) * wc + mbx * 16 + cq * 4)) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int i = l + 32 * k, pl = i / 36, kk = i % 36, r = kk / 3 - 4, cq = kk % 3 - 1;  // row -4..7, quads -1..1
+      const bool ok = i < 72 && !((r < 0 && mby == 0) || (cq < 0 && mbx == 0));
+      tc[k] = ok ? ld_u32_cg((const uint32_t *)((pl ? Cr : Cb) + (int64_t)(mby * 8 + r) * cw + mbx * 8 + cq * 4)) : 0u;
+    }
+#if !HWB_DEVICE_BUILD
+    for (int k = 0; k < 4; ++k) sm->pre_l[l][k] = tl[k];
+    for (int k = 0; k < 3; ++k) sm->pre_c[l][k] = tc[k];
+#endif
+  HWB_LANES_END
+
   // ---- boundary strengths: one lane per (direction, edge, 4-sample segment)
   HWB_LANES(l)
     const int dir = l >> 4, e = (l >> 2) & 3, s = l & 3;
@@ -144,21 +170,21 @@ HWB_FN void deblock_mb(const ChunkCtx &c, int pic, int mbx, int mby, DeblockScra
 #endif
   if (!any) return;
 
-  // ---- load tile (coherent loads: neighbours were written by other warps of this launch)
+  // ---- tile to shared memory
   HWB_LANES(l)
-#pragma unroll 1
-    for (int i = l; i < 100; i += 32) {
-      int r = i / 5 - 4, cq = i % 5 - 1;  // row -4..15, column quad -1..3
-      if ((r < 0 && mby == 0) || (cq < 0 && mbx == 0)) continue;
-      *(uint32_t *)(sm->luma + (r + 4) * DL_STRIDE + DL_OFF + cq * 4) =
-          ld_u32_cg((const uint32_t *)(Y + (int64_t)(mby * 16 + r) * wc + mbx * 16 + cq * 4));
+#if !HWB_DEVICE_BUILD
+    for (int k = 0; k < 4; ++k) tl[k] = sm->pre_l[l][k];
+    for (int k = 0; k < 3; ++k) tc[k] = sm->pre_c[l][k];
+#endif
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = l + 32 * k, r = i / 5 - 4, cq = i % 5 - 1;
+      if (i < 100 && !((r < 0 && mby == 0) || (cq < 0 && mbx == 0))) *(uint32_t *)(sm->luma + (r + 4) * DL_STRIDE + DL_OFF + cq * 4) = tl[k];
     }
-#pragma unroll 1
-    for (int i = l; i < 72; i += 32) {
-      int pl = i / 36, k = i % 36, r = k / 3 - 4, cq = k % 3 - 1;  // row -4..7, quads -1..1
-      if ((r < 0 && mby == 0) || (cq < 0 && mbx == 0)) continue;
-      *(uint32_t *)(sm->chroma[pl] + (r + 4) * DC_STRIDE + DC_OFF + cq * 4) =
-          ld_u32_cg((const uint32_t *)((pl ? Cr : Cb) + (int64_t)(mby * 8 + r) * cw + mbx * 8 + cq * 4));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int i = l + 32 * k, pl = i / 36, kk = i % 36, r = kk / 3 - 4, cq = kk % 3 - 1;
+      if (i < 72 && !((r < 0 && mby == 0) || (cq < 0 && mbx == 0))) *(uint32_t *)(sm->chroma[pl] + (r + 4) * DC_STRIDE + DC_OFF + cq * 4) = tc[k];
     }
   HWB_LANES_END
 

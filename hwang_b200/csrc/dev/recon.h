@@ -532,7 +532,7 @@ HWB_FN void recon_mb(const ChunkCtx &c, int pic, int mbx, int mby, ReconScratch 
           if (by == 0) aC = (bx + N < 16) ? av.top : av.topright;
           else if (bx + N >= 16) aC = false;
           else aC = N == 8 ? (blk == 2) : (xy2z((bx >> 2) + 1, (by >> 2) - 1) < blk);
-          const int mode = mb.i4modes[blk];
+          const int mode = mbs[mbaddr].i4modes[blk];  // from memory: a dynamic index into the register copy `mb` would push all of it to local memory
           HWB_LANES(l)
             // each lane builds the (tiny) edge array itself; 2N+... reads from shared
             uint8_t E[26];
