@@ -85,16 +85,21 @@ HWB_ENTROPY_KERNEL(entropy_cabac_ip_kernel, hwb::ent_cabac_ip)  // CABAC, no B s
 // ------------------------------------------------------------------------------------ reconstruction
 __device__ __forceinline__ void wait_progress(const int32_t *p, int need) {
   if ((threadIdx.x & 31) == 0) {
-    while (*((volatile const int32_t *)p) < need) __nanosleep(40);
+    int32_t v;
+    for (;;) {  // relaxed GPU-scope poll; the data it guards is read with ld.global.cg (L2) by the callers
+      asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+      if (v >= need) break;
+      __nanosleep(40);
+    }
   }
   __syncwarp();
 }
+// Release store at GPU scope: orders the warp's earlier writes (made visible to lane 0 by __syncwarp) before the
+// flag.  Unlike __threadfence() + volatile store (MEMBAR.SC + CCTL.IVALL + a system-scope store) it does not
+// invalidate the SM's L1 on every macroblock, which the table and MbInfo loads of the other warps live in.
 __device__ __forceinline__ void publish_progress(int32_t *p, int v) {
   __syncwarp();
-  if ((threadIdx.x & 31) == 0) {
-    __threadfence();
-    *((volatile int32_t *)p) = v;
-  }
+  if ((threadIdx.x & 31) == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // 6 blocks (24 warps) per SM: 80 registers.  Measured on the benchmark clip: 4 blocks/SM (128 registers) 173 ms,

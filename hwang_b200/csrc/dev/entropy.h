@@ -1236,9 +1236,9 @@ HWB_FN void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states
     if (mbx == 0 || end || addr == c.nmb) {
 #if HWB_DEVICE_BUILD
       __syncwarp();
-      if ((threadIdx.x & 31) == 0) {
-        __threadfence();
-        *((volatile int32_t *)(c.entropy_prog + slice_idx)) = (end || addr == c.nmb) ? c.nmb : addr;
+      if ((threadIdx.x & 31) == 0) {  // release store: no L1 invalidation (see publish_progress in kernels.cu)
+        const int32_t v = (end || addr == c.nmb) ? c.nmb : addr;
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(c.entropy_prog + slice_idx), "r"(v) : "memory");
       }
 #else
       c.entropy_prog[slice_idx] = (end || addr == c.nmb) ? c.nmb : addr;
