@@ -326,10 +326,10 @@ def run_ours(args):
         'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': (a1['h2d_bytes'] - a0['h2d_bytes']) // args.steps,
                 'd2h_bytes_per_step': (a1['d2h_bytes'] - a0['d2h_bytes']) // args.steps, 'ms_per_step': 1000.0 * e2e_s / args.steps},
         'gpu_launches': int(d['kernel_launches'] + (a1['kernel_launches'] - a0['kernel_launches'])),
-        'roofline': {'bound': 'hbm', 'kernel': {'entropy': 'entropy_cabac_kernel'}.get(dom, dom + '_kernel'), 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+        'roofline': {'bound': 'hbm', 'kernel': {'entropy': 'entropy_cabac_ip_kernel'}.get(dom, dom + '_kernel'), 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                      'frac': achieved / peak, 'traffic': traffic, 'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback',
                      'whole_pipeline_frac': (alg / dev_s / 1e9) / peak,
-                     'note': 'the dominant kernel is bound by instruction fetch (GPC instruction cache at 83% of peak, profiles/r1b_entropy_3000_ncu_summary.json), not by HBM',
+                     'note': 'the dominant kernel is bound by instruction fetch and per-slice latency (no_instruction 4.1 of 10 stall cycles per issued instruction, GPC instruction cache at 76% of its peak request rate: profiles/r1b_entropy_3000_ncu_summary.json), not by HBM',
                      'stage_ms_per_step': {k: v[0] / args.steps for k, v in stage.items()}},
         'cpu_baseline': cpu,
         'clocks': sampler.result(),

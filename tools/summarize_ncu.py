@@ -1,12 +1,14 @@
 """Summarise an ncu report (run here, no GPU needed): headline metrics, stall breakdown, instruction-cache counters.
-  python tools/summarize_ncu.py gpurun_out/x.ncu-rep "workload description" > profiles/x.json
+  python tools/summarize_ncu.py gpurun_out/x.ncu-rep "workload description" [launch index] > profiles/x.json
 """
 import csv, json, subprocess, sys
 
 rep, workload = sys.argv[1], sys.argv[2]
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
-hdr, units, val = rows[0], rows[1], rows[-1]
+hdr, units = rows[0], rows[1]
+which = int(sys.argv[3]) if len(sys.argv) > 3 else -1   # which captured launch (row) to summarise
+val = rows[2:][which]
 m = {h: (v, u) for h, u, v in zip(hdr, units, val)}
 
 
