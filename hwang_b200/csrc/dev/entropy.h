@@ -587,23 +587,56 @@ HWB_HD void coef_emit(SliceDec &s, int bit, int nslots) {
   s.out.nzmask |= ((1u << nslots) - 1u) << bit;
 }
 
-// One residual block in CABAC mode: coded_block_flag (context increment cbf_inc; < 0: none, the block is coded),
-// levels into s.coef, slot(s) to the arena.  Returns the number of non-zero coefficients.
-HWB_FN int cabac_block(SliceDec &s, int cat, int cbf_inc, int bit) {
+// Residual blocks in CABAC mode with the arithmetic decoder held in registers across the whole group:
+//   kind 0: one block of category `cat`; coded_block_flag context increment `arg` (< 0: no flag, the block is
+//           coded), nzmask item `bit0`.  Returns its number of non-zero coefficients.
+//   kind 1: the four 4x4 luma blocks of quadrant q (cat 1 = Intra16x16 AC, cat 2 = other luma)
+//   kind 4: the four chroma AC blocks of plane q
+//   for kinds 1 and 4 `arg` is the coded_block_flag value assumed for unavailable neighbours; the neighbour
+//   caches (total_coeff per block) are read and updated here.
+HWB_FN int cabac_blocks(SliceDec &s, int kind, int q, int cat, int arg, int bit0) {
   Cabac cab = s.cab;
   const uint8_t *base = s.br.base;
+  const int nblk = kind == 0 ? 1 : 4;
+  const int maxc = cat == 5 ? 64 : (cat == 3 ? 4 : ((cat == 1 || cat == 4) ? 15 : 16));
   int n = 0;
-  bool coded = true;
-  if (cbf_inc >= 0) coded = cabac_decision(cab, base, s.states + 85 + 4 * (cat == 5 ? 0 : cat) + cbf_inc) != 0;
-  if (coded) {
-    coef_clear(s, cat == 5 ? 64 : 16);
-    n = cabac_residual_impl(s, cab, base, s.states, cat, cat == 5 ? 64 : (cat == 3 ? 4 : ((cat == 1 || cat == 4) ? 15 : 16)),
-                            (cat == 1 || cat == 4) ? 1 : 0);
-    coef_emit(s, bit, cat == 5 ? 4 : 1);
+#pragma unroll 1
+  for (int k = 0; k < nblk; ++k) {
+    int inc = arg, bit = bit0;
+    uint8_t *nzp = nullptr;
+    if (kind == 1) {
+      const int z = q * 4 + k, ci = HWB_CI(z2x(z), z2y(z));
+      const int na = s.nz_cache[ci - 1], nb = s.nz_cache[ci - 8];
+      inc = (na == 0x80 ? arg : (na != 0)) + 2 * (nb == 0x80 ? arg : (nb != 0));
+      bit = NZ_LUMA0 + z; nzp = s.nz_cache + ci;
+    } else if (kind == 4) {
+      const int bx = k & 1, by = k >> 1;
+      const int na = s.cnz_cache[q][(by + 1) * 4 + bx], nb = s.cnz_cache[q][by * 4 + bx + 1];
+      inc = (na == 0x80 ? arg : (na != 0)) + 2 * (nb == 0x80 ? arg : (nb != 0));
+      bit = (q ? NZ_CR0 : NZ_CB0) + k; nzp = &s.cnz_cache[q][(by + 1) * 4 + bx + 1];
+    }
+    n = 0;
+    bool coded = true;
+    if (inc >= 0) coded = cabac_decision(cab, base, s.states + 85 + 4 * (cat == 5 ? 0 : cat) + inc) != 0;
+    if (coded) {
+      coef_clear(s, cat == 5 ? 64 : 16);
+      n = cabac_residual_impl(s, cab, base, s.states, cat, maxc, (cat == 1 || cat == 4) ? 1 : 0);
+      coef_emit(s, bit, cat == 5 ? 4 : 1);
+    }
+    if (nzp) *nzp = (uint8_t)n;
   }
   s.cab = cab;
   return n;
 }
+// Hides a constant from the compiler's interprocedural constant propagation: with literal `kind` arguments it cloned
+// cabac_blocks once per call pattern (three 6.5 KB copies of the residual decoder in a fetch-bound kernel).
+HWB_HD int opaque(int v) {
+#if HWB_DEVICE_BUILD
+  asm volatile("" : "+r"(v));
+#endif
+  return v;
+}
+HWB_HD int cabac_block(SliceDec &s, int cat, int cbf_inc, int bit) { return cabac_blocks(s, opaque(0), 0, cat, cbf_inc, bit); }
 
 // identity scan for blocks whose coefficients are already in raster order
 HWB_TABLE uint8_t scan_ident4[4] = {0, 1, 2, 3};
@@ -648,19 +681,14 @@ HWB_FN void decode_residual(SliceDec &s, bool i16, int cbp, bool t8) {
         if (n) coef_emit(s, NZ_LUMA0 + q * 4, 4);
       }
     } else {
+      if (cabac) { cabac_blocks(s, opaque(1), q, i16 ? 1 : 2, cbf_unavail, 0); continue; }
 #pragma unroll 1
       for (int k = 0; k < 4; ++k) {
         int z = q * 4 + k, bx = z2x(z), by = z2y(z);
         int na = s.nz_cache[HWB_CI(bx - 1, by)], nb = s.nz_cache[HWB_CI(bx, by - 1)];
-        int n = 0;
-        if (cabac) {
-          int a = na == 0x80 ? cbf_unavail : (na != 0), bq = nb == 0x80 ? cbf_unavail : (nb != 0);
-          n = cabac_block(s, i16 ? 1 : 2, a + 2 * bq, NZ_LUMA0 + z);
-        } else {
-          coef_clear(s, 16);
-          n = cavlc_residual(s, cavlc_nc(na, nb), i16 ? 15 : 16, i16 ? 1 : 0, zigzag4x4, nullptr, 0);
-          if (n) coef_emit(s, NZ_LUMA0 + z, 1);
-        }
+        coef_clear(s, 16);
+        int n = cavlc_residual(s, cavlc_nc(na, nb), i16 ? 15 : 16, i16 ? 1 : 0, zigzag4x4, nullptr, 0);
+        if (n) coef_emit(s, NZ_LUMA0 + z, 1);
         s.nz_cache[HWB_CI(bx, by)] = (uint8_t)n;
       }
     }
@@ -682,22 +710,18 @@ HWB_FN void decode_residual(SliceDec &s, bool i16, int cbp, bool t8) {
   }
   if (cbp & 0x20) {
 #pragma unroll 1
-    for (int p = 0; p < 2; ++p)
+    for (int p = 0; p < 2; ++p) {
+      if (cabac) { cabac_blocks(s, opaque(4), p, opaque(4), cbf_unavail, 0); continue; }
 #pragma unroll 1
       for (int k = 0; k < 4; ++k) {
         int bx = k & 1, by = k >> 1;
         int na = s.cnz_cache[p][(by + 1) * 4 + bx], nb = s.cnz_cache[p][by * 4 + bx + 1];
-        int n = 0;
-        if (cabac) {
-          int a = na == 0x80 ? cbf_unavail : (na != 0), bq = nb == 0x80 ? cbf_unavail : (nb != 0);
-          n = cabac_block(s, 4, a + 2 * bq, (p ? NZ_CR0 : NZ_CB0) + k);
-        } else {
-          coef_clear(s, 16);
-          n = cavlc_residual(s, cavlc_nc(na, nb), 15, 1, zigzag4x4, nullptr, 0);
-          if (n) coef_emit(s, (p ? NZ_CR0 : NZ_CB0) + k, 1);
-        }
+        coef_clear(s, 16);
+        int n = cavlc_residual(s, cavlc_nc(na, nb), 15, 1, zigzag4x4, nullptr, 0);
+        if (n) coef_emit(s, (p ? NZ_CR0 : NZ_CB0) + k, 1);
         s.cnz_cache[p][(by + 1) * 4 + bx + 1] = (uint8_t)n;
       }
+    }
   }
 }
 
