@@ -9,7 +9,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-PRODUCT_LIB = os.path.join(_HERE, 'libhwang_b200.so')
+PRODUCT_LIB = os.environ.get('HWB_PRODUCT_LIB') or os.path.join(_HERE, 'libhwang_b200.so')  # override: A/B runs of two builds on one box
 _lib = None
 _path = None
 

@@ -794,38 +794,24 @@ HWB_FN int cabac_ref_idx(SliceDec &s, int l, int bx, int by) {
   return ref;
 }
 
-// One motion vector difference component; the arithmetic decoder stays in registers for the whole element.
 HWB_FN int cabac_mvd(SliceDec &s, int base, int amvd, int &absout) {
-  Cabac cab = s.cab;
-  const uint8_t *bs = s.br.base;
-  uint8_t *st = s.states + base;
-  const int inc = amvd < 3 ? 0 : (amvd > 32 ? 2 : 1);
-  int mvd = 0;
-  if (cabac_decision(cab, bs, st + inc)) {
-    mvd = 1;
-    int ctx = 3;
+  int inc = amvd < 3 ? 0 : (amvd > 32 ? 2 : 1);
+  if (!cabac_bin(s, base + inc)) { absout = 0; return 0; }
+  int mvd = 1, ctx = base + 3;
 #pragma unroll 1
-    while (mvd < 9 && cabac_decision(cab, bs, st + ctx)) { if (mvd < 4) ctx++; mvd++; }
-    if (mvd >= 9) {
-      int k = 3;
+  while (mvd < 9 && cabac_bin(s, ctx)) { if (mvd < 4) ctx++; mvd++; }
+  if (mvd >= 9) {
+    int k = 3;
 #pragma unroll 1
-      while (cabac_bypass(cab, bs)) { mvd += 1 << k; k++; if (k > 24) { sd_fail(s, 41); mvd = 0; break; } }
+    while (cabac_byp(s)) { mvd += 1 << k; k++; if (k > 24) { sd_fail(s, 41); return 0; } }
 #pragma unroll 1
-      while (k-- > 0 && !s.error) mvd += cabac_bypass(cab, bs) << k;
-    }
-    absout = mvd < 70 ? mvd : 70;
-    if (cabac_bypass(cab, bs)) mvd = -mvd;
-  } else {
-    absout = 0;
+    while (k--) mvd += cabac_byp(s) << k;
   }
-  s.cab = cab;
-  return mvd;
+  absout = mvd < 70 ? mvd : 70;
+  return cabac_byp(s) ? -mvd : mvd;
 }
 
 HWB_FN int cabac_cbp(SliceDec &s) {
-  Cabac cab = s.cab;
-  const uint8_t *bs = s.br.base;
-  uint8_t *st = s.states;
   const LeftCtx &L = s.left;
   // luma: cbp bits of neighbours; unavailable / I_PCM behave as "all coded"
   int cbpa = s.availA ? ((L.flags & NBF_IPCM) ? 0x2F : L.cbp) : 0x0F;
@@ -835,15 +821,14 @@ HWB_FN int cabac_cbp(SliceDec &s) {
   for (int b8 = 0; b8 < 4; ++b8) {
     int a = (b8 & 1) ? !((cbp >> (b8 - 1)) & 1) : !((cbpa >> (b8 + 1)) & 1);
     int bq = (b8 & 2) ? !((cbp >> (b8 - 2)) & 1) : !((cbpb >> (b8 + 2)) & 1);
-    cbp |= cabac_decision(cab, bs, st + 73 + a + 2 * bq) << b8;
+    cbp |= cabac_bin(s, 73 + a + 2 * bq) << b8;
   }
   int ca = s.availA ? (cbpa >> 4) & 3 : 0, cb = s.availB ? (cbpb >> 4) & 3 : 0;
   int ctx = (ca > 0) + 2 * (cb > 0);
-  if (cabac_decision(cab, bs, st + 77 + ctx)) {
+  if (cabac_bin(s, 77 + ctx)) {
     ctx = 4 + (ca == 2) + 2 * (cb == 2);
-    cbp |= (1 + cabac_decision(cab, bs, st + 77 + ctx)) << 4;
+    cbp |= (1 + cabac_bin(s, 77 + ctx)) << 4;
   }
-  s.cab = cab;
   return cbp;
 }
 
