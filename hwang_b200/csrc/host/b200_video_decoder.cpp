@@ -134,6 +134,9 @@ Result B200VideoDecoder::feed(const uint8_t *encoded_buffer, size_t encoded_size
   if (!cur_) {
     if (!idr) return Result(false, "B200 decoder: interval does not start with an IDR picture");
     cur_.reset(new Chunk());
+    // the previous chunk's staging buffer is recycled: fresh memory would cost one page fault per 4 KB of bitstream
+    cur_->bitstream = std::move(spare_bits_);
+    cur_->bitstream.clear();
     cur_->bitstream.reserve(last_chunk_bytes_ + (last_chunk_bytes_ >> 2) + (1 << 20));
     stream_.reset_dpb();
   }
@@ -218,6 +221,8 @@ Result B200VideoDecoder::submit_current() {
   c.entropy_order = (const int32_t *)(b + o_order);
   rc |= hwb_dev_memset(dev_, st, sync, 0, n_sync * 4);
   stats_.h2d_bytes += ch->bitstream.size() + (size_t)P * sizeof(PicDesc) + (size_t)S * sizeof(SliceDesc) + (size_t)P * 4;
+  // a copy from pageable memory has been staged by the time cudaMemcpyAsync returns: the buffer can be reused
+  spare_bits_ = std::move(ch->bitstream);
   rc |= hwb_dev_event_record(dev_, ch->ev_begin, st);  // inputs are resident in HBM from here on
   auto mark = [&]() { if (profile_) { hwb_event *e = hwb_dev_event_create(dev_); hwb_dev_event_record(dev_, e, st); ch->stage_ev.push_back(e); } };
   mark();

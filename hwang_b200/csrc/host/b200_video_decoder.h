@@ -57,7 +57,7 @@ class B200VideoDecoder : public VideoDecoderInterface {
  private:
   struct Slab { uint8_t *base = nullptr; size_t size = 0; };
   struct Chunk {
-    std::vector<uint8_t> bitstream;
+    std::vector<uint8_t> bitstream;  // slice RBSPs of the chunk being fed; handed back to spare_bits_ once uploaded
     std::vector<hwb::PicDesc> pics;
     std::vector<hwb::SliceDesc> slices;
     std::vector<int64_t> out_keys;
@@ -99,6 +99,7 @@ class B200VideoDecoder : public VideoDecoderInterface {
   size_t live_bytes_ = 0;
   size_t last_chunk_bytes_ = 0;
   // output staging
+  std::vector<uint8_t> spare_bits_;
   static const int kRing = 8;
   uint8_t *rgb_dev_[kRing] = {nullptr};
   uint8_t *rgb_pinned_[kRing] = {nullptr};
