@@ -107,6 +107,10 @@ __device__ __forceinline__ void publish_progress(int32_t *p, int v) {
 __global__ void __launch_bounds__(kThreads, 6) recon_kernel(const __grid_constant__ ChunkCtx c, const int32_t *pics, int npics, int32_t *ticket) {
   __shared__ ReconScratch sm[kWarpsPerBlock];
   ReconScratch *my = &sm[threadIdx.x >> 5];
+  // A corrupt or unsupported stream leaves MbInfo / coefficient offsets of the failed slice undefined: the entropy
+  // kernel (complete by now: same-stream order or an event) has raised the chunk's error flag, the host reports it
+  // when the chunk's first frame is popped, and nothing may be dereferenced here.
+  if (*((volatile const int32_t *)c.error_flag) != 0) return;
   const int total = npics * c.mb_h;
   for (;;) {
     const int t = warp_ticket(ticket);
@@ -133,6 +137,7 @@ __global__ void __launch_bounds__(kThreads, 6) recon_kernel(const __grid_constan
 __global__ void __launch_bounds__(kThreads, 8) deblock_kernel(const __grid_constant__ ChunkCtx c, const int32_t *pics, int npics, int32_t *ticket) {
   __shared__ DeblockScratch sm[kWarpsPerBlock];
   DeblockScratch *my = &sm[threadIdx.x >> 5];
+  if (*((volatile const int32_t *)c.error_flag) != 0) return;  // see recon_kernel
   const int total = npics * c.mb_h;
   for (;;) {
     const int t = warp_ticket(ticket);

@@ -41,6 +41,7 @@ int hwb_dev_entropy(hwb_dev *d, int, const ChunkCtx *c, int32_t *, int) {
   return 0;
 }
 int hwb_dev_recon(hwb_dev *d, int, const ChunkCtx *c, const int32_t *pics, int npics, int32_t *) {
+  if (*c->error_flag) { d->launches++; return 0; }  // as the CUDA kernels: nothing is dereferenced after an entropy error
   ReconScratch sm;
   for (int i = 0; i < npics; ++i)
     for (int y = 0; y < c->mb_h; ++y)
@@ -49,6 +50,7 @@ int hwb_dev_recon(hwb_dev *d, int, const ChunkCtx *c, const int32_t *pics, int n
   return 0;
 }
 int hwb_dev_deblock(hwb_dev *d, int, const ChunkCtx *c, const int32_t *pics, int npics, int32_t *) {
+  if (*c->error_flag) { d->launches++; return 0; }
   DeblockScratch sm;
   for (int i = 0; i < npics; ++i)
     for (int y = 0; y < c->mb_h; ++y)

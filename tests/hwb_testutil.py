@@ -77,3 +77,43 @@ FEATURE_CLIPS = {
     'tiny_16x16': dict(frames=5, gop=5, width=16, height=16, profile=1, seed=36, bframes=1),
     'cropped_1080': dict(frames=4, gop=4, width=1920, height=1080, profile=2, seed=34, num_ref=2, bframes=2, qp=30),
 }
+
+
+def decode_corrupted_then_clean(seed_list=(1, 2, 3)):
+    """Flip bytes inside slice payloads: the decoder must either report an error or return frames, never hang or
+    fault, and must decode a clean clip bit-exactly afterwards (same process, same device context)."""
+    import random
+    kw = dict(width=320, height=240, frames=12, gop=6, profile=1, seed=71, num_ref=2, qp=28)
+    mp4, index, samples, kf = make_clip(**kw)
+    outcomes = []
+    for seed in seed_list:
+        rng = random.Random(seed)
+        bad = list(samples)
+        for victim in (1, 4, 7):  # two P pictures and one picture of the second GOP
+            b = bytearray(bad[victim])
+            for _ in range(8):
+                pos = rng.randrange(16, len(b))  # keep the NAL length field and the slice header mostly intact
+                b[pos] ^= 1 << rng.randrange(8)
+            bad[victim] = bytes(b)
+        dec = hw.VideoDecoder(0)
+        dec.configure(kw['width'], kw['height'], index.format(), index.metadata_bytes())
+        try:
+            for s, k in zip(bad, kf):
+                dec.feed(s, k)
+            dec.feed(None)
+            dec.flush()
+            got = 0
+            deadline = time.time() + 120
+            while got < len(bad) and time.time() < deadline:
+                n = dec.frames_ready()
+                if n != 0:
+                    dec.get_frame_yuv()
+                    got += 1
+                else:
+                    time.sleep(0.0005)
+            outcomes.append('frames' if got == len(bad) else 'timeout')
+        except RuntimeError as e:
+            outcomes.append('error: ' + str(e)[:60])
+    assert 'timeout' not in outcomes, outcomes
+    assert_yuv_parity(kw)  # the decoder (and the device context) still work
+    return outcomes

@@ -117,3 +117,8 @@ def test_corrupt_stream_reports_error(emu, built):
     dec.configure(64, 48, 'avc1', index.metadata_bytes())
     with pytest.raises(RuntimeError):
         dec.feed(samples[0][:20], True)  # NAL length runs past the sample
+
+
+def test_corrupted_payload_is_survivable_host_emulation(emu, built):
+    outcomes = util.decode_corrupted_then_clean()
+    assert len(outcomes) == 3

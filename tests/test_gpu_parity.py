@@ -181,3 +181,10 @@ def test_config2_full_size_properties(gpu):
     # (c) seek == sequential
     single = hw.Decoder(io.BytesIO(mp4), video_index=index).retrieve([50 * 30 + 29])
     assert np.array_equal(np.asarray(single[0]).reshape(-1), keep[50 * 30 + 29])
+
+
+def test_corrupted_payload_is_survivable(gpu):
+    """Bit flips inside slice payloads: an error or garbage frames, never a hang or a device fault; a clean clip
+    decodes bit-exactly afterwards in the same process."""
+    outcomes = util.decode_corrupted_then_clean()
+    assert len(outcomes) == 3
