@@ -122,3 +122,24 @@ def test_corrupt_stream_reports_error(emu, built):
 def test_corrupted_payload_is_survivable_host_emulation(emu, built):
     outcomes = util.decode_corrupted_then_clean()
     assert len(outcomes) == 3
+
+
+def test_batch_retrieval_across_workers(emu, built):
+    """hwang_b200.batch.retrieve_many: several clips, sparse rows, two workers (both on the emulated device): the
+    frames equal what a single Decoder returns for the same rows."""
+    from hwang_b200 import batch
+    clips = [dict(width=64, height=48, frames=12, gop=4, profile=1, seed=81, bframes=1),
+             dict(width=96, height=64, frames=9, gop=3, profile=0, seed=82),
+             dict(width=64, height=64, frames=10, gop=5, profile=2, seed=83, bframes=2)]
+    reqs, want = [], []
+    for i, kw in enumerate(clips):
+        mp4, index, samples, kf = util.make_clip(**kw)
+        rows = [0, 2, 5, kw['frames'] - 1] if i != 1 else list(range(kw['frames']))
+        reqs.append((mp4, rows))
+        want.append(hw.Decoder(io.BytesIO(mp4), video_index=index).retrieve(sorted(set(rows))))
+    got = batch.retrieve_many(reqs, devices=[0, 0])
+    assert len(got) == len(clips)
+    for g, w in zip(got, want):
+        assert len(g) == len(w)
+        for a, b in zip(g, w):
+            assert np.array_equal(np.asarray(a), np.asarray(b))
