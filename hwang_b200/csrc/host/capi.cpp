@@ -1,4 +1,5 @@
 // C ABI (include/hwang_b200.h) over the C++ host side.  No exceptions cross this boundary.
+#include <algorithm>
 #include "../../../include/hwang_b200.h"
 
 #include <string.h>
@@ -143,9 +144,14 @@ hwb_automata *hwb_automata_create(int device_type, int device_id, int num_device
 }
 void hwb_automata_destroy(hwb_automata *a) { if (a) { delete a->a; delete a; } }
 int hwb_automata_initialize(hwb_automata *a, const hwb_encoded_data *iv, size_t n, const uint8_t *extra, size_t nextra) {
+  // the previous call's interval buffers are recycled (largest first): assign() into existing capacity touches no new pages
+  std::vector<DecoderAutomata::EncodedData> old = a->a->release_intervals();
+  std::sort(old.begin(), old.end(), [](const DecoderAutomata::EncodedData &x, const DecoderAutomata::EncodedData &y) {
+    return x.encoded_video.capacity() > y.encoded_video.capacity(); });
   std::vector<DecoderAutomata::EncodedData> v(n);
   for (size_t i = 0; i < n; ++i) {
     auto &d = v[i];
+    if (i < old.size()) d.encoded_video = std::move(old[i].encoded_video);
     d.encoded_video.assign(iv[i].encoded_video, iv[i].encoded_video + iv[i].encoded_video_size);
     d.width = iv[i].width; d.height = iv[i].height; d.start_keyframe = iv[i].start_keyframe; d.end_keyframe = iv[i].end_keyframe;
     d.format = iv[i].format ? iv[i].format : "";

@@ -89,6 +89,14 @@ Result DecoderAutomata::initialize(std::vector<EncodedData> &&encoded_data, cons
   return Result();
 }
 
+std::vector<DecoderAutomata::EncodedData> DecoderAutomata::release_intervals() {
+  stop_feeder();
+  std::vector<EncodedData> old = std::move(encoded_data_);
+  encoded_data_.clear();
+  interval_ = 0; popped_ = 0; valid_idx_ = 0;
+  return old;
+}
+
 void DecoderAutomata::feeder() {
   // reference: decoder_automata.cpp:259-404
   for (;;) {
