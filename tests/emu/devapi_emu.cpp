@@ -85,4 +85,46 @@ int hwb_dev_stream_wait(hwb_dev *, int, hwb_event *) { return 0; }
 int hwb_dev_stream_sync(hwb_dev *, int) { return 0; }
 int hwb_dev_event_elapsed(hwb_dev *, hwb_event *, hwb_event *, float *ms) { *ms = 0; return 0; }
 uint64_t hwb_dev_launch_count(hwb_dev *d) { return d->launches; }
+
+// ---- self-test of the arithmetic decoding engine (csrc/dev/bits.h) against a literal restatement of
+// H.264 9.3.3.2 (9-bit codIRange / codIOffset, one bit read per renormalisation step, rangeTabLPS / transIdxLPS /
+// transIdxMPS tables).  `ops[i]`: 0..127 = decision with context ops[i] % nctx, 128 = bypass, 129 = terminate.
+// Returns the index of the first mismatch, or -1.
+struct SpecCabac {
+  const uint8_t *d; size_t n, bitpos; uint32_t range, offset;
+  uint32_t bit() { uint32_t v = bitpos / 8 < n ? (d[bitpos / 8] >> (7 - bitpos % 8)) & 1 : 0; bitpos++; return v; }
+  void start(size_t byte) { bitpos = byte * 8; range = 510; offset = 0; for (int i = 0; i < 9; ++i) offset = (offset << 1) | bit(); }
+  int decision(uint8_t &st) {
+    const uint32_t p = st >> 1, mps = st & 1, rlps = cabac_range_lps[p * 4 + ((range >> 6) & 3)];
+    int bin;
+    range -= rlps;
+    if (offset >= range) { bin = (int)(mps ^ 1); offset -= range; range = rlps; st = (uint8_t)((cabac_trans_lps[p] << 1) | (p == 0 ? mps ^ 1 : mps)); }
+    else { bin = (int)mps; st = (uint8_t)(((p < 62 ? p + 1 : p) << 1) | mps); }
+    while (range < 256) { range <<= 1; offset = (offset << 1) | bit(); }
+    return bin;
+  }
+  int bypass() { offset = (offset << 1) | bit(); if (offset >= range) { offset -= range; return 1; } return 0; }
+  int terminate() {
+    range -= 2;
+    if (offset >= range) return 1;
+    while (range < 256) { range <<= 1; offset = (offset << 1) | bit(); }
+    return 0;
+  }
+};
+int hwb_emu_cabac_selftest(const uint8_t *data, size_t n, size_t start_byte, const uint8_t *ops, size_t nops, int nctx) {
+  uint8_t st_a[128], st_b[128];
+  for (int i = 0; i < 128; ++i) st_a[i] = st_b[i] = (uint8_t)((i * 37 + 11) & 127);
+  Cabac c; cabac_start(c, data, (uint32_t)start_byte);
+  SpecCabac r; r.d = data; r.n = n; r.start(start_byte);
+  for (size_t i = 0; i < nops; ++i) {
+    int a, b;
+    if (ops[i] < 128) { const int k = ops[i] % nctx; a = cabac_decision(c, data, st_a + k); b = r.decision(st_b[k]); if (st_a[k] != st_b[k]) return (int)i; }
+    else if (ops[i] == 128) { a = cabac_bypass(c, data); b = r.bypass(); }
+    else { a = cabac_terminate(c, data); b = r.terminate(); if (a != b) return (int)i; if (a) return -1; }
+    if (a != b) return (int)i;
+    if (cabac_bitpos(c) != r.bitpos) return (int)i;  // bits consumed: 9 at start + one per renormalisation shift
+    if ((size_t)c.pos + 4 > n) return -1;            // ran out of test data
+  }
+  return -1;
+}
 }

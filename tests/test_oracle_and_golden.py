@@ -104,3 +104,32 @@ def test_rgb_restatement_matches_swscale_on_random_planes():
         sws = fo.SwsRgb24(w, h)
         assert np.array_equal(sws(y, u, v), fo.yuv420_to_rgb24(y, u, v))
         sws.close()
+
+
+def test_cabac_engine_against_literal_spec_decoder(built):
+    """csrc/dev/bits.h (32-bit engine scaled by 2^23, 16-bit refills, fused table) against a literal restatement of
+    H.264 9.3.3.2 on random bytes and random operation sequences: every bin, every context state and the number of
+    consumed bits must agree, from even and odd start positions."""
+    import ctypes
+    import numpy as np
+    from hwang_b200 import build
+    L = ctypes.CDLL(build.EMU)
+    L.hwb_emu_cabac_selftest.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int]
+    rng = np.random.default_rng(5)
+    for trial in range(40):
+        n = 4096
+        # mixtures of random bytes and runs of 0x00 / 0xFF (long MPS / LPS runs, offset near the range boundaries)
+        data = rng.integers(0, 256, n, dtype=np.uint8)
+        if trial % 3 == 1:
+            data[rng.integers(0, n, n // 2)] = 0
+        if trial % 3 == 2:
+            data[rng.integers(0, n, n // 2)] = 255
+        ops = rng.integers(0, 128, 20000, dtype=np.uint8)
+        kinds = rng.random(20000)
+        ops[kinds < 0.15] = 128          # bypass
+        ops[kinds > 0.995] = 129         # terminate (ends the run when it returns 1)
+        nctx = [1, 3, 17, 128][trial % 4]
+        for start in (0, 1, 7, 16):
+            data[start] &= 0x7F  # codIOffset < codIRange at initialisation, as in any conforming stream (9.3.1.2)
+            bad = L.hwb_emu_cabac_selftest(data.tobytes() + bytes(16), n, start, ops.tobytes(), len(ops), nctx)
+            assert bad == -1, 'engine and spec decoder disagree at operation %d (trial %d, start %d)' % (bad, trial, start)
