@@ -97,6 +97,19 @@ std::vector<DecoderAutomata::EncodedData> DecoderAutomata::release_intervals() {
   return old;
 }
 
+// Samples of an interval that are actually fed.  The reference's feeder stops once the consumer has its frames
+// (decoder_automata.cpp:287), so the tail of a GOP after the last wanted frame is not decoded; here the cut is a
+// function of the request alone, which lets the feeder and the consumer agree on it without talking: everything up
+// to the last wanted frame plus the largest possible reorder depth (16 frames: a picture's position in decode order
+// exceeds its position in display order by at most the DPB size), so that every picture displayed up to the last
+// wanted one has been fed, pops stay contiguous from the interval start, and the few extra ones are dropped.
+uint64_t DecoderAutomata::fed_samples(const EncodedData &d) {
+  const uint64_t n = d.end_keyframe - d.start_keyframe;
+  if (d.valid_frames.empty()) return 0;
+  const uint64_t need = d.valid_frames.back() - d.start_keyframe + 1 + 16;
+  return need < n ? need : n;
+}
+
 void DecoderAutomata::feeder() {
   // reference: decoder_automata.cpp:259-404
   for (;;) {
@@ -112,7 +125,7 @@ void DecoderAutomata::feeder() {
     bool failed = false;
     for (size_t di = 0; di < encoded_data_.size() && !abort_ && !failed; ++di) {
       const EncodedData &d = encoded_data_[di];
-      const uint64_t n = d.end_keyframe - d.start_keyframe;
+      const uint64_t n = fed_samples(d);
       size_t next_kf = 0;
       for (uint64_t i = 0; i < n && !abort_; ++i) {
         while (!abort_ && decoder_->decoded_frames_buffered() > MAX_BUFFERED_FRAMES) std::this_thread::yield();
@@ -141,7 +154,7 @@ Result DecoderAutomata::get_frames(uint8_t *buffer, int32_t num_frames) {
     // advance past exhausted intervals (their unwanted tail frames are popped and dropped)
     if (interval_ >= encoded_data_.size()) return Result(false, "get_frames: requested more frames than the intervals contain");
     const EncodedData &d = encoded_data_[interval_];
-    const uint64_t total = d.end_keyframe - d.start_keyframe;
+    const uint64_t total = fed_samples(d);
     if (popped_ >= total) { interval_++; popped_ = 0; valid_idx_ = 0; continue; }
     if (valid_idx_ >= d.valid_frames.size()) {
       // nothing more wanted here: make sure later intervals still hold wanted frames before waiting on this tail

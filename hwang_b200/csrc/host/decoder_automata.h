@@ -64,6 +64,7 @@ class DecoderAutomata {
  private:
   void feeder();
   void stop_feeder();  // abort the current feed pass and wait until the feeder is parked
+  static uint64_t fed_samples(const EncodedData &d);  // how many samples of an interval are fed (see the .cpp)
   Result validate(const std::vector<EncodedData> &encoded_data) const;
 
   const int32_t MAX_BUFFERED_FRAMES = 8;  // reference: decoder_automata.cpp:288

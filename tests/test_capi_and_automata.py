@@ -143,3 +143,25 @@ def test_batch_retrieval_across_workers(emu, built):
         assert len(g) == len(w)
         for a, b in zip(g, w):
             assert np.array_equal(np.asarray(a), np.asarray(b))
+
+
+def test_feeder_stops_after_the_last_wanted_frame(emu, built):
+    """The tail of a GOP after the last wanted frame is not decoded (reference: decoder_automata.cpp:287).  Long GOP
+    with B pictures, one early row per request: the returned frame is bit-exact and far fewer pictures than the GOP
+    holds were decoded; rows at the very end of the GOP still decode all of it."""
+    kw = dict(width=96, height=64, frames=80, gop=40, profile=2, bframes=3, num_ref=2, seed=91, qp=30)
+    mp4, index, samples, kf = util.make_clip(**kw)
+    ref = [fo.yuv420_to_rgb24(*f) for f in util.oracle_frames(index, samples, kf)]
+    # (the reference's interval slicer starts row 41's interval at keyframe 0: the two GOPs are byte-adjacent,
+    # video_index.cpp:76-84 -- so 42 + 16 pictures are fed there, still short of the 80 the interval holds)
+    for row, max_decoded in ((1, 18), (5, 22), (41, 58), (39, 40), (79, 80)):
+        dec = hw.Decoder(io.BytesIO(mp4), video_index=index)
+        s0 = dec._decoder.stats()['pictures_decoded']
+        f = dec.retrieve([row])
+        assert np.array_equal(np.asarray(f[0]), ref[row]), row
+        assert dec._decoder.stats()['pictures_decoded'] - s0 <= max_decoded, row
+    # several rows spread over both GOPs in one call
+    rows = [0, 3, 9, 44, 52]
+    frames = hw.Decoder(io.BytesIO(mp4), video_index=index).retrieve(rows)
+    for r, f in zip(rows, frames):
+        assert np.array_equal(np.asarray(f), ref[r]), r
