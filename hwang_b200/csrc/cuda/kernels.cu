@@ -71,7 +71,7 @@ __device__ __forceinline__ int warp_ticket(int32_t *ticket) {
     const int w = threadIdx.x >> 5;                                                                   \
     for (;;) {                                                                                        \
       const int t = warp_ticket(ticket);                                                              \
-      if (t >= c.num_slices) return;                                                                  \
+      if (t >= c.num_tickets) return;                                                                  \
       const int s = c.entropy_order[t];                                                               \
       NS::decode_slice(c, s, nullptr, &sdec[w]);                                                      \
       __syncwarp();                                                                                   \
@@ -282,7 +282,7 @@ int hwb_dev_entropy(hwb_dev *d, int s, const ChunkCtx *c, int32_t *ticket, int m
   // cycles are "no instruction", gcc instruction requests at 67% of peak).  Sweep on the 3000-slice benchmark chunk:
   // 1 block/SM 561 ms, 2: 411, 3: 394, 4: 402, 5: 409, 8: 430.  HWB_ENTROPY_BLOCKS_PER_SM overrides.
   static int bpsm = [] { const char *e = getenv("HWB_ENTROPY_BLOCKS_PER_SM"); int v = e ? atoi(e) : 0; return v > 0 ? v : 3; }();
-  const int grid = grid_for(d, c->num_slices, bpsm);
+  const int grid = grid_for(d, c->num_tickets, bpsm);
   if (mode == 3) entropy_cabac_ip_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);
   else if (mode == 1) entropy_cabac_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);
   else if (mode == 0) entropy_cavlc_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);

@@ -93,6 +93,7 @@ Result B200VideoDecoder::configure(const FrameInfo &metadata, const std::vector<
   const bool same_geometry = configured_ && width_ == metadata.width && height_ == metadata.height;
   if (same_geometry) reset_keep_memory(); else release_all();
   sticky_error_.clear();
+  hint_valid_ = false; interval_submitted_ = 0;
   std::string err = stream_.configure(extradata.data(), extradata.size());
   if (!err.empty()) { configured_ = false; return Result(false, "B200 decoder: " + err); }
   if ((uint32_t)stream_.width() != metadata.width || (uint32_t)stream_.height() != metadata.height)
@@ -107,6 +108,11 @@ Result B200VideoDecoder::configure(const FrameInfo &metadata, const std::vector<
   }
   configured_ = true;
   return Result();
+}
+
+void B200VideoDecoder::set_interval_hint(uint64_t start_frame, const std::vector<uint64_t> &wanted) {
+  std::lock_guard<std::mutex> lk(mu_);
+  hint_valid_ = true; hint_start_ = start_frame; hint_wanted_ = wanted; interval_submitted_ = 0;
 }
 
 B200VideoDecoder::Slab B200VideoDecoder::take_slab(size_t n) {
@@ -160,11 +166,23 @@ Result B200VideoDecoder::submit_current() {
   ch->order.resize(P);
   for (int i = 0; i < P; ++i) ch->order[i] = i;
   std::stable_sort(ch->order.begin(), ch->order.end(), [&](int a, int b) { return ch->out_keys[a] < ch->out_keys[b]; });
+  // unrequested non-reference pictures are not decoded at all (their frame buffers stay undefined: nothing
+  // references them and the consumer drops them)
+  ch->skipped.assign(P, 0);
+  int nskipped = 0;
+  if (hint_valid_) {
+    for (int j = 0; j < P; ++j) {
+      const int pic = ch->order[j];
+      const uint64_t frame = hint_start_ + interval_submitted_ + (uint64_t)j;
+      if (!ch->pics[pic].is_ref && !std::binary_search(hint_wanted_.begin(), hint_wanted_.end(), frame)) { ch->skipped[pic] = 1; nskipped++; }
+    }
+  }
+  interval_submitted_ += (uint64_t)P;
   // levels
   int nlevels = 0;
   for (auto &p : ch->pics) nlevels = std::max(nlevels, p.level + 1);
   std::vector<std::vector<int32_t>> by_level(nlevels);
-  for (int i = 0; i < P; ++i) by_level[ch->pics[i].level].push_back(i);
+  for (int i = 0; i < P; ++i) if (!ch->skipped[i]) by_level[ch->pics[i].level].push_back(i);
   std::vector<int32_t> level_list;
   for (auto &v : by_level) level_list.insert(level_list.end(), v.begin(), v.end());
 
@@ -210,15 +228,16 @@ Result B200VideoDecoder::submit_current() {
   rc |= hwb_dev_h2d(dev_, st, b + o_bits, ch->bitstream.data(), ch->bitstream.size());
   rc |= hwb_dev_h2d(dev_, st, b + o_pics, ch->pics.data(), (size_t)P * sizeof(PicDesc));
   rc |= hwb_dev_h2d(dev_, st, b + o_slices, ch->slices.data(), (size_t)S * sizeof(SliceDesc));
-  rc |= hwb_dev_h2d(dev_, st, b + o_levels, level_list.data(), (size_t)P * 4);
+  if (!level_list.empty()) rc |= hwb_dev_h2d(dev_, st, b + o_levels, level_list.data(), level_list.size() * 4);
   // Entropy tickets: intra slices carry several times the bits of inter slices and wait on nothing, so they start
   // first; everything else keeps decode order (a B slice's co-located picture then always holds an earlier ticket).
   std::vector<int32_t> order;
   order.reserve(S);
-  for (int i = 0; i < S; ++i) if (ch->slices[i].slice_type == hwb::SLICE_I) order.push_back(i);
-  for (int i = 0; i < S; ++i) if (ch->slices[i].slice_type != hwb::SLICE_I) order.push_back(i);
-  rc |= hwb_dev_h2d(dev_, st, b + o_order, order.data(), (size_t)S * 4);
+  for (int i = 0; i < S; ++i) if (ch->slices[i].slice_type == hwb::SLICE_I && !ch->skipped[ch->slices[i].pic]) order.push_back(i);
+  for (int i = 0; i < S; ++i) if (ch->slices[i].slice_type != hwb::SLICE_I && !ch->skipped[ch->slices[i].pic]) order.push_back(i);
+  if (!order.empty()) rc |= hwb_dev_h2d(dev_, st, b + o_order, order.data(), order.size() * 4);
   c.entropy_order = (const int32_t *)(b + o_order);
+  c.num_tickets = (int32_t)order.size();
   rc |= hwb_dev_memset(dev_, st, sync, 0, n_sync * 4);
   stats_.h2d_bytes += ch->bitstream.size() + (size_t)P * sizeof(PicDesc) + (size_t)S * sizeof(SliceDesc) + (size_t)P * 4;
   // a copy from pageable memory has been staged by the time cudaMemcpyAsync returns: the buffer can be reused
@@ -247,18 +266,18 @@ Result B200VideoDecoder::submit_current() {
   for (int l = 0; l < nlevels; ++l) {
     const int n = (int)by_level[l].size();
     const int32_t *pl = (const int32_t *)(b + o_levels) + lo;
-    rc |= hwb_dev_recon(dev_, st_recon, &c, pl, n, tickets + 1 + 2 * l);
+    if (n > 0) rc |= hwb_dev_recon(dev_, st_recon, &c, pl, n, tickets + 1 + 2 * l);
     mark_recon();
-    rc |= hwb_dev_deblock(dev_, st_recon, &c, pl, n, tickets + 2 + 2 * l);
+    if (n > 0) rc |= hwb_dev_deblock(dev_, st_recon, &c, pl, n, tickets + 2 + 2 * l);
     mark_recon();
     lo += n;
   }
   rc |= hwb_dev_event_record(dev_, ch->ev_done, st_recon);
   if (rc) { sticky_error_ = std::string("B200 decoder: CUDA launch failed: ") + hwb_dev_error(dev_); return Result(false, sticky_error_); }
-  for (auto &p : ch->pics) ch->alg_bytes += fs + (p.has_inter ? fs : 0);
+  for (int i = 0; i < P; ++i) if (!ch->skipped[i]) ch->alg_bytes += fs + (ch->pics[i].has_inter ? fs : 0);
   ch->submitted = true;
   stats_.chunks++;
-  stats_.pictures_decoded += P;
+  stats_.pictures_decoded += P - nskipped;
   queue_.push_back(std::move(ch));
   return Result();
 }
@@ -269,6 +288,7 @@ Result B200VideoDecoder::flush() {
   if (!configured_) return Result();
   Result r = submit_current();
   stream_.reset_dpb();
+  hint_valid_ = false; interval_submitted_ = 0;  // the hint covers one interval
   return r;
 }
 
@@ -359,6 +379,7 @@ Result B200VideoDecoder::pop_common(int mode, uint8_t *buf, size_t size, uint8_t
   Chunk &c = *queue_.front();
   HWANG_RETURN_ON_ERROR(finish_chunk(c));
   const int frame = c.order[c.next_out++];
+  if (mode != 3 && c.skipped[frame]) return Result(false, "B200 decoder: this frame was declared unwanted (set_interval_hint) and has not been decoded");
   if (mode == 3) {
     if (c.next_out >= c.order.size()) retire_front();
     return Result();

@@ -38,6 +38,12 @@ class B200VideoDecoder : public VideoDecoderInterface {
   Result configure(const FrameInfo &metadata, const std::vector<uint8_t> &extradata) override;
   Result feed(const uint8_t *encoded_buffer, size_t encoded_size, bool keyframe) override;
   Result flush() override;
+  // Optional hint from the automaton (not part of the reference's 7-method interface): the pictures fed from now
+  // until the next flush() are absolute frames `start_frame`, `start_frame`+1, ... in display order, and only the
+  // frames in `wanted` (ascending) will be fetched with get_frame; the rest will be dropped with discard_frame.
+  // The decoder then skips unrequested NON-REFERENCE pictures altogether (the reference decodes and
+  // drops them, decoder_automata.cpp:235).  Without a hint everything is decoded.
+  void set_interval_hint(uint64_t start_frame, const std::vector<uint64_t> &wanted);
   Result discard_frame() override;
   Result get_frame(uint8_t *decoded_buffer, size_t decoded_size) override;
   int decoded_frames_buffered() override;
@@ -62,6 +68,7 @@ class B200VideoDecoder : public VideoDecoderInterface {
     std::vector<hwb::SliceDesc> slices;
     std::vector<int64_t> out_keys;
     std::vector<int> order;  // display order -> frame index
+    std::vector<uint8_t> skipped;  // [frame] not decoded: unrequested non-reference picture (set_interval_hint)
     size_t next_out = 0;
     Slab slab;
     hwb::ChunkCtx ctx;
@@ -100,6 +107,9 @@ class B200VideoDecoder : public VideoDecoderInterface {
   size_t last_chunk_bytes_ = 0;
   // output staging
   std::vector<uint8_t> spare_bits_;
+  bool hint_valid_ = false;
+  uint64_t hint_start_ = 0, interval_submitted_ = 0;
+  std::vector<uint64_t> hint_wanted_;
   static const int kRing = 8;
   uint8_t *rgb_dev_[kRing] = {nullptr};
   uint8_t *rgb_pinned_[kRing] = {nullptr};

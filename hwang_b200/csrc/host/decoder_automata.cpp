@@ -1,5 +1,7 @@
 #include "decoder_automata.h"
 
+#include "b200_video_decoder.h"
+
 #include <chrono>
 
 namespace hwang {
@@ -127,6 +129,9 @@ void DecoderAutomata::feeder() {
       const EncodedData &d = encoded_data_[di];
       const uint64_t n = fed_samples(d);
       size_t next_kf = 0;
+      // our own backend is told which frames will be fetched, so that it can leave out unrequested non-reference
+      // pictures; any other VideoDecoderInterface implementation just sees the 7 reference methods
+      if (B200VideoDecoder *b = dynamic_cast<B200VideoDecoder *>(decoder_.get())) b->set_interval_hint(d.start_keyframe, d.valid_frames);
       for (uint64_t i = 0; i < n && !abort_; ++i) {
         while (!abort_ && decoder_->decoded_frames_buffered() > MAX_BUFFERED_FRAMES) std::this_thread::yield();
         if (abort_) break;

@@ -36,7 +36,7 @@ int hwb_dev_memset(hwb_dev *, int, void *dst, int v, size_t n) { memset(dst, v, 
 
 int hwb_dev_entropy(hwb_dev *d, int, const ChunkCtx *c, int32_t *, int) {
   uint8_t states[1024];
-  for (int s = 0; s < c->num_slices; ++s) { SliceDec sd; decode_slice(*c, s, states, &sd); }
+  for (int t = 0; t < c->num_tickets; ++t) { SliceDec sd; decode_slice(*c, c->entropy_order[t], states, &sd); }
   d->launches++;
   return 0;
 }

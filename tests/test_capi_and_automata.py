@@ -165,3 +165,29 @@ def test_feeder_stops_after_the_last_wanted_frame(emu, built):
     frames = hw.Decoder(io.BytesIO(mp4), video_index=index).retrieve(rows)
     for r, f in zip(rows, frames):
         assert np.array_equal(np.asarray(f), ref[r]), r
+
+
+def test_unrequested_non_reference_pictures_are_skipped(emu, built):
+    """Sparse rows over a clip with non-reference B pictures: every returned frame is bit-exact, and the pictures
+    that were neither requested nor referenced were not decoded at all (the reference decodes and drops them,
+    decoder_automata.cpp:235; SURVEY 8a row A2 allows a backend to skip them)."""
+    kw = dict(width=96, height=64, frames=48, gop=24, profile=2, bframes=2, num_ref=2, seed=92, qp=30)
+    mp4, index, samples, kf = util.make_clip(**kw)
+    ref = [fo.yuv420_to_rgb24(*f) for f in util.oracle_frames(index, samples, kf)]
+    # dense: nothing may be skipped
+    dec = hw.Decoder(io.BytesIO(mp4), video_index=index)
+    frames = dec.retrieve(list(range(48)))
+    assert dec._decoder.stats()['pictures_decoded'] == 48
+    for r, f in enumerate(frames):
+        assert np.array_equal(np.asarray(f), ref[r]), r
+    # every 5th frame: B pictures that are not requested are left out
+    rows = list(range(0, 48, 5))
+    dec = hw.Decoder(io.BytesIO(mp4), video_index=index)
+    frames = dec.retrieve(rows)
+    for r, f in zip(rows, frames):
+        assert np.array_equal(np.asarray(f), ref[r]), r
+    decoded = dec._decoder.stats()['pictures_decoded']
+    assert decoded < 40, decoded  # 48 fed; two of every three pictures are non-reference B pictures
+    # a plain VideoDecoder (no automaton, no hint) decodes everything
+    got, d2 = util.decode_yuv(index, samples, kf)
+    assert d2.stats()['pictures_decoded'] == 48
