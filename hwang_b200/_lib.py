@@ -59,6 +59,7 @@ SIGNATURES = {
     'hwb_decoder_get_frame_device': (I, [P, PP]),
     'hwb_decoder_frames_ready': (I, [P]),
     'hwb_decoder_set_chunk_pictures': (I, [P, I]),
+    'hwb_decoder_set_interval_hint': (I, [P, U64, P, SZ]),
     'hwb_decoder_get_stats': (I, [P, ctypes.POINTER(Stats)]),
     'hwb_alloc_pinned': (P, [SZ]),
     'hwb_free_pinned': (V, [P]),

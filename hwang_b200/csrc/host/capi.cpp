@@ -70,6 +70,11 @@ int hwb_decoder_get_frame_yuv(hwb_decoder *d, uint8_t *b, size_t n) { return d->
 int hwb_decoder_get_frame_device(hwb_decoder *d, uint8_t **p) { return d->b200 ? ret(d, d->b200->get_frame_device(p)) : 1; }
 int hwb_decoder_frames_ready(hwb_decoder *d) { return d->b200 ? d->b200->frames_ready() : d->dec->decoded_frames_buffered(); }
 int hwb_decoder_set_chunk_pictures(hwb_decoder *d, int n) { if (!d->b200) return 1; d->b200->set_chunk_pictures(n); return 0; }
+int hwb_decoder_set_interval_hint(hwb_decoder *d, uint64_t start_frame, const uint64_t *wanted, size_t n) {
+  if (!d->b200) return 1;
+  d->b200->set_interval_hint(start_frame, std::vector<uint64_t>(wanted, wanted + n));
+  return 0;
+}
 int hwb_decoder_get_stats(hwb_decoder *d, hwb_stats *out) { if (!d->b200) return 1; fill_stats(d->b200->stats(), out); return 0; }
 
 void *hwb_alloc_pinned(size_t n) {

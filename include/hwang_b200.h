@@ -58,6 +58,12 @@ int hwb_decoder_get_frame_yuv(hwb_decoder *d, uint8_t *decoded_buffer, size_t de
 int hwb_decoder_get_frame_device(hwb_decoder *d, uint8_t **device_rgb);                      /* RGB24 left in device memory */
 int hwb_decoder_frames_ready(hwb_decoder *d);              /* exact count (decoded_frames_buffered saturates at 8) */
 int hwb_decoder_set_chunk_pictures(hwb_decoder *d, int n); /* pictures per GPU batch (cut at IDR boundaries) */
+/* Optional hint, to be called before the first feed() of an interval (what DecoderAutomata::feeder knows at
+ * decoder_automata.cpp:296-318): the pictures fed until the next flush() are the absolute frames start_frame,
+ * start_frame+1, ... in display order, and only the `n` ascending frame numbers in `wanted` will be fetched with
+ * get_frame -- the others will be dropped with discard_frame (decoder_automata.cpp:235).  Unrequested non-reference
+ * pictures are then not decoded at all.  Without the call everything is decoded, as the reference backends do. */
+int hwb_decoder_set_interval_hint(hwb_decoder *d, uint64_t start_frame, const uint64_t *wanted, size_t n);
 
 typedef struct hwb_stats {
   uint64_t pictures_decoded, frames_returned, chunks, bitstream_bytes, kernel_launches, h2d_bytes, d2h_bytes, algorithmic_bytes;
