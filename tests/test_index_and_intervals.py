@@ -4,6 +4,7 @@ import glob
 import io
 import json
 import os
+import struct
 
 import numpy as np
 import pytest
@@ -142,3 +143,78 @@ def test_indexer_error_paths(emu, built):
     b = run_indexer(mp4, 64).get_video_index()
     c = run_indexer(mp4, 1 << 20).get_video_index()
     assert a.sample_offsets() == b.sample_offsets() == c.sample_offsets()
+
+
+def _boxes(buf, start, end):
+    out = []
+    p = start
+    while p + 8 <= end:
+        size, typ = struct.unpack('>I4s', buf[p:p + 8])
+        if size < 8:
+            break
+        out.append((typ, p, size))
+        p += size
+    return out
+
+
+def _to_co64_stz2(mp4):
+    """Rewrite an unfragmented ftyp/moov/mdat file so that it uses 64-bit chunk offsets (co64) and the compact
+    sample-size box (stz2, 16-bit field) when every size fits; parent box sizes and chunk offsets are fixed up."""
+    buf = bytearray(mp4)
+    top = _boxes(buf, 0, len(buf))
+    names = [t for t, _, _ in top]
+    assert names.index(b'moov') < names.index(b'mdat')
+    path = [b'moov', b'trak', b'mdia', b'minf', b'stbl']
+    parents = []
+    lo, hi = 0, len(buf)
+    for name in path:
+        t, p, size = next(b for b in _boxes(buf, lo, hi) if b[0] == name)
+        parents.append(p)
+        lo, hi = p + 8, p + size
+    stbl = {t: (p, size) for t, p, size in _boxes(buf, lo, hi)}
+    # stco -> co64
+    p, size = stbl[b'stco']
+    n = struct.unpack('>I', buf[p + 12:p + 16])[0]
+    offs = struct.unpack('>%dI' % n, buf[p + 16:p + 16 + 4 * n])
+    new_stco = lambda delta: struct.pack('>I4sII', 16 + 8 * n, b'co64', 0, n) + struct.pack('>%dQ' % n, *[o + delta for o in offs])
+    # stsz -> stz2 when all sizes fit in 16 bits
+    q, qsize = stbl[b'stsz']
+    fixed, cnt = struct.unpack('>II', buf[q + 12:q + 20])
+    sizes = [fixed] * cnt if fixed else list(struct.unpack('>%dI' % cnt, buf[q + 20:q + 20 + 4 * cnt]))
+    new_stsz = bytes(buf[q:q + qsize])
+    if max(sizes) < 65536:
+        new_stsz = struct.pack('>I4sI3xBI', 20 + 2 * cnt, b'stz2', 0, 16, cnt) + struct.pack('>%dH' % cnt, *sizes)
+    delta = (16 + 8 * n - size) + (len(new_stsz) - qsize)
+    pieces = sorted([(p, size, new_stco(delta)), (q, qsize, new_stsz)], reverse=True)
+    for pos, old, new in pieces:
+        buf[pos:pos + old] = new
+    for pp in parents:
+        s0 = struct.unpack('>I', buf[pp:pp + 4])[0]
+        buf[pp:pp + 4] = struct.pack('>I', s0 + delta)
+    return bytes(buf), delta
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_index_of_co64_stz2_variant(emu, name):
+    """64-bit chunk offsets and compact sample sizes.  The rewritten file must index to the same
+    table shifted by the growth of the moov box; checked against the reference's own indexer when it is built here."""
+    mp4, g = load(name)
+    ri = g['reference_index']
+    top = [t for t, _, _ in _boxes(mp4, 0, len(mp4))]
+    if b'moof' in top or b'mdat' not in top or top.index(b'moov') > top.index(b'mdat'):
+        pytest.skip('fragmented or mdat-first layout')
+    v64, delta = _to_co64_stz2(mp4)
+    ic = run_indexer(v64)
+    assert not ic.is_error(), ic.error_message()
+    vi = ic.get_video_index()
+    assert vi.sample_offsets() == [o + delta for o in ri['offsets']]
+    assert vi.sample_sizes() == ri['sizes']
+    assert vi.keyframe_indices() == ri['keyframes']
+    tool = os.path.join(os.path.dirname(GOLDEN), '..', 'oracle', '_ref', 'ref_tool')
+    if os.path.exists(tool):
+        import subprocess, tempfile
+        with tempfile.NamedTemporaryFile(suffix='.mp4') as f:
+            f.write(v64); f.flush()
+            ref = json.loads(subprocess.run([tool, 'index', f.name], capture_output=True, text=True, timeout=60).stdout)
+        assert 'error' not in ref, ref
+        assert (ref['offsets'], ref['sizes'], ref['keyframes']) == (vi.sample_offsets(), vi.sample_sizes(), vi.keyframe_indices())
