@@ -218,3 +218,52 @@ def test_index_of_co64_stz2_variant(emu, name):
             ref = json.loads(subprocess.run([tool, 'index', f.name], capture_output=True, text=True, timeout=60).stdout)
         assert 'error' not in ref, ref
         assert (ref['offsets'], ref['sizes'], ref['keyframes']) == (vi.sample_offsets(), vi.sample_sizes(), vi.keyframe_indices())
+
+
+def _mdat_first(mp4):
+    """ftyp/moov/mdat -> ftyp/mdat/moov (the layout most encoders write without "faststart"): chunk offsets move
+    back by the size of the moov box."""
+    top = _boxes(mp4, 0, len(mp4))
+    by = {t: (p, size) for t, p, size in top}
+    assert [t for t, _, _ in top] == [b'ftyp', b'moov', b'mdat']
+    mp, ms = by[b'moov']
+    moov = bytearray(mp4[mp:mp + ms])
+    # find stco inside moov and shift its entries
+    lo, hi = 8, ms
+    for name in (b'trak', b'mdia', b'minf', b'stbl'):
+        t, p, size = next(b for b in _boxes(moov, lo, hi) if b[0] == name)
+        lo, hi = p + 8, p + size
+    t, p, size = next(b for b in _boxes(moov, lo, hi) if b[0] == b'stco')
+    n = struct.unpack('>I', moov[p + 12:p + 16])[0]
+    offs = struct.unpack('>%dI' % n, moov[p + 16:p + 16 + 4 * n])
+    moov[p + 16:p + 16 + 4 * n] = struct.pack('>%dI' % n, *[o - ms for o in offs])
+    fp, fs = by[b'ftyp']
+    dp, ds = by[b'mdat']
+    return mp4[fp:fp + fs] + mp4[dp:dp + ds] + bytes(moov), -ms
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_index_of_mdat_first_variant(emu, name):
+    """moov after mdat: the pull parser must skip the media data without asking for it, then read the moov box."""
+    mp4, g = load(name)
+    ri = g['reference_index']
+    if [t for t, _, _ in _boxes(mp4, 0, len(mp4))] != [b'ftyp', b'moov', b'mdat']:
+        pytest.skip('not an ftyp/moov/mdat file')
+    v, delta = _mdat_first(mp4)
+    ic = hw.MP4IndexCreator(len(v))
+    off, size, asked = 0, 1024, 0
+    while not ic.is_done():
+        asked += size
+        _, off, size = ic.feed(v[off:off + size], size)
+    assert not ic.is_error(), ic.error_message()
+    vi = ic.get_video_index()
+    assert vi.sample_offsets() == [o + delta for o in ri['offsets']]
+    assert vi.sample_sizes() == ri['sizes'] and vi.keyframe_indices() == ri['keyframes']
+    tool = os.path.join(os.path.dirname(GOLDEN), '..', 'oracle', '_ref', 'ref_tool')
+    if os.path.exists(tool):
+        import subprocess, tempfile
+        with tempfile.NamedTemporaryFile(suffix='.mp4') as f:
+            f.write(v); f.flush()
+            ref = json.loads(subprocess.run([tool, 'index', f.name], capture_output=True, text=True, timeout=60).stdout)
+        assert 'error' not in ref, ref
+        assert (ref['offsets'], ref['sizes'], ref['keyframes']) == (vi.sample_offsets(), vi.sample_sizes(), vi.keyframe_indices())
