@@ -191,3 +191,83 @@ def test_unrequested_non_reference_pictures_are_skipped(emu, built):
     # a plain VideoDecoder (no automaton, no hint) decodes everything
     got, d2 = util.decode_yuv(index, samples, kf)
     assert d2.stats()['pictures_decoded'] == 48
+
+
+class _Bits:
+    def __init__(self):
+        self.b = []
+
+    def u(self, n, v):
+        self.b += [(v >> (n - 1 - i)) & 1 for i in range(n)]
+
+    def ue(self, v):
+        v += 1
+        n = v.bit_length()
+        self.u(n - 1, 0)
+        self.u(n, v)
+
+    def se(self, v):
+        self.ue(2 * v - 1 if v > 0 else -2 * v)
+
+    def rbsp(self):
+        bits = self.b + [1]
+        bits += [0] * (-len(bits) % 8)
+        raw = bytes(int(''.join(map(str, bits[i:i + 8])), 2) for i in range(0, len(bits), 8))
+        out = bytearray()
+        zeros = 0
+        for x in raw:  # emulation prevention
+            if zeros >= 2 and x <= 3:
+                out.append(3)
+                zeros = 0
+            out.append(x)
+            zeros = zeros + 1 if x == 0 else 0
+        return bytes(out)
+
+
+def _sps(profile=66, chroma=1, depth=8, frame_mbs_only=1, mbw=4, mbh=3):
+    b = _Bits()
+    b.u(8, profile); b.u(8, 0xC0 if profile == 66 else 0); b.u(8, 30)
+    b.ue(0)
+    if profile >= 100:
+        b.ue(chroma)
+        if chroma == 3:
+            b.u(1, 0)
+        b.ue(depth - 8); b.ue(depth - 8); b.u(1, 0); b.u(1, 0)  # bit depths, qpprime bypass, no scaling matrix
+    b.ue(0); b.ue(2)            # log2_max_frame_num_minus4, pic_order_cnt_type 2
+    b.ue(1); b.u(1, 0)          # max_num_ref_frames, gaps
+    b.ue(mbw - 1); b.ue(mbh - 1)
+    b.u(1, frame_mbs_only)
+    if not frame_mbs_only:
+        b.u(1, 0)               # mb_adaptive_frame_field_flag
+    b.u(1, 1); b.u(1, 0); b.u(1, 0)  # direct_8x8_inference, no cropping, no VUI
+    return bytes([0x67]) + b.rbsp()
+
+
+def _pps(slice_groups=1, cabac=0):
+    b = _Bits()
+    b.ue(0); b.ue(0); b.u(1, cabac); b.u(1, 0)
+    b.ue(slice_groups - 1)
+    if slice_groups > 1:
+        b.ue(0)                 # slice_group_map_type 0: run lengths
+        for _ in range(slice_groups):
+            b.ue(0)
+    b.ue(0); b.ue(0); b.u(1, 0); b.u(2, 0); b.se(0); b.se(0); b.se(0); b.u(1, 1); b.u(1, 0); b.u(1, 0)
+    return bytes([0x68]) + b.rbsp()
+
+
+def _avcc(sps, pps):
+    return bytes([1, sps[1], sps[2], sps[3], 0xFF, 0xE1]) + len(sps).to_bytes(2, 'big') + sps + bytes([1]) + len(pps).to_bytes(2, 'big') + pps
+
+
+def test_unsupported_stream_features_are_refused_at_configure(emu):
+    """The supported subset is enforced with an error Result, never with silent garbage."""
+    dec = hw.VideoDecoder(0)
+    dec.configure(64, 48, 'avc1', _avcc(_sps(), _pps()))  # the hand-made parameter sets themselves are fine
+    for avcc, msg in ((_avcc(_sps(frame_mbs_only=0), _pps()), 'interlaced'),
+                      (_avcc(_sps(profile=100, chroma=2), _pps()), '4:2:0 8-bit'),
+                      (_avcc(_sps(profile=100, depth=10), _pps()), '4:2:0 8-bit'),
+                      (_avcc(_sps(), _pps(slice_groups=2)), 'FMO')):
+        with pytest.raises(RuntimeError, match=msg):
+            hw.VideoDecoder(0).configure(64, 48, 'avc1', avcc)
+    with pytest.raises(RuntimeError, match='does not match the SPS'):
+        hw.VideoDecoder(0).configure(128, 48, 'avc1', _avcc(_sps(), _pps()))
