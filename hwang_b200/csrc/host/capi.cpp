@@ -1,5 +1,6 @@
 // C ABI (include/hwang_b200.h) over the C++ host side.  No exceptions cross this boundary.
 #include <algorithm>
+#include <atomic>
 #include "../../../include/hwang_b200.h"
 
 #include <string.h>
@@ -28,6 +29,9 @@ namespace {
 int ret(hwb_decoder *d, const Result &r) { if (!r.ok) { d->err = r.message; return 1; } return 0; }
 int ret(hwb_automata *a, const Result &r) { if (!r.ok) { a->err = r.message; return 1; } return 0; }
 hwb_dev *g_pin_dev = nullptr;
+// Device the process decodes on (the last one a decoder or an automaton was created for): the page-locked output
+// buffers are allocated through its context, so that a rank of a multi-GPU job never opens a context on GPU 0.
+std::atomic<int> g_last_device{0};
 void fill_stats(const B200Stats &s, hwb_stats *o) {
   o->pictures_decoded = s.pictures_decoded; o->frames_returned = s.frames_returned; o->chunks = s.chunks; o->bitstream_bytes = s.bitstream_bytes;
   o->kernel_launches = s.kernel_launches; o->h2d_bytes = s.h2d_bytes; o->d2h_bytes = s.d2h_bytes; o->algorithmic_bytes = s.algorithmic_bytes;
@@ -51,6 +55,7 @@ int hwb_decoder_create(int device_type, int device_id, int num_devices, int deco
   hwb_decoder *d = new (std::nothrow) hwb_decoder();
   if (!d) { delete dec; return 1; }
   d->dec = dec; d->b200 = dynamic_cast<B200VideoDecoder *>(dec);
+  if (device_id >= 0) g_last_device = device_id;
   *out = d;
   return 0;
 }
@@ -78,7 +83,7 @@ int hwb_decoder_set_interval_hint(hwb_decoder *d, uint64_t start_frame, const ui
 int hwb_decoder_get_stats(hwb_decoder *d, hwb_stats *out) { if (!d->b200) return 1; fill_stats(d->b200->stats(), out); return 0; }
 
 void *hwb_alloc_pinned(size_t n) {
-  if (!g_pin_dev && hwb_dev_open(0, &g_pin_dev) != 0) return nullptr;
+  if (!g_pin_dev && hwb_dev_open(g_last_device.load(), &g_pin_dev) != 0) return nullptr;
   return hwb_dev_malloc_host(g_pin_dev, n);
 }
 void hwb_free_pinned(void *p) { if (g_pin_dev && p) hwb_dev_free_host(g_pin_dev, p); }
@@ -145,6 +150,7 @@ hwb_automata *hwb_automata_create(int device_type, int device_id, int num_device
   hwb_automata *w = new (std::nothrow) hwb_automata();
   if (!w) { delete a; return nullptr; }
   w->a = a;
+  if (device_id >= 0) g_last_device = device_id;
   return w;
 }
 void hwb_automata_destroy(hwb_automata *a) { if (a) { delete a->a; delete a; } }
