@@ -282,6 +282,10 @@ def run_ours(args):
     if dist:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     dev_s, e2e_s = float(times[0]), float(times[1])
+    if dist:  # every rank leaves the process group together; rank 0 then times the CPU baseline on its own
+        dist.barrier()
+        dist.destroy_process_group()
+        dist = None
     if rank != 0:
         return
     frames_total = n * args.steps * world
@@ -336,8 +340,6 @@ def run_ours(args):
         'checksum': checksum[0],
     }
     print(json.dumps(line), flush=True)
-    if dist:
-        dist.destroy_process_group()
 
 
 def main():
