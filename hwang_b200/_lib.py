@@ -20,8 +20,8 @@ c_u64p = ctypes.POINTER(ctypes.c_uint64)
 class Stats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint64) for n in ('pictures_decoded', 'frames_returned', 'chunks', 'bitstream_bytes',
                                                'kernel_launches', 'h2d_bytes', 'd2h_bytes', 'algorithmic_bytes')] + \
-               [(n, ctypes.c_double) for n in ('decode_ms', 'entropy_ms', 'recon_ms', 'deblock_ms', 'rgb_ms')] + \
-               [(n, ctypes.c_uint64) for n in ('entropy_launches', 'recon_launches', 'deblock_launches', 'rgb_launches')]
+               [(n, ctypes.c_double) for n in ('wall_ms', 'entropy_ms', 'picture_ms')] + \
+               [(n, ctypes.c_uint64) for n in ('entropy_launches', 'picture_launches', 'aux_launches')]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -60,9 +60,14 @@ SIGNATURES = {
     'hwb_decoder_frames_ready': (I, [P]),
     'hwb_decoder_set_chunk_pictures': (I, [P, I]),
     'hwb_decoder_set_interval_hint': (I, [P, U64, P, SZ]),
+    'hwb_decoder_set_defer_submit': (I, [P, I]),
+    'hwb_decoder_submit_pending': (I, [P]),
     'hwb_decoder_get_stats': (I, [P, ctypes.POINTER(Stats)]),
     'hwb_alloc_pinned': (P, [SZ]),
     'hwb_free_pinned': (V, [P]),
+    'hwb_alloc_device': (P, [I, SZ]),
+    'hwb_free_device': (V, [I, P]),
+    'hwb_copy_device_to_host': (I, [I, P, P, SZ]),
     'hwb_index_creator_create': (P, [U64]),
     'hwb_index_creator_destroy': (V, [P]),
     'hwb_index_creator_feed': (I, [P, P, SZ, c_u64p, c_u64p]),
@@ -90,6 +95,7 @@ SIGNATURES = {
     'hwb_automata_destroy': (V, [P]),
     'hwb_automata_initialize': (I, [P, ctypes.POINTER(EncodedDataC), SZ, P, SZ]),
     'hwb_automata_get_frames': (I, [P, P, ctypes.c_int32]),
+    'hwb_automata_set_chunk_pictures': (I, [P, I]),
     'hwb_automata_last_error': (CP, [P]),
     'hwb_automata_get_stats': (I, [P, ctypes.POINTER(Stats)]),
 }

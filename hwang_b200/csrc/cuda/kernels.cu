@@ -21,8 +21,8 @@
 __shared__ __align__(8) uint32_t hwb_fused_sm[256];
 #define HWB_CABAC_FUSED hwb_fused_sm
 
-#include "../dev/deblock.h"
 #include "../dev/devapi.h"
+#include "../dev/picture.h"
 #include "../dev/entropy.h"  // generic (runtime entropy_coding_mode): namespace hwb::ent
 #define HWB_ENT_NS ent_cabac
 #define HWB_ENT_MODE 1
@@ -41,8 +41,6 @@ __shared__ __align__(8) uint32_t hwb_fused_sm[256];
 #undef HWB_ENT_NS
 #undef HWB_ENT_MODE
 #undef HWB_ENT_NO_B
-#include "../dev/recon.h"
-#include "../dev/rgb.h"
 
 using namespace hwb;
 
@@ -82,73 +80,43 @@ HWB_ENTROPY_KERNEL(entropy_cabac_kernel, hwb::ent_cabac)  // every picture of th
 HWB_ENTROPY_KERNEL(entropy_cavlc_kernel, hwb::ent_cavlc)  // every picture of the chunk is CAVLC
 HWB_ENTROPY_KERNEL(entropy_cabac_ip_kernel, hwb::ent_cabac_ip)  // CABAC, no B slice in the chunk
 
-// ------------------------------------------------------------------------------------ reconstruction
-__device__ __forceinline__ void wait_progress(const int32_t *p, int need) {
-  if ((threadIdx.x & 31) == 0) {
-    int32_t v;
-    for (;;) {  // relaxed GPU-scope poll; the data it guards is read with ld.global.cg (L2) by the callers
-      asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-      if (v >= need) break;
-      __nanosleep(40);
-    }
-  }
-  __syncwarp();
-}
-// Release store at GPU scope: orders the warp's earlier writes (made visible to lane 0 by __syncwarp) before the
-// flag.  Unlike __threadfence() + volatile store (MEMBAR.SC + CCTL.IVALL + a system-scope store) it does not
-// invalidate the SM's L1 on every macroblock, which the table and MbInfo loads of the other warps live in.
-__device__ __forceinline__ void publish_progress(int32_t *p, int v) {
-  __syncwarp();
-  if ((threadIdx.x & 31) == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
+// ------------------------------------------------------------------------------------ picture kernel
+// Reconstruction, deblocking and the RGB24 writeback of every picture of a chunk in ONE launch: see csrc/dev/picture.h
+// for the work items, their dependencies and why the hand-out order makes the spin waits deadlock-free.
+union PictureScratch {
+  ReconScratch recon;
+  DeblockScratch deblock;
+};
 
-// 6 blocks (24 warps) per SM: 80 registers.  Measured on the benchmark clip: 4 blocks/SM (128 registers) 173 ms,
-// 6: 156 ms, 8 (64 registers): 163 ms per 3000 pictures.
-__global__ void __launch_bounds__(kThreads, 6) recon_kernel(const __grid_constant__ ChunkCtx c, const int32_t *pics, int npics, int32_t *ticket) {
-  __shared__ ReconScratch sm[kWarpsPerBlock];
-  ReconScratch *my = &sm[threadIdx.x >> 5];
+// 6 blocks (24 warps) per SM: 80 registers.  Warps whose global index modulo 5 is below `split` (1..3) take deblocking
+// items, the others reconstruction items, and either kind moves to the other list once its own is exhausted.  Static
+// roles because (a) both stages are bound by instruction fetch: a warp that stays in one of the two code bodies
+// keeps the instruction caches for it, and (b) the no-deadlock argument above needs somebody to be working on each
+// list at all times: warps 0..3 of every block cover both roles for any split in 1..3.
+__global__ void __launch_bounds__(kThreads, 6) picture_kernel(const __grid_constant__ ChunkCtx c, int32_t *ticket, int split) {
+  __shared__ PictureScratch sm[kWarpsPerBlock];
+  PictureScratch *my = &sm[threadIdx.x >> 5];
   // A corrupt or unsupported stream leaves MbInfo / coefficient offsets of the failed slice undefined: the entropy
-  // kernel (complete by now: same-stream order or an event) has raised the chunk's error flag, the host reports it
+  // kernel (complete by now: an event orders the launches) has raised the chunk's error flag, the host reports it
   // when the chunk's first frame is popped, and nothing may be dereferenced here.
   if (*((volatile const int32_t *)c.error_flag) != 0) return;
-  const int total = npics * c.mb_h;
-  for (;;) {
-    const int t = warp_ticket(ticket);
-    if (t >= total) return;
-    // row-major over the pictures of the level: consecutive tickets are the same row of different pictures, so a
-    // row's predecessor (same picture, row above) was handed out npics tickets earlier and is far ahead
-    const int pic = pics[t % npics], y = t / npics;
-    const MbInfo *mbs = pic_mbinfo(c, c.pics[pic].frame);
-    int32_t *prog = c.recon_prog + (size_t)pic * c.mb_h;
-    const bool has_inter = c.pics[pic].has_inter != 0;
-    for (int x = 0; x < c.mb_w; ++x) {
-      // intra macroblocks read the unfiltered row above up to the top-right neighbour
-      if (y > 0 && mbs[y * c.mb_w + x].mbtype != MB_INTER) wait_progress(prog + y - 1, x + 2 < c.mb_w ? x + 2 : c.mb_w);
-      recon_mb(c, pic, x, y, my);
-      // only intra macroblocks of the row below consume this; pictures with inter slices have few of them, so the
-      // fence + flag store is amortised over 4 macroblocks there
-      if (!has_inter || (x & 3) == 3 || x == c.mb_w - 1) publish_progress(prog + y, x + 1);
+  const int gw = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  bool deblock_role = (gw % 5) < split;
+  bool recon_left = c.num_recon_items > 0, deblock_left = c.num_deblock_items > 0;
+  while (recon_left || deblock_left) {
+    if (deblock_role ? !deblock_left : !recon_left) deblock_role = !deblock_role;
+    if (deblock_role) {
+      const int t = warp_ticket(ticket + 1);
+      if (t >= c.num_deblock_items) { deblock_left = false; continue; }
+      const uint32_t it = c.deblock_items[t];
+      deblock_row(c, item_pic(it), item_row(it), &my->deblock);
+    } else {
+      const int t = warp_ticket(ticket);
+      if (t >= c.num_recon_items) { recon_left = false; continue; }
+      const uint32_t it = c.recon_items[t];
+      recon_row(c, item_pic(it), item_row(it), &my->recon);
     }
-  }
-}
-
-// 64 registers, 8 blocks (32 warps) per SM; squeezing it to 40 / 32 registers for 48 / 64 warps measured slower
-// (118 / 124 ms against 103 ms per 3000 pictures).
-__global__ void __launch_bounds__(kThreads, 8) deblock_kernel(const __grid_constant__ ChunkCtx c, const int32_t *pics, int npics, int32_t *ticket) {
-  __shared__ DeblockScratch sm[kWarpsPerBlock];
-  DeblockScratch *my = &sm[threadIdx.x >> 5];
-  if (*((volatile const int32_t *)c.error_flag) != 0) return;  // see recon_kernel
-  const int total = npics * c.mb_h;
-  for (;;) {
-    const int t = warp_ticket(ticket);
-    if (t >= total) return;
-    const int pic = pics[t % npics], y = t / npics;
-    int32_t *prog = c.dbl_prog + (size_t)pic * c.mb_h;
-    for (int x = 0; x < c.mb_w; ++x) {
-      if (y > 0) wait_progress(prog + y - 1, x + 2 < c.mb_w ? x + 2 : c.mb_w);
-      deblock_mb(c, pic, x, y, my);
-      publish_progress(prog + y, x + 1);
-    }
+    __syncwarp();
   }
 }
 
@@ -208,13 +176,12 @@ int hwb_dev_open(int device, hwb_dev **out) {
   hwb_dev *d = new hwb_dev();
   d->device = device;
   cudaDeviceGetAttribute(&d->sms, cudaDevAttrMultiProcessorCount, device);
-  // Priorities, highest first: copy-out and colour conversion (stream DECODE+2), then reconstruction (DECODE+1), then
-  // entropy decoding (DECODE+0): a chunk finishes -- and its frames start travelling to the host -- while the next
-  // chunk is still being entropy-decoded
+  // Priorities, highest first: copies to the host, then the picture kernel (a chunk finishes -- and its frames start
+  // travelling to the host -- while later chunks are still being entropy-decoded), then entropy decoding
   int least = 0, greatest = 0;
   cudaDeviceGetStreamPriorityRange(&least, &greatest);
   for (int i = 0; i < HWB_NUM_STREAMS; ++i) {
-    int prio = (i == HWB_STREAM_COPY || i == HWB_STREAM_DECODE + 2) ? greatest : (i == HWB_STREAM_DECODE + 1 ? greatest + 1 : greatest + 2);
+    int prio = (i == HWB_STREAM_COPY || i == HWB_STREAM_AUX) ? greatest : (i == HWB_STREAM_PICTURE ? greatest + 1 : greatest + 2);
     if (prio > least) prio = least;
     if (cudaStreamCreateWithPriority(&d->streams[i], cudaStreamNonBlocking, prio) != cudaSuccess) { delete d; return 1; }
   }
@@ -245,11 +212,16 @@ void *hwb_dev_malloc_host(hwb_dev *d, size_t n) {
   return p;
 }
 void hwb_dev_free_host(hwb_dev *d, void *p) { cudaSetDevice(d->device); cudaFreeHost(p); }
-int hwb_dev_is_pinned(hwb_dev *d, const void *p) {
+int hwb_dev_pointer_kind(hwb_dev *d, const void *p) {
   cudaPointerAttributes a;
   cudaSetDevice(d->device);
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return 0; }
-  return a.type == cudaMemoryTypeHost ? 1 : 0;
+  return a.type == cudaMemoryTypeHost ? 1 : ((a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? 2 : 0);
+}
+int hwb_dev_mem_info(hwb_dev *d, size_t *free_bytes, size_t *total_bytes) {
+  cudaSetDevice(d->device);
+  HWB_CUDA(d, cudaMemGetInfo(free_bytes, total_bytes));
+  return 0;
 }
 
 int hwb_dev_h2d(hwb_dev *d, int s, void *dst, const void *src, size_t n) {
@@ -260,6 +232,11 @@ int hwb_dev_h2d(hwb_dev *d, int s, void *dst, const void *src, size_t n) {
 int hwb_dev_d2h(hwb_dev *d, int s, void *dst, const void *src, size_t n) {
   cudaSetDevice(d->device);
   HWB_CUDA(d, cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, d->streams[s]));
+  return 0;
+}
+int hwb_dev_d2d(hwb_dev *d, int s, void *dst, const void *src, size_t n) {
+  cudaSetDevice(d->device);
+  HWB_CUDA(d, cudaMemcpyAsync(dst, src, n, cudaMemcpyDefault, d->streams[s]));  // the destination may live on a peer GPU
   return 0;
 }
 int hwb_dev_memset(hwb_dev *d, int s, void *dst, int v, size_t n) {
@@ -291,18 +268,14 @@ int hwb_dev_entropy(hwb_dev *d, int s, const ChunkCtx *c, int32_t *ticket, int m
   d->launches++;
   return 0;
 }
-int hwb_dev_recon(hwb_dev *d, int s, const ChunkCtx *c, const int32_t *pics, int npics, int32_t *ticket) {
+int hwb_dev_picture(hwb_dev *d, int s, const ChunkCtx *c, int32_t *ticket) {
   cudaSetDevice(d->device);
-  static int bpsm = [] { const char *e = getenv("HWB_RECON_BLOCKS_PER_SM"); int v = e ? atoi(e) : 0; return v > 0 ? v : 8; }();
-  recon_kernel<<<grid_for(d, npics * c->mb_h, bpsm), kThreads, 0, d->streams[s]>>>(*c, pics, npics, ticket);
-  HWB_CUDA(d, cudaGetLastError());
-  d->launches++;
-  return 0;
-}
-int hwb_dev_deblock(hwb_dev *d, int s, const ChunkCtx *c, const int32_t *pics, int npics, int32_t *ticket) {
-  cudaSetDevice(d->device);
-  static int bpsm = [] { const char *e = getenv("HWB_DEBLOCK_BLOCKS_PER_SM"); int v = e ? atoi(e) : 0; return v > 0 ? v : 8; }();
-  deblock_kernel<<<grid_for(d, npics * c->mb_h, bpsm), kThreads, 0, d->streams[s]>>>(*c, pics, npics, ticket);
+  static int bpsm = [] { const char *e = getenv("HWB_PICTURE_BLOCKS_PER_SM"); int v = e ? atoi(e) : 0; return v > 0 ? v : 6; }();
+  // deblocking warps per 5 (1..3: every block of 4 warps must hold both roles, see picture_kernel)
+  static int split = [] { const char *e = getenv("HWB_PICTURE_SPLIT"); int v = e ? atoi(e) : 0; return v >= 1 && v <= 3 ? v : 2; }();
+  const int items = c->num_recon_items + c->num_deblock_items;
+  if (items == 0) return 0;
+  picture_kernel<<<grid_for(d, items, bpsm), kThreads, 0, d->streams[s]>>>(*c, ticket, split);
   HWB_CUDA(d, cudaGetLastError());
   d->launches++;
   return 0;

@@ -15,9 +15,12 @@ extern "C" {
 
 typedef struct hwb_dev hwb_dev;  // one per (host decoder instance, GPU)
 
-// Chunks are submitted round-robin on several decode streams, so the (latency-bound) entropy kernel of a chunk runs
-// while earlier chunks are being reconstructed and copied out.
-enum { HWB_STREAM_DECODE = 0, HWB_NUM_DECODE_STREAMS = 4, HWB_STREAM_COPY = 4, HWB_NUM_STREAMS = 5 };
+// Streams.  The entropy kernel of a chunk is latency-bound (one warp per slice, an intra slice of a 1080p picture
+// takes a quarter of a second on its own), so the entropy kernels of many chunks must be in flight at once: chunks
+// rotate over HWB_NUM_ENTROPY_STREAMS streams (inputs are uploaded on the same stream).  The picture kernels of
+// all chunks share one stream (chunks complete in submission order), copies to the host have their own, and the
+// auxiliary stream serves the test-only planar output and the conversion of frames nobody announced.
+enum { HWB_STREAM_ENTROPY0 = 0, HWB_NUM_ENTROPY_STREAMS = 16, HWB_STREAM_PICTURE = 16, HWB_STREAM_COPY = 17, HWB_STREAM_AUX = 18, HWB_NUM_STREAMS = 19 };
 
 int hwb_dev_count(void);
 int hwb_dev_open(int device, hwb_dev **out);
@@ -28,18 +31,22 @@ void *hwb_dev_malloc(hwb_dev *d, size_t n);
 void hwb_dev_free(hwb_dev *d, void *p);
 void *hwb_dev_malloc_host(hwb_dev *d, size_t n);  // pinned
 void hwb_dev_free_host(hwb_dev *d, void *p);
-int hwb_dev_is_pinned(hwb_dev *d, const void *p);
 
 int hwb_dev_h2d(hwb_dev *d, int stream, void *dst, const void *src, size_t n);
 int hwb_dev_d2h(hwb_dev *d, int stream, void *dst, const void *src, size_t n);
+int hwb_dev_d2d(hwb_dev *d, int stream, void *dst, const void *src, size_t n);
+// 1 = page-locked host memory, 2 = device memory (of any device), 0 = pageable host memory
+int hwb_dev_pointer_kind(hwb_dev *d, const void *p);
+// bytes of device memory currently free / total
+int hwb_dev_mem_info(hwb_dev *d, size_t *free_bytes, size_t *total_bytes);
 int hwb_dev_memset(hwb_dev *d, int stream, void *dst, int value, size_t n);
 
 // Decode stages.  `c` is a host copy of the chunk context (its pointers are device pointers).
-// tickets: device int32[4] zeroed by the caller, used for ordered work distribution.
+// ticket: device int32[1] (entropy) / int32[2] (picture kernel) zeroed by the caller, used for ordered work distribution.
 // mode: 1 = every picture of the chunk is CABAC, 3 = CABAC and no B slice, 0 = every picture is CAVLC, -1 = mixed (generic kernel)
 int hwb_dev_entropy(hwb_dev *d, int stream, const hwb::ChunkCtx *c, int32_t *ticket, int mode);
-int hwb_dev_recon(hwb_dev *d, int stream, const hwb::ChunkCtx *c, const int32_t *pics_dev, int npics, int32_t *ticket);
-int hwb_dev_deblock(hwb_dev *d, int stream, const hwb::ChunkCtx *c, const int32_t *pics_dev, int npics, int32_t *ticket);
+// Reconstruction + deblocking + RGB24 writeback of every picture of the chunk (work lists in the context).
+int hwb_dev_picture(hwb_dev *d, int stream, const hwb::ChunkCtx *c, int32_t *ticket);
 // Cropped planar 4:2:0 -> packed RGB24 (reference: sws_scale in SoftwareVideoDecoder::get_frame,
 // software_video_decoder.cpp:292-325; arithmetic of SURVEY.md section 8a row R).
 int hwb_dev_rgb24(hwb_dev *d, int stream, const hwb::ChunkCtx *c, int frame, int crop_x, int crop_y, int w, int h, uint8_t *dst_dev);

@@ -78,6 +78,7 @@ struct SliceDec {
   alignas(4) int16_t tl_mv[2][2];  // copied as 32-bit words
   NbCtx *line;  // [mb_w] top context
   uint32_t coef_next;  // next free slot in the picture arena
+  int32_t row_reach;   // 1 + lowest reference macroblock row read by the inter macroblocks of the current row so far (0 = none)
   // ---- current macroblock
   int mbx, mby, mbaddr;
   bool availA, availB, availC, availD;
@@ -896,11 +897,18 @@ HWB_FN void finish_mb(SliceDec &s, bool skipped, bool direct16, bool is_pcm) {
   s.top_words[1] = cbf;
   s.top_words[2] = s.cnz_cache[0][9] | ((uint32_t)s.cnz_cache[0][10] << 8) | ((uint32_t)s.cnz_cache[1][9] << 16) | ((uint32_t)s.cnz_cache[1][10] << 24);
   s.top_words[3] = 0;
+  int reach = 0;  // per lane on the device, accumulated over the lane loop on the host
   HWB_LANES(l)
   if (inter) {
     const int k = l >> 4, i = l & 15;
     if (k < nl) {
-      ((uint32_t *)(s.o_mv[k] + (uint64_t)s.mbaddr * 32))[i] = *(const uint32_t *)s.mv_cache[k][HWB_CI(i & 3, i >> 2)];
+      const uint32_t mvw = *(const uint32_t *)s.mv_cache[k][HWB_CI(i & 3, i >> 2)];
+      ((uint32_t *)(s.o_mv[k] + (uint64_t)s.mbaddr * 32))[i] = mvw;
+      if (s.ref_cache[k][HWB_CI(i & 3, i >> 2)] >= 0) {
+        // bottom sample row of the block, displaced, plus the 3 rows the 6-tap filter reads below it
+        const int row = (s.mby * 16 + (i >> 2) * 4 + 3 + ((int)(int16_t)(mvw >> 16) >> 2) + 3) >> 4;
+        reach = imax(reach, 1 + clip3(0, c.mb_h - 1, row));
+      }
       if (i < 4) {
         const int r = s.ref_cache[k][HWB_CI((i & 1) * 2, (i >> 1) * 2)];
         s.o_refidx[k][(uint64_t)s.mbaddr * 4 + i] = (int8_t)r;
@@ -913,6 +921,12 @@ HWB_FN void finish_mb(SliceDec &s, bool skipped, bool direct16, bool is_pcm) {
   }
   if (l < 20) ((uint32_t *)n)[l] = *(const uint32_t *)((const uint8_t *)&s + line_tab[l]);
   HWB_LANES_END
+  if (inter) {
+#if HWB_DEVICE_BUILD
+    reach = (int)__reduce_max_sync(0xffffffffu, (unsigned)reach);
+#endif
+    if (reach > s.row_reach) s.row_reach = reach;
+  }
   s.left.flags = flags; s.left.cbp = o.cbp; s.left.cmode = o.cmode; s.left.cbf = cbf;
 }
 
@@ -1208,7 +1222,7 @@ HWB_FN void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states
     while (!((last >> tz) & 1)) ++tz;
     s.stop_bitpos = (uint32_t)(n > 0 ? (n - 1) * 8 + (7 - tz) : 0);
   }
-  s.qp = sd.qp; s.last_dqp = 0;
+  s.qp = sd.qp; s.last_dqp = 0; s.row_reach = 0;
   init_caches(s);
   s.line = (NbCtx *)(c.ectx + (uint64_t)slice_idx * c.ectx_stride);
   // the arena region of a slice starts at its first macroblock's worst-case offset
@@ -1224,7 +1238,8 @@ HWB_FN void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states
   // CAVLC mb_skip_run state: -1 = read a new run before the next macroblock, 0 = the next
   // macroblock is coded, >0 = macroblocks still to skip
   int run = -1;
-  while (!end && addr < c.nmb) {
+  const int end_mb = sd.end_mb < c.nmb ? sd.end_mb : c.nmb;  // the slice must cover [first_mb, end_mb) exactly
+  while (!end && addr < end_mb) {
     s.mbaddr = addr; s.mbx = mbx; s.mby = mby;
     s.availA = s.mbx > 0 && addr - 1 >= first;
     s.availB = addr - c.mb_w >= first;
@@ -1239,7 +1254,7 @@ HWB_FN void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states
       } else {
         if (run < 0) {
           run = (int)s_ue(s);
-          if (run > c.nmb - addr) { sd_fail(s, 60); break; }
+          if (run > end_mb - addr) { sd_fail(s, 60); break; }
         }
         if (run > 0) { skipped = true; run--; }
       }
@@ -1257,18 +1272,28 @@ HWB_FN void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states
     }
     addr++;
     if (++mbx == c.mb_w) { mbx = 0; ++mby; }
-    if (mbx == 0 || end || addr == c.nmb) {
+    if (mbx == 0 || end || addr == end_mb) {
+      // the row just completed (or the part of it this slice covers): what the picture kernel must wait for in the
+      // reference pictures before it predicts this row; several slices may share a row, hence the atomic maximum
+      int32_t *rr = c.mv_reach + (size_t)sd.pic * c.mb_h + (addr - 1) / c.mb_w;
 #if HWB_DEVICE_BUILD
       __syncwarp();
       if ((threadIdx.x & 31) == 0) {  // release store: no L1 invalidation (see publish_progress in kernels.cu)
-        const int32_t v = (end || addr == c.nmb) ? c.nmb : addr;
+        if (s.row_reach) atomicMax(rr, s.row_reach);
+        const int32_t v = (end || addr == end_mb) ? c.nmb : addr;
         asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(c.entropy_prog + slice_idx), "r"(v) : "memory");
       }
 #else
-      c.entropy_prog[slice_idx] = (end || addr == c.nmb) ? c.nmb : addr;
+      if (s.row_reach > *rr) *rr = s.row_reach;
+      c.entropy_prog[slice_idx] = (end || addr == end_mb) ? c.nmb : addr;
 #endif
+      s.row_reach = 0;
     }
   }
+  // A slice that stops before the next slice's first macroblock (or runs out of data at it without its end flag)
+  // would leave macroblock records of the picture undefined: the picture is refused (error 61), nothing of the chunk
+  // is reconstructed.  In CABAC mode end_of_slice_flag must also have been seen at the last macroblock.
+  if (!s.error && !s.br.overrun && (addr != end_mb || (HWB_IS_CABAC(s) && !end))) s.error = 61;
   if (s.error || s.br.overrun) {
 #if HWB_DEVICE_BUILD
     __syncwarp();

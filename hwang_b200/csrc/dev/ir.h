@@ -55,7 +55,10 @@ struct PicDesc {
   uint8_t is_ref;
   uint8_t has_inter;
   int8_t chroma_qp_offset[2];
-  uint8_t pad[2];
+  uint8_t num_dep;      // distinct reference frames of all slices of the picture (dep[]), for the picture kernel's waits
+  uint8_t pad[1];
+  int32_t rgb_slot;     // slot of the chunk's RGB24 arena this picture is converted into by the deblocking pass, -1 = not returned
+  int16_t dep[32];      // frame indices this picture predicts from
   uint8_t scaling4[6][16];  // raster order: Y-intra, Cb-intra, Cr-intra, Y-inter, Cb-inter, Cr-inter
   uint8_t scaling8[2][64];  // raster order: intra, inter
 };
@@ -63,6 +66,7 @@ struct PicDesc {
 struct SliceDesc {
   int32_t pic;         // picture index inside the chunk
   int32_t first_mb;
+  int32_t end_mb;      // first macroblock of the next slice of the picture (number of macroblocks for the last slice): the slice must end exactly here
   uint32_t data_off;   // byte offset of the slice RBSP (NAL header stripped, emulation bytes removed)
   uint32_t data_size;  // RBSP bytes
   uint32_t bit_off;    // bit offset of slice_data() inside the RBSP
@@ -108,7 +112,16 @@ struct ChunkCtx {
   int32_t *entropy_prog;   // [slice] first macroblock address not yet entropy-decoded (B direct col dependency)
   int32_t *recon_prog;     // [pic][mb_h] macroblocks reconstructed per row
   int32_t *dbl_prog;       // [pic][mb_h] macroblocks deblocked per row
+  int32_t *mv_reach;       // [pic][mb_h] 1 + lowest macroblock row of a reference picture that inter prediction of this row reads (0 = none); written by the entropy stage
   int32_t *error_flag;     // set non-zero by any kernel that meets an unsupported/corrupt stream
+  // ---- picture kernel (reconstruction + deblocking + RGB24 writeback of a whole chunk in one launch)
+  // Work items: pic << 12 | macroblock row << 1 | kind (0 reconstruct the row, 1 deblock it and emit RGB24).
+  // Each list is ordered so that every item only waits on items that come earlier (in its own or the other list).
+  const uint32_t *recon_items, *deblock_items;
+  int32_t num_recon_items, num_deblock_items;
+  uint8_t *rgb;            // [slot] packed RGB24, out_w * out_h * 3 bytes each (tight)
+  uint64_t rgb_stride;
+  int32_t crop_x, crop_y, out_w, out_h;  // cropping rectangle of the output frames inside the coded picture
 };
 
 HWB_HD uint8_t *frame_y(const ChunkCtx &c, int f) { return c.frames + (uint64_t)f * c.frame_stride; }

@@ -1,0 +1,133 @@
+// Row work items of the picture kernel: reconstruction, deblocking and the RGB24 writeback of every picture of a
+// chunk run in ONE launch (csrc/cuda/kernels.cu picture_kernel; the unit tests' host emulation runs the same
+// functions serially).  Work items are macroblock rows: "reconstruct row y of picture p" and "deblock row y of
+// picture p (and convert what became final to RGB24)".  A warp walks its row left to right; everything an item needs
+// is tracked by per-row progress counters in global memory:
+//   reconstruct (p,y) at x : intra macroblocks need row y-1 reconstructed up to x+1 (unfiltered top / top-right
+//                            samples); inter rows need the rows of their reference pictures that the entropy stage
+//                            found them to reach (ChunkCtx::mv_reach) completely deblocked;
+//   deblock (p,y) at x     : (x,y) reconstructed; row y+1 reconstructed up to x+1 (its intra macroblocks read the
+//                            UNFILTERED samples of row y, so they must be done before the filter runs in place);
+//                            row y-1 deblocked up to x+1 (H.264 filters in raster order).
+// Both item lists are ordered by (dependency level of the picture, row, picture), so an item only ever waits on
+// items that were handed out before it (to its own or the other list): whoever holds the oldest unfinished item can
+// always run, no deadlock whatever the number of resident warps.  Pictures of consecutive levels overlap as a
+// diagonal wavefront (a P picture starts as soon as the first rows of its reference are final) instead of one launch
+// pair per level -- a GOP of 250 pictures used to cost 500 launches with a latency floor each.
+//
+// Replaces, on the GPU, the per-macroblock loop of libavcodec's h264 decoder behind avcodec_send_packet and the
+// sws_scale call of SoftwareVideoDecoder::get_frame (hwang/impls/software/software_video_decoder.cpp:292-325,349-402).
+#pragma once
+#include "deblock.h"
+#include "recon.h"
+#include "rgb.h"
+
+namespace hwb {
+
+struct Progress {  // a counter watched by this warp, with the last value seen (counters only grow)
+  const int32_t *p;
+  int seen;
+};
+
+#if HWB_DEVICE_BUILD
+__device__ __forceinline__ void wait_progress(Progress &g, int need) {
+  if (g.seen >= need) return;
+  int32_t v = 0;
+  if ((threadIdx.x & 31) == 0) {
+    for (;;) {  // relaxed GPU-scope poll; the data it guards is read with ld.global.cg (L2) by the callers
+      asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(g.p) : "memory");
+      if (v >= need) break;
+      __nanosleep(64);
+    }
+  }
+  g.seen = __shfl_sync(0xffffffffu, v, 0);
+}
+// Release store at GPU scope: orders the warp's earlier writes (made visible to lane 0 by __syncwarp) before the
+// flag.  Unlike __threadfence() + volatile store (MEMBAR.SC + CCTL.IVALL + a system-scope store) it does not
+// invalidate the SM's L1 on every macroblock, which the table and MbInfo loads of the other warps live in.
+__device__ __forceinline__ void publish_progress(int32_t *p, int v) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+#else
+// Host emulation: items run one after the other in an order the emulation has checked to be ready, so a wait that is
+// not already satisfied means the host scheduler produced a wrong order.
+static thread_local int g_unsatisfied_waits = 0;
+static inline void wait_progress(Progress &g, int need) {
+  if (g.seen >= need) return;
+  g.seen = *g.p;
+  if (g.seen < need) g_unsatisfied_waits++;
+}
+static inline void publish_progress(int32_t *p, int v) { *p = v; }
+#endif
+
+enum { ITEM_ROW_BITS = 11, ITEM_PIC_SHIFT = 12 };
+HWB_HD uint32_t make_item(int pic, int row, int kind) { return ((uint32_t)pic << ITEM_PIC_SHIFT) | ((uint32_t)row << 1) | (uint32_t)kind; }
+HWB_HD int item_pic(uint32_t it) { return (int)(it >> ITEM_PIC_SHIFT); }
+HWB_HD int item_row(uint32_t it) { return (int)((it >> 1) & ((1u << ITEM_ROW_BITS) - 1)); }
+
+// Macroblock row of a reference picture that must be completely deblocked before row y of `pic` may be predicted
+// (-1: the row has no inter macroblock).  Rows < reach are final once row `reach` is deblocked (its top-edge filter is
+// the last thing that modifies row reach-1).
+HWB_HD int reference_row_needed(const ChunkCtx &c, int pic, int y) {
+  const int reach = c.mv_reach[(size_t)pic * c.mb_h + y];
+  if (reach <= 0) return -1;
+  return reach < c.mb_h ? reach : c.mb_h - 1;
+}
+
+HWB_FN void recon_row(const ChunkCtx &c, int pic, int y, ReconScratch *my) {
+  const PicDesc &pd = c.pics[pic];
+  const MbInfo *mbs = pic_mbinfo(c, pd.frame);
+  int32_t *prog = c.recon_prog + (size_t)pic * c.mb_h;
+  const bool has_inter = pd.has_inter != 0;
+  if (has_inter) {
+    // frame index == picture index inside a chunk, so a reference's counters are found by its frame index
+    const int row = reference_row_needed(c, pic, y);
+    if (row >= 0)
+      for (int i = 0; i < pd.num_dep; ++i) {
+        Progress ref = {c.dbl_prog + (size_t)pd.dep[i] * c.mb_h + row, -1};
+        wait_progress(ref, c.mb_w);
+      }
+  }
+  Progress above = {prog + y - 1, y > 0 ? -1 : (1 << 30)};
+  for (int x = 0; x < c.mb_w; ++x) {
+    // intra macroblocks read the unfiltered row above up to the top-right neighbour
+    if (mbs[y * c.mb_w + x].mbtype != MB_INTER) wait_progress(above, x + 2 < c.mb_w ? x + 2 : c.mb_w);
+    recon_mb(c, pic, x, y, my);
+    // consumers: intra macroblocks of the row below and the deblocking pass; pictures with inter slices have few
+    // intra macroblocks, so the fence + flag store is amortised over 4 macroblocks there
+    if (!has_inter || (x & 3) == 3 || x == c.mb_w - 1) publish_progress(prog + y, x + 1);
+  }
+}
+
+HWB_FN void deblock_row(const ChunkCtx &c, int pic, int y, DeblockScratch *my) {
+  const PicDesc &pd = c.pics[pic];
+  int32_t *prog = c.dbl_prog + (size_t)pic * c.mb_h;
+  const int32_t *rprog = c.recon_prog + (size_t)pic * c.mb_h;
+  uint8_t *rgb = pd.rgb_slot >= 0 ? c.rgb + (uint64_t)pd.rgb_slot * c.rgb_stride : nullptr;
+  const bool last_row = y == c.mb_h - 1;
+  Progress mine = {rprog + y, -1};
+  Progress below = {rprog + y + 1, last_row ? (1 << 30) : -1};
+  Progress above = {prog + y - 1, y > 0 ? -1 : (1 << 30)};
+  for (int x = 0; x < c.mb_w; ++x) {
+    const int lag = x + 2 < c.mb_w ? x + 2 : c.mb_w;
+    wait_progress(mine, x + 1);
+    wait_progress(below, lag);
+    wait_progress(above, lag);
+    deblock_mb(c, pic, x, y, my);
+    publish_progress(prog + y, x + 1);
+    if (rgb) {
+      // RGB24 writeback fused into this pass: with (x,y) filtered, macroblock (x,y-1) is final (its right edge was
+      // filtered by (x+1,y-1), which the wait above covers; its bottom edge just now), and so is (x-1,y) on the
+      // last row.  Two macroblocks per step: 32 lanes x 16 pixels, three 16-byte stores each.
+      const bool flush = x == c.mb_w - 1;
+      if (y > 0 && ((x & 1) || flush)) rgb24_macroblocks(c, pd.frame, rgb, x & ~1, (x & 1) ? 2 : 1, y - 1);
+      if (last_row) {
+        if (x >= 2 && !(x & 1)) rgb24_macroblocks(c, pd.frame, rgb, x - 2, 2, y);
+        if (flush) rgb24_macroblocks(c, pd.frame, rgb, (x & 1) ? x - 1 : x, (x & 1) ? 2 : 1, y);
+      }
+    }
+  }
+}
+
+}  // namespace hwb

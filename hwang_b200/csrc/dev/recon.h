@@ -187,20 +187,21 @@ HWB_FN void mc_luma_4x2(const uint8_t *ref, int w, int h, int px, int py, int fx
 #pragma unroll 1
     for (int r = 0; r < 2; ++r) {
       int yy = clip3(0, h - 1, py + r);
-      for (int c = 0; c < 4; ++c) out[r * 4 + c] = ref[yy * w + clip3(0, w - 1, px + c)];
+      for (int c = 0; c < 4; ++c) out[r * 4 + c] = ld_u8_cg(ref + yy * w + clip3(0, w - 1, px + c));
     }
     return;
   }
   if (inside) {
 #if HWB_DEVICE_BUILD
     // three aligned 32-bit loads per window row instead of nine byte loads (the row is 9 bytes at any alignment;
-    // the over-read of at most 3 bytes stays inside the frame buffer)
+    // the over-read of at most 3 bytes stays inside the frame buffer).  ld.global.cg: the reference picture was
+    // written by other warps of the same launch (picture kernel), the non-coherent path is not allowed here
     const uint8_t *p0 = ref + (py - 2) * w + px - 2;
     const int sh = (int)(((uintptr_t)p0) & 3) * 8;  // rows are a multiple of 16 bytes apart: same alignment for every row
 #pragma unroll
     for (int r = 0; r < 7; ++r) {
       const uint32_t *q = (const uint32_t *)((uintptr_t)(p0 + r * w) & ~(uintptr_t)3);
-      const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+      const uint32_t w0 = __ldcg(q), w1 = __ldcg(q + 1), w2 = __ldcg(q + 2);
       const uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh), x2 = w2 >> sh;
       win[r][0] = (uint8_t)x0; win[r][1] = (uint8_t)(x0 >> 8); win[r][2] = (uint8_t)(x0 >> 16); win[r][3] = (uint8_t)(x0 >> 24);
       win[r][4] = (uint8_t)x1; win[r][5] = (uint8_t)(x1 >> 8); win[r][6] = (uint8_t)(x1 >> 16); win[r][7] = (uint8_t)(x1 >> 24);
@@ -218,7 +219,7 @@ HWB_FN void mc_luma_4x2(const uint8_t *ref, int w, int h, int px, int py, int fx
     for (int r = 0; r < 7; ++r) {
       int yy = clip3(0, h - 1, py - 2 + r);
 #pragma unroll
-      for (int c = 0; c < 9; ++c) win[r][c] = ref[yy * w + clip3(0, w - 1, px - 2 + c)];
+      for (int c = 0; c < 9; ++c) win[r][c] = ld_u8_cg(ref + yy * w + clip3(0, w - 1, px - 2 + c));
     }
   }
 #define HWB_H1(r, c) tap6(win[r][(c)], win[r][(c) + 1], win[r][(c) + 2], win[r][(c) + 3], win[r][(c) + 4], win[r][(c) + 5])
@@ -273,7 +274,7 @@ HWB_FN void mc_chroma_2x2(const uint8_t *ref, int w, int h, int cx, int cy, int 
   int v[3][3];
   for (int r = 0; r < 3; ++r) {
     int yy = clip3(0, h - 1, y0 + r);
-    for (int c = 0; c < 3; ++c) v[r][c] = ref[yy * w + clip3(0, w - 1, x0 + c)];
+    for (int c = 0; c < 3; ++c) v[r][c] = ld_u8_cg(ref + yy * w + clip3(0, w - 1, x0 + c));
   }
   for (int r = 0; r < 2; ++r)
     for (int c = 0; c < 2; ++c)

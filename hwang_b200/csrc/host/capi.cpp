@@ -35,9 +35,8 @@ std::atomic<int> g_last_device{0};
 void fill_stats(const B200Stats &s, hwb_stats *o) {
   o->pictures_decoded = s.pictures_decoded; o->frames_returned = s.frames_returned; o->chunks = s.chunks; o->bitstream_bytes = s.bitstream_bytes;
   o->kernel_launches = s.kernel_launches; o->h2d_bytes = s.h2d_bytes; o->d2h_bytes = s.d2h_bytes; o->algorithmic_bytes = s.algorithmic_bytes;
-  o->decode_ms = s.decode_ms;
-  o->entropy_ms = s.entropy_ms; o->recon_ms = s.recon_ms; o->deblock_ms = s.deblock_ms; o->rgb_ms = s.rgb_ms;
-  o->entropy_launches = s.entropy_launches; o->recon_launches = s.recon_launches; o->deblock_launches = s.deblock_launches; o->rgb_launches = s.rgb_launches;
+  o->wall_ms = s.wall_ms; o->entropy_ms = s.entropy_ms; o->picture_ms = s.picture_ms;
+  o->entropy_launches = s.entropy_launches; o->picture_launches = s.picture_launches; o->aux_launches = s.aux_launches;
 }
 }  // namespace
 
@@ -80,6 +79,8 @@ int hwb_decoder_set_interval_hint(hwb_decoder *d, uint64_t start_frame, const ui
   d->b200->set_interval_hint(start_frame, std::vector<uint64_t>(wanted, wanted + n));
   return 0;
 }
+int hwb_decoder_set_defer_submit(hwb_decoder *d, int on) { if (!d->b200) return 1; d->b200->set_defer_submit(on != 0); return 0; }
+int hwb_decoder_submit_pending(hwb_decoder *d) { return d->b200 ? ret(d, d->b200->submit_pending()) : 1; }
 int hwb_decoder_get_stats(hwb_decoder *d, hwb_stats *out) { if (!d->b200) return 1; fill_stats(d->b200->stats(), out); return 0; }
 
 void *hwb_alloc_pinned(size_t n) {
@@ -87,6 +88,28 @@ void *hwb_alloc_pinned(size_t n) {
   return hwb_dev_malloc_host(g_pin_dev, n);
 }
 void hwb_free_pinned(void *p) { if (g_pin_dev && p) hwb_dev_free_host(g_pin_dev, p); }
+// Device-memory destinations for DeviceType::GPU output (callers without a CUDA runtime of their own: tests, ctypes)
+void *hwb_alloc_device(int device_id, size_t n) {
+  hwb_dev *d = nullptr;
+  if (hwb_dev_open(device_id, &d) != 0) return nullptr;
+  void *p = hwb_dev_malloc(d, n);
+  hwb_dev_close(d);
+  return p;
+}
+void hwb_free_device(int device_id, void *p) {
+  hwb_dev *d = nullptr;
+  if (!p || hwb_dev_open(device_id, &d) != 0) return;
+  hwb_dev_free(d, p);
+  hwb_dev_close(d);
+}
+int hwb_copy_device_to_host(int device_id, void *dst, const void *src, size_t n) {
+  hwb_dev *d = nullptr;
+  if (hwb_dev_open(device_id, &d) != 0) return 1;
+  int rc = hwb_dev_d2h(d, HWB_STREAM_AUX, dst, src, n);
+  rc |= hwb_dev_stream_sync(d, HWB_STREAM_AUX);
+  hwb_dev_close(d);
+  return rc;
+}
 
 // ---------------------------------------------------------------------------------------- index
 hwb_index_creator *hwb_index_creator_create(uint64_t file_size) { return new (std::nothrow) hwb_index_creator(file_size); }
@@ -174,6 +197,12 @@ int hwb_automata_initialize(hwb_automata *a, const hwb_encoded_data *iv, size_t 
   return ret(a, a->a->initialize(std::move(v), std::vector<uint8_t>(extra, extra + nextra)));
 }
 int hwb_automata_get_frames(hwb_automata *a, uint8_t *buffer, int32_t n) { return ret(a, a->a->get_frames(buffer, n)); }
+int hwb_automata_set_chunk_pictures(hwb_automata *a, int n) {
+  B200VideoDecoder *b = dynamic_cast<B200VideoDecoder *>(a->a->decoder());
+  if (!b) return 1;
+  b->set_chunk_pictures(n);
+  return 0;
+}
 const char *hwb_automata_last_error(hwb_automata *a) { return a->err.c_str(); }
 int hwb_automata_get_stats(hwb_automata *a, hwb_stats *out) {
   B200VideoDecoder *b = dynamic_cast<B200VideoDecoder *>(a->a->decoder());

@@ -14,7 +14,9 @@ enum class DeviceType {
 struct DeviceHandle {
   bool operator==(const DeviceHandle &o) const { return type == o.type && id == o.id; }
   bool operator!=(const DeviceHandle &o) const { return !(*this == o); }
-  bool operator<(const DeviceHandle &o) const { return type < o.type && id < o.id; }
+  // strict weak order (type, then id), so that DeviceHandle can key a std::map; the reference's version
+  // (hwang/common.h:33-35: `type < o.type && id < o.id`) is not one: {CPU,1} and {GPU,0} compare equivalent both ways
+  bool operator<(const DeviceHandle &o) const { return type != o.type ? type < o.type : id < o.id; }
   bool can_copy_to(const DeviceHandle &o) const {
     return !(type == DeviceType::GPU && o.type == DeviceType::GPU && id != o.id);
   }

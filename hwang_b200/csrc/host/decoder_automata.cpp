@@ -20,6 +20,8 @@ DecoderAutomata *DecoderAutomata::make_with_decoder(VideoDecoderInterface *decod
 
 DecoderAutomata::DecoderAutomata(DeviceHandle device_handle, int32_t num_devices, VideoDecoderType decoder_type, VideoDecoderInterface *decoder)
     : device_handle_(device_handle), num_devices_(num_devices), decoder_type_(decoder_type), decoder_(decoder) {
+  // our own backend applies back-pressure in bytes of device memory inside feed(): legal here, feed() runs on the feeder thread
+  if (B200VideoDecoder *b = dynamic_cast<B200VideoDecoder *>(decoder_.get())) b->set_feeder_may_block(true);
   feeder_thread_ = std::thread(&DecoderAutomata::feeder, this);
 }
 

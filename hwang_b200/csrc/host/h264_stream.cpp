@@ -591,6 +591,28 @@ std::string H264Stream::parse_sample(const uint8_t *data, size_t n, int pic_inde
   std::sort(out.slices.begin(), out.slices.end(), [](const SliceDesc &a, const SliceDesc &b) { return a.first_mb < b.first_mb; });
   if (out.slices[0].first_mb != 0) return "unsupported: picture does not start at macroblock 0 (ASO / lost slice)";
   out.desc.num_slices = (int)out.slices.size();
+  // Every macroblock must be covered by exactly one slice: reconstruction and deblocking read the entropy stage's
+  // per-macroblock records of the whole picture, so a lost or duplicated slice is refused here and a slice that ends
+  // early or late is caught by the entropy stage (SliceDesc::end_mb).
+  for (size_t i = 0; i < out.slices.size(); ++i) {
+    const int next = i + 1 < out.slices.size() ? out.slices[i + 1].first_mb : mb_w_ * mb_h_;
+    if (next <= out.slices[i].first_mb) return "unsupported: two slices start at the same macroblock (redundant slices)";
+    out.slices[i].end_mb = next;
+  }
+  // distinct reference frames of the picture (what the picture kernel waits for)
+  out.desc.num_dep = 0;
+  for (auto &sd : out.slices)
+    for (int l = 0; l < 2; ++l)
+      for (int i = 0; i < sd.num_ref[l] && sd.slice_type != SLICE_I; ++i) {
+        const int16_t f = sd.ref_frame[l][i];
+        bool seen = false;
+        for (int k = 0; k < out.desc.num_dep; ++k) seen |= out.desc.dep[k] == f;
+        if (!seen) {
+          if (out.desc.num_dep >= 32) return "unsupported: more than 32 distinct reference frames in one picture";
+          out.desc.dep[out.desc.num_dep++] = f;
+        }
+      }
+  out.desc.rgb_slot = -1;
   levels_.resize(std::max<size_t>(levels_.size(), (size_t)pic_index + 1));
   levels_[pic_index] = out.desc.level;
   if (first.nal_ref_idc) mark_references(*sps0, first, pic_index, cur_poc);

@@ -25,7 +25,8 @@ VideoDecoderInterface *VideoDecoderFactory::make_from_config(DeviceHandle device
     case VideoDecoderType::NVIDIA:
     case VideoDecoderType::B200: {
       if (device_handle.type != DeviceType::GPU) return nullptr;
-      B200VideoDecoder *d = new B200VideoDecoder(device_handle.id, DeviceType::CPU, num_devices);
+      // as the reference does for its GPU backend (video_decoder_factory.cpp:76-77), the handle's type is the output type
+      B200VideoDecoder *d = new B200VideoDecoder(device_handle.id, device_handle.type, num_devices);
       if (!d->ok()) { delete d; return nullptr; }
       return d;
     }

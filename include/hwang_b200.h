@@ -49,13 +49,16 @@ int hwb_decoder_configure(hwb_decoder *d, uint32_t width, uint32_t height, const
 int hwb_decoder_feed(hwb_decoder *d, const uint8_t *encoded_buffer, size_t encoded_size, int keyframe);
 int hwb_decoder_flush(hwb_decoder *d);                                                   /* interface.h:41 */
 int hwb_decoder_discard_frame(hwb_decoder *d);                                           /* interface.h:43 */
-int hwb_decoder_get_frame(hwb_decoder *d, uint8_t *decoded_buffer, size_t decoded_size); /* interface.h:45, RGB24 W*H*3 */
+/* interface.h:45, RGB24 W*H*3.  decoded_buffer may be pageable host memory, page-locked host memory (written by the
+ * copy engine directly) or DEVICE memory (hwang::DeviceType::GPU output, hwang/common.h:20-50: the frame never crosses PCIe). */
+int hwb_decoder_get_frame(hwb_decoder *d, uint8_t *decoded_buffer, size_t decoded_size);
 int hwb_decoder_decoded_frames_buffered(hwb_decoder *d);                                 /* interface.h:47 */
 int hwb_decoder_wait_until_frames_copied(hwb_decoder *d);                                /* interface.h:49 */
 const char *hwb_decoder_last_error(hwb_decoder *d);
 /* extensions (parity tests / benchmark): */
 int hwb_decoder_get_frame_yuv(hwb_decoder *d, uint8_t *decoded_buffer, size_t decoded_size); /* cropped planar I420, W*H*3/2 */
-int hwb_decoder_get_frame_device(hwb_decoder *d, uint8_t **device_rgb);                      /* RGB24 left in device memory */
+/* zero-copy: RGB24 in the decoder's own device memory, valid until the next wait_until_frames_copied / configure */
+int hwb_decoder_get_frame_device(hwb_decoder *d, uint8_t **device_rgb);
 int hwb_decoder_frames_ready(hwb_decoder *d);              /* exact count (decoded_frames_buffered saturates at 8) */
 int hwb_decoder_set_chunk_pictures(hwb_decoder *d, int n); /* pictures per GPU batch (cut at IDR boundaries) */
 /* Optional hint, to be called before the first feed() of an interval (what DecoderAutomata::feeder knows at
@@ -65,17 +68,30 @@ int hwb_decoder_set_chunk_pictures(hwb_decoder *d, int n); /* pictures per GPU b
  * pictures are then not decoded at all.  Without the call everything is decoded, as the reference backends do. */
 int hwb_decoder_set_interval_hint(hwb_decoder *d, uint64_t start_frame, const uint64_t *wanted, size_t n);
 
+/* Batch retrieval (python/hwang/decoder.py:30-69 decodes one interval of one video at a time and re-configures in
+ * between): with deferred submission the pictures of consecutive intervals -- of one clip or of several clips of equal
+ * geometry, re-configured in between -- are collected into ONE GPU batch, so that a single entropy launch sees all
+ * their slices.  Frames still pop interval by interval, in display order.  hwb_decoder_submit_pending closes the batch. */
+int hwb_decoder_set_defer_submit(hwb_decoder *d, int on);
+int hwb_decoder_submit_pending(hwb_decoder *d);
+
 typedef struct hwb_stats {
   uint64_t pictures_decoded, frames_returned, chunks, bitstream_bytes, kernel_launches, h2d_bytes, d2h_bytes, algorithmic_bytes;
-  double decode_ms; /* device time of the decode stages, CUDA events */
-  double entropy_ms, recon_ms, deblock_ms, rgb_ms; /* per-stage device time (CUDA events on the launching stream) */
-  uint64_t entropy_launches, recon_launches, deblock_launches, rgb_launches;
+  /* Device time from CUDA events on the launching streams.  wall_ms: inputs of a batch resident in HBM -> its last picture
+   * kernel done, summed over busy periods.  entropy_ms / picture_ms: per-stage sums over batches; batches overlap, so
+   * these may exceed wall_ms. */
+  double wall_ms, entropy_ms, picture_ms;
+  uint64_t entropy_launches, picture_launches, aux_launches;
 } hwb_stats;
 int hwb_decoder_get_stats(hwb_decoder *d, hwb_stats *out);
 
 /* pinned host memory for output buffers (get_frame copies straight into pinned buffers) */
 void *hwb_alloc_pinned(size_t n);
 void hwb_free_pinned(void *p);
+/* device memory for DeviceType::GPU output buffers, for callers without a CUDA runtime of their own (ctypes, tests) */
+void *hwb_alloc_device(int device_id, size_t n);
+void hwb_free_device(int device_id, void *p);
+int hwb_copy_device_to_host(int device_id, void *dst, const void *src, size_t n);
 
 /* ---------------------------------------------------------------------------------------------
  * Index: hwang::MP4IndexCreator (hwang/mp4_index_creator.h:23-45) and hwang::VideoIndex
@@ -142,8 +158,9 @@ typedef struct hwb_encoded_data { /* DecoderAutomata::EncodedData, decoder_autom
 hwb_automata *hwb_automata_create(int device_type, int device_id, int num_devices, int decoder_type);
 void hwb_automata_destroy(hwb_automata *a);
 int hwb_automata_initialize(hwb_automata *a, const hwb_encoded_data *intervals, size_t num_intervals, const uint8_t *extradata, size_t extradata_size);
-/* n tightly packed W*H*3 RGB24 frames at buffer + k*W*H*3 */
+/* n tightly packed W*H*3 RGB24 frames at buffer + k*W*H*3; buffer may be host (pageable / page-locked) or device memory */
 int hwb_automata_get_frames(hwb_automata *a, uint8_t *buffer, int32_t num_frames);
+int hwb_automata_set_chunk_pictures(hwb_automata *a, int n); /* pictures per GPU batch of the automaton's decoder */
 const char *hwb_automata_last_error(hwb_automata *a);
 int hwb_automata_get_stats(hwb_automata *a, hwb_stats *out);
 

@@ -158,6 +158,31 @@ class FFmpegH264:
             n += 1
             self.avutil.av_frame_unref(self.frame)
 
+    def send_raw(self, annexb, on_frame):
+        """As send(), but every decoded AVFrame is handed to on_frame(address of the AVFrame) before it is released:
+        no plane is copied on the Python side (the benchmark's reference arm converts straight from the AVFrame, as
+        SoftwareVideoDecoder::get_frame does, software_video_decoder.cpp:300-325)."""
+        if annexb is None:
+            r = self.avcodec.avcodec_send_packet(self.ctx, None)
+        else:
+            self.avcodec.av_new_packet(self.pkt, len(annexb))
+            dptr = ctypes.c_void_p.from_address(self.pkt.value + 24).value
+            ctypes.memmove(dptr, annexb, len(annexb))
+            r = self.avcodec.avcodec_send_packet(self.ctx, self.pkt)
+            self.avcodec.av_packet_unref(self.pkt)
+        if r < 0 and r != AVERROR_EOF:
+            raise RuntimeError('avcodec_send_packet error %d' % r)
+        n = 0
+        while True:
+            r = self.avcodec.avcodec_receive_frame(self.ctx, self.frame)
+            if r == AVERROR_EAGAIN or r == AVERROR_EOF:
+                return n
+            if r < 0:
+                raise RuntimeError('avcodec_receive_frame error %d' % r)
+            on_frame(self.frame.value)
+            n += 1
+            self.avutil.av_frame_unref(self.frame)
+
     def send(self, annexb, sink):
         """avcodec_send_packet(annexb) (None = drain signal) then receive until EAGAIN/EOF."""
         if annexb is None:
@@ -210,6 +235,13 @@ class SwsRgb24:
         dst_st = (ctypes.c_int * 4)(self.w * 3, 0, 0, 0)
         self.sws.sws_scale(self.ctx, src, sst, 0, self.h, dp, dst_st)
         return dst
+
+    def scale_avframe(self, frame_addr, dst_addr):
+        """sws_scale straight from an AVFrame (data[] at offset 0, linesize[] at offset 64) into dst (W*3 stride):
+        the call at software_video_decoder.cpp:325 with no intermediate copy."""
+        dp = (ctypes.c_void_p * 4)(dst_addr, None, None, None)
+        dst_st = (ctypes.c_int * 4)(self.w * 3, 0, 0, 0)
+        self.sws.sws_scale(self.ctx, ctypes.c_void_p(frame_addr), ctypes.c_void_p(frame_addr + 64), 0, self.h, dp, dst_st)
 
     def close(self):
         if self.ctx:

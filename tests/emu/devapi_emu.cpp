@@ -8,16 +8,15 @@
 #include <string.h>
 #include <string>
 
-#include "../../hwang_b200/csrc/dev/deblock.h"
 #include "../../hwang_b200/csrc/dev/devapi.h"
 #include "../../hwang_b200/csrc/dev/entropy.h"
-#include "../../hwang_b200/csrc/dev/recon.h"
-#include "../../hwang_b200/csrc/dev/rgb.h"
+#include "../../hwang_b200/csrc/dev/picture.h"
 
 using namespace hwb;
 
 struct hwb_dev { std::string err; uint64_t launches = 0; };
 struct hwb_event { int dummy; };
+struct PictureScratchEmu { ReconScratch recon; DeblockScratch deblock; };
 
 extern "C" {
 
@@ -29,9 +28,11 @@ void *hwb_dev_malloc(hwb_dev *, size_t n) { return malloc(n ? n : 1); }
 void hwb_dev_free(hwb_dev *, void *p) { free(p); }
 void *hwb_dev_malloc_host(hwb_dev *, size_t n) { return malloc(n ? n : 1); }
 void hwb_dev_free_host(hwb_dev *, void *p) { free(p); }
-int hwb_dev_is_pinned(hwb_dev *, const void *) { return 0; }
+int hwb_dev_pointer_kind(hwb_dev *, const void *) { return 0; }
+int hwb_dev_mem_info(hwb_dev *, size_t *free_bytes, size_t *total_bytes) { *free_bytes = (size_t)8 << 30; *total_bytes = (size_t)8 << 30; return 0; }
 int hwb_dev_h2d(hwb_dev *, int, void *dst, const void *src, size_t n) { memcpy(dst, src, n); return 0; }
 int hwb_dev_d2h(hwb_dev *, int, void *dst, const void *src, size_t n) { memcpy(dst, src, n); return 0; }
+int hwb_dev_d2d(hwb_dev *, int, void *dst, const void *src, size_t n) { memcpy(dst, src, n); return 0; }
 int hwb_dev_memset(hwb_dev *, int, void *dst, int v, size_t n) { memset(dst, v, n); return 0; }
 
 int hwb_dev_entropy(hwb_dev *d, int, const ChunkCtx *c, int32_t *, int) {
@@ -40,22 +41,36 @@ int hwb_dev_entropy(hwb_dev *d, int, const ChunkCtx *c, int32_t *, int) {
   d->launches++;
   return 0;
 }
-int hwb_dev_recon(hwb_dev *d, int, const ChunkCtx *c, const int32_t *pics, int npics, int32_t *) {
-  if (*c->error_flag) { d->launches++; return 0; }  // as the CUDA kernels: nothing is dereferenced after an entropy error
-  ReconScratch sm;
-  for (int i = 0; i < npics; ++i)
-    for (int y = 0; y < c->mb_h; ++y)
-      for (int x = 0; x < c->mb_w; ++x) recon_mb(*c, pics[i], x, y, &sm);
+// The picture kernel's two work lists, executed serially: an item runs once everything it waits for is complete
+// (whole rows here), taking from either list; if neither head is ready the host scheduler has produced an order that
+// could deadlock on the GPU, which is reported as a device error.
+int hwb_dev_picture(hwb_dev *d, int, const ChunkCtx *c, int32_t *) {
   d->launches++;
-  return 0;
-}
-int hwb_dev_deblock(hwb_dev *d, int, const ChunkCtx *c, const int32_t *pics, int npics, int32_t *) {
-  if (*c->error_flag) { d->launches++; return 0; }
-  DeblockScratch sm;
-  for (int i = 0; i < npics; ++i)
-    for (int y = 0; y < c->mb_h; ++y)
-      for (int x = 0; x < c->mb_w; ++x) deblock_mb(*c, pics[i], x, y, &sm);
-  d->launches++;
+  if (*c->error_flag) return 0;  // as the CUDA kernel: nothing is dereferenced after an entropy error
+  PictureScratchEmu *smp = new PictureScratchEmu(); PictureScratchEmu &sm = *smp;
+  auto rows_done = [&](const int32_t *prog, int pic, int y) { return y < 0 || y >= c->mb_h || prog[(size_t)pic * c->mb_h + y] >= c->mb_w; };
+  auto recon_ready = [&](uint32_t it) {
+    const int pic = item_pic(it), y = item_row(it);
+    if (!rows_done(c->recon_prog, pic, y - 1)) return false;
+    const int row = c->pics[pic].has_inter ? reference_row_needed(*c, pic, y) : -1;
+    if (row >= 0)
+      for (int i = 0; i < c->pics[pic].num_dep; ++i) if (!rows_done(c->dbl_prog, c->pics[pic].dep[i], row)) return false;
+    return true;
+  };
+  auto deblock_ready = [&](uint32_t it) {
+    const int pic = item_pic(it), y = item_row(it);
+    return rows_done(c->recon_prog, pic, y) && rows_done(c->recon_prog, pic, y + 1) && rows_done(c->dbl_prog, pic, y - 1);
+  };
+  int ir = 0, id = 0;
+  g_unsatisfied_waits = 0;
+  while (ir < c->num_recon_items || id < c->num_deblock_items) {
+    bool progressed = false;
+    while (ir < c->num_recon_items && recon_ready(c->recon_items[ir])) { recon_row(*c, item_pic(c->recon_items[ir]), item_row(c->recon_items[ir]), &sm.recon); ir++; progressed = true; }
+    while (id < c->num_deblock_items && deblock_ready(c->deblock_items[id])) { deblock_row(*c, item_pic(c->deblock_items[id]), item_row(c->deblock_items[id]), &sm.deblock); id++; progressed = true; }
+    if (!progressed) { *c->error_flag = 901; d->err = "emulation: work lists are not in dependency order"; break; }
+  }
+  if (g_unsatisfied_waits) { *c->error_flag = 902; d->err = "emulation: a wait was not satisfied"; }
+  delete smp;
   return 0;
 }
 int hwb_dev_rgb24(hwb_dev *d, int, const ChunkCtx *c, int frame, int crop_x, int crop_y, int w, int h, uint8_t *dst) {
