@@ -33,7 +33,7 @@ B200VideoDecoder::~B200VideoDecoder() {
 
 void B200VideoDecoder::recycle(std::unique_ptr<Chunk> &c, bool keep_slab) {
   if (!c) return;
-  if (c->ev_begin && c->ev_begin != interval_begin_) hwb_dev_event_destroy(dev_, c->ev_begin);
+  if (c->ev_begin) hwb_dev_event_destroy(dev_, c->ev_begin);
   if (c->ev_entropy) hwb_dev_event_destroy(dev_, c->ev_entropy);
   if (c->ev_picture) hwb_dev_event_destroy(dev_, c->ev_picture);
   if (c->ev_done) hwb_dev_event_destroy(dev_, c->ev_done);
@@ -337,7 +337,7 @@ Result B200VideoDecoder::submit_current() {
   // a copy from pageable memory has been staged by the time cudaMemcpyAsync returns: the buffer can be reused
   spare_bits_ = std::move(ch->bitstream);
   rc |= hwb_dev_event_record(dev_, ch->ev_begin, st);  // inputs are resident in HBM from here on
-  if (!interval_begin_) interval_begin_ = ch->ev_begin;
+  if (!interval_begin_) { interval_begin_ = hwb_dev_event_create(dev_); if (interval_begin_) rc |= hwb_dev_event_record(dev_, interval_begin_, st); }  // a busy period of the device starts
   int mode = ch->pics[0].cabac ? 1 : 0;
   for (auto &p : ch->pics) if ((p.cabac ? 1 : 0) != mode) mode = -1;
   if (mode == 1) {  // CABAC throughout: the copy of the kernel without B-slice support when the chunk has none
@@ -388,7 +388,7 @@ Result B200VideoDecoder::finish_chunk(Chunk &c) {
       for (auto &q : queue_) if (q.get() != &c && q->submitted && !q->checked) last_in_flight = false;
       if (last_in_flight && !cur_) {
         stats_.wall_ms += ms;
-        if (interval_begin_ != c.ev_begin) hwb_dev_event_destroy(dev_, interval_begin_);
+        hwb_dev_event_destroy(dev_, interval_begin_);
         interval_begin_ = nullptr;
       }
     }

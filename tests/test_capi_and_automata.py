@@ -271,3 +271,28 @@ def test_unsupported_stream_features_are_refused_at_configure(emu):
             hw.VideoDecoder(0).configure(64, 48, 'avc1', avcc)
     with pytest.raises(RuntimeError, match='does not match the SPS'):
         hw.VideoDecoder(0).configure(128, 48, 'avc1', _avcc(_sps(), _pps()))
+
+
+def test_many_batches_device_pointers_and_reuse(emu, built):
+    """Several GPU batches in flight (one GOP each), frames fetched as borrowed device pointers, then the same decoder
+    re-configured and used again: exercises batch retirement / memory recycling (the emulated device's pointers are
+    host pointers, so the borrowed frames can be read directly)."""
+    import ctypes
+    kw = dict(width=64, height=48, frames=20, gop=4, profile=1, seed=91, bframes=1)
+    mp4, index, samples, kf = util.make_clip(**kw)
+    ref = util.oracle_frames(index, samples, kf)
+    dec = hw.VideoDecoder(0)
+    dec.set_chunk_pictures(1)
+    fs = 64 * 48 * 3
+    for rep in range(3):
+        dec.configure(64, 48, index.format(), index.metadata_bytes())
+        for s, k in zip(samples, kf):
+            dec.feed(s, k)
+        dec.feed(None)
+        dec.flush()
+        ptrs = [dec.get_frame_device() for _ in range(len(samples))]
+        for i, p in enumerate(ptrs):
+            got = np.ctypeslib.as_array((ctypes.c_uint8 * fs).from_address(p)).reshape(48, 64, 3)
+            assert np.array_equal(got, fo.yuv420_to_rgb24(*ref[i])), (rep, i)
+        dec.wait_until_frames_copied()
+        assert dec.stats()['chunks'] == 5 * (rep + 1)
