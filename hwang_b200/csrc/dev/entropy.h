@@ -79,6 +79,7 @@ struct SliceDec {
   NbCtx *line;  // [mb_w] top context
   uint32_t coef_next;  // next free slot in the picture arena
   int32_t row_reach;   // 1 + lowest reference macroblock row read by the inter macroblocks of the current row so far (0 = none)
+  int32_t row_reach_x; // reference macroblock columns needed beyond a macroblock's own column (see ChunkCtx::mv_reach_x)
   // ---- current macroblock
   int mbx, mby, mbaddr;
   bool availA, availB, availC, availD;
@@ -897,7 +898,7 @@ HWB_FN void finish_mb(SliceDec &s, bool skipped, bool direct16, bool is_pcm) {
   s.top_words[1] = cbf;
   s.top_words[2] = s.cnz_cache[0][9] | ((uint32_t)s.cnz_cache[0][10] << 8) | ((uint32_t)s.cnz_cache[1][9] << 16) | ((uint32_t)s.cnz_cache[1][10] << 24);
   s.top_words[3] = 0;
-  int reach = 0;  // per lane on the device, accumulated over the lane loop on the host
+  int reach = 0, reach_x = 0;  // per lane on the device, accumulated over the lane loop on the host
   HWB_LANES(l)
   if (inter) {
     const int k = l >> 4, i = l & 15;
@@ -908,6 +909,10 @@ HWB_FN void finish_mb(SliceDec &s, bool skipped, bool direct16, bool is_pcm) {
         // bottom sample row of the block, displaced, plus the 3 rows the 6-tap filter reads below it
         const int row = (s.mby * 16 + (i >> 2) * 4 + 3 + ((int)(int16_t)(mvw >> 16) >> 2) + 3) >> 4;
         reach = imax(reach, 1 + clip3(0, c.mb_h - 1, row));
+        // rightmost sample column read (+3 filter taps); it is final once the macroblock holding column + 3 has been
+        // deblocked (the next macroblock's left edge changes up to 3 columns): progress needed = that column + 1
+        const int col = s.mbx * 16 + (i & 3) * 4 + 3 + ((int)(int16_t)(mvw & 0xffff) >> 2) + 3;
+        reach_x = imax(reach_x, clip3(1, c.mb_w, ((col + 3) >> 4) + 1 - s.mbx));
       }
       if (i < 4) {
         const int r = s.ref_cache[k][HWB_CI((i & 1) * 2, (i >> 1) * 2)];
@@ -923,9 +928,11 @@ HWB_FN void finish_mb(SliceDec &s, bool skipped, bool direct16, bool is_pcm) {
   HWB_LANES_END
   if (inter) {
 #if HWB_DEVICE_BUILD
-    reach = (int)__reduce_max_sync(0xffffffffu, (unsigned)reach);
+    reach = (int)__reduce_max_sync(0xffffffffu, (unsigned)((reach << 16) | reach_x));  // reach > 0 implies reach_x >= 1
+    reach_x = reach & 0xffff; reach >>= 16;
 #endif
     if (reach > s.row_reach) s.row_reach = reach;
+    if (reach_x > s.row_reach_x) s.row_reach_x = reach_x;
   }
   s.left.flags = flags; s.left.cbp = o.cbp; s.left.cmode = o.cmode; s.left.cbf = cbf;
 }
@@ -1222,7 +1229,7 @@ HWB_FN void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states
     while (!((last >> tz) & 1)) ++tz;
     s.stop_bitpos = (uint32_t)(n > 0 ? (n - 1) * 8 + (7 - tz) : 0);
   }
-  s.qp = sd.qp; s.last_dqp = 0; s.row_reach = 0;
+  s.qp = sd.qp; s.last_dqp = 0; s.row_reach = 0; s.row_reach_x = 0;
   init_caches(s);
   s.line = (NbCtx *)(c.ectx + (uint64_t)slice_idx * c.ectx_stride);
   // the arena region of a slice starts at its first macroblock's worst-case offset
@@ -1276,18 +1283,20 @@ HWB_FN void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states
       // the row just completed (or the part of it this slice covers): what the picture kernel must wait for in the
       // reference pictures before it predicts this row; several slices may share a row, hence the atomic maximum
       int32_t *rr = c.mv_reach + (size_t)sd.pic * c.mb_h + (addr - 1) / c.mb_w;
+      int32_t *rx = c.mv_reach_x + (size_t)sd.pic * c.mb_h + (addr - 1) / c.mb_w;
 #if HWB_DEVICE_BUILD
       __syncwarp();
       if ((threadIdx.x & 31) == 0) {  // release store: no L1 invalidation (see publish_progress in kernels.cu)
-        if (s.row_reach) atomicMax(rr, s.row_reach);
+        if (s.row_reach) { atomicMax(rr, s.row_reach); atomicMax(rx, s.row_reach_x); }
         const int32_t v = (end || addr == end_mb) ? c.nmb : addr;
         asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(c.entropy_prog + slice_idx), "r"(v) : "memory");
       }
 #else
       if (s.row_reach > *rr) *rr = s.row_reach;
+      if (s.row_reach_x > *rx) *rx = s.row_reach_x;
       c.entropy_prog[slice_idx] = (end || addr == end_mb) ? c.nmb : addr;
 #endif
-      s.row_reach = 0;
+      s.row_reach = 0; s.row_reach_x = 0;
     }
   }
   // A slice that stops before the next slice's first macroblock (or runs out of data at it without its end flag)

@@ -113,6 +113,7 @@ struct ChunkCtx {
   int32_t *recon_prog;     // [pic][mb_h] macroblocks reconstructed per row
   int32_t *dbl_prog;       // [pic][mb_h] macroblocks deblocked per row
   int32_t *mv_reach;       // [pic][mb_h] 1 + lowest macroblock row of a reference picture that inter prediction of this row reads (0 = none); written by the entropy stage
+  int32_t *mv_reach_x;     // [pic][mb_h] how many macroblocks of those reference rows, counted from a macroblock's own column, must be deblocked before the macroblock can be predicted (>= 1)
   int32_t *error_flag;     // set non-zero by any kernel that meets an unsupported/corrupt stream
   // ---- picture kernel (reconstruction + deblocking + RGB24 writeback of a whole chunk in one launch)
   // Work items: pic << 12 | macroblock row << 1 | kind (0 reconstruct the row, 1 deblock it and emit RGB24).

@@ -75,24 +75,54 @@ HWB_HD int reference_row_needed(const ChunkCtx &c, int pic, int y) {
   return reach < c.mb_h ? reach : c.mb_h - 1;
 }
 
+enum { MAX_TRACKED_DEPS = 4 };
+
 HWB_FN void recon_row(const ChunkCtx &c, int pic, int y, ReconScratch *my) {
   const PicDesc &pd = c.pics[pic];
   const MbInfo *mbs = pic_mbinfo(c, pd.frame);
   int32_t *prog = c.recon_prog + (size_t)pic * c.mb_h;
   const bool has_inter = pd.has_inter != 0;
+  // Inter prediction: the reference rows this row reaches must be deblocked as far as the macroblock at hand reaches
+  // to the right (frame index == picture index inside a chunk, so a reference's counters are found by its frame
+  // index).  Waiting per macroblock instead of for whole rows lets a picture follow its reference at a distance of a
+  // few macroblocks: the pictures of a GOP form one long diagonal wavefront.  Pictures with more references than
+  // are tracked here wait for complete rows.
+  Progress dep[MAX_TRACKED_DEPS];
+  int ndep = 0, reach_x = 0;
   if (has_inter) {
-    // frame index == picture index inside a chunk, so a reference's counters are found by its frame index
     const int row = reference_row_needed(c, pic, y);
-    if (row >= 0)
-      for (int i = 0; i < pd.num_dep; ++i) {
-        Progress ref = {c.dbl_prog + (size_t)pd.dep[i] * c.mb_h + row, -1};
-        wait_progress(ref, c.mb_w);
+    if (row >= 0) {
+      reach_x = c.mv_reach_x[(size_t)pic * c.mb_h + y];
+      if (pd.num_dep <= MAX_TRACKED_DEPS) {
+        ndep = pd.num_dep;
+        for (int i = 0; i < MAX_TRACKED_DEPS; ++i)
+          if (i < ndep) { dep[i].p = c.dbl_prog + (size_t)pd.dep[i] * c.mb_h + row; dep[i].seen = -1; }
+      } else {
+        for (int i = 0; i < pd.num_dep; ++i) {
+          Progress ref = {c.dbl_prog + (size_t)pd.dep[i] * c.mb_h + row, -1};
+          wait_progress(ref, c.mb_w);
+        }
       }
+    }
   }
   Progress above = {prog + y - 1, y > 0 ? -1 : (1 << 30)};
   for (int x = 0; x < c.mb_w; ++x) {
-    // intra macroblocks read the unfiltered row above up to the top-right neighbour
-    if (mbs[y * c.mb_w + x].mbtype != MB_INTER) wait_progress(above, x + 2 < c.mb_w ? x + 2 : c.mb_w);
+    if (mbs[y * c.mb_w + x].mbtype != MB_INTER) {
+      // intra macroblocks read the unfiltered row above up to the top-right neighbour
+      wait_progress(above, x + 2 < c.mb_w ? x + 2 : c.mb_w);
+    } else if (ndep) {
+      const int need = x + reach_x < c.mb_w ? x + reach_x : c.mb_w;
+#pragma unroll
+      for (int i = 0; i < MAX_TRACKED_DEPS; ++i) if (i < ndep) wait_progress(dep[i], need);
+    }
+#if !HWB_DEVICE_BUILD
+    {  // what the waits above guarantee to be final in the reference pictures (see McWindow)
+      const int reach = has_inter ? c.mv_reach[(size_t)pic * c.mb_h + y] : 0;
+      const int X = x + reach_x < c.mb_w ? x + reach_x : c.mb_w;
+      g_mc_window.max_row = reach * 16 - 1;
+      g_mc_window.max_col = X >= c.mb_w ? (1 << 30) : 16 * X - 4;
+    }
+#endif
     recon_mb(c, pic, x, y, my);
     // consumers: intra macroblocks of the row below and the deblocking pass; pictures with inter slices have few
     // intra macroblocks, so the fence + flag store is amortised over 4 macroblocks there

@@ -177,6 +177,15 @@ HWB_HD int intra_dir_pred(int mode, int N, const uint8_t *E, int x, int y) {
 // ---------------------------------------------------------------------------------------------
 HWB_HD int tap6(int a, int b, int c, int d, int e, int f) { return a - 5 * b + 20 * c + 20 * d - 5 * e + f; }
 
+#if !HWB_DEVICE_BUILD
+// Host emulation only: the window of the reference pictures the current macroblock was promised to stay inside
+// (what the picture kernel waited for: ChunkCtx::mv_reach / mv_reach_x).  Every reference sample fetched is checked
+// against it, so a reach computed too small by the entropy stage fails a CPU test instead of racing on the GPU.
+struct McWindow { int max_row = 1 << 30, max_col = 1 << 30, violations = 0; };
+static thread_local McWindow g_mc_window;
+static inline void mc_check(int row, int col) { if (row > g_mc_window.max_row || col > g_mc_window.max_col) g_mc_window.violations++; }
+#endif
+
 // Luma prediction of a 4 (wide) x 2 (high) region whose top-left integer position (already
 // displaced by mv>>2) is (px,py); fx,fy = mv&3.  ref is a coded luma plane (w x h, pitch w).
 HWB_FN void mc_luma_4x2(const uint8_t *ref, int w, int h, int px, int py, int fx, int fy, int *out, uint32_t *scratch) {
@@ -189,6 +198,9 @@ HWB_FN void mc_luma_4x2(const uint8_t *ref, int w, int h, int px, int py, int fx
       int yy = clip3(0, h - 1, py + r);
       for (int c = 0; c < 4; ++c) out[r * 4 + c] = ld_u8_cg(ref + yy * w + clip3(0, w - 1, px + c));
     }
+#if !HWB_DEVICE_BUILD
+    mc_check(clip3(0, h - 1, py + 1), clip3(0, w - 1, px + 3));
+#endif
     return;
   }
   if (inside) {
@@ -213,6 +225,7 @@ HWB_FN void mc_luma_4x2(const uint8_t *ref, int w, int h, int px, int py, int fx
       const uint8_t *p = ref + (py - 2 + r) * w + px - 2;
       for (int c = 0; c < 9; ++c) win[r][c] = p[c];
     }
+    mc_check(py + 4, px + 6);
 #endif
   } else {
 #pragma unroll 1
@@ -221,6 +234,9 @@ HWB_FN void mc_luma_4x2(const uint8_t *ref, int w, int h, int px, int py, int fx
 #pragma unroll
       for (int c = 0; c < 9; ++c) win[r][c] = ld_u8_cg(ref + yy * w + clip3(0, w - 1, px - 2 + c));
     }
+#if !HWB_DEVICE_BUILD
+    mc_check(clip3(0, h - 1, py + 4), clip3(0, w - 1, px + 6));
+#endif
   }
 #define HWB_H1(r, c) tap6(win[r][(c)], win[r][(c) + 1], win[r][(c) + 2], win[r][(c) + 3], win[r][(c) + 4], win[r][(c) + 5])
 #define HWB_V1(r, c) tap6(win[(r)][c], win[(r) + 1][c], win[(r) + 2][c], win[(r) + 3][c], win[(r) + 4][c], win[(r) + 5][c])
@@ -276,6 +292,9 @@ HWB_FN void mc_chroma_2x2(const uint8_t *ref, int w, int h, int cx, int cy, int 
     int yy = clip3(0, h - 1, y0 + r);
     for (int c = 0; c < 3; ++c) v[r][c] = ld_u8_cg(ref + yy * w + clip3(0, w - 1, x0 + c));
   }
+#if !HWB_DEVICE_BUILD
+  mc_check(2 * clip3(0, h - 1, y0 + 2) + 1, 2 * clip3(0, w - 1, x0 + 2) + 1);  // in luma units
+#endif
   for (int r = 0; r < 2; ++r)
     for (int c = 0; c < 2; ++c)
       out[r * 2 + c] = ((8 - fx) * (8 - fy) * v[r][c] + fx * (8 - fy) * v[r][c + 1] + (8 - fx) * fy * v[r + 1][c] +

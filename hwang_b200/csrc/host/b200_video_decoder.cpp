@@ -264,7 +264,7 @@ Result B200VideoDecoder::submit_current() {
                o_ritems = take(recon_items.size() * 4), o_ditems = take(deblock_items.size() * 4), o_order = take((size_t)S * 4),
                o_rgb = take(rgb_bytes * (size_t)nrgb);
   // counters zeroed per chunk: tickets (entropy, recon, deblock) + per-slice entropy progress + per-row progress x2 + mv reach + error flag
-  const size_t n_sync = 4 + (size_t)S + 3 * (size_t)P * mb_h + 4;
+  const size_t n_sync = 4 + (size_t)S + 4 * (size_t)P * mb_h + 4;
   const size_t o_sync = take(n_sync * 4);
   if (feeder_may_block_ && memory_budget_) {
     // Back-pressure in bytes: wait for the consumer to retire chunks instead of running the device out of memory.
@@ -302,7 +302,8 @@ Result B200VideoDecoder::submit_current() {
   c.recon_prog = c.entropy_prog + S;
   c.dbl_prog = c.recon_prog + (size_t)P * mb_h;
   c.mv_reach = c.dbl_prog + (size_t)P * mb_h;
-  c.error_flag = c.mv_reach + (size_t)P * mb_h;
+  c.mv_reach_x = c.mv_reach + (size_t)P * mb_h;
+  c.error_flag = c.mv_reach_x + (size_t)P * mb_h;
   ch->error_dev = c.error_flag;
 
   // Inputs + entropy decoding on one of the rotating entropy streams, the picture kernel on the (single) picture

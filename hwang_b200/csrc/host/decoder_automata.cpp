@@ -84,7 +84,14 @@ Result DecoderAutomata::initialize(std::vector<EncodedData> &&encoded_data, cons
   encoded_data_ = std::move(encoded_data);
   info_.width = encoded_data_[0].width; info_.height = encoded_data_[0].height; info_.format = encoded_data_[0].format;
   frame_size_ = (size_t)info_.width * info_.height * 3;
-  HWANG_RETURN_ON_ERROR(decoder_->configure(info_, extradata));
+  {
+    Result r = decoder_->configure(info_, extradata);
+    if (!r.ok) {  // nothing will be fed: a later get_frames must report this instead of waiting for frames
+      encoded_data_.clear();
+      feeder_result_ = r; result_set_ = true;
+      return r;
+    }
+  }
   {
     std::unique_lock<std::mutex> lk(mu_);
     work_ = true;  // consumed by the feeder; no lost wake-up even if the thread has not reached its wait yet

@@ -117,8 +117,10 @@ std::string H264Stream::parse_sps(const std::vector<uint8_t> &rbsp) {
   }
   if (s.chroma_format_idc != 1 || s.bit_depth_luma != 8 || s.bit_depth_chroma != 8) return "unsupported: only 4:2:0 8-bit";
   s.log2_max_frame_num = 4 + (int)r.ue();
+  if (s.log2_max_frame_num > 16) return "SPS: log2_max_frame_num_minus4 out of range";
   s.poc_type = (int)r.ue();
-  if (s.poc_type == 0) s.log2_max_poc_lsb = 4 + (int)r.ue();
+  if (s.poc_type > 2) return "SPS: pic_order_cnt_type out of range";
+  if (s.poc_type == 0) { s.log2_max_poc_lsb = 4 + (int)r.ue(); if (s.log2_max_poc_lsb > 16) return "SPS: log2_max_pic_order_cnt_lsb_minus4 out of range"; }
   else if (s.poc_type == 1) {
     s.delta_pic_order_always_zero = r.u1();
     s.offset_for_non_ref_pic = r.se(); s.offset_for_top_to_bottom = r.se();
@@ -615,7 +617,11 @@ std::string H264Stream::parse_sample(const uint8_t *data, size_t n, int pic_inde
   out.desc.rgb_slot = -1;
   levels_.resize(std::max<size_t>(levels_.size(), (size_t)pic_index + 1));
   levels_[pic_index] = out.desc.level;
+  // mark_references leaves prev_had_mmco5_ = "THIS picture carried MMCO 5" (what compute_poc of the next picture
+  // needs); a non-reference picture has no marking at all, so the flag is cleared for it here -- otherwise every
+  // non-reference picture after an MMCO 5 picture would start an output period of its own
   if (first.nal_ref_idc) mark_references(*sps0, first, pic_index, cur_poc);
+  else prev_had_mmco5_ = false;
   if (prev_had_mmco5_) { out_period_++; cur_poc = 0; }
   out.out_key = (out_period_ << 32) + (int64_t)cur_poc + (1ll << 31);
   (void)pps0;

@@ -63,6 +63,7 @@ int hwb_dev_picture(hwb_dev *d, int, const ChunkCtx *c, int32_t *) {
   };
   int ir = 0, id = 0;
   g_unsatisfied_waits = 0;
+  g_mc_window.violations = 0;
   while (ir < c->num_recon_items || id < c->num_deblock_items) {
     bool progressed = false;
     while (ir < c->num_recon_items && recon_ready(c->recon_items[ir])) { recon_row(*c, item_pic(c->recon_items[ir]), item_row(c->recon_items[ir]), &sm.recon); ir++; progressed = true; }
@@ -70,6 +71,7 @@ int hwb_dev_picture(hwb_dev *d, int, const ChunkCtx *c, int32_t *) {
     if (!progressed) { *c->error_flag = 901; d->err = "emulation: work lists are not in dependency order"; break; }
   }
   if (g_unsatisfied_waits) { *c->error_flag = 902; d->err = "emulation: a wait was not satisfied"; }
+  if (g_mc_window.violations) { *c->error_flag = 903; d->err = "emulation: inter prediction read reference samples beyond the reach the entropy stage announced"; }
   delete smp;
   return 0;
 }

@@ -79,6 +79,28 @@ FEATURE_CLIPS = {
 }
 
 
+# Syntax a real encoder emits that the reference's own clips would exercise (x264: B pyramid, reference list
+# modification for duplicate references, MMCO on scene cuts / long-term references): the generator writes it, libavcodec
+# decodes it, and both the generator's reconstruction and our decoder must equal libavcodec's output.
+SYNTAX_CLIPS = {
+    'b_pyramid_spatial': dict(frames=26, gop=13, width=176, height=144, profile=2, seed=101, num_ref=3, bframes=3, b_pyramid=1, weighted=2),
+    'b_pyramid_temporal_multislice': dict(frames=26, gop=13, width=176, height=144, profile=2, seed=102, num_ref=4, bframes=3, b_pyramid=1,
+                                          direct_spatial=0, weighted=2, slices=2),
+    'ref_list_modification_p': dict(frames=20, gop=10, width=176, height=144, profile=1, seed=103, num_ref=4, rplm_pct=70),
+    'ref_list_modification_b': dict(frames=24, gop=12, width=176, height=144, profile=2, seed=104, num_ref=4, bframes=2, rplm_pct=70, weighted=2),
+    'mmco_long_term_p': dict(frames=40, gop=20, width=176, height=144, profile=1, seed=105, num_ref=3, mmco=1),
+    'mmco_long_term_b_temporal': dict(frames=40, gop=20, width=176, height=144, profile=2, seed=106, num_ref=4, bframes=2, mmco=1, rplm_pct=50,
+                                      direct_spatial=0),
+    'mmco_cavlc_baseline': dict(frames=40, gop=20, width=176, height=144, profile=0, seed=107, num_ref=3, mmco=1, rplm_pct=30),
+    'poc_type1_p': dict(frames=20, gop=10, width=176, height=144, profile=1, seed=108, num_ref=2, poc_type=1),
+    'poc_type1_b_pyramid': dict(frames=26, gop=13, width=176, height=144, profile=2, seed=109, num_ref=3, bframes=3, b_pyramid=1, poc_type=1),
+    'poc_type1_mmco5': dict(frames=40, gop=20, width=176, height=144, profile=1, seed=110, num_ref=3, poc_type=1, mmco=1),
+    'poc_type2_mmco5': dict(frames=40, gop=20, width=176, height=144, profile=0, seed=111, num_ref=3, poc_type=2, mmco=1),
+    'everything_weighted_p_pyramid': dict(frames=34, gop=17, width=176, height=144, profile=2, seed=112, num_ref=4, bframes=3, b_pyramid=1, mmco=1,
+                                          rplm_pct=40, weighted=2, slices=2, qp_jitter=2, intra_in_p_pct=6, scaling_lists=1),
+}
+
+
 def decode_corrupted_then_clean(seed_list=(1, 2, 3)):
     """Flip bytes inside slice payloads: the decoder must either report an error or return frames, never hang or
     fault, and must decode a clean clip bit-exactly afterwards (same process, same device context)."""

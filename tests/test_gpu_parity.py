@@ -16,6 +16,12 @@ def test_yuv_bit_exact(gpu, name):
     util.assert_yuv_parity(util.FEATURE_CLIPS[name])
 
 
+@pytest.mark.parametrize('name', sorted(util.SYNTAX_CLIPS))
+def test_real_encoder_syntax_bit_exact(gpu, name):
+    """B pyramid, reference list modification, MMCO / long-term references, POC types 1 and 2 (hwb_testutil.SYNTAX_CLIPS)."""
+    util.assert_yuv_parity(util.SYNTAX_CLIPS[name])
+
+
 def test_small_chunks_match(gpu):
     # chunk boundaries at every GOP: results must not depend on batching
     util.assert_yuv_parity(dict(frames=30, gop=5, width=176, height=144, profile=1, seed=41, bframes=1), chunk_pictures=1)

@@ -178,9 +178,11 @@ static inline int qround(float x, float rnd) {
 }
 
 // ------------------------------------------------------------------------------------------ encoder
-enum { NSLOT = 8, MAXSL = 8 };
+enum { NSLOT = 12, MAXSL = 8 };
+enum { kPoc1NonRefOffset = -1 };
 
-struct RefEntry { int slot, frame_num, poc, t; };
+struct RefEntry { int slot, frame_num, poc, t; bool long_term = false; int lt_idx = 0; };
+struct MmcoOp { int op, a; };
 
 struct Encoder {
   hwgen_params P;
@@ -198,6 +200,7 @@ struct Encoder {
   int32_t errflag = 0;
   std::vector<uint8_t> srcY, srcU, srcV;
   std::vector<RefEntry> dpb;
+  std::vector<MmcoOp> rplm_ops[2];  // ref_pic_list_modification of the picture being encoded (op = modification_of_pic_nums_idc)
   Rng rng;
   ReconScratch rs;
   DeblockScratch ds;
@@ -244,6 +247,11 @@ struct Encoder {
     b.ue(0);  // log2_max_frame_num_minus4
     b.ue((uint32_t)P.poc_type);
     if (P.poc_type == 0) b.ue(4);  // log2_max_pic_order_cnt_lsb_minus4 -> 8 bits
+    if (P.poc_type == 1) {
+      // delta_pic_order_always_zero_flag (only legal here when POC follows decode order), offset_for_non_ref_pic,
+      // offset_for_top_to_bottom_field, one-entry cycle: a reference frame advances the expected POC by 2
+      b.put1(P.bframes == 0); b.se(kPoc1NonRefOffset); b.se(0); b.ue(1); b.se(2);
+    }
     b.ue((uint32_t)P.num_ref);
     b.put1(0);
     b.ue((uint32_t)(mb_w - 1)); b.ue((uint32_t)(mb_h - 1));
@@ -259,8 +267,9 @@ struct Encoder {
     b.put1(0);  // pic_struct
     b.put1(1);  // bitstream_restriction
     b.put1(1); b.ue(0); b.ue(0); b.ue(16); b.ue(16);
-    b.ue((uint32_t)(P.bframes > 0 ? 1 : 0));
-    b.ue((uint32_t)std::max(P.num_ref, P.bframes > 0 ? 2 : 1));
+    const int reorder = P.bframes > 0 ? (P.b_pyramid && P.bframes >= 2 ? 2 : 1) : 0;
+    b.ue((uint32_t)reorder);
+    b.ue((uint32_t)std::max(P.num_ref, reorder + 1));
     b.trailing();
     return b.buf;
   }
@@ -304,19 +313,31 @@ struct Encoder {
   }
 
   // -------------------------------------------------------------------------------- helpers
-  int free_slot() const {
+  // Least recently used free slot: motion data of pictures still in the DPB names its references by slot (refpic), so a
+  // slot must not be handed out again while such a picture can still be the co-located picture of a B slice (a
+  // reference dropped by MMCO 1 and its slot reused at once made temporal direct prediction find the wrong picture).
+  int slot_stamp[NSLOT] = {0};
+  int stamp = 0;
+  int free_slot() {
+    int best = -1;
     for (int s = 0; s < NSLOT; ++s) {
       bool used = false;
       for (auto &r : dpb) if (r.slot == s) used = true;
-      if (!used) return s;
+      if (!used && (best < 0 || slot_stamp[s] < slot_stamp[best])) best = s;
     }
-    return -1;
+    if (best >= 0) slot_stamp[best] = ++stamp;
+    return best;
   }
   const uint8_t *src_plane(int p) const { return p == 0 ? srcY.data() : (p == 1 ? srcU.data() : srcV.data()); }
 
   struct PicState {
     int slot, t, type, frame_num, poc, gop_t0;
     bool is_ref, idr;
+    int delta_poc = 0;            // poc_type 1: delta_pic_order_cnt[0]
+    bool long_term_idr = false;   // IDR with long_term_reference_flag
+    std::vector<MmcoOp> mmco;     // adaptive_ref_pic_marking_mode_flag = 1 when not empty
+    int mmco3_lt_idx = 0;         // long_term_frame_idx of MMCO 3 / 6
+    bool rplm = false;            // the slices reorder their reference lists
   };
 
   // quantise the residual of the current macroblock (source minus what recon_mb predicted into the
@@ -608,13 +629,19 @@ struct Encoder {
     b.put((uint32_t)(ps.frame_num & 15), 4);
     if (nal_type == 5) b.ue((uint32_t)idr_id);
     if (P.poc_type == 0) b.put((uint32_t)(ps.poc & 255), 8);
+    if (P.poc_type == 1 && P.bframes != 0) b.se(ps.delta_poc);
     if (sd.slice_type == SLICE_B) b.put1(sd.direct_spatial);
     if (sd.slice_type != SLICE_I) {
       bool ovr = sd.num_ref[0] != 1 || (sd.slice_type == SLICE_B && sd.num_ref[1] != 1);
       b.put1(ovr);
       if (ovr) { b.ue((uint32_t)(sd.num_ref[0] - 1)); if (sd.slice_type == SLICE_B) b.ue((uint32_t)(sd.num_ref[1] - 1)); }
-      b.put1(0);  // ref_pic_list_modification_flag_l0
-      if (sd.slice_type == SLICE_B) b.put1(0);
+      for (int l = 0; l < (sd.slice_type == SLICE_B ? 2 : 1); ++l) {
+        b.put1(!rplm_ops[l].empty());  // ref_pic_list_modification_flag_lX
+        if (!rplm_ops[l].empty()) {
+          for (auto &m : rplm_ops[l]) { b.ue((uint32_t)m.op); b.ue((uint32_t)m.a); }
+          b.ue(3);
+        }
+      }
     }
     if (sd.use_weights == 1) {
       b.ue(sd.luma_log2_denom); b.ue(sd.chroma_log2_denom);
@@ -630,8 +657,14 @@ struct Encoder {
         }
     }
     if (ps.is_ref) {
-      if (nal_type == 5) { b.put1(0); b.put1(0); }
-      else b.put1(0);  // adaptive_ref_pic_marking_mode_flag: sliding window
+      if (nal_type == 5) { b.put1(0); b.put1(ps.long_term_idr); }
+      else {
+        b.put1(!ps.mmco.empty());  // adaptive_ref_pic_marking_mode_flag (0: sliding window)
+        if (!ps.mmco.empty()) {
+          for (auto &m : ps.mmco) { b.ue((uint32_t)m.op); if (m.op != 5) b.ue((uint32_t)m.a); if (m.op == 3) b.ue((uint32_t)ps.mmco3_lt_idx); }
+          b.ue(0);
+        }
+      }
     }
     if (cabac && sd.slice_type != SLICE_I) b.ue(sd.cabac_init_idc);
     b.se((int)sd.qp - 26);
@@ -652,20 +685,53 @@ struct Encoder {
     pd.chroma_qp_offset[0] = (int8_t)P.chroma_qp_offset; pd.chroma_qp_offset[1] = (int8_t)(high ? P.chroma_qp_offset - 1 : P.chroma_qp_offset);
     memcpy(pd.scaling4, scaling4, sizeof(scaling4)); memcpy(pd.scaling8, scaling8, sizeof(scaling8));
 
-    // reference lists
-    std::vector<RefEntry> l0, l1;
-    if (ps.type == SLICE_P) { l0.assign(dpb.rbegin(), dpb.rend()); }
-    else if (ps.type == SLICE_B) {
+    // reference lists: initialisation (8.2.4.2: short-term by PicNum / POC, then long-term by LongTermPicNum), then the
+    // optional modification (8.2.4.3) whose syntax write_slice_header emits from rplm_ops
+    std::vector<RefEntry> l0, l1, lt;
+    for (auto &r : dpb) if (r.long_term) lt.push_back(r);
+    std::sort(lt.begin(), lt.end(), [](const RefEntry &a, const RefEntry &b) { return a.lt_idx < b.lt_idx; });
+    if (ps.type == SLICE_P) {
+      for (auto it = dpb.rbegin(); it != dpb.rend(); ++it) if (!it->long_term) l0.push_back(*it);  // decode order reversed = PicNum descending
+      l0.insert(l0.end(), lt.begin(), lt.end());
+    } else if (ps.type == SLICE_B) {
       std::vector<RefEntry> before, after;
-      for (auto &r : dpb) (r.poc < ps.poc ? before : after).push_back(r);
+      for (auto &r : dpb) if (!r.long_term) (r.poc < ps.poc ? before : after).push_back(r);
       std::sort(before.begin(), before.end(), [](const RefEntry &a, const RefEntry &b) { return a.poc > b.poc; });
       std::sort(after.begin(), after.end(), [](const RefEntry &a, const RefEntry &b) { return a.poc < b.poc; });
-      l0 = before; l0.insert(l0.end(), after.begin(), after.end());
-      l1 = after; l1.insert(l1.end(), before.begin(), before.end());
+      l0 = before; l0.insert(l0.end(), after.begin(), after.end()); l0.insert(l0.end(), lt.begin(), lt.end());
+      l1 = after; l1.insert(l1.end(), before.begin(), before.end()); l1.insert(l1.end(), lt.begin(), lt.end());
       if (l1.size() > 1 && l0.size() == l1.size()) {
         bool same = true;
         for (size_t i = 0; i < l0.size(); ++i) same &= l0[i].slot == l1[i].slot;
         if (same) std::swap(l1[0], l1[1]);
+      }
+    }
+    rplm_ops[0].clear(); rplm_ops[1].clear();
+    if (ps.rplm) {
+      const int active[2] = {std::min<int>((int)l0.size(), P.num_ref), std::min<int>((int)l1.size(), 2)};
+      for (int l = 0; l < (ps.type == SLICE_B ? 2 : 1); ++l) {
+        std::vector<RefEntry> &lst = l ? l1 : l0;
+        if (active[l] < 2) continue;
+        lst.resize(active[l]);  // entries beyond num_ref_idx_active are dropped before the modification
+        // move one or two entries to the front.  picNumPred starts at CurrPicNum; a short-term target is named by the
+        // difference to the prediction (idc 0 subtract / 1 add), a long-term one by its LongTermPicNum (idc 2)
+        auto pic_num = [&](const RefEntry &r) { return r.frame_num > ps.frame_num ? r.frame_num - 16 : r.frame_num; };
+        int pred = ps.frame_num;
+        const int nops = 1 + (active[l] > 2 && rng.pct(50));
+        for (int k = 0; k < nops; ++k) {
+          const int src = k + 1 + rng.below(active[l] - k - 1);  // an entry behind position k
+          RefEntry tgt = lst[src];
+          if (tgt.long_term) rplm_ops[l].push_back({2, tgt.lt_idx});
+          else {
+            const int pn = pic_num(tgt);
+            if (pn < pred) rplm_ops[l].push_back({0, pred - pn - 1});
+            else if (pn > pred) rplm_ops[l].push_back({1, pn - pred - 1});
+            else { rplm_ops[l].push_back({0, 15}); }  // same picture again: a full wrap (MaxPicNum = 16)
+            pred = pn;
+          }
+          lst.erase(lst.begin() + src);
+          lst.insert(lst.begin() + k, tgt);
+        }
       }
     }
     int nrefs_total[2] = {(int)l0.size(), (int)l1.size()};
@@ -687,7 +753,10 @@ struct Encoder {
       sd.num_ref[1] = (uint8_t)std::min<int>((int)l1.size(), 2);
       for (int l = 0; l < 2; ++l) {
         const auto &lst = l ? l1 : l0;
-        for (int i = 0; i < sd.num_ref[l]; ++i) { sd.ref_frame[l][i] = (int16_t)lst[i].slot; sd.ref_poc[l][i] = lst[i].poc; }
+        for (int i = 0; i < sd.num_ref[l]; ++i) {
+          sd.ref_frame[l][i] = (int16_t)lst[i].slot; sd.ref_poc[l][i] = lst[i].poc;
+          if (lst[i].long_term) sd.ref_long[l] |= 1u << i;
+        }
       }
       sd.luma_log2_denom = 5; sd.chroma_log2_denom = 5;
       for (int l = 0; l < 2; ++l) for (int i = 0; i < 32; ++i) { sd.luma_w[l][i] = 32; sd.chroma_w[l][i][0] = sd.chroma_w[l][i][1] = 32; }
@@ -1067,6 +1136,8 @@ static int encode_clip(const hwgen_params &P, std::vector<uint8_t> &mp4, uint8_t
   if (P.slices < 1 || P.slices > MAXSL) { g_err = "slices out of range"; return -1; }
   if (P.profile == 0 && (P.bframes || (P.cabac == 1))) { g_err = "baseline: no B pictures / CABAC"; return -1; }
   if (P.poc_type == 2 && P.bframes) { g_err = "poc_type 2 requires bframes == 0"; return -1; }
+  if (P.poc_type < 0 || P.poc_type > 2) { g_err = "poc_type must be 0, 1 or 2"; return -1; }
+  if (P.b_pyramid && P.num_ref < 3) { g_err = "b_pyramid needs num_ref >= 3 (two anchors and the reference B picture)"; return -1; }
   Content content;
   content.init(P.width, P.height, P.seed, P.weighted >= 1);
   const int ngop = (P.frames + P.gop - 1) / P.gop;
@@ -1089,18 +1160,97 @@ static int encode_clip(const hwgen_params &P, std::vector<uint8_t> &mp4, uint8_t
       const int t0 = g * P.gop, n = std::min(P.gop, P.frames - t0);
       enc.rng = Rng(P.seed * 1000003ull + g);
       enc.dpb.clear();
-      // decode order within the GOP
-      std::vector<int> order, types;
-      order.push_back(0); types.push_back(SLICE_I);
+      // decode order within the GOP: anchors (I, then P every bframes+1 pictures), each followed by the B pictures
+      // it closes; with b_pyramid the middle B picture of a run is coded first and kept as a reference
+      struct Plan { int t, type; bool is_ref; };
+      std::vector<Plan> plan;
+      plan.push_back({0, SLICE_I, true});
       int step = P.bframes + 1, i = 0;
-      while (i + step < n) { order.push_back(i + step); types.push_back(SLICE_P); for (int b = 1; b <= P.bframes; ++b) { order.push_back(i + b); types.push_back(SLICE_B); } i += step; }
-      for (int k = i + 1; k < n; ++k) { order.push_back(k); types.push_back(SLICE_P); }
+      while (i + step < n) {
+        plan.push_back({i + step, SLICE_P, true});
+        const int mid = (P.b_pyramid && P.bframes >= 2) ? (P.bframes + 1) / 2 : 0;
+        if (mid) plan.push_back({i + mid, SLICE_B, true});
+        for (int b = 1; b <= P.bframes; ++b) if (b != mid) plan.push_back({i + b, SLICE_B, false});
+        i += step;
+      }
+      for (int k = i + 1; k < n; ++k) plan.push_back({k, SLICE_P, true});
       int frame_num = 0;
-      for (size_t k = 0; k < order.size(); ++k) {
+      // POC bookkeeping of the generator itself: `poc_base` moves when MMCO 5 restarts the numbering
+      int poc_base = 0, frame_num_offset = 0, prev_frame_num = 0;
+      bool prev_mmco5 = false;
+      int max_lt_idx = -1;  // MaxLongTermFrameIdx ("no long-term frame indices")
+      for (size_t k = 0; k < plan.size(); ++k) {
         Encoder::PicState ps;
-        ps.t = t0 + order[k]; ps.type = types[k]; ps.idr = k == 0; ps.is_ref = types[k] != SLICE_B;
-        ps.poc = 2 * order[k]; ps.frame_num = frame_num; ps.gop_t0 = t0;
+        ps.t = t0 + plan[k].t; ps.type = plan[k].type; ps.idr = k == 0; ps.is_ref = plan[k].is_ref;
+        ps.poc = 2 * plan[k].t - poc_base; ps.frame_num = frame_num; ps.gop_t0 = t0;
         ps.slot = enc.free_slot();
+        if (ps.slot < 0) { errs[tid] = "generator: out of frame slots"; return; }
+        ps.rplm = ps.type != SLICE_I && P.rplm_pct > 0 && enc.rng.pct(P.rplm_pct);
+        if (P.poc_type == 1) {
+          // 8.2.1.2 with a one-entry cycle (offset_for_ref_frame[0] = 2): expected POC from frame_num alone
+          if (ps.idr) frame_num_offset = 0;
+          else if (prev_mmco5) frame_num_offset = 0;
+          else if (prev_frame_num > frame_num) frame_num_offset += 16;
+          int abs_fn = frame_num_offset + frame_num;
+          if (!ps.is_ref && abs_fn > 0) abs_fn--;
+          int expected = abs_fn > 0 ? 2 * abs_fn : 0;
+          if (!ps.is_ref) expected += kPoc1NonRefOffset;
+          ps.delta_poc = ps.poc - expected;
+          if (P.bframes == 0 && ps.delta_poc != 0) { errs[tid] = "generator: poc_type 1 without B pictures must follow the expected POC"; return; }
+        }
+        // ---- adaptive reference marking: decided before the picture is coded (it is slice-header syntax), applied after
+        std::vector<RefEntry> &dpb = enc.dpb;
+        auto pic_num = [&](const RefEntry &r) { return r.frame_num > frame_num ? r.frame_num - 16 : r.frame_num; };
+        int n_short = 0, n_long = 0;
+        for (auto &r : dpb) (r.long_term ? n_long : n_short)++;
+        bool cur_long = false; int cur_lt_idx = 0; bool mmco5 = false;
+        if (P.mmco && ps.idr && enc.rng.pct(50) && P.num_ref >= 2) { ps.long_term_idr = true; cur_long = true; cur_lt_idx = 0; }
+        if (P.mmco && ps.is_ref && !ps.idr && P.num_ref >= 2 && enc.rng.pct(40)) {
+          const int choice = enc.rng.below(P.bframes == 0 ? 5 : 4);
+          if (choice == 4 && ps.type == SLICE_P && n_short + n_long > 0) {
+            ps.mmco.push_back({5, 0}); mmco5 = true;            // everything before this picture is forgotten
+          } else if (choice == 0 && n_short >= 2) {
+            const RefEntry *victim = nullptr;                     // MMCO 1: drop the OLDEST short-term reference by name
+            for (auto &r : dpb) if (!r.long_term) { victim = &r; break; }
+            ps.mmco.push_back({1, frame_num - pic_num(*victim) - 1});
+          } else if (choice == 1 && n_long == 0 && n_short >= 2) {
+            if (max_lt_idx < 0) ps.mmco.push_back({4, 1});      // MMCO 4: one long-term index; MMCO 3: oldest short-term -> long-term 0
+            const RefEntry *victim = nullptr;
+            for (auto &r : dpb) if (!r.long_term) { victim = &r; break; }
+            ps.mmco.push_back({3, frame_num - pic_num(*victim) - 1});
+            ps.mmco.push_back({-3, 0});                          // (argument 2 of MMCO 3: long_term_frame_idx, written below)
+          } else if (choice == 2 && n_long > 0) {
+            for (auto &r : dpb) if (r.long_term) { ps.mmco.push_back({2, r.lt_idx}); break; }  // MMCO 2: release the long-term picture
+          } else if (choice == 3 && n_long == 0 && n_short >= 1) {
+            if (max_lt_idx < 0) ps.mmco.push_back({4, 1});
+            ps.mmco.push_back({6, 0});                            // MMCO 6: the current picture becomes long-term 0
+            cur_long = true; cur_lt_idx = 0;
+          }
+          // adaptive marking does no sliding window: when the DPB is full, name one more short-term picture to drop
+          if (!ps.mmco.empty() && !mmco5) {
+            int after_short = n_short, after_long = n_long;
+            for (auto &m : ps.mmco) { if (m.op == 1) after_short--; if (m.op == 3) { after_short--; after_long++; } if (m.op == 2) after_long--; }
+            if (after_short + after_long + 1 > P.num_ref) {
+              // the oldest short-term picture not already named
+              int skip = 0;
+              for (auto &m : ps.mmco) if (m.op == 1 || m.op == 3) skip++;
+              const RefEntry *victim = nullptr;
+              for (auto &r : dpb) if (!r.long_term) { if (skip-- == 0) { victim = &r; break; } }
+              if (victim) ps.mmco.insert(ps.mmco.begin(), {1, frame_num - pic_num(*victim) - 1});
+              else ps.mmco.clear();
+            }
+          }
+        }
+        // flatten MMCO 3's second argument into the op stream the slice header writer emits (op, a) pairs
+        {
+          std::vector<MmcoOp> flat;
+          for (size_t q = 0; q < ps.mmco.size(); ++q) {
+            if (ps.mmco[q].op == -3) continue;
+            flat.push_back(ps.mmco[q]);
+          }
+          ps.mmco3_lt_idx = 0;
+          ps.mmco = flat;
+        }
         samples[t0 + (int)k] = enc.encode_picture(ps, g & 0xFFFF);
         if (recon_yuv) {
           uint8_t *dst = recon_yuv + (size_t)ps.t * fsz;
@@ -1108,9 +1258,43 @@ static int encode_clip(const hwgen_params &P, std::vector<uint8_t> &mp4, uint8_t
           for (int y = 0; y < P.height; ++y) memcpy(dst + (size_t)y * P.width, Y + (size_t)y * enc.wc, P.width);
           for (int y = 0; y < P.height / 2; ++y) { memcpy(dst + ysz + (size_t)y * P.width / 2, U + (size_t)y * enc.wc / 2, P.width / 2); memcpy(dst + ysz + ysz / 4 + (size_t)y * P.width / 2, V + (size_t)y * enc.wc / 2, P.width / 2); }
         }
+        prev_frame_num = frame_num;
+        prev_mmco5 = false;
         if (ps.is_ref) {
-          enc.dpb.push_back({ps.slot, ps.frame_num, ps.poc, ps.t});
-          if ((int)enc.dpb.size() > P.num_ref) enc.dpb.erase(enc.dpb.begin());
+          // ---- decoded reference picture marking (8.2.5) mirrored on the generator's DPB
+          if (ps.idr) {
+            dpb.clear();
+            max_lt_idx = ps.long_term_idr ? 0 : -1;
+          } else if (ps.mmco.empty()) {
+            if (n_short + n_long >= P.num_ref)  // sliding window: the oldest short-term picture goes
+              for (size_t q = 0; q < dpb.size(); ++q) if (!dpb[q].long_term) { dpb.erase(dpb.begin() + q); break; }
+          } else {
+            for (auto &m : ps.mmco) {
+              if (m.op == 1 || m.op == 3) {
+                const int target = frame_num - (m.a + 1);
+                for (size_t q = 0; q < dpb.size(); ++q)
+                  if (!dpb[q].long_term && pic_num(dpb[q]) == target) {
+                    if (m.op == 1) dpb.erase(dpb.begin() + q);
+                    else { dpb[q].long_term = true; dpb[q].lt_idx = 0; }
+                    break;
+                  }
+              } else if (m.op == 2) {
+                for (size_t q = 0; q < dpb.size(); ++q) if (dpb[q].long_term && dpb[q].lt_idx == m.a) { dpb.erase(dpb.begin() + q); break; }
+              } else if (m.op == 4) {
+                max_lt_idx = m.a - 1;
+              } else if (m.op == 5) {
+                dpb.clear(); max_lt_idx = -1;
+              }
+            }
+          }
+          RefEntry cur{ps.slot, ps.frame_num, ps.poc, ps.t};
+          cur.long_term = cur_long; cur.lt_idx = cur_lt_idx;
+          if (mmco5) {
+            // 8.2.1: after MMCO 5 the picture counts as frame_num 0 / POC 0; later pictures continue from there
+            cur.frame_num = 0; cur.poc = 0;
+            poc_base += ps.poc; frame_num = 0; prev_frame_num = 0; prev_mmco5 = true; frame_num_offset = 0;
+          }
+          dpb.push_back(cur);
           frame_num = (frame_num + 1) & 15;
         }
       }
@@ -1119,6 +1303,7 @@ static int encode_clip(const hwgen_params &P, std::vector<uint8_t> &mp4, uint8_t
   std::vector<std::thread> th;
   for (int t = 0; t < nthreads; ++t) th.emplace_back(worker, t);
   for (auto &t : th) t.join();
+  for (auto &e : errs) if (!e.empty()) { g_err = e; return -1; }
   std::vector<int> keyframes;
   for (int g = 0; g < ngop; ++g) keyframes.push_back(g * P.gop);
   mp4 = mux_mp4(P.width, P.height, avcc, samples, keyframes, P.fragmented, P.gop);

@@ -29,11 +29,14 @@ typedef struct hwgen_params {
   int32_t cabac_init_idc;  // 0..2, -1 = vary per slice
   int32_t chroma_qp_offset;   // pps chroma_qp_index_offset (second offset = this - 1 in High)
   int32_t scaling_lists;   // high: 1 = custom scaling matrices in the PPS
-  int32_t poc_type;        // 0 or 2 (2 only without B pictures)
+  int32_t poc_type;        // 0, 1 (expected-delta cycle + delta_pic_order_cnt) or 2 (2 only without B pictures)
   int32_t fragmented;      // mp4: 1 = moof/trun fragments (one per GOP)
   int32_t threads;         // encoder threads (GOP parallel); 0 = hardware concurrency
   int32_t qp_jitter;       // random mb_qp_delta magnitude (0 = constant QP)
-  int32_t reserved[8];
+  int32_t b_pyramid;       // 1: the middle B picture of every run of B pictures is a reference picture (one B-reference level)
+  int32_t rplm_pct;        // percent of P/B pictures whose slices carry ref_pic_list_modification (reorders list 0 / list 1)
+  int32_t mmco;            // 1: adaptive reference marking (MMCO 1-4, 6, long-term IDR; MMCO 5 when bframes == 0) on some reference pictures
+  int32_t reserved[5];
 } hwgen_params;
 
 void hwgen_default_params(hwgen_params *p);
