@@ -423,6 +423,11 @@ def run_ours(args):
         dist = None
     if rank != 0:
         return
+    if args.quick:  # development aid: the two throughputs and the stage sums only
+        d_ = {k: round(v / args.steps, 1) for k, v in d.items() if k.endswith('_ms')}
+        print(json.dumps({'quick': True, 'value': frames_step * args.steps / dev_s, 'e2e': frames_step * args.steps / e2e_s, 'per_step': d_,
+                          'launches': d['kernel_launches'] // args.steps, 'env': {k: v for k, v in os.environ.items() if k.startswith('HWB_')}}), flush=True)
+        return
     frames_total = frames_step * args.steps
     value = frames_total / dev_s
     e2e_value = frames_total / e2e_s
@@ -495,6 +500,7 @@ def main():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours')
+    ap.add_argument('--quick', action='store_true', help='print the two throughputs only (no CPU baseline, no sparse section)')
     ap.add_argument('--frames', type=int, default=int(os.environ.get('HWB_BENCH_FRAMES', '3000')))
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -274,6 +274,13 @@ class DecoderAutomata:
             out = [_Owned(f, buf) for f in out]
         return out
 
+    def get_frames_into(self, ptr, num_frames):
+        """num_frames tightly packed RGB24 frames to caller-owned memory at `ptr`: pageable or page-locked host memory,
+        or device memory (DeviceType::GPU output)."""
+        L = _lib.lib()
+        if L.hwb_automata_get_frames(self._h, ptr, num_frames) != 0:
+            raise RuntimeError(L.hwb_automata_last_error(self._h).decode())
+
     def stats(self):
         s = Stats()
         _lib.lib().hwb_automata_get_stats(self._h, ctypes.byref(s))
@@ -362,6 +369,18 @@ class VideoDecoder:
     def set_chunk_pictures(self, n):
         _lib.lib().hwb_decoder_set_chunk_pictures(self._h, n)
 
+    def set_interval_hint(self, start_frame, wanted):
+        """Before the first feed() of an interval: the frames that will be fetched (the rest will be discarded)."""
+        w, wp = _u64(wanted)
+        _lib.lib().hwb_decoder_set_interval_hint(self._h, start_frame, wp, len(w))
+
+    def set_defer_submit(self, on):
+        """Collect the pictures of consecutive intervals / clips of equal geometry into one GPU batch (see hwang_b200.h)."""
+        self._chk(_lib.lib().hwb_decoder_set_defer_submit(self._h, int(bool(on))))
+
+    def submit_pending(self):
+        self._chk(_lib.lib().hwb_decoder_submit_pending(self._h))
+
     def stats(self):
         s = Stats()
         _lib.lib().hwb_decoder_get_stats(self._h, ctypes.byref(s))
@@ -392,44 +411,96 @@ def index_video(f_or_string):
     return w(f_or_string)
 
 
+class DeviceFrames:
+    """n RGB24 frames (n, H, W, 3) uint8 in DEVICE memory (hwang::DeviceType::GPU as the output location,
+    hwang/common.h:20-50).  Implements __cuda_array_interface__, so `torch.as_tensor(frames, device='cuda:%d' % id)`
+    / cupy.asarray wrap it without a copy; to_host() brings it back for callers without a CUDA runtime."""
+
+    def __init__(self, device_id, n, height, width):
+        self.device_id, self.shape = device_id, (n, height, width, 3)
+        self.nbytes = n * height * width * 3
+        self.ptr = _lib.lib().hwb_alloc_device(device_id, max(1, self.nbytes))
+        if not self.ptr:
+            raise MemoryError('hwb_alloc_device(%d bytes) failed' % self.nbytes)
+
+    @property
+    def __cuda_array_interface__(self):
+        return {'shape': self.shape, 'typestr': '|u1', 'data': (self.ptr, False), 'version': 2, 'strides': None}
+
+    def to_host(self):
+        out = np.empty(self.shape, np.uint8)
+        if self.nbytes and _lib.lib().hwb_copy_device_to_host(self.device_id, out.ctypes.data, self.ptr, self.nbytes) != 0:
+            raise RuntimeError('device to host copy failed')
+        return out
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                _lib.lib().hwb_free_device(self.device_id, self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def encoded_intervals(f, video_index, rows):
+    """rows -> one EncodedData per keyframe-delimited interval that holds wanted rows (what the body of the
+    reference's Decoder.retrieve loop builds, python/hwang/decoder.py:41-64: one contiguous read per interval, offsets
+    rebased to it)."""
+    offs, sizes = video_index.sample_offsets(), video_index.sample_sizes()
+    kfs = video_index.keyframe_indices()
+    w, h, fmt = video_index.frame_width(), video_index.frame_height(), video_index.format()
+    out = []
+    for (a, b), valid in slice_into_video_intervals(video_index, rows):
+        ed = EncodedData()
+        ed.width, ed.height, ed.format = w, h, fmt
+        ed.start_keyframe, ed.end_keyframe = a, b
+        base = offs[a]
+        f.seek(base, 0)
+        ed.encoded_video = f.read(offs[b - 1] + sizes[b - 1] - base)
+        ed.sample_offsets = [o - base for o in offs[a:b]]
+        ed.sample_sizes = sizes[a:b]
+        ed.valid_frames = list(valid)
+        ed.keyframes = [k for k in kfs if a <= k <= b]
+        out.append(ed)
+    return out
+
+
 class Decoder(object):
-    """python/hwang/decoder.py:5-69.  device_type defaults to GPU here (the only backend); CPU raises."""
+    """hwang.Decoder (python/hwang/decoder.py:5-69): sparse random-access frame retrieval from one video.
+    device_type defaults to GPU here (the only backend); CPU raises.
+
+    Unlike the reference, which initialises the automaton once per interval (decoder.py:65), a request's intervals go
+    to the automaton in ONE initialize call: its feeder collects their pictures into common GPU batches, so the
+    (latency-bound) entropy stage sees the slices of all intervals at once."""
 
     def __init__(self, f_or_path, video_index=None, device_type=DeviceType.GPU, device_id=0):
         if video_index is None:
             video_index = index_video(f_or_path)
         self.video_index = video_index
         self.f = open(f_or_path, 'rb') if isinstance(f_or_path, str) else f_or_path
-        handle = DeviceHandle(device_type, device_id)
-        decoder_type = VideoDecoderType.SOFTWARE
-        if device_type == DeviceType.GPU:
-            decoder_type = VideoDecoderType.NVIDIA  # the reference's mapping (decoder.py:25-28); the factory routes it to B200
-        self._decoder = DecoderAutomata(handle, 1, decoder_type)
+        self.device_id = device_id
+        # the reference's mapping (decoder.py:25-28): GPU -> NVIDIA, which the factory routes to the B200 backend
+        decoder_type = VideoDecoderType.NVIDIA if device_type == DeviceType.GPU else VideoDecoderType.SOFTWARE
+        self._decoder = DecoderAutomata(DeviceHandle(device_type, device_id), 1, decoder_type)
+
+    def _start(self, rows):
+        intervals = encoded_intervals(self.f, self.video_index, rows)
+        if intervals:
+            self._decoder.initialize(intervals, self.video_index.metadata_bytes())
+        return sum(len(ed.valid_frames) for ed in intervals)
 
     def retrieve(self, rows):
-        video_intervals = slice_into_video_intervals(self.video_index, rows)
-        frames = []
-        sample_offsets = self.video_index.sample_offsets()
-        sample_sizes = self.video_index.sample_sizes()
-        sample_offsets.append(sample_offsets[-1] + sample_sizes[-1])
-        sample_sizes.append(0)
-        keyframe_indices = self.video_index.keyframe_indices()
-        for (start_index, end_index), valid_frames in video_intervals:
-            start_offset = sample_offsets[start_index]
-            end_offset = sample_offsets[end_index] + sample_sizes[end_index]
-            self.f.seek(start_offset, 0)
-            encoded_data = self.f.read(end_offset - start_offset)
-            data = EncodedData()
-            data.width = self.video_index.frame_width()
-            data.height = self.video_index.frame_height()
-            data.format = self.video_index.format()
-            data.start_keyframe = start_index
-            data.end_keyframe = end_index
-            data.sample_offsets = [o - start_offset for o in sample_offsets[start_index:end_index]]
-            data.sample_sizes = sample_sizes[start_index:end_index]
-            data.valid_frames = valid_frames
-            data.keyframes = [k for k in keyframe_indices if k >= start_index and k <= end_index]
-            data.encoded_video = encoded_data
-            self._decoder.initialize([data], self.video_index.metadata_bytes())
-            frames += self._decoder.get_frames(self.video_index, len(valid_frames))
-        return frames
+        """rows (ascending frame numbers) -> list of (H, W, 3) uint8 arrays (views of one page-locked buffer)."""
+        n = self._start(rows)
+        return self._decoder.get_frames(self.video_index, n) if n else []
+
+    def retrieve_device(self, rows):
+        """As retrieve(), but the frames stay in device memory: -> DeviceFrames (n, H, W, 3)."""
+        n = self._start(rows)
+        out = DeviceFrames(self.device_id, n, self.video_index.frame_height(), self.video_index.frame_width())
+        if n:
+            self._decoder.get_frames_into(out.ptr, n)
+        return out

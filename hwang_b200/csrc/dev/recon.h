@@ -22,13 +22,18 @@ struct ReconScratch {
   int16_t res[24][16];  // residual per 4x4 block: 16 luma (z order; 8x8 blocks use 4 slots as 64), 4 Cb, 4 Cr
   int32_t dc[24];       // dequantised DC per block (Intra16x16 luma DC, chroma DC)
   uint32_t has_res;     // bit b: res[b] is non-zero
-  // Per-lane motion-compensation scratch: the 7x9 reference window (63 bytes), the intermediate column b1[7] and
-  // the two prediction arrays.  They are indexed dynamically, so as thread-local arrays they lived in local memory
-  // (measured: 164 M local loads/stores per launch, 1.5 TB/s of L2 traffic, long-scoreboard the second largest
-  // stall); a stride of 41 words keeps the 32 lanes on different banks.
-  uint32_t lane_scratch[32][41];
+  // Motion compensation (staged reference tiles, BASELINE.json north_star "shared-memory staging of reference-block
+  // halos"): the warp loads the (w+5) x (h+5) luma window of a partition once, as aligned 32-bit words straight into
+  // `mc_luma` (row stride MC_LS bytes = 9 words: consecutive rows fall on different banks), likewise the two chroma
+  // windows, and every lane interpolates its samples from shared memory.  `mc_h` holds the unrounded horizontal
+  // half-sample intermediates of the positions that need the two-dimensional filter.  `pred` receives the prediction of
+  // each list when two lists or weights have to be combined.
+  uint8_t mc_luma[21 * 36];
+  uint8_t mc_chroma[2][9 * 12];
+  int16_t mc_h[21 * 16];
+  uint8_t pred[2][384];
 };
-enum { LS_WIN = 0, LS_B1 = 16, LS_P0 = 24, LS_P1 = 32 };  // word offsets inside a lane's scratch
+enum { MC_LS = 36, MC_CS = 12 };
 
 // ---------------------------------------------------------------------------------------------
 // transforms
@@ -186,119 +191,175 @@ static thread_local McWindow g_mc_window;
 static inline void mc_check(int row, int col) { if (row > g_mc_window.max_row || col > g_mc_window.max_col) g_mc_window.violations++; }
 #endif
 
-// Luma prediction of a 4 (wide) x 2 (high) region whose top-left integer position (already
-// displaced by mv>>2) is (px,py); fx,fy = mv&3.  ref is a coded luma plane (w x h, pitch w).
-HWB_FN void mc_luma_4x2(const uint8_t *ref, int w, int h, int px, int py, int fx, int fy, int *out, uint32_t *scratch) {
-  uint8_t (*win)[9] = (uint8_t (*)[9])(scratch + LS_WIN);  // rows py-2..py+4, cols px-2..px+6
-  int *b1 = (int *)(scratch + LS_B1);
-  const bool inside = (px >= 2) && (px + 6 < w) && (py >= 2) && (py + 4 < h);
-  if (fx == 0 && fy == 0) {
+// One motion-compensated partition: w x h luma samples (16x16, 8x8 or 4x4) at (x0,y0) of the picture, motion vector
+// (mvx,mvy) in quarter samples, predicted from frame `rf` into dst_y (stride ds_y) and dst_c[2] (stride ds_c).
+// Warp-cooperative: stage the reference windows, then lane l computes `ppl` consecutive samples of one row.
+HWB_FN void mc_partition(const ChunkCtx &c, int rf, int x0, int y0, int w, int h, int mvx, int mvy, uint8_t *dst_y, int ds_y,
+                         uint8_t *dst_cb, uint8_t *dst_cr, int ds_c, ReconScratch *sm) {
+  const int W = c.wc, H = c.hc;
+  const uint8_t *ref = frame_y(c, rf);
+  const int fx = mvx & 3, fy = mvy & 3;
+  const int ox = x0 + (mvx >> 2) - 2, oy = y0 + (mvy >> 2) - 2;  // window origin
+  const int cols = w + 5, rows = h + 5;
+  const bool inside = ox >= 0 && oy >= 0 && ox + cols <= W && oy + rows <= H;
+  const int sh = inside ? (ox & 3) : 0;
+  // ---- stage luma
+  HWB_LANES(l)
+    if (inside) {
+      const int nw = (sh + cols + 3) >> 2;  // aligned words per row (<= 7); the over-read of <= 3 bytes stays inside the slab
+      const uint8_t *base = ref + (int64_t)oy * W + (ox - sh);
 #pragma unroll 1
-    for (int r = 0; r < 2; ++r) {
-      int yy = clip3(0, h - 1, py + r);
-      for (int c = 0; c < 4; ++c) out[r * 4 + c] = ld_u8_cg(ref + yy * w + clip3(0, w - 1, px + c));
-    }
-#if !HWB_DEVICE_BUILD
-    mc_check(clip3(0, h - 1, py + 1), clip3(0, w - 1, px + 3));
-#endif
-    return;
-  }
-  if (inside) {
-#if HWB_DEVICE_BUILD
-    // three aligned 32-bit loads per window row instead of nine byte loads (the row is 9 bytes at any alignment;
-    // the over-read of at most 3 bytes stays inside the frame buffer).  ld.global.cg: the reference picture was
-    // written by other warps of the same launch (picture kernel), the non-coherent path is not allowed here
-    const uint8_t *p0 = ref + (py - 2) * w + px - 2;
-    const int sh = (int)(((uintptr_t)p0) & 3) * 8;  // rows are a multiple of 16 bytes apart: same alignment for every row
-#pragma unroll
-    for (int r = 0; r < 7; ++r) {
-      const uint32_t *q = (const uint32_t *)((uintptr_t)(p0 + r * w) & ~(uintptr_t)3);
-      const uint32_t w0 = __ldcg(q), w1 = __ldcg(q + 1), w2 = __ldcg(q + 2);
-      const uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh), x2 = w2 >> sh;
-      win[r][0] = (uint8_t)x0; win[r][1] = (uint8_t)(x0 >> 8); win[r][2] = (uint8_t)(x0 >> 16); win[r][3] = (uint8_t)(x0 >> 24);
-      win[r][4] = (uint8_t)x1; win[r][5] = (uint8_t)(x1 >> 8); win[r][6] = (uint8_t)(x1 >> 16); win[r][7] = (uint8_t)(x1 >> 24);
-      win[r][8] = (uint8_t)x2;
-    }
-#else
-#pragma unroll 1
-    for (int r = 0; r < 7; ++r) {
-      const uint8_t *p = ref + (py - 2 + r) * w + px - 2;
-      for (int c = 0; c < 9; ++c) win[r][c] = p[c];
-    }
-    mc_check(py + 4, px + 6);
-#endif
-  } else {
-#pragma unroll 1
-    for (int r = 0; r < 7; ++r) {
-      int yy = clip3(0, h - 1, py - 2 + r);
-#pragma unroll
-      for (int c = 0; c < 9; ++c) win[r][c] = ld_u8_cg(ref + yy * w + clip3(0, w - 1, px - 2 + c));
-    }
-#if !HWB_DEVICE_BUILD
-    mc_check(clip3(0, h - 1, py + 4), clip3(0, w - 1, px + 6));
-#endif
-  }
-#define HWB_H1(r, c) tap6(win[r][(c)], win[r][(c) + 1], win[r][(c) + 2], win[r][(c) + 3], win[r][(c) + 4], win[r][(c) + 5])
-#define HWB_V1(r, c) tap6(win[(r)][c], win[(r) + 1][c], win[(r) + 2][c], win[(r) + 3][c], win[(r) + 4][c], win[(r) + 5][c])
-  // pixel (r,c) of the region is win[r+2][c+2]
-  if (fy == 0) {
-#pragma unroll 1
-    for (int r = 0; r < 2; ++r)
-      for (int c = 0; c < 4; ++c) {
-        int b = clip8((HWB_H1(r + 2, c) + 16) >> 5);
-        out[r * 4 + c] = fx == 2 ? b : (b + win[r + 2][c + 2 + (fx == 3)] + 1) >> 1;
+      for (int i = l; i < rows * nw; i += 32) {
+        const int r = i / nw, k = i - r * nw;
+        *(uint32_t *)(sm->mc_luma + r * MC_LS + 4 * k) = ld_u32_cg((const uint32_t *)(base + (int64_t)r * W) + k);
       }
-  } else if (fx == 0) {
+    } else {
 #pragma unroll 1
-    for (int r = 0; r < 2; ++r)
-      for (int c = 0; c < 4; ++c) {
-        int hh = clip8((HWB_V1(r, c + 2) + 16) >> 5);
-        out[r * 4 + c] = fy == 2 ? hh : (hh + win[r + 2 + (fy == 3)][c + 2] + 1) >> 1;
+      for (int i = l; i < rows * cols; i += 32) {
+        const int r = i / cols, k = i - r * cols;
+        sm->mc_luma[r * MC_LS + k] = ld_u8_cg(ref + (int64_t)clip3(0, H - 1, oy + r) * W + clip3(0, W - 1, ox + k));
       }
-  } else if (fx == 2 || fy == 2) {
-    for (int c = 0; c < 4; ++c) {
+    }
+  HWB_LANES_END
+#if !HWB_DEVICE_BUILD
+  mc_check(clip3(0, H - 1, oy + rows - 1), clip3(0, W - 1, ox + cols - 1));
+#endif
+  // ---- stage chroma: (w/2+1) x (h/2+1) per plane
+  const int cw = W >> 1, ch = H >> 1;
+  const int cx = (x0 >> 1) + (mvx >> 3), cy = (y0 >> 1) + (mvy >> 3);
+  const int ccols = (w >> 1) + 1, crows = (h >> 1) + 1;
+  const bool cinside = cx >= 0 && cy >= 0 && cx + ccols <= cw && cy + crows <= ch;
+  const int csh = cinside ? (cx & 3) : 0;
+  HWB_LANES(l)
+    if (cinside) {
+      const int nw = (csh + ccols + 3) >> 2;  // <= 3
 #pragma unroll 1
-      for (int r = 0; r < 7; ++r) b1[r] = HWB_H1(r, c);
+      for (int i = l; i < 2 * crows * nw; i += 32) {
+        const int pl = i / (crows * nw), j = i - pl * crows * nw, r = j / nw, k = j - r * nw;
+        const uint8_t *base = (pl ? frame_cr(c, rf) : frame_cb(c, rf)) + (int64_t)(cy + r) * cw + (cx - csh);
+        *(uint32_t *)(sm->mc_chroma[pl] + r * MC_CS + 4 * k) = ld_u32_cg((const uint32_t *)base + k);
+      }
+    } else {
 #pragma unroll 1
-      for (int r = 0; r < 2; ++r) {
-        int j = clip8((tap6(b1[r], b1[r + 1], b1[r + 2], b1[r + 3], b1[r + 4], b1[r + 5]) + 512) >> 10);
+      for (int i = l; i < 2 * crows * ccols; i += 32) {
+        const int pl = i / (crows * ccols), j = i - pl * crows * ccols, r = j / ccols, k = j - r * ccols;
+        const uint8_t *P = pl ? frame_cr(c, rf) : frame_cb(c, rf);
+        sm->mc_chroma[pl][r * MC_CS + k] = ld_u8_cg(P + (int64_t)clip3(0, ch - 1, cy + r) * cw + clip3(0, cw - 1, cx + k));
+      }
+    }
+  HWB_LANES_END
+  // ---- luma interpolation (8.4.2.2.1).  T(r,k): window sample, the partition's sample (0,0) is T(2,2).
+  const uint8_t *T = sm->mc_luma + sh;
+  const int ppl = w == 16 ? 8 : (w == 8 ? 2 : 1), lpr = w / ppl;  // samples per lane, lanes per row
+#define HWB_T(r, k) ((int)T[(r) * MC_LS + (k)])
+#define HWB_HRAW(r, k) tap6(HWB_T(r, k), HWB_T(r, (k) + 1), HWB_T(r, (k) + 2), HWB_T(r, (k) + 3), HWB_T(r, (k) + 4), HWB_T(r, (k) + 5))
+#define HWB_VRAW(r, k) tap6(HWB_T(r, k), HWB_T((r) + 1, k), HWB_T((r) + 2, k), HWB_T((r) + 3, k), HWB_T((r) + 4, k), HWB_T((r) + 5, k))
+  const bool need_j = (fx == 2 && fy != 0) || (fy == 2 && fx != 0);
+  if (need_j) {
+    // unrounded horizontal half samples of every window row, then the vertical filter runs over them
+    HWB_LANES(l)
+#pragma unroll 1
+      for (int i = l; i < rows * w; i += 32) {
+        const int r = i / w, k = i - r * w;
+        sm->mc_h[r * 16 + k] = (int16_t)HWB_HRAW(r, k);
+      }
+    HWB_LANES_END
+  }
+  HWB_LANES(l)
+    const int y = l / lpr, xs = (l - y * lpr) * ppl;
+    if (y < h) {
+#pragma unroll 1
+      for (int i = 0; i < ppl; ++i) {
+        const int x = xs + i;
         int v;
-        if (fx == 2 && fy == 2) v = j;
-        else if (fx == 2) v = (j + clip8((b1[r + 2 + (fy == 3)] + 16) >> 5) + 1) >> 1;
-        else v = (j + clip8((HWB_V1(r, c + 2 + (fx == 3)) + 16) >> 5) + 1) >> 1;
-        out[r * 4 + c] = v;
+        if (fx == 0 && fy == 0) v = HWB_T(y + 2, x + 2);
+        else if (fy == 0) {
+          const int b = clip8((HWB_HRAW(y + 2, x) + 16) >> 5);
+          v = fx == 2 ? b : (b + HWB_T(y + 2, x + 2 + (fx == 3)) + 1) >> 1;
+        } else if (fx == 0) {
+          const int hh = clip8((HWB_VRAW(y, x + 2) + 16) >> 5);
+          v = fy == 2 ? hh : (hh + HWB_T(y + 2 + (fy == 3), x + 2) + 1) >> 1;
+        } else if (need_j) {
+          const int16_t *hr = sm->mc_h + y * 16 + x;
+          const int j = clip8((tap6(hr[0], hr[16], hr[32], hr[48], hr[64], hr[80]) + 512) >> 10);
+          if (fx == 2 && fy == 2) v = j;
+          else if (fx == 2) v = (j + clip8((sm->mc_h[(y + 2 + (fy == 3)) * 16 + x] + 16) >> 5) + 1) >> 1;
+          else v = (j + clip8((HWB_VRAW(y, x + 2 + (fx == 3)) + 16) >> 5) + 1) >> 1;
+        } else {
+          const int b = clip8((HWB_HRAW(y + 2 + (fy == 3), x) + 16) >> 5);
+          const int hh = clip8((HWB_VRAW(y, x + 2 + (fx == 3)) + 16) >> 5);
+          v = (b + hh + 1) >> 1;
+        }
+        dst_y[y * ds_y + x] = (uint8_t)v;
       }
     }
-  } else {
+  HWB_LANES_END
+#undef HWB_T
+#undef HWB_HRAW
+#undef HWB_VRAW
+  // ---- chroma: bilinear eighth-sample interpolation (8.4.2.2.2), both planes at once
+  {
+    const int cfx = mvx & 7, cfy = mvy & 7;
+    const int pw = w >> 1, ph = h >> 1;             // samples per plane: 8x8, 4x4 or 2x2
+    const int cppl = pw == 8 ? 4 : 1, clpr = pw / cppl;  // 16 lanes per plane for 8x8 and 4x4, 4 lanes for 2x2
+    const int lanes_pp = clpr * ph;
+    HWB_LANES(l)
+      const int pl = l / lanes_pp, k = l - pl * lanes_pp;
+      if (pl < 2) {
+        const int y = k / clpr, xs = (k - y * clpr) * cppl;
+        const uint8_t *Tc = sm->mc_chroma[pl] + csh;
+        uint8_t *d = (pl ? dst_cr : dst_cb) + y * ds_c;
 #pragma unroll 1
-    for (int r = 0; r < 2; ++r)
-      for (int c = 0; c < 4; ++c) {
-        int b = clip8((HWB_H1(r + 2 + (fy == 3), c) + 16) >> 5);
-        int hh = clip8((HWB_V1(r, c + 2 + (fx == 3)) + 16) >> 5);
-        out[r * 4 + c] = (b + hh + 1) >> 1;
+        for (int i = 0; i < cppl; ++i) {
+          const int x = xs + i;
+          const int a = Tc[y * MC_CS + x], b = Tc[y * MC_CS + x + 1], cc = Tc[(y + 1) * MC_CS + x], dd = Tc[(y + 1) * MC_CS + x + 1];
+          d[x] = (uint8_t)(((8 - cfx) * (8 - cfy) * a + cfx * (8 - cfy) * b + (8 - cfx) * cfy * cc + cfx * cfy * dd + 32) >> 6);
+        }
       }
+    HWB_LANES_END
   }
-#undef HWB_H1
-#undef HWB_V1
+#if !HWB_DEVICE_BUILD
+  mc_check(2 * clip3(0, ch - 1, cy + crows - 1) + 1, 2 * clip3(0, cw - 1, cx + ccols - 1) + 1);  // in luma units
+#endif
 }
 
-// Chroma prediction of a 2x2 region at chroma position (cx,cy) (block origin, before mv); mv in
-// quarter luma samples = eighth chroma samples.  ref: chroma plane (w x h).
-HWB_FN void mc_chroma_2x2(const uint8_t *ref, int w, int h, int cx, int cy, int mvx, int mvy, int *out) {
-  int x0 = cx + (mvx >> 3), y0 = cy + (mvy >> 3);
-  int fx = mvx & 7, fy = mvy & 7;
-  int v[3][3];
-  for (int r = 0; r < 3; ++r) {
-    int yy = clip3(0, h - 1, y0 + r);
-    for (int c = 0; c < 3; ++c) v[r][c] = ld_u8_cg(ref + yy * w + clip3(0, w - 1, x0 + c));
+// All partitions of one list of an inter macroblock.  Motion is stored per 4x4 block: a macroblock whose 16 vectors and
+// 4 references agree is one 16x16 partition (P_Skip, 16x16: the bulk of inter macroblocks), otherwise every 8x8
+// quadrant is one partition if its four vectors agree and four 4x4 partitions if not.
+HWB_FN void mc_list(const ChunkCtx &c, const SliceDesc &sd, int list, const int16_t *mv, const int8_t *ri, int mbx, int mby,
+                    uint8_t *dst_y, int ds_y, uint8_t *dst_cb, uint8_t *dst_cr, int ds_c, ReconScratch *sm) {
+  const uint32_t *mw = (const uint32_t *)mv;  // [16] raster 4x4, x | y << 16
+  const int r0 = ri[0];
+  bool uni = r0 >= 0 && ri[1] == r0 && ri[2] == r0 && ri[3] == r0;
+  const uint32_t m0 = mw[0];
+  if (uni) {
+#pragma unroll 1
+    for (int i = 1; i < 16; ++i) uni &= mw[i] == m0;
   }
-#if !HWB_DEVICE_BUILD
-  mc_check(2 * clip3(0, h - 1, y0 + 2) + 1, 2 * clip3(0, w - 1, x0 + 2) + 1);  // in luma units
-#endif
-  for (int r = 0; r < 2; ++r)
-    for (int c = 0; c < 2; ++c)
-      out[r * 2 + c] = ((8 - fx) * (8 - fy) * v[r][c] + fx * (8 - fy) * v[r][c + 1] + (8 - fx) * fy * v[r + 1][c] +
-                        fx * fy * v[r + 1][c + 1] + 32) >> 6;
+  if (uni) {
+    mc_partition(c, sd.ref_frame[list][r0], mbx * 16, mby * 16, 16, 16, (int16_t)(m0 & 0xffff), (int16_t)(m0 >> 16), dst_y, ds_y, dst_cb, dst_cr, ds_c, sm);
+    return;
+  }
+#pragma unroll 1
+  for (int q = 0; q < 4; ++q) {
+    const int r = ri[q];
+    if (r < 0) continue;
+    const int bx = (q & 1) * 2, by = (q >> 1) * 2, b0 = by * 4 + bx;
+    const int rf = sd.ref_frame[list][r];
+    const uint32_t a = mw[b0];
+    if (mw[b0 + 1] == a && mw[b0 + 4] == a && mw[b0 + 5] == a) {
+      mc_partition(c, rf, mbx * 16 + bx * 4, mby * 16 + by * 4, 8, 8, (int16_t)(a & 0xffff), (int16_t)(a >> 16),
+                   dst_y + by * 4 * ds_y + bx * 4, ds_y, dst_cb + by * 2 * ds_c + bx * 2, dst_cr + by * 2 * ds_c + bx * 2, ds_c, sm);
+    } else {
+#pragma unroll 1
+      for (int k = 0; k < 4; ++k) {
+        const int x = bx + (k & 1), y = by + (k >> 1);
+        const uint32_t m = mw[y * 4 + x];
+        mc_partition(c, rf, mbx * 16 + x * 4, mby * 16 + y * 4, 4, 4, (int16_t)(m & 0xffff), (int16_t)(m >> 16),
+                     dst_y + y * 4 * ds_y + x * 4, ds_y, dst_cb + y * 2 * ds_c + x * 2, dst_cr + y * 2 * ds_c + x * 2, ds_c, sm);
+      }
+    }
+  }
 }
 
 // Implicit bi-prediction weights (8.4.2.3.1): returns w1 (w0 = 64 - w1).
@@ -459,57 +520,48 @@ HWB_FN void recon_mb(const ChunkCtx &c, int pic, int mbx, int mby, ReconScratch 
     HWB_LANES_END
 
     if (!intra) {
-      // ---- inter prediction straight into the tile
+      // ---- inter prediction.  One list and no weights (almost every P macroblock): the partitions are predicted
+      // straight into the tile; otherwise each list goes to its own buffer and the lists are combined with the weights
+      // of the macroblock's 8x8 quadrants (8.4.2.3).
       const int16_t *mv0 = pic_mv(c, pd.frame, 0) + (uint64_t)mbaddr * 32;
       const int16_t *mv1 = pic_mv(c, pd.frame, 1) + (uint64_t)mbaddr * 32;
       const int8_t *ri0 = pic_refidx(c, pd.frame, 0) + (uint64_t)mbaddr * 4;
       const int8_t *ri1 = pic_refidx(c, pd.frame, 1) + (uint64_t)mbaddr * 4;
       const bool bslice = sd.slice_type == SLICE_B;
-      HWB_LANES(l)
-        {  // luma: raster 4x4 block l>>1, rows (l&1)*2..+1
-          int br = l >> 1, bx = br & 3, by = br >> 2, q = (by >> 1) * 2 + (bx >> 1);
-          int r0 = ri0[q], r1 = bslice ? ri1[q] : -1;
-          uint32_t *ls = sm->lane_scratch[l];
-          int *p0 = (int *)(ls + LS_P0), *p1 = (int *)(ls + LS_P1);
-          int x = mbx * 16 + bx * 4, y = mby * 16 + by * 4 + (l & 1) * 2;
-          if (r0 >= 0) {
-            int mx = mv0[br * 2], my = mv0[br * 2 + 1];
-            mc_luma_4x2(frame_y(c, sd.ref_frame[0][r0]), c.wc, c.hc, x + (mx >> 2), y + (my >> 2), mx & 3, my & 3, p0, ls);
-          }
-          if (r1 >= 0) {
-            int mx = mv1[br * 2], my = mv1[br * 2 + 1];
-            mc_luma_4x2(frame_y(c, sd.ref_frame[1][r1]), c.wc, c.hc, x + (mx >> 2), y + (my >> 2), mx & 3, my & 3, p1, ls);
-          }
-          WeightSel ws = select_weights(pd, sd, 0, r0, r1);
-          uint8_t *t = sm->luma + (by * 4 + (l & 1) * 2 + 1) * LT_STRIDE + LT_OFF + bx * 4;
+      uint8_t *tile_y = sm->luma + LT_STRIDE + LT_OFF, *tile_cb = sm->chroma[0] + CT_STRIDE + CT_OFF, *tile_cr = sm->chroma[1] + CT_STRIDE + CT_OFF;
+      if (!bslice && sd.use_weights == 0) {
+        mc_list(c, sd, 0, mv0, ri0, mbx, mby, tile_y, LT_STRIDE, tile_cb, tile_cr, CT_STRIDE, sm);
+      } else {
+        bool any0 = false, any1 = false;
+        for (int q = 0; q < 4; ++q) { any0 |= ri0[q] >= 0; any1 |= bslice && ri1[q] >= 0; }
+        if (any0) mc_list(c, sd, 0, mv0, ri0, mbx, mby, sm->pred[0], 16, sm->pred[0] + 256, sm->pred[0] + 320, 8, sm);
+        if (any1) mc_list(c, sd, 1, mv1, ri1, mbx, mby, sm->pred[1], 16, sm->pred[1] + 256, sm->pred[1] + 320, 8, sm);
+        HWB_LANES(l)
+          {  // luma: 8 consecutive samples of row l>>1 (one 8x8 quadrant: one pair of references)
+            const int y = l >> 1, xs = (l & 1) * 8, q = (y >> 3) * 2 + (xs >> 3);
+            const int r0 = ri0[q], r1 = bslice ? ri1[q] : -1;
+            const WeightSel ws = select_weights(pd, sd, 0, r0, r1);
 #pragma unroll 1
-          for (int i = 0; i < 8; ++i) {
-            int v = (r0 >= 0 && r1 >= 0) ? weight_bi(ws, p0[i], p1[i]) : (r0 >= 0 ? weight_uni(ws, p0[i], ws.w0, ws.o0) : weight_uni(ws, p1[i], ws.w1, ws.o1));
-            t[(i >> 2) * LT_STRIDE + (i & 3)] = (uint8_t)v;
+            for (int i = 0; i < 8; ++i) {
+              const int p0 = sm->pred[0][y * 16 + xs + i], p1 = sm->pred[1][y * 16 + xs + i];
+              const int v = (r0 >= 0 && r1 >= 0) ? weight_bi(ws, p0, p1) : (r0 >= 0 ? weight_uni(ws, p0, ws.w0, ws.o0) : weight_uni(ws, p1, ws.w1, ws.o1));
+              tile_y[y * LT_STRIDE + xs + i] = (uint8_t)v;
+            }
           }
-        }
-        {  // chroma: plane l>>4, luma block l&15 -> 2x2 chroma samples
-          int pl = l >> 4, br = l & 15, bx = br & 3, by = br >> 2, q = (by >> 1) * 2 + (bx >> 1);
-          int r0 = ri0[q], r1 = bslice ? ri1[q] : -1;
-          int *p0 = (int *)(sm->lane_scratch[l] + LS_P0), *p1 = (int *)(sm->lane_scratch[l] + LS_P1);
-          int cx = mbx * 8 + bx * 2, cy = mby * 8 + by * 2;
-          if (r0 >= 0) {
-            const uint8_t *rp = pl ? frame_cr(c, sd.ref_frame[0][r0]) : frame_cb(c, sd.ref_frame[0][r0]);
-            mc_chroma_2x2(rp, cw, c.hc >> 1, cx, cy, mv0[br * 2], mv0[br * 2 + 1], p0);
-          }
-          if (r1 >= 0) {
-            const uint8_t *rp = pl ? frame_cr(c, sd.ref_frame[1][r1]) : frame_cb(c, sd.ref_frame[1][r1]);
-            mc_chroma_2x2(rp, cw, c.hc >> 1, cx, cy, mv1[br * 2], mv1[br * 2 + 1], p1);
-          }
-          WeightSel ws = select_weights(pd, sd, 1 + pl, r0, r1);
-          uint8_t *t = sm->chroma[pl] + (by * 2 + 1) * CT_STRIDE + CT_OFF + bx * 2;
+          {  // chroma: plane l>>4, 4 consecutive samples of row (l&15)>>1
+            const int pl = l >> 4, y = (l & 15) >> 1, xs = (l & 1) * 4, q = (y >> 2) * 2 + (xs >> 2);
+            const int r0 = ri0[q], r1 = bslice ? ri1[q] : -1;
+            const WeightSel ws = select_weights(pd, sd, 1 + pl, r0, r1);
+            uint8_t *t = (pl ? tile_cr : tile_cb) + y * CT_STRIDE + xs;
 #pragma unroll 1
-          for (int i = 0; i < 4; ++i) {
-            int v = (r0 >= 0 && r1 >= 0) ? weight_bi(ws, p0[i], p1[i]) : (r0 >= 0 ? weight_uni(ws, p0[i], ws.w0, ws.o0) : weight_uni(ws, p1[i], ws.w1, ws.o1));
-            t[(i >> 1) * CT_STRIDE + (i & 1)] = (uint8_t)v;
+            for (int i = 0; i < 4; ++i) {
+              const int p0 = sm->pred[0][256 + pl * 64 + y * 8 + xs + i], p1 = sm->pred[1][256 + pl * 64 + y * 8 + xs + i];
+              const int v = (r0 >= 0 && r1 >= 0) ? weight_bi(ws, p0, p1) : (r0 >= 0 ? weight_uni(ws, p0, ws.w0, ws.o0) : weight_uni(ws, p1, ws.w1, ws.o1));
+              t[i] = (uint8_t)v;
+            }
           }
-        }
-      HWB_LANES_END
+        HWB_LANES_END
+      }
     } else {
       // ---- intra luma
       if (mb.mbtype == MB_I16x16) {

@@ -60,7 +60,7 @@ HWB_HD void rgb24_item(const ChunkCtx &c, int frame, int crop_x, int crop_y, int
 // macroblock converts the macroblocks that became final with it (see picture_kernel) straight from L2 into the
 // chunk's RGB arena.  Converts `nmb` (1 or 2) macroblocks starting at (mbx0, mby): lane = (sample row, macroblock).
 // Crop offsets must be even (they are: 4:2:0 cropping units), the part outside the cropping rectangle is skipped.
-HWB_HD void rgb24_macroblocks(const ChunkCtx &c, int frame, uint8_t *dst, int mbx0, int nmb, int mby) {
+HWB_FN void rgb24_macroblocks(const ChunkCtx &c, int frame, uint8_t *dst, int mbx0, int nmb, int mby) {
   HWB_LANES(l)
   for (int it = l; it < 16 * nmb; it += 32) {
     const int row = nmb == 2 ? it >> 1 : it, seg = nmb == 2 ? (it & 1) : 0;

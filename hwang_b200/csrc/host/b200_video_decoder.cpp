@@ -161,11 +161,11 @@ Result B200VideoDecoder::feed(const uint8_t *encoded_buffer, size_t encoded_size
   (void)keyframe;
   const bool idr = stream_.next_is_idr(encoded_buffer, encoded_size);
   // A chunk is cut at IDR pictures only (nothing refers across), once it holds chunk_target_ pictures or its device
-  // footprint reaches a quarter of the memory budget; a single GOP larger than the budget cannot be decoded.
+  // footprint reaches half of the memory budget; a single GOP larger than the budget cannot be decoded.
   const size_t pb = picture_bytes();
   if (cur_ && idr) {
     const size_t n = cur_->pics.size();
-    if ((int)n >= chunk_target_ || (n + 1) * pb > memory_budget_ / 4) {
+    if ((int)n >= chunk_target_ || (n + 1) * pb > memory_budget_ / 2) {
       Result r = submit_current();
       if (!r.ok) return r;
     }

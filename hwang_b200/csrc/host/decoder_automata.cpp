@@ -134,6 +134,11 @@ void DecoderAutomata::feeder() {
       parked_ = false;
     }
     bool failed = false;
+    // Our own backend collects the pictures of ALL intervals of this request into as few GPU batches as its batch size
+    // allows (one entropy launch sees the slices of many short intervals: sparse requests are latency-bound per slice),
+    // instead of one small batch per interval; the last interval's flush is followed by submit_pending().
+    B200VideoDecoder *batching = dynamic_cast<B200VideoDecoder *>(decoder_.get());
+    if (batching) batching->set_defer_submit(encoded_data_.size() > 1);
     for (size_t di = 0; di < encoded_data_.size() && !abort_ && !failed; ++di) {
       const EncodedData &d = encoded_data_[di];
       const uint64_t n = fed_samples(d);
@@ -155,7 +160,12 @@ void DecoderAutomata::feeder() {
       // end of interval: everything fed must become poppable (reference :383-397)
       Result r = decoder_->feed(nullptr, 0, false);
       if (r.ok) r = decoder_->flush();
+      if (r.ok && batching && di + 1 == encoded_data_.size()) r = batching->submit_pending();
       if (!r.ok) { feeder_result_ = r; result_set_ = true; failed = true; }
+    }
+    if (batching) {
+      if (abort_ || failed) batching->submit_pending();  // nothing may stay half-collected
+      batching->set_defer_submit(false);
     }
   }
 }
