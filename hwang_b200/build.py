@@ -46,7 +46,9 @@ def build_gen(force=False):
     if not force and not _newer(GEN, _all_sources()):
         return GEN
     os.makedirs(os.path.dirname(GEN), exist_ok=True)
-    _run(['g++'] + CXXFLAGS + ['-O3', '-shared', 'tools/h264gen/h264gen.cpp', '-o', GEN])
+    tmp = GEN + '.tmp%d' % os.getpid()  # link beside the target, then rename: a process that has the old library mapped keeps it
+    _run(['g++'] + CXXFLAGS + ['-O3', '-shared', 'tools/h264gen/h264gen.cpp', '-o', tmp])
+    os.replace(tmp, GEN)
     return GEN
 
 
@@ -54,7 +56,9 @@ def build_emu(force=False):
     if not force and not _newer(EMU, _all_sources()):
         return EMU
     srcs = ['hwang_b200/csrc/host/' + s for s in HOST_SRCS] + ['tests/emu/devapi_emu.cpp']
-    _run(['g++'] + CXXFLAGS + ['-shared'] + srcs + ['-o', EMU])
+    tmp = EMU + '.tmp%d' % os.getpid()
+    _run(['g++'] + CXXFLAGS + ['-shared'] + srcs + ['-o', tmp])
+    os.replace(tmp, EMU)
     return EMU
 
 
@@ -73,7 +77,9 @@ def build_product(force=False):
     _run([nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC',
           '-Xptxas', '-v', '-c', 'hwang_b200/csrc/cuda/kernels.cu', '-o', ko])
     objs.append(ko)
-    _run([nvcc, '-shared', '-o', PRODUCT] + objs + ['-lcudart_static', '-lpthread', '-ldl', '-lrt'])
+    tmp = PRODUCT + '.tmp%d' % os.getpid()
+    _run([nvcc, '-shared', '-o', tmp] + objs + ['-lcudart_static', '-lpthread', '-ldl', '-lrt'])
+    os.replace(tmp, PRODUCT)
     return PRODUCT
 
 

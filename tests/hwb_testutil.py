@@ -139,3 +139,86 @@ def decode_corrupted_then_clean(seed_list=(1, 2, 3)):
     assert 'timeout' not in outcomes, outcomes
     assert_yuv_parity(kw)  # the decoder (and the device context) still work
     return outcomes
+
+
+# ------------------------------------------------------------------------------------------ full-size workloads
+# The oracle side of the BASELINE-size parity tests: libavcodec (threads=1 per worker, as the reference runs it) +
+# sws_scale in a pool of worker processes, one keyframe-delimited GOP per job, returning one Adler-32 per wanted frame
+# (the RGB24 frames themselves would be tens of GB).  The CUDA side computes the same checksum over the bytes it returns.
+_POOL_G = {}
+
+
+def _oracle_gop_job(job):
+    import zlib
+    a, b, want = job  # absolute sample range of one closed GOP, wanted absolute frame numbers inside it
+    nls, sps, pps = fo.parse_avcc(_POOL_G['avcc'])
+    w, h = _POOL_G['w'], _POOL_G['h']
+    samples = _POOL_G['samples']
+    sws = fo.SwsRgb24(w, h)
+    dst = np.empty(w * h * 3, np.uint8)
+    out = {}
+    k = [a]
+    wanted = set(want)
+    last = max(want)
+
+    def on_frame(addr):
+        if k[0] in wanted:
+            sws.scale_avframe(addr, dst.ctypes.data)
+            out[k[0]] = zlib.adler32(dst)
+        k[0] += 1
+    dec = fo.FFmpegH264(threads=1)
+    for i in range(a, b):
+        dec.send_raw(fo.avcc_to_annexb(samples[i], nls, sps, pps, i == a), on_frame)
+        if k[0] > last:
+            break
+    else:
+        dec.send_raw(None, on_frame)
+    dec.close()
+    sws.close()
+    return out
+
+
+def oracle_rgb_checksums(mp4, index, rows, procs=None):
+    """{frame number: adler32 of its RGB24 bytes} for the wanted rows, decoded by the reference's ffmpeg path."""
+    import multiprocessing as mp
+    import os
+    offs, sizes = index.sample_offsets(), index.sample_sizes()
+    kfs = list(index.keyframe_indices()) + [index.frames()]
+    _POOL_G.update(avcc=index.metadata_bytes(), w=index.frame_width(), h=index.frame_height(),
+                   samples=[mp4[o:o + s] for o, s in zip(offs, sizes)])
+    rows = sorted(rows)
+    jobs, j = [], 0
+    for a, b in zip(kfs[:-1], kfs[1:]):
+        want = []
+        while j < len(rows) and rows[j] < b:
+            want.append(rows[j])
+            j += 1
+        if want:
+            jobs.append((a, b, want))
+    procs = procs or os.cpu_count() or 1
+    out = {}
+    with mp.get_context('fork').Pool(min(procs, max(1, len(jobs)))) as pool:
+        for part in pool.imap_unordered(_oracle_gop_job, jobs):
+            out.update(part)
+    return out
+
+
+def automaton_rgb_checksums(index, intervals, total, batch=32, device=0):
+    """Adler-32 of every frame DecoderAutomata.get_frames returns for `intervals` (EncodedData list), streamed through one
+    page-locked buffer of `batch` frames: [checksum] in request order."""
+    import zlib
+    from hwang_b200 import _lib
+    L = _lib.lib()
+    fs = index.frame_width() * index.frame_height() * 3
+    auto = hw.DecoderAutomata(hw.DeviceHandle(hw.DeviceType.GPU, device), 1, hw.VideoDecoderType.B200)
+    auto.initialize(intervals, index.metadata_bytes())
+    pinned = hw.api.PinnedBuffer(fs * batch)
+    sums, done = [], 0
+    while done < total:
+        k = min(batch, total - done)
+        if L.hwb_automata_get_frames(auto._h, pinned.ptr, k) != 0:
+            raise RuntimeError(L.hwb_automata_last_error(auto._h).decode())
+        view = pinned.array[:fs * k].reshape(k, fs)
+        sums += [zlib.adler32(view[i]) for i in range(k)]
+        done += k
+    return sums

@@ -296,3 +296,34 @@ def test_many_batches_device_pointers_and_reuse(emu, built):
             assert np.array_equal(got, fo.yuv420_to_rgb24(*ref[i])), (rep, i)
         dec.wait_until_frames_copied()
         assert dec.stats()['chunks'] == 5 * (rep + 1)
+
+
+def test_device_frames_and_oracle_checksum_helpers(emu, built):
+    """Decoder.retrieve_device on the emulated device (its "device memory" is host memory) and the full-size tests'
+    oracle helper on a small clip: both agree with the per-frame oracle."""
+    import zlib
+    kw = dict(width=96, height=64, frames=24, gop=6, profile=2, bframes=2, b_pyramid=0, num_ref=3, weighted=2, seed=95)
+    mp4, index, samples, kf = util.make_clip(**kw)
+    ref = util.oracle_frames(index, samples, kf)
+    rows = [0, 3, 5, 6, 17, 23]
+    dev = hw.Decoder(io.BytesIO(mp4), video_index=index).retrieve_device(rows)
+    host = dev.to_host()
+    for k, r in enumerate(rows):
+        assert np.array_equal(host[k], fo.yuv420_to_rgb24(*ref[r])), r
+    sums = util.oracle_rgb_checksums(mp4, index, rows, procs=2)
+    assert sums == {r: zlib.adler32(fo.yuv420_to_rgb24(*ref[r]).reshape(-1)) for r in rows}
+
+
+def test_batch_retrieval_collects_clips_into_common_batches(emu, built):
+    """retrieve_many: intervals of several clips of equal geometry go through one decoder with deferred submission, so
+    they share GPU batches: 3 clips x 4 intervals decode in fewer batches than intervals."""
+    from hwang_b200 import batch
+    reqs, refs = [], []
+    for i in range(3):
+        mp4, index, samples, kf = util.make_clip(width=64, height=48, frames=16, gop=4, profile=1, seed=120 + i, bframes=i % 2)
+        refs.append(util.oracle_frames(index, samples, kf))
+        reqs.append((mp4, [1, 6, 9, 15]))
+    got = batch.retrieve_many(reqs, devices=[0])
+    for frames, ref in zip(got, refs):
+        for r, f in zip([1, 6, 9, 15], frames):
+            assert np.array_equal(np.asarray(f), fo.yuv420_to_rgb24(*ref[r]))

@@ -120,73 +120,147 @@ def test_get_frames_in_batches_of_8_and_reconfigure(gpu):
             assert np.array_equal(np.asarray(f), fo.yuv420_to_rgb24(*ref[r])), (rep, r)
 
 
-def test_config2_full_size_properties(gpu):
-    """BASELINE configs[1] at full size: the 3000-frame 1080p Main/CABAC GOP-30 clip of bench.py, dense, through
-    DecoderAutomata.get_frames.  The oracle cannot decode 3000 frames in seconds, so full size is covered by
-    (a) bit-exact RGB against libavcodec + the swscale arithmetic on three whole GOPs (first, middle, last),
-    (b) a checksum of per-frame checksums that must not depend on how the clip is cut into chunks (one chunk of
-        3000 pictures against chunks of 10 GOPs), which also makes two independent decodes reproduce each other,
-    (c) seek == sequential at full size: a sparse request for the last frame of a GOP in the middle of the clip
-        returns the bytes the dense pass returned."""
+# ---------------------------------------------------------------------------------------- BASELINE.json configs at full size
+# Every returned frame is compared with the reference's ffmpeg path (libavcodec + sws_scale in a process pool) through a
+# per-frame Adler-32 of the RGB24 bytes.  The clips are deterministic generator outputs cached under tests/_cache; a
+# missing clip is generated when HWB_GENERATE_WORKLOADS=1 (minutes of CPU) and the test is skipped otherwise.
+def _workload(spec):
+    import os
+    from hwang_b200.testing import workloads as wl
+    mp4 = wl.load(spec, generate=os.environ.get('HWB_GENERATE_WORKLOADS', '0') == '1')
+    if mp4 is None:
+        pytest.skip('%s.mp4 not in tests/_cache (set HWB_GENERATE_WORKLOADS=1 to generate it)' % spec['name'])
+    return mp4
+
+
+def test_config2_full_size_every_frame(gpu):
+    """BASELINE configs[1]: 1920x1080 Main CABAC GOP 30, 3000 frames, dense, through DecoderAutomata.get_frames: ALL
+    3000 frames bit-exact against libavcodec + swscale; seek == sequential (decoder_automata_test.cpp:262-342)."""
     import zlib
     import bench
-    from hwang_b200 import _lib as lib_mod
-    mp4 = bench.get_clip(3000)
+    from hwang_b200.testing import workloads as wl
+    mp4 = _workload(wl.CONFIG2)
     index = hw.index_video(io.BytesIO(mp4))
-    offs, sizes = index.sample_offsets(), index.sample_sizes()
-    kfs = sorted(index.keyframe_indices())
-    n = len(offs)
-    assert n == 3000 and len(kfs) == 100
-    W, H = bench.W, bench.H
-    fs = W * H * 3
-    L = lib_mod.lib()
-
-    def dense_checksums(chunk_pictures):
-        import os
-        os.environ['HWB_CHUNK_PICTURES'] = str(chunk_pictures)
-        try:
-            auto = hw.DecoderAutomata(hw.DeviceHandle(hw.DeviceType.GPU, 0), 1, hw.VideoDecoderType.B200)
-        finally:
-            del os.environ['HWB_CHUNK_PICTURES']
-        ed = hw.EncodedData()
-        ed.width, ed.height, ed.format = W, H, index.format()
-        ed.start_keyframe, ed.end_keyframe = 0, n
-        ed.sample_offsets = [o - offs[0] for o in offs]
-        ed.sample_sizes = sizes
-        ed.keyframes = kfs
-        ed.valid_frames = list(range(n))
-        ed.encoded_video = mp4[offs[0]:offs[-1] + sizes[-1]]
-        auto.initialize([ed], index.metadata_bytes())
-        batch = 50
-        pinned = hw.api.PinnedBuffer(fs * batch)
-        sums, keep = [], {}
-        done = 0
-        while done < n:
-            k = min(batch, n - done)
-            assert L.hwb_automata_get_frames(auto._h, pinned.ptr, k) == 0, L.hwb_automata_last_error(auto._h).decode()
-            view = pinned.array[:fs * k].reshape(k, fs)
-            for i in range(k):
-                sums.append(zlib.adler32(view[i]))
-                if (done + i) // 30 in (0, 50, 99):
-                    keep[done + i] = view[i].copy()
-            done += k
-        return sums, keep
-
-    sums_one, keep = dense_checksums(1 << 30)
-    sums_cut, _ = dense_checksums(300)
-    assert len(sums_one) == n
-    assert sums_one == sums_cut, 'result depends on the chunking'
-    assert zlib.adler32(np.asarray(sums_one, np.uint32).tobytes()) == zlib.adler32(np.asarray(sums_cut, np.uint32).tobytes())
-    # (a) three whole GOPs against the oracle
-    for g in (0, 50, 99):
-        samples = [mp4[offs[i]:offs[i] + sizes[i]] for i in range(g * 30, g * 30 + 30)]
-        ref = fo.decode_samples(index.metadata_bytes(), samples, [i == 0 for i in range(30)])
-        for i in range(30):
-            exp = fo.yuv420_to_rgb24(*ref[i]).reshape(-1)
-            assert np.array_equal(keep[g * 30 + i], exp), 'frame %d differs from the oracle' % (g * 30 + i)
-    # (c) seek == sequential
+    n = index.frames()
+    assert n == 3000 and len(index.keyframe_indices()) == 100
+    want = util.oracle_rgb_checksums(mp4, index, range(n))
+    intervals = hw.api.encoded_intervals(io.BytesIO(mp4), index, list(range(n)))
+    assert len(intervals) == 1  # dense rows collapse into one interval (video_index.cpp:76-84)
+    got = util.automaton_rgb_checksums(index, intervals, n, batch=50)
+    bad = [i for i in range(n) if got[i] != want[i]]
+    assert not bad, 'frames differ from the oracle: %s' % bad[:10]
     single = hw.Decoder(io.BytesIO(mp4), video_index=index).retrieve([50 * 30 + 29])
-    assert np.array_equal(np.asarray(single[0]).reshape(-1), keep[50 * 30 + 29])
+    assert zlib.adler32(np.asarray(single[0]).reshape(-1)) == want[50 * 30 + 29]
+
+
+def test_config3_full_size_every_17th_frame(gpu):
+    """BASELINE configs[2]: 1920x1080 High (8x8 transform, runs of 3 B pictures with one B-reference level, implicit
+    weighted bi-prediction), 3000 frames, rows 0,17,34,... through hwang.Decoder.retrieve."""
+    import zlib
+    from hwang_b200.testing import workloads as wl
+    mp4 = _workload(wl.CONFIG3)
+    index = hw.index_video(io.BytesIO(mp4))
+    rows = wl.config3_rows(index.frames())
+    assert len(rows) == 177
+    want = util.oracle_rgb_checksums(mp4, index, rows)
+    frames = hw.Decoder(io.BytesIO(mp4), video_index=index).retrieve(rows)
+    assert len(frames) == len(rows)
+    bad = [r for r, f in zip(rows, frames) if zlib.adler32(np.asarray(f).reshape(-1)) != want[r]]
+    assert not bad, 'rows differ from the oracle: %s' % bad[:10]
+
+
+def test_config4_full_size_4k_gop250_random_rows(gpu):
+    """BASELINE configs[3]: 3840x2160 High, GOP 250, 1000 frames, 64 seeded random rows (seed 0, sorted)."""
+    import zlib
+    from hwang_b200.testing import workloads as wl
+    mp4 = _workload(wl.CONFIG4)
+    index = hw.index_video(io.BytesIO(mp4))
+    assert index.frames() == 1000 and len(index.keyframe_indices()) == 4
+    rows = wl.config4_rows(1000)
+    want = util.oracle_rgb_checksums(mp4, index, rows)
+    frames = hw.Decoder(io.BytesIO(mp4), video_index=index).retrieve(rows)
+    assert len(frames) == len(rows)
+    bad = [r for r, f in zip(rows, frames) if zlib.adler32(np.asarray(f).reshape(-1)) != want[r]]
+    assert not bad, 'rows differ from the oracle: %s' % bad[:10]
+
+
+def test_config5_full_size_64_clips_gop_sharded(gpu):
+    """BASELINE configs[4]: 64 clips of mixed resolution / profile / GOP length, 300 frames each, dense.  The GOP work
+    items of every clip are assigned to two workers by shard.partition (what 2 GPUs would each get); each worker's
+    intervals go through one DecoderAutomata.initialize; every one of the 19200 frames is compared with the oracle."""
+    from hwang_b200 import shard
+    from hwang_b200.testing import workloads as wl
+    clips = wl.config5_clips()
+    if not all(wl.available(c) for c in clips):
+        _workload(clips[[wl.available(c) for c in clips].index(False)])  # generates or skips
+    total = 0
+    for ci, spec in enumerate(clips):
+        mp4 = _workload(spec)
+        index = hw.index_video(io.BytesIO(mp4))
+        n = index.frames()
+        assert n == 300
+        want = util.oracle_rgb_checksums(mp4, index, range(n))
+        seen = {}
+        for part in shard.partition(shard.gop_work_items(index, ci), 2):
+            rows = [r for it in part for r in it[4]]
+            if not rows:
+                continue
+            intervals = hw.api.encoded_intervals(io.BytesIO(mp4), index, rows)
+            got = util.automaton_rgb_checksums(index, intervals, len(rows), batch=16 if index.frame_width() >= 3840 else 64)
+            for r, v in zip(rows, got):
+                assert r not in seen
+                seen[r] = v
+        bad = [r for r in range(n) if seen.get(r) != want[r]]
+        assert not bad, 'clip %s: frames differ from the oracle: %s' % (spec['name'], bad[:10])
+        total += n
+    assert total == 64 * 300
+
+
+def test_batch_retrieval_shares_gpu_batches_across_clips(gpu):
+    """retrieve_many packs the intervals of different clips of equal geometry into common GPU batches (one
+    entropy launch sees all their slices): sparse rows from 6 clips, 3 geometries; frames bit-exact, and far fewer
+    batches than intervals."""
+    from hwang_b200 import batch
+    specs = [dict(width=640, height=480, profile=0, seed=71), dict(width=640, height=480, profile=1, bframes=1, seed=72),
+             dict(width=640, height=480, profile=2, bframes=2, seed=73), dict(width=320, height=240, profile=1, seed=74),
+             dict(width=320, height=240, profile=2, bframes=1, seed=75), dict(width=1280, height=720, profile=1, seed=76)]
+    reqs, refs = [], []
+    for sp in specs:
+        kw = dict(frames=48, gop=8, qp=30, num_ref=2)
+        kw.update(sp)
+        mp4, index, samples, kf = util.make_clip(**kw)
+        refs.append(util.oracle_frames(index, samples, kf))
+        reqs.append((mp4, [1, 9, 10, 26, 47]))
+    got = batch.retrieve_many(reqs, devices=[0])
+    for ci, (frames, ref) in enumerate(zip(got, refs)):
+        assert len(frames) == 5
+        for r, f in zip([1, 9, 10, 26, 47], frames):
+            assert np.array_equal(np.asarray(f), fo.yuv420_to_rgb24(*ref[r])), (ci, r)
+
+
+def test_device_memory_output(gpu):
+    """SURVEY 8f-1, hwang/common.h:20-50: DeviceType::GPU as the output location.  Decoder.retrieve_device leaves the frames
+    in caller-owned device memory (the automaton's get_frames is handed a device pointer); copied back they equal the host
+    path's frames and the oracle; nothing crossed PCIe on the way out."""
+    kw = dict(width=640, height=480, frames=60, gop=15, profile=2, bframes=2, num_ref=3, weighted=2, seed=77, qp=28)
+    mp4, index, samples, kf = util.make_clip(**kw)
+    ref = util.oracle_frames(index, samples, kf)
+    rows = [0, 7, 14, 15, 31, 44, 59]
+    dec = hw.Decoder(io.BytesIO(mp4), video_index=index)
+    d2h_before = dec._decoder.stats()['d2h_bytes']
+    dev = dec.retrieve_device(rows)
+    assert dec._decoder.stats()['d2h_bytes'] == d2h_before
+    host = dev.to_host()
+    assert host.shape == (len(rows), 480, 640, 3)
+    for k, r in enumerate(rows):
+        assert np.array_equal(host[k], fo.yuv420_to_rgb24(*ref[r])), r
+    try:
+        import torch
+    except ImportError:
+        return
+    t = torch.as_tensor(dev, device='cuda:0')  # zero-copy view through __cuda_array_interface__
+    assert t.shape == (len(rows), 480, 640, 3) and t.dtype == torch.uint8
+    assert np.array_equal(t.cpu().numpy(), host)
 
 
 def test_corrupted_payload_is_survivable(gpu):
