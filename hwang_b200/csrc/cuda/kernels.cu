@@ -88,11 +88,22 @@ union PictureScratch {
   DeblockScratch deblock;
 };
 
-// 6 blocks (24 warps) per SM: 80 registers.  Warps whose global index modulo 5 is below `split` (1..3) take deblocking
-// items, the others reconstruction items, and either kind moves to the other list once its own is exhausted.  Static
-// roles because (a) both stages are bound by instruction fetch: a warp that stays in one of the two code bodies
-// keeps the instruction caches for it, and (b) the no-deadlock argument above needs somebody to be working on each
-// list at all times: warps 0..3 of every block cover both roles for any split in 1..3.
+// 6 blocks (24 warps) per SM: 80 registers.  Every warp is a generalist and chooses the kind of its next item when it
+// takes it: the head of the deblocking list if the rows it consumes are already being produced (the reconstruction of
+// the row below has started), otherwise the head of the reconstruction list, otherwise (reconstruction exhausted)
+// the deblocking head whatever its state.  Deblocking first: it completes pictures, which releases the rows of the
+// next level waiting for their reference and the frames waiting to be copied out.
+// Why this cannot deadlock (see also csrc/dev/picture.h): let X be the earliest unfinished item in the global
+// (level, row, picture) order.  Taken items only wait on earlier items, so if X is held it completes.  If X is never
+// taken, look at the last pick any warp ever makes (a pick of X itself completes and is followed by another pick).
+// That pick took from the other list: either
+// the reconstruction head while X heads the deblocking list -- but everything X consumes is earlier than X, hence
+// finished, hence started, so X was "ready" and would have been preferred; or a ready deblocking item Z while X heads
+// the reconstruction list -- Z's reconstruction rows were handed out before X (same list), so they precede X and are
+// finished, and the deblocking row above Z (handed out before Z) needs only such rows and its own predecessor: the whole
+// chain completes, Z finishes, and its warp picks again.  Either way that pick was not the last one.
+// `split` (HWB_PICTURE_SPLIT, 0 = dynamic) keeps the static assignment for experiments: warps whose global index modulo
+// 5 is below it take deblocking items only until those run out.
 __global__ void __launch_bounds__(kThreads, 6) picture_kernel(const __grid_constant__ ChunkCtx c, int32_t *ticket, int split) {
   __shared__ PictureScratch sm[kWarpsPerBlock];
   PictureScratch *my = &sm[threadIdx.x >> 5];
@@ -100,24 +111,64 @@ __global__ void __launch_bounds__(kThreads, 6) picture_kernel(const __grid_const
   // kernel (complete by now: an event orders the launches) has raised the chunk's error flag, the host reports it
   // when the chunk's first frame is popped, and nothing may be dereferenced here.
   if (*((volatile const int32_t *)c.error_flag) != 0) return;
-  const int gw = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  bool deblock_role = (gw % 5) < split;
+  // split > 0: static roles by SM: an SM whose (scrambled) id falls below `split` percent only takes deblocking items
+  // (until they run out), the others only reconstruction items.  Both stages are bound by instruction fetch; an SM that
+  // stays inside one of the two code bodies keeps its instruction caches for it (measured on the 3000-picture batch:
+  // 369 ms against 484 ms with the same roles assigned per warp and 544 ms with every warp choosing dynamically).
+  // The host only passes split > 0 when the grid puts blocks on every SM (both roles are then present); small grids
+  // use the dynamic choice below, which needs no such assumption.
+  bool fixed_deblock = false;
+  if (split > 0) {
+    unsigned smid, nsmid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm("mov.u32 %0, %%nsmid;" : "=r"(nsmid));
+    const int mode = split / 1000, pct = split % 1000;  // experiments: how the SMs of the two roles are spread over the chip
+    if (mode == 1) fixed_deblock = (int)(smid * 100u / nsmid) < pct;               // one contiguous range of SM ids
+    else if (mode == 2) fixed_deblock = (int)(((smid >> 1) * 37u) % 100u) < pct;   // whole TPCs (SM pairs), scattered
+    else if (mode == 3) fixed_deblock = (int)(smid % 5u) * 20 < pct;               // runs of 2-3 adjacent SMs
+    else fixed_deblock = (int)((smid * 37u) % 100u) < pct;                         // single SMs, scattered
+  }
   bool recon_left = c.num_recon_items > 0, deblock_left = c.num_deblock_items > 0;
+  ProfClock life(c.prof);
   while (recon_left || deblock_left) {
-    if (deblock_role ? !deblock_left : !recon_left) deblock_role = !deblock_role;
-    if (deblock_role) {
+    ProfClock pick(c.prof);
+    bool take_deblock;
+    if (!recon_left) take_deblock = true;
+    else if (!deblock_left) take_deblock = false;
+    else if (split > 0) take_deblock = fixed_deblock;
+    else {
+      // is the deblocking head ready?  (lane 0 looks, everybody follows)
+      int ready = 0;
+      if ((threadIdx.x & 31) == 0) {
+        int32_t t;
+        asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(t) : "l"(ticket + 1) : "memory");
+        if (t < c.num_deblock_items) {
+          const uint32_t it = c.deblock_items[t];
+          const int pic = item_pic(it), y = item_row(it);
+          const int32_t *p = c.recon_prog + (size_t)pic * c.mb_h + (y + 1 < c.mb_h ? y + 1 : y);
+          int32_t v;
+          asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+          ready = v >= 1;
+        }
+      }
+      take_deblock = __shfl_sync(0xffffffffu, ready, 0) != 0;
+    }
+    if (take_deblock) {
       const int t = warp_ticket(ticket + 1);
       if (t >= c.num_deblock_items) { deblock_left = false; continue; }
       const uint32_t it = c.deblock_items[t];
+      pick.mark(PROF_PICK);
       deblock_row(c, item_pic(it), item_row(it), &my->deblock);
     } else {
       const int t = warp_ticket(ticket);
       if (t >= c.num_recon_items) { recon_left = false; continue; }
       const uint32_t it = c.recon_items[t];
+      pick.mark(PROF_PICK);
       recon_row(c, item_pic(it), item_row(it), &my->recon);
     }
     __syncwarp();
   }
+  life.mark(PROF_LIFETIME);
 }
 
 // ------------------------------------------------------------------------------------ output
@@ -271,11 +322,14 @@ int hwb_dev_entropy(hwb_dev *d, int s, const ChunkCtx *c, int32_t *ticket, int m
 int hwb_dev_picture(hwb_dev *d, int s, const ChunkCtx *c, int32_t *ticket) {
   cudaSetDevice(d->device);
   static int bpsm = [] { const char *e = getenv("HWB_PICTURE_BLOCKS_PER_SM"); int v = e ? atoi(e) : 0; return v > 0 ? v : 6; }();
-  // deblocking warps per 5 (1..3: every block of 4 warps must hold both roles, see picture_kernel)
-  static int split = [] { const char *e = getenv("HWB_PICTURE_SPLIT"); int v = e ? atoi(e) : 0; return v >= 1 && v <= 3 ? v : 2; }();
+  // percent of the SMs that deblock (0 = every warp chooses dynamically, see picture_kernel)
+  static int split_pct = [] { const char *e = getenv("HWB_PICTURE_SPLIT"); int v = e ? atoi(e) : -1; return v >= 0 && v <= 90 ? v : 46; }();
   const int items = c->num_recon_items + c->num_deblock_items;
   if (items == 0) return 0;
-  picture_kernel<<<grid_for(d, items, bpsm), kThreads, 0, d->streams[s]>>>(*c, ticket, split);
+  const int grid = grid_for(d, items, bpsm);
+  static int rolemap = [] { const char *e = getenv("HWB_PICTURE_ROLEMAP"); int v = e ? atoi(e) : 0; return v >= 0 && v <= 3 ? v : 0; }();
+  const int split = (grid >= 2 * d->sms && split_pct > 0) ? split_pct + 1000 * rolemap : 0;  // static roles need blocks on every SM
+  picture_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket, split);
   HWB_CUDA(d, cudaGetLastError());
   d->launches++;
   return 0;

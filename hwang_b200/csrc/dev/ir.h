@@ -123,6 +123,8 @@ struct ChunkCtx {
   uint8_t *rgb;            // [slot] packed RGB24, out_w * out_h * 3 bytes each (tight)
   uint64_t rgb_stride;
   int32_t crop_x, crop_y, out_w, out_h;  // cropping rectangle of the output frames inside the coded picture
+  // optional (HWB_PICTURE_PROFILE=1): warp cycles of the picture kernel by activity, see picture.h PROF_*; nullptr = off
+  unsigned long long *prof;
 };
 
 HWB_HD uint8_t *frame_y(const ChunkCtx &c, int f) { return c.frames + (uint64_t)f * c.frame_stride; }

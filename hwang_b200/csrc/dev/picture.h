@@ -10,10 +10,11 @@
 //                            UNFILTERED samples of row y, so they must be done before the filter runs in place);
 //                            row y-1 deblocked up to x+1 (H.264 filters in raster order).
 // Both item lists are ordered by (dependency level of the picture, row, picture), so an item only ever waits on
-// items that were handed out before it (to its own or the other list): whoever holds the oldest unfinished item can
-// always run, no deadlock whatever the number of resident warps.  Pictures of consecutive levels overlap as a
-// diagonal wavefront (a P picture starts as soon as the first rows of its reference are final) instead of one launch
-// pair per level -- a GOP of 250 pictures used to cost 500 launches with a latency floor each.
+// items that come before it in that global order; a warp decides which list to take from when it takes (kernels.cu
+// picture_kernel, with the argument why the spin waits cannot deadlock whatever the number of resident warps).
+// Pictures of consecutive levels overlap as a diagonal wavefront (a P picture follows its reference at a distance of
+// a few macroblocks) instead of one launch pair per level -- a GOP of 250 pictures used to cost 500 launches with a
+// latency floor each.
 //
 // Replaces, on the GPU, the per-macroblock loop of libavcodec's h264 decoder behind avcodec_send_packet and the
 // sws_scale call of SoftwareVideoDecoder::get_frame (hwang/impls/software/software_video_decoder.cpp:292-325,349-402).
@@ -23,6 +24,28 @@
 #include "rgb.h"
 
 namespace hwb {
+
+// Where the warps of the picture kernel spend their cycles (lane 0's clock64 deltas, summed over all warps), recorded
+// only when the host asked for it (ChunkCtx::prof): the kernel is bound by dependencies and instruction issue, not by
+// memory, so this is the profile that explains it.
+enum { PROF_RECON_MB = 0, PROF_DEBLOCK_MB, PROF_RGB, PROF_WAIT_REF, PROF_WAIT_INTRA, PROF_WAIT_RECON, PROF_WAIT_DEBLOCK_ABOVE, PROF_PICK, PROF_LIFETIME,
+       PROF_POLLS, PROF_COUNTERS = 16 };
+#if HWB_DEVICE_BUILD
+struct ProfClock {
+  unsigned long long *out;
+  long long t;
+  __device__ __forceinline__ explicit ProfClock(unsigned long long *p) : out(p), t(0) { if (out) t = clock64(); }
+  // charge the cycles since the last mark to `what`
+  __device__ __forceinline__ void mark(int what) {
+    if (!out) return;
+    const long long now = clock64();
+    if ((threadIdx.x & 31) == 0) atomicAdd(out + what, (unsigned long long)(now - t));
+    t = now;
+  }
+};
+#else
+struct ProfClock { explicit ProfClock(unsigned long long *) {} void mark(int) {} };
+#endif
 
 struct Progress {  // a counter watched by this warp, with the last value seen (counters only grow)
   const int32_t *p;
@@ -106,14 +129,17 @@ HWB_FN void recon_row(const ChunkCtx &c, int pic, int y, ReconScratch *my) {
     }
   }
   Progress above = {prog + y - 1, y > 0 ? -1 : (1 << 30)};
+  ProfClock pc(c.prof);
   for (int x = 0; x < c.mb_w; ++x) {
     if (mbs[y * c.mb_w + x].mbtype != MB_INTER) {
       // intra macroblocks read the unfiltered row above up to the top-right neighbour
       wait_progress(above, x + 2 < c.mb_w ? x + 2 : c.mb_w);
+      pc.mark(PROF_WAIT_INTRA);
     } else if (ndep) {
       const int need = x + reach_x < c.mb_w ? x + reach_x : c.mb_w;
 #pragma unroll
       for (int i = 0; i < MAX_TRACKED_DEPS; ++i) if (i < ndep) wait_progress(dep[i], need);
+      pc.mark(PROF_WAIT_REF);
     }
 #if !HWB_DEVICE_BUILD
     {  // what the waits above guarantee to be final in the reference pictures (see McWindow)
@@ -127,6 +153,7 @@ HWB_FN void recon_row(const ChunkCtx &c, int pic, int y, ReconScratch *my) {
     // consumers: intra macroblocks of the row below and the deblocking pass; pictures with inter slices have few
     // intra macroblocks, so the fence + flag store is amortised over 4 macroblocks there
     if (!has_inter || (x & 3) == 3 || x == c.mb_w - 1) publish_progress(prog + y, x + 1);
+    pc.mark(PROF_RECON_MB);
   }
 }
 
@@ -139,13 +166,17 @@ HWB_FN void deblock_row(const ChunkCtx &c, int pic, int y, DeblockScratch *my) {
   Progress mine = {rprog + y, -1};
   Progress below = {rprog + y + 1, last_row ? (1 << 30) : -1};
   Progress above = {prog + y - 1, y > 0 ? -1 : (1 << 30)};
+  ProfClock pc(c.prof);
   for (int x = 0; x < c.mb_w; ++x) {
     const int lag = x + 2 < c.mb_w ? x + 2 : c.mb_w;
     wait_progress(mine, x + 1);
     wait_progress(below, lag);
+    pc.mark(PROF_WAIT_RECON);
     wait_progress(above, lag);
+    pc.mark(PROF_WAIT_DEBLOCK_ABOVE);
     deblock_mb(c, pic, x, y, my);
     publish_progress(prog + y, x + 1);
+    pc.mark(PROF_DEBLOCK_MB);
     if (rgb) {
       // RGB24 writeback fused into this pass: with (x,y) filtered, macroblock (x,y-1) is final (its right edge was
       // filtered by (x+1,y-1), which the wait above covers; its bottom edge just now), and so is (x-1,y) on the
@@ -156,6 +187,7 @@ HWB_FN void deblock_row(const ChunkCtx &c, int pic, int y, DeblockScratch *my) {
         if (x >= 2 && !(x & 1)) rgb24_macroblocks(c, pd.frame, rgb, x - 2, 2, y);
         if (flush) rgb24_macroblocks(c, pd.frame, rgb, (x & 1) ? x - 1 : x, (x & 1) ? 2 : 1, y);
       }
+      pc.mark(PROF_RGB);
     }
   }
 }

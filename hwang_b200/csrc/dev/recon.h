@@ -192,8 +192,10 @@ static inline void mc_check(int row, int col) { if (row > g_mc_window.max_row ||
 #endif
 
 // One motion-compensated partition: w x h luma samples (16x16, 8x8 or 4x4) at (x0,y0) of the picture, motion vector
-// (mvx,mvy) in quarter samples, predicted from frame `rf` into dst_y (stride ds_y) and dst_c[2] (stride ds_c).
-// Warp-cooperative: stage the reference windows, then lane l computes `ppl` consecutive samples of one row.
+// (mvx,mvy) in quarter samples, predicted from frame `rf` into dst_y (stride ds_y) and dst_cb / dst_cr (stride ds_c).
+// Warp-cooperative: stage the reference windows, then lane l computes `ppl` consecutive samples of one row.  Written for
+// few instructions and a small footprint (this stage is bound by instruction fetch, not by memory): lane mappings are
+// shifts and masks, horizontal filters slide a six-sample window along the row (one load per sample).
 HWB_FN void mc_partition(const ChunkCtx &c, int rf, int x0, int y0, int w, int h, int mvx, int mvy, uint8_t *dst_y, int ds_y,
                          uint8_t *dst_cb, uint8_t *dst_cr, int ds_c, ReconScratch *sm) {
   const int W = c.wc, H = c.hc;
@@ -203,124 +205,131 @@ HWB_FN void mc_partition(const ChunkCtx &c, int rf, int x0, int y0, int w, int h
   const int cols = w + 5, rows = h + 5;
   const bool inside = ox >= 0 && oy >= 0 && ox + cols <= W && oy + rows <= H;
   const int sh = inside ? (ox & 3) : 0;
-  // ---- stage luma
-  HWB_LANES(l)
-    if (inside) {
-      const int nw = (sh + cols + 3) >> 2;  // aligned words per row (<= 7); the over-read of <= 3 bytes stays inside the slab
-      const uint8_t *base = ref + (int64_t)oy * W + (ox - sh);
-#pragma unroll 1
-      for (int i = l; i < rows * nw; i += 32) {
-        const int r = i / nw, k = i - r * nw;
-        *(uint32_t *)(sm->mc_luma + r * MC_LS + 4 * k) = ld_u32_cg((const uint32_t *)(base + (int64_t)r * W) + k);
-      }
-    } else {
-#pragma unroll 1
-      for (int i = l; i < rows * cols; i += 32) {
-        const int r = i / cols, k = i - r * cols;
-        sm->mc_luma[r * MC_LS + k] = ld_u8_cg(ref + (int64_t)clip3(0, H - 1, oy + r) * W + clip3(0, W - 1, ox + k));
-      }
-    }
-  HWB_LANES_END
-#if !HWB_DEVICE_BUILD
-  mc_check(clip3(0, H - 1, oy + rows - 1), clip3(0, W - 1, ox + cols - 1));
-#endif
-  // ---- stage chroma: (w/2+1) x (h/2+1) per plane
   const int cw = W >> 1, ch = H >> 1;
   const int cx = (x0 >> 1) + (mvx >> 3), cy = (y0 >> 1) + (mvy >> 3);
   const int ccols = (w >> 1) + 1, crows = (h >> 1) + 1;
   const bool cinside = cx >= 0 && cy >= 0 && cx + ccols <= cw && cy + crows <= ch;
   const int csh = cinside ? (cx & 3) : 0;
+  // ---- stage luma (aligned words: lane = (row & 3, word)) and chroma (lane = (plane, row & 3, word))
   HWB_LANES(l)
-    if (cinside) {
-      const int nw = (csh + ccols + 3) >> 2;  // <= 3
+    if (inside) {
+      const int nw = (sh + cols + 3) >> 2;  // aligned words per row (<= 7); the over-read of <= 3 bytes stays inside the slab
+      const int k = l & 7;
+      const uint8_t *base = ref + (int64_t)oy * W + (ox - sh) + 4 * k;
+      if (k < nw) {
 #pragma unroll 1
-      for (int i = l; i < 2 * crows * nw; i += 32) {
-        const int pl = i / (crows * nw), j = i - pl * crows * nw, r = j / nw, k = j - r * nw;
-        const uint8_t *base = (pl ? frame_cr(c, rf) : frame_cb(c, rf)) + (int64_t)(cy + r) * cw + (cx - csh);
-        *(uint32_t *)(sm->mc_chroma[pl] + r * MC_CS + 4 * k) = ld_u32_cg((const uint32_t *)base + k);
+        for (int r = l >> 3; r < rows; r += 4) *(uint32_t *)(sm->mc_luma + r * MC_LS + 4 * k) = ld_u32_cg((const uint32_t *)(base + (int64_t)r * W));
       }
-    } else {
+    } else if (l < cols) {  // window crosses the picture edge: one (clamped) column per lane
+      const uint8_t *col = ref + clip3(0, W - 1, ox + l);
 #pragma unroll 1
-      for (int i = l; i < 2 * crows * ccols; i += 32) {
-        const int pl = i / (crows * ccols), j = i - pl * crows * ccols, r = j / ccols, k = j - r * ccols;
-        const uint8_t *P = pl ? frame_cr(c, rf) : frame_cb(c, rf);
-        sm->mc_chroma[pl][r * MC_CS + k] = ld_u8_cg(P + (int64_t)clip3(0, ch - 1, cy + r) * cw + clip3(0, cw - 1, cx + k));
+      for (int r = 0; r < rows; ++r) sm->mc_luma[r * MC_LS + l] = ld_u8_cg(col + (int64_t)clip3(0, H - 1, oy + r) * W);
+    }
+    {
+      const int pl = l >> 4;
+      const uint8_t *P = pl ? frame_cr(c, rf) : frame_cb(c, rf);
+      if (cinside) {
+        const int nw = (csh + ccols + 3) >> 2, k = l & 3;  // <= 3 words
+        if (k < nw) {
+#pragma unroll 1
+          for (int r = (l >> 2) & 3; r < crows; r += 4)
+            *(uint32_t *)(sm->mc_chroma[pl] + r * MC_CS + 4 * k) = ld_u32_cg((const uint32_t *)(P + (int64_t)(cy + r) * cw + (cx - csh)) + k);
+        }
+      } else if ((l & 15) < ccols) {
+        const uint8_t *col = P + clip3(0, cw - 1, cx + (l & 15));
+#pragma unroll 1
+        for (int r = 0; r < crows; ++r) sm->mc_chroma[pl][r * MC_CS + (l & 15)] = ld_u8_cg(col + (int64_t)clip3(0, ch - 1, cy + r) * cw);
       }
     }
   HWB_LANES_END
+#if !HWB_DEVICE_BUILD
+  mc_check(clip3(0, H - 1, oy + rows - 1), clip3(0, W - 1, ox + cols - 1));
+  mc_check(2 * clip3(0, ch - 1, cy + crows - 1) + 1, 2 * clip3(0, cw - 1, cx + ccols - 1) + 1);  // in luma units
+#endif
   // ---- luma interpolation (8.4.2.2.1).  T(r,k): window sample, the partition's sample (0,0) is T(2,2).
   const uint8_t *T = sm->mc_luma + sh;
-  const int ppl = w == 16 ? 8 : (w == 8 ? 2 : 1), lpr = w / ppl;  // samples per lane, lanes per row
 #define HWB_T(r, k) ((int)T[(r) * MC_LS + (k)])
-#define HWB_HRAW(r, k) tap6(HWB_T(r, k), HWB_T(r, (k) + 1), HWB_T(r, (k) + 2), HWB_T(r, (k) + 3), HWB_T(r, (k) + 4), HWB_T(r, (k) + 5))
-#define HWB_VRAW(r, k) tap6(HWB_T(r, k), HWB_T((r) + 1, k), HWB_T((r) + 2, k), HWB_T((r) + 3, k), HWB_T((r) + 4, k), HWB_T((r) + 5, k))
   const bool need_j = (fx == 2 && fy != 0) || (fy == 2 && fx != 0);
   if (need_j) {
-    // unrounded horizontal half samples of every window row, then the vertical filter runs over them
+    // unrounded horizontal half samples of every window row (one row per lane), the vertical filter runs over them
     HWB_LANES(l)
+      if (l < rows) {
+        const uint8_t *row = T + l * MC_LS;
+        int a0 = row[0], a1 = row[1], a2 = row[2], a3 = row[3], a4 = row[4];
 #pragma unroll 1
-      for (int i = l; i < rows * w; i += 32) {
-        const int r = i / w, k = i - r * w;
-        sm->mc_h[r * 16 + k] = (int16_t)HWB_HRAW(r, k);
+        for (int k = 0; k < w; ++k) {
+          const int a5 = row[k + 5];
+          sm->mc_h[l * 16 + k] = (int16_t)tap6(a0, a1, a2, a3, a4, a5);
+          a0 = a1; a1 = a2; a2 = a3; a3 = a4; a4 = a5;
+        }
       }
     HWB_LANES_END
   }
-  HWB_LANES(l)
-    const int y = l / lpr, xs = (l - y * lpr) * ppl;
-    if (y < h) {
+  {
+    // lane -> `ppl` consecutive samples of row y: 16x16: 8 samples, 2 lanes per row; 8x8: 2 and 4; 4x4: 1 and 4 (16 lanes)
+    const int lg_ppl = w == 16 ? 3 : (w == 8 ? 1 : 0), lg_lpr = w == 16 ? 1 : 2;
+    const bool use_b = fx != 0 && !need_j;                // rounded horizontal half sample, from window row rb
+    const bool use_v = fy != 0 && !(need_j && fx == 2);   // rounded vertical half sample, from window column x + cv
+    const int cv = 2 + ((fx == 3) ? 1 : 0);
+    HWB_LANES(l)
+      const int y = l >> lg_lpr, xs = (l & ((1 << lg_lpr) - 1)) << lg_ppl;
+      if (y < h) {
+        const int rb = y + 2 + ((fy == 3) ? 1 : 0);
+        const uint8_t *row = T + rb * MC_LS + xs;
+        int a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+        if (use_b) { a0 = row[0]; a1 = row[1]; a2 = row[2]; a3 = row[3]; a4 = row[4]; }
 #pragma unroll 1
-      for (int i = 0; i < ppl; ++i) {
-        const int x = xs + i;
-        int v;
-        if (fx == 0 && fy == 0) v = HWB_T(y + 2, x + 2);
-        else if (fy == 0) {
-          const int b = clip8((HWB_HRAW(y + 2, x) + 16) >> 5);
-          v = fx == 2 ? b : (b + HWB_T(y + 2, x + 2 + (fx == 3)) + 1) >> 1;
-        } else if (fx == 0) {
-          const int hh = clip8((HWB_VRAW(y, x + 2) + 16) >> 5);
-          v = fy == 2 ? hh : (hh + HWB_T(y + 2 + (fy == 3), x + 2) + 1) >> 1;
-        } else if (need_j) {
-          const int16_t *hr = sm->mc_h + y * 16 + x;
-          const int j = clip8((tap6(hr[0], hr[16], hr[32], hr[48], hr[64], hr[80]) + 512) >> 10);
-          if (fx == 2 && fy == 2) v = j;
-          else if (fx == 2) v = (j + clip8((sm->mc_h[(y + 2 + (fy == 3)) * 16 + x] + 16) >> 5) + 1) >> 1;
-          else v = (j + clip8((HWB_VRAW(y, x + 2 + (fx == 3)) + 16) >> 5) + 1) >> 1;
-        } else {
-          const int b = clip8((HWB_HRAW(y + 2 + (fy == 3), x) + 16) >> 5);
-          const int hh = clip8((HWB_VRAW(y, x + 2 + (fx == 3)) + 16) >> 5);
-          v = (b + hh + 1) >> 1;
+        for (int i = 0; i < (1 << lg_ppl); ++i) {
+          const int x = xs + i;
+          int b = 0, hh = 0, v;
+          if (use_b) {
+            const int a5 = row[i + 5];
+            b = clip8((tap6(a0, a1, a2, a3, a4, a5) + 16) >> 5);
+            if (fy == 0 && fx != 2) b = (b + (fx == 3 ? a3 : a2) + 1) >> 1;  // quarter sample next to an integer sample of the same row
+            a0 = a1; a1 = a2; a2 = a3; a3 = a4; a4 = a5;
+          }
+          if (use_v) {
+            const uint8_t *col = T + y * MC_LS + x + (fx == 0 ? 2 : cv);
+            hh = clip8((tap6(col[0], col[MC_LS], col[2 * MC_LS], col[3 * MC_LS], col[4 * MC_LS], col[5 * MC_LS]) + 16) >> 5);
+          }
+          if (fx == 0 && fy == 0) v = HWB_T(y + 2, x + 2);
+          else if (fy == 0) v = b;
+          else if (fx == 0) v = fy == 2 ? hh : (hh + HWB_T(rb, x + 2) + 1) >> 1;
+          else if (need_j) {
+            const int16_t *hr = sm->mc_h + y * 16 + x;
+            const int j = clip8((tap6(hr[0], hr[16], hr[32], hr[48], hr[64], hr[80]) + 512) >> 10);
+            if (fx == 2 && fy == 2) v = j;
+            else if (fx == 2) v = (j + clip8((sm->mc_h[rb * 16 + x] + 16) >> 5) + 1) >> 1;
+            else v = (j + hh + 1) >> 1;
+          } else v = (b + hh + 1) >> 1;
+          dst_y[y * ds_y + x] = (uint8_t)v;
         }
-        dst_y[y * ds_y + x] = (uint8_t)v;
       }
-    }
-  HWB_LANES_END
+    HWB_LANES_END
+  }
 #undef HWB_T
-#undef HWB_HRAW
-#undef HWB_VRAW
   // ---- chroma: bilinear eighth-sample interpolation (8.4.2.2.2), both planes at once
   {
     const int cfx = mvx & 7, cfy = mvy & 7;
-    const int pw = w >> 1, ph = h >> 1;             // samples per plane: 8x8, 4x4 or 2x2
-    const int cppl = pw == 8 ? 4 : 1, clpr = pw / cppl;  // 16 lanes per plane for 8x8 and 4x4, 4 lanes for 2x2
-    const int lanes_pp = clpr * ph;
+    // samples per plane 8x8 / 4x4 / 2x2: lanes per plane 16 / 16 / 4, lanes per row 2 / 4 / 2, samples per lane 4 / 1 / 1
+    const int lg_lpp = w == 4 ? 2 : 4, lg_clpr = w == 8 ? 2 : 1, lg_cppl = w == 16 ? 2 : 0;
+    const int wa = (8 - cfx) * (8 - cfy), wb = cfx * (8 - cfy), wc2 = (8 - cfx) * cfy, wd = cfx * cfy;
     HWB_LANES(l)
-      const int pl = l / lanes_pp, k = l - pl * lanes_pp;
+      const int pl = l >> lg_lpp, k = l & ((1 << lg_lpp) - 1);
       if (pl < 2) {
-        const int y = k / clpr, xs = (k - y * clpr) * cppl;
-        const uint8_t *Tc = sm->mc_chroma[pl] + csh;
-        uint8_t *d = (pl ? dst_cr : dst_cb) + y * ds_c;
+        const int y = k >> lg_clpr, xs = (k & ((1 << lg_clpr) - 1)) << lg_cppl;
+        const uint8_t *t0 = sm->mc_chroma[pl] + csh + y * MC_CS + xs, *t1 = t0 + MC_CS;
+        uint8_t *d = (pl ? dst_cr : dst_cb) + y * ds_c + xs;
+        int a = t0[0], cc = t1[0];
 #pragma unroll 1
-        for (int i = 0; i < cppl; ++i) {
-          const int x = xs + i;
-          const int a = Tc[y * MC_CS + x], b = Tc[y * MC_CS + x + 1], cc = Tc[(y + 1) * MC_CS + x], dd = Tc[(y + 1) * MC_CS + x + 1];
-          d[x] = (uint8_t)(((8 - cfx) * (8 - cfy) * a + cfx * (8 - cfy) * b + (8 - cfx) * cfy * cc + cfx * cfy * dd + 32) >> 6);
+        for (int i = 0; i < (1 << lg_cppl); ++i) {
+          const int b = t0[i + 1], dd = t1[i + 1];
+          d[i] = (uint8_t)((wa * a + wb * b + wc2 * cc + wd * dd + 32) >> 6);
+          a = b; cc = dd;
         }
       }
     HWB_LANES_END
   }
-#if !HWB_DEVICE_BUILD
-  mc_check(2 * clip3(0, ch - 1, cy + crows - 1) + 1, 2 * clip3(0, cw - 1, cx + ccols - 1) + 1);  // in luma units
-#endif
 }
 
 // All partitions of one list of an inter macroblock.  Motion is stored per 4x4 block: a macroblock whose 16 vectors and

@@ -1,5 +1,6 @@
 #include "b200_video_decoder.h"
 
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
@@ -23,6 +24,8 @@ const int kMaxChunkPictures = 32767;  // frame indices travel as int16 (SliceDes
 B200VideoDecoder::B200VideoDecoder(int device_id, DeviceType output_type, int) : device_id_(device_id), output_type_(output_type) {
   if (hwb_dev_open(device_id, &dev_) != 0) dev_ = nullptr;
   if (const char *e = getenv("HWB_CHUNK_PICTURES")) { int v = atoi(e); if (v > 0) chunk_target_ = v; }
+  if (const char *e = getenv("HWB_PICTURE_PROFILE")) picture_profile_ = atoi(e) != 0;
+  if (const char *e = getenv("HWB_NO_RGB")) no_rgb_ = atoi(e) != 0;  // experiments: no fused RGB24 writeback (frames are converted on demand)
 }
 
 B200VideoDecoder::~B200VideoDecoder() {
@@ -237,7 +240,7 @@ Result B200VideoDecoder::submit_current() {
       bool want = true;
       if (hinted) want = std::binary_search(hint.second.begin(), hint.second.end(), hint.first + (uint64_t)(j - a));
       if (!want && !ch->pics[pic].is_ref) { ch->skipped[pic] = 1; nskipped++; }
-      ch->pics[pic].rgb_slot = want ? nrgb++ : -1;
+      ch->pics[pic].rgb_slot = (want && !no_rgb_) ? nrgb++ : -1;
     }
   }
   // ---- work lists of the picture kernel: (level, row, picture), see csrc/dev/picture.h
@@ -264,7 +267,7 @@ Result B200VideoDecoder::submit_current() {
                o_ritems = take(recon_items.size() * 4), o_ditems = take(deblock_items.size() * 4), o_order = take((size_t)S * 4),
                o_rgb = take(rgb_bytes * (size_t)nrgb);
   // counters zeroed per chunk: tickets (entropy, recon, deblock) + per-slice entropy progress + per-row progress x2 + mv reach + error flag
-  const size_t n_sync = 4 + (size_t)S + 4 * (size_t)P * mb_h + 4;
+  const size_t n_sync = 4 + (size_t)S + 4 * (size_t)P * mb_h + 4 + 2 * hwb::PROF_COUNTERS + 2;
   const size_t o_sync = take(n_sync * 4);
   if (feeder_may_block_ && memory_budget_) {
     // Back-pressure in bytes: wait for the consumer to retire chunks instead of running the device out of memory.
@@ -305,6 +308,7 @@ Result B200VideoDecoder::submit_current() {
   c.mv_reach_x = c.mv_reach + (size_t)P * mb_h;
   c.error_flag = c.mv_reach_x + (size_t)P * mb_h;
   ch->error_dev = c.error_flag;
+  if (picture_profile_) c.prof = (unsigned long long *)(((uintptr_t)(c.error_flag + 2) + 7) & ~(uintptr_t)7);
 
   // Inputs + entropy decoding on one of the rotating entropy streams, the picture kernel on the (single) picture
   // stream: entropy decoding of later chunks (latency-bound: one warp per slice) runs under the picture kernels of
@@ -393,6 +397,16 @@ Result B200VideoDecoder::finish_chunk(Chunk &c) {
         interval_begin_ = nullptr;
       }
     }
+  }
+  if (c.ctx.prof) {  // HWB_PICTURE_PROFILE=1: where the picture kernel's warps spent their cycles
+    unsigned long long v[hwb::PROF_COUNTERS] = {0};
+    hwb_dev_d2h(dev_, HWB_STREAM_AUX, v, c.ctx.prof, sizeof(v));
+    hwb_dev_stream_sync(dev_, HWB_STREAM_AUX);
+    const double life = (double)v[hwb::PROF_LIFETIME] > 0 ? (double)v[hwb::PROF_LIFETIME] : 1.0;
+    fprintf(stderr, "[hwb picture profile] pictures %d: recon_mb %.1f%% deblock_mb %.1f%% rgb %.1f%% | wait ref %.1f%% intra %.1f%% recon %.1f%% deblock-above %.1f%% | pick %.1f%% (warp-cycles %.3g)\n",
+            c.ctx.num_pics, 100 * v[hwb::PROF_RECON_MB] / life, 100 * v[hwb::PROF_DEBLOCK_MB] / life, 100 * v[hwb::PROF_RGB] / life,
+            100 * v[hwb::PROF_WAIT_REF] / life, 100 * v[hwb::PROF_WAIT_INTRA] / life, 100 * v[hwb::PROF_WAIT_RECON] / life,
+            100 * v[hwb::PROF_WAIT_DEBLOCK_ABOVE] / life, 100 * v[hwb::PROF_PICK] / life, life);
   }
   stats_.algorithmic_bytes += c.alg_bytes;
   c.finished = true; c.checked = true;

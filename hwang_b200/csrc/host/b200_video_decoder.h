@@ -128,7 +128,7 @@ class B200VideoDecoder : public VideoDecoderInterface {
   // rotate), which overlaps host parsing, entropy decoding of later batches, the picture kernel of earlier ones and the
   // copies to the host.
   int chunk_target_ = 240;
-  bool feeder_may_block_ = false, defer_submit_ = false;
+  bool feeder_may_block_ = false, defer_submit_ = false, no_rgb_ = false, picture_profile_ = false;
   std::unique_ptr<Chunk> cur_;
   std::deque<std::unique_ptr<Chunk>> queue_;    // submitted chunks, oldest first
   std::vector<std::unique_ptr<Chunk>> retired_;  // fully popped, slab reusable after the next copy-stream sync

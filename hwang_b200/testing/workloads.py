@@ -27,18 +27,19 @@ def config4_rows(n=1000):
     return sorted(set(int(x) for x in rng.integers(0, n, 64)))
 
 
-def config5_clips():
+def config5_clips(frames=300):
     """64 clips, seeded mix of {640x480, 1280x720, 1920x1080, 3840x2160}, profiles cycling CBP / Main / High, GOP 30-60,
-    300 frames each."""
+    300 frames each (about 700 MB: more than a gpurun snapshot may carry, so the GPU box only gets them in dedicated
+    runs).  frames=60: the same 64 clips cut to 60 frames ('config5s_*', about 140 MB, shipped with every snapshot)."""
     rng = np.random.default_rng(5)
     sizes = [(640, 480), (1280, 720), (1920, 1080), (3840, 2160)]
     out = []
     for i in range(64):
         w, h = sizes[int(rng.integers(0, 4))]
         profile = i % 3
-        kw = dict(width=w, height=h, frames=300, gop=int(rng.integers(30, 61)), profile=profile, seed=500 + i, qp=28 + (2 if w >= 3840 else 0),
+        kw = dict(width=w, height=h, frames=frames, gop=int(rng.integers(30, 61)), profile=profile, seed=500 + i, qp=28 + (2 if w >= 3840 else 0),
                   num_ref=2 + profile, bframes=[0, 1, 2][profile], weighted=[0, 0, 2][profile], slices=1 + (i % 5 == 0))
-        out.append(dict(name='config5_%02d_%dx%d_p%d' % (i, w, h, profile), kw=kw))
+        out.append(dict(name='%s_%02d_%dx%d_p%d' % ('config5' if frames == 300 else 'config5s', i, w, h, profile), kw=kw))
     return out
 
 
