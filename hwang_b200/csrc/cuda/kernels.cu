@@ -111,10 +111,11 @@ __global__ void __launch_bounds__(kThreads, 6) picture_kernel(const __grid_const
   // kernel (complete by now: an event orders the launches) has raised the chunk's error flag, the host reports it
   // when the chunk's first frame is popped, and nothing may be dereferenced here.
   if (*((volatile const int32_t *)c.error_flag) != 0) return;
-  // split > 0: static roles by SM: an SM whose (scrambled) id falls below `split` percent only takes deblocking items
+  // split > 0: static roles by SM: the SMs whose id falls into the first `split` percent only take deblocking items
   // (until they run out), the others only reconstruction items.  Both stages are bound by instruction fetch; an SM that
-  // stays inside one of the two code bodies keeps its instruction caches for it (measured on the 3000-picture batch:
-  // 369 ms against 484 ms with the same roles assigned per warp and 544 ms with every warp choosing dynamically).
+  // stays inside one of the two code bodies keeps its instruction caches for it, and the two SMs of a TPC must agree
+  // (measured on the 3000-picture batch: every warp choosing dynamically 544 ms, roles per warp 484 ms, roles per SM
+  // scattered over the chip 452 ms, per TPC 292 ms, one contiguous range of SM ids 276 ms).
   // The host only passes split > 0 when the grid puts blocks on every SM (both roles are then present); small grids
   // use the dynamic choice below, which needs no such assumption.
   bool fixed_deblock = false;
@@ -258,7 +259,7 @@ void hwb_dev_free(hwb_dev *d, void *p) { cudaSetDevice(d->device); cudaFree(p); 
 void *hwb_dev_malloc_host(hwb_dev *d, size_t n) {
   cudaSetDevice(d->device);
   void *p = nullptr;
-  cudaError_t e = cudaHostAlloc(&p, n ? n : 1, cudaHostAllocPortable);
+  cudaError_t e = cudaHostAlloc(&p, n ? n : 1, cudaHostAllocPortable | cudaHostAllocMapped);  // mapped: the picture kernel writes completion flags into it
   if (e != cudaSuccess) { d->err = std::string("cudaHostAlloc: ") + cudaGetErrorString(e); cudaGetLastError(); return nullptr; }
   return p;
 }
@@ -323,11 +324,11 @@ int hwb_dev_picture(hwb_dev *d, int s, const ChunkCtx *c, int32_t *ticket) {
   cudaSetDevice(d->device);
   static int bpsm = [] { const char *e = getenv("HWB_PICTURE_BLOCKS_PER_SM"); int v = e ? atoi(e) : 0; return v > 0 ? v : 6; }();
   // percent of the SMs that deblock (0 = every warp chooses dynamically, see picture_kernel)
-  static int split_pct = [] { const char *e = getenv("HWB_PICTURE_SPLIT"); int v = e ? atoi(e) : -1; return v >= 0 && v <= 90 ? v : 46; }();
+  static int split_pct = [] { const char *e = getenv("HWB_PICTURE_SPLIT"); int v = e ? atoi(e) : -1; return v >= 0 && v <= 90 ? v : 40; }();
   const int items = c->num_recon_items + c->num_deblock_items;
   if (items == 0) return 0;
   const int grid = grid_for(d, items, bpsm);
-  static int rolemap = [] { const char *e = getenv("HWB_PICTURE_ROLEMAP"); int v = e ? atoi(e) : 0; return v >= 0 && v <= 3 ? v : 0; }();
+  static int rolemap = [] { const char *e = getenv("HWB_PICTURE_ROLEMAP"); int v = e ? atoi(e) : 1; return v >= 0 && v <= 3 ? v : 1; }();
   const int split = (grid >= 2 * d->sms && split_pct > 0) ? split_pct + 1000 * rolemap : 0;  // static roles need blocks on every SM
   picture_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket, split);
   HWB_CUDA(d, cudaGetLastError());

@@ -928,8 +928,8 @@ HWB_FN void finish_mb(SliceDec &s, bool skipped, bool direct16, bool is_pcm) {
   HWB_LANES_END
   if (inter) {
 #if HWB_DEVICE_BUILD
-    reach = (int)__reduce_max_sync(0xffffffffu, (unsigned)((reach << 16) | reach_x));  // reach > 0 implies reach_x >= 1
-    reach_x = reach & 0xffff; reach >>= 16;
+    reach = (int)__reduce_max_sync(0xffffffffu, (unsigned)reach);  // two independent maxima
+    reach_x = (int)__reduce_max_sync(0xffffffffu, (unsigned)reach_x);
 #endif
     if (reach > s.row_reach) s.row_reach = reach;
     if (reach_x > s.row_reach_x) s.row_reach_x = reach_x;

@@ -123,6 +123,12 @@ struct ChunkCtx {
   uint8_t *rgb;            // [slot] packed RGB24, out_w * out_h * 3 bytes each (tight)
   uint64_t rgb_stride;
   int32_t crop_x, crop_y, out_w, out_h;  // cropping rectangle of the output frames inside the coded picture
+  // Completion of single pictures, so that frames travel to the host while the picture kernel is still working on the
+  // rest of the batch: rows_done[pic] counts deblocked rows (device memory); the warp that completes the last row of a
+  // picture sets pic_done[pic] = 1 in page-locked HOST memory (mapped into the device address space), which the host
+  // polls before it copies the frame out.
+  int32_t *rows_done;
+  int32_t *pic_done;
   // optional (HWB_PICTURE_PROFILE=1): warp cycles of the picture kernel by activity, see picture.h PROF_*; nullptr = off
   unsigned long long *prof;
 };

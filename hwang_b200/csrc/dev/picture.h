@@ -190,6 +190,20 @@ HWB_FN void deblock_row(const ChunkCtx &c, int pic, int y, DeblockScratch *my) {
       pc.mark(PROF_RGB);
     }
   }
+  // picture complete?  Every row's samples and RGB24 were written before its count (fence), so whoever counts the last
+  // row may tell the host (system-scope fence: the copy engine reads what the host was promised).
+#if HWB_DEVICE_BUILD
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {
+    __threadfence();
+    if (atomicAdd(c.rows_done + pic, 1) == c.mb_h - 1) {
+      __threadfence_system();
+      *((volatile int32_t *)c.pic_done + pic) = 1;
+    }
+  }
+#else
+  if (++c.rows_done[pic] == c.mb_h) c.pic_done[pic] = 1;
+#endif
 }
 
 }  // namespace hwb

@@ -24,6 +24,7 @@ const int kMaxChunkPictures = 32767;  // frame indices travel as int16 (SliceDes
 B200VideoDecoder::B200VideoDecoder(int device_id, DeviceType output_type, int) : device_id_(device_id), output_type_(output_type) {
   if (hwb_dev_open(device_id, &dev_) != 0) dev_ = nullptr;
   if (const char *e = getenv("HWB_CHUNK_PICTURES")) { int v = atoi(e); if (v > 0) chunk_target_ = v; }
+  if (const char *e = getenv("HWB_GROUP_PICTURES")) { int v = atoi(e); if (v > 0) group_target_ = v; }
   if (const char *e = getenv("HWB_PICTURE_PROFILE")) picture_profile_ = atoi(e) != 0;
   if (const char *e = getenv("HWB_NO_RGB")) no_rgb_ = atoi(e) != 0;  // experiments: no fused RGB24 writeback (frames are converted on demand)
 }
@@ -41,6 +42,7 @@ void B200VideoDecoder::recycle(std::unique_ptr<Chunk> &c, bool keep_slab) {
   if (c->ev_picture) hwb_dev_event_destroy(dev_, c->ev_picture);
   if (c->ev_done) hwb_dev_event_destroy(dev_, c->ev_done);
   if (c->ev_copied) hwb_dev_event_destroy(dev_, c->ev_copied);
+  if (c->done_host) { free_flags_.push_back({(int32_t *)c->done_host, c->done_capacity}); c->done_host = nullptr; }
   if (c->slab.base) {
     if (keep_slab) free_slabs_.push_back(c->slab);
     else { live_bytes_ -= c->slab.size; hwb_dev_free(dev_, c->slab.base); }
@@ -56,6 +58,8 @@ void B200VideoDecoder::release_all() {
   retired_.clear();
   for (auto &s : free_slabs_) { live_bytes_ -= s.size; hwb_dev_free(dev_, s.base); }
   free_slabs_.clear();
+  for (auto &f : free_flags_) hwb_dev_free_host(dev_, f.first);
+  free_flags_.clear();
   cur_.reset();
   for (int i = 0; i < kRing; ++i) {
     if (stage_dev_[i]) hwb_dev_free(dev_, stage_dev_[i]);
@@ -243,17 +247,29 @@ Result B200VideoDecoder::submit_current() {
       ch->pics[pic].rgb_slot = (want && !no_rgb_) ? nrgb++ : -1;
     }
   }
-  // ---- work lists of the picture kernel: (level, row, picture), see csrc/dev/picture.h
-  int nlevels = 0;
-  for (auto &p : ch->pics) nlevels = std::max(nlevels, p.level + 1);
-  std::vector<std::vector<int32_t>> by_level(nlevels);
-  for (int i = 0; i < P; ++i) if (!ch->skipped[i]) by_level[ch->pics[i].level].push_back(i);
+  // ---- work lists of the picture kernel, see csrc/dev/picture.h.  The batch is cut into groups of whole GOPs (about
+  // group_target_ pictures); inside a group items are ordered (level, row, picture), groups follow one another.  The
+  // warps flow from one group into the next without a launch boundary, while the groups -- and with them the frames, in
+  // display order -- complete one after the other, so the copies to the host start long before the kernel ends.
   std::vector<uint32_t> recon_items, deblock_items;
   recon_items.reserve((size_t)(P - nskipped) * mb_h);
   deblock_items.reserve((size_t)(P - nskipped) * mb_h);
-  for (auto &v : by_level)
-    for (int y = 0; y < mb_h; ++y)
-      for (int32_t pic : v) { recon_items.push_back(hwb::make_item(pic, y, 0)); deblock_items.push_back(hwb::make_item(pic, y, 1)); }
+  {
+    std::vector<std::vector<int32_t>> by_level;
+    int g0 = 0;
+    while (g0 < P) {
+      int g1 = g0 + 1;  // pictures of level 0 start a GOP (intra pictures): extend to whole GOPs until the group is large enough
+      while (g1 < P && !(ch->pics[g1].level == 0 && g1 - g0 >= group_target_)) ++g1;
+      int nlevels = 0;
+      for (int i = g0; i < g1; ++i) nlevels = std::max(nlevels, ch->pics[i].level + 1);
+      by_level.assign(nlevels, std::vector<int32_t>());
+      for (int i = g0; i < g1; ++i) if (!ch->skipped[i]) by_level[ch->pics[i].level].push_back(i);
+      for (auto &v : by_level)
+        for (int y = 0; y < mb_h; ++y)
+          for (int32_t pic : v) { recon_items.push_back(hwb::make_item(pic, y, 0)); deblock_items.push_back(hwb::make_item(pic, y, 1)); }
+      g0 = g1;
+    }
+  }
 
   // ---- device layout
   const size_t fs = (size_t)mb_w * 16 * mb_h * 16 * 3 / 2;
@@ -267,7 +283,7 @@ Result B200VideoDecoder::submit_current() {
                o_ritems = take(recon_items.size() * 4), o_ditems = take(deblock_items.size() * 4), o_order = take((size_t)S * 4),
                o_rgb = take(rgb_bytes * (size_t)nrgb);
   // counters zeroed per chunk: tickets (entropy, recon, deblock) + per-slice entropy progress + per-row progress x2 + mv reach + error flag
-  const size_t n_sync = 4 + (size_t)S + 4 * (size_t)P * mb_h + 4 + 2 * hwb::PROF_COUNTERS + 2;
+  const size_t n_sync = 4 + (size_t)S + 4 * (size_t)P * mb_h + (size_t)P + 4 + 2 * hwb::PROF_COUNTERS + 2;
   const size_t o_sync = take(n_sync * 4);
   if (feeder_may_block_ && memory_budget_) {
     // Back-pressure in bytes: wait for the consumer to retire chunks instead of running the device out of memory.
@@ -306,8 +322,19 @@ Result B200VideoDecoder::submit_current() {
   c.dbl_prog = c.recon_prog + (size_t)P * mb_h;
   c.mv_reach = c.dbl_prog + (size_t)P * mb_h;
   c.mv_reach_x = c.mv_reach + (size_t)P * mb_h;
-  c.error_flag = c.mv_reach_x + (size_t)P * mb_h;
+  c.rows_done = c.mv_reach_x + (size_t)P * mb_h;
+  c.error_flag = c.rows_done + P;
   ch->error_dev = c.error_flag;
+  // completion flags in page-locked host memory (recycled between chunks)
+  for (size_t i = 0; i < free_flags_.size(); ++i)
+    if (free_flags_[i].second >= (size_t)P) { ch->done_host = free_flags_[i].first; ch->done_capacity = free_flags_[i].second; free_flags_.erase(free_flags_.begin() + i); break; }
+  if (!ch->done_host) {
+    ch->done_capacity = std::max<size_t>((size_t)P, 1024);
+    ch->done_host = (int32_t *)hwb_dev_malloc_host(dev_, ch->done_capacity * 4);
+    if (!ch->done_host) return Result(false, std::string("B200 decoder: page-locked allocation failed: ") + hwb_dev_error(dev_));
+  }
+  memset((void *)ch->done_host, 0, (size_t)P * 4);
+  c.pic_done = (int32_t *)ch->done_host;
   if (picture_profile_) c.prof = (unsigned long long *)(((uintptr_t)(c.error_flag + 2) + 7) & ~(uintptr_t)7);
 
   // Inputs + entropy decoding on one of the rotating entropy streams, the picture kernel on the (single) picture
@@ -414,6 +441,11 @@ Result B200VideoDecoder::finish_chunk(Chunk &c) {
   return Result();
 }
 
+bool B200VideoDecoder::picture_done(Chunk &c, int frame) {
+  return c.finished || c.skipped[frame] || c.done_host[frame] != 0;
+}
+
+// Frames that can be popped without waiting: pictures complete in display order from the front of the queue.
 int B200VideoDecoder::frames_ready() {
   std::lock_guard<std::mutex> lk(mu_);
   if (!sticky_error_.empty()) return -1;
@@ -424,11 +456,27 @@ int B200VideoDecoder::frames_ready() {
       int st = hwb_dev_event_done(dev_, c->ev_done);
       if (st < 0) { sticky_error_ = std::string("B200 decoder: CUDA error: ") + hwb_dev_error(dev_); return -1; }
       if (st == 1) c->finished = true;
-      else break;  // chunks complete in order
     }
-    n += (int)(c->order.size() - c->next_out);
+    size_t k = c->next_out;
+    while (k < c->order.size() && picture_done(*c, c->order[k])) ++k;
+    n += (int)(k - c->next_out);
+    if (k < c->order.size()) break;
   }
   return n;
+}
+
+// Wait for one picture (its completion flag in host memory), not for the whole batch.  The flag never comes when the
+// entropy stage found the stream corrupt (the picture kernel then does nothing): the batch's end event ends the wait.
+Result B200VideoDecoder::wait_picture(Chunk &c, int frame) {
+  int spins = 0;
+  while (!picture_done(c, frame)) {
+    const int st = hwb_dev_event_done(dev_, c.ev_done);
+    if (st < 0) { sticky_error_ = std::string("B200 decoder: CUDA error: ") + hwb_dev_error(dev_); return Result(false, sticky_error_); }
+    if (st == 1) { c.finished = true; break; }
+    if (++spins > 64) std::this_thread::sleep_for(std::chrono::microseconds(20));
+  }
+  if (c.finished) return finish_chunk(c);  // whole batch done: error flag, statistics
+  return Result();
 }
 
 // reference: SoftwareVideoDecoder::decoded_frames_buffered, software_video_decoder.cpp:341-343.
@@ -447,6 +495,7 @@ int B200VideoDecoder::decoded_frames_buffered() {
 void B200VideoDecoder::retire_front() {
   std::unique_ptr<Chunk> c = std::move(queue_.front());
   queue_.pop_front();
+  if (!c->checked) finish_chunk(*c);  // every frame has left: the kernel is at most a few warps from its end
   c->ev_copied = hwb_dev_event_create(dev_);
   hwb_event *aux = hwb_dev_event_create(dev_);
   if (aux) { hwb_dev_event_record(dev_, aux, HWB_STREAM_AUX); hwb_dev_stream_wait(dev_, HWB_STREAM_COPY, aux); hwb_dev_event_destroy(dev_, aux); }
@@ -511,8 +560,9 @@ Result B200VideoDecoder::pop_common(int mode, uint8_t *buf, size_t size, uint8_t
   while (!queue_.empty() && queue_.front()->next_out >= queue_.front()->order.size()) retire_front();
   if (queue_.empty()) return Result(false, "B200 decoder: no decoded frame buffered");
   Chunk &c = *queue_.front();
-  HWANG_RETURN_ON_ERROR(finish_chunk(c));
-  const int frame = c.order[c.next_out++];
+  const int frame = c.order[c.next_out];
+  HWANG_RETURN_ON_ERROR(wait_picture(c, frame));
+  c.next_out++;
   if (mode != 3 && c.skipped[frame]) return Result(false, "B200 decoder: this frame was declared unwanted (set_interval_hint) and has not been decoded");
   if (mode == 3) {
     if (c.next_out >= c.order.size()) retire_front();

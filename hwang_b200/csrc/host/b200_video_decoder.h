@@ -96,6 +96,8 @@ class B200VideoDecoder : public VideoDecoderInterface {
     bool submitted = false, finished = false, checked = false;
     bool lent = false;  // a device pointer into this chunk's RGB arena was handed out (get_frame_device)
     int32_t *error_dev = nullptr;
+    volatile int32_t *done_host = nullptr;  // [pic] page-locked, written by the picture kernel when the picture is complete
+    size_t done_capacity = 0;
     uint64_t alg_bytes = 0;
     int crop_x = 0, crop_y = 0;
   };
@@ -103,6 +105,8 @@ class B200VideoDecoder : public VideoDecoderInterface {
 
   Result submit_current();
   Result finish_chunk(Chunk &c);  // wait for completion, check the device error flag
+  Result wait_picture(Chunk &c, int frame);  // wait until one picture of a submitted chunk is complete
+  bool picture_done(Chunk &c, int frame);
   Result pop_common(int mode, uint8_t *buf, size_t size, uint8_t **dev_out);
   Result stage_slot(int *slot);
   void retire_front();
@@ -127,12 +131,14 @@ class B200VideoDecoder : public VideoDecoderInterface {
   // latency-bound per slice, so a batch must hold many slices; several batches are in flight at once (entropy streams
   // rotate), which overlaps host parsing, entropy decoding of later batches, the picture kernel of earlier ones and the
   // copies to the host.
-  int chunk_target_ = 240;
+  int chunk_target_ = 960;
+  int group_target_ = 300;  // pictures per GOP group inside a batch: groups complete (and their frames leave) one after the other
   bool feeder_may_block_ = false, defer_submit_ = false, no_rgb_ = false, picture_profile_ = false;
   std::unique_ptr<Chunk> cur_;
   std::deque<std::unique_ptr<Chunk>> queue_;    // submitted chunks, oldest first
   std::vector<std::unique_ptr<Chunk>> retired_;  // fully popped, slab reusable after the next copy-stream sync
   std::vector<Slab> free_slabs_;
+  std::vector<std::pair<int32_t *, size_t>> free_flags_;  // page-locked completion-flag arrays of recycled chunks
   size_t live_bytes_ = 0;     // device memory held (slabs in use + cached)
   size_t memory_budget_ = 0;  // in-flight limit, a fraction of what was free at configure()
   size_t last_chunk_bytes_ = 0;
