@@ -8,14 +8,54 @@
 
 namespace hwb {
 
-enum { DL_STRIDE = 32, DL_OFF = 16, DC_STRIDE = 16, DC_OFF = 4 };
+enum { DL_STRIDE = 32, DL_OFF = 16, DC_STRIDE = 16, DC_OFF = 8 };  // column 0 of every tile row is 16- (luma) / 8-byte (chroma) aligned
 
-struct DeblockScratch {
+// 16- and 8-byte moves: the macroblock's own 16 luma / 8 chroma columns of a row travel as one 128-bit / 64-bit access
+// (ld.global.cg: the samples were written by other warps of the same launch), the 4 columns left of it as one word.
+struct alignas(16) Vec16 { uint32_t w[4]; };
+struct alignas(8) Vec8 { uint32_t w[2]; };
+HWB_HD Vec16 ld_v16_cg(const uint8_t *p) {
+  Vec16 v;
+#if HWB_DEVICE_BUILD
+  const uint4 t = __ldcg((const uint4 *)p);
+  v.w[0] = t.x; v.w[1] = t.y; v.w[2] = t.z; v.w[3] = t.w;
+#else
+  memcpy(&v, p, 16);
+#endif
+  return v;
+}
+HWB_HD Vec8 ld_v8_cg(const uint8_t *p) {
+  Vec8 v;
+#if HWB_DEVICE_BUILD
+  const uint2 t = __ldcg((const uint2 *)p);
+  v.w[0] = t.x; v.w[1] = t.y;
+#else
+  memcpy(&v, p, 8);
+#endif
+  return v;
+}
+HWB_HD void st_v16(uint8_t *p, const Vec16 &v) {
+#if HWB_DEVICE_BUILD
+  *(uint4 *)p = make_uint4(v.w[0], v.w[1], v.w[2], v.w[3]);
+#else
+  memcpy(p, &v, 16);
+#endif
+}
+HWB_HD void st_v8(uint8_t *p, const Vec8 &v) {
+#if HWB_DEVICE_BUILD
+  *(uint2 *)p = make_uint2(v.w[0], v.w[1]);
+#else
+  memcpy(p, &v, 8);
+#endif
+}
+
+struct alignas(16) DeblockScratch {
   uint8_t luma[20 * DL_STRIDE];       // rows -4..15 (row r at (r+4)), col c at DL_OFF + c (c = -4..15)
   uint8_t chroma[2][12 * DC_STRIDE];  // rows -4..7, col c at DC_OFF + c (c = -4..7)
   uint8_t bs[32];                     // [dir][edge][segment]
 #if !HWB_DEVICE_BUILD
-  uint32_t pre_l[32][4], pre_c[32][3];  // host emulation only: per-lane registers that live across lane blocks
+  Vec16 pre_l[32][2];                 // host emulation only: per-lane registers that live across lane blocks
+  Vec8 pre_c[32][2];
 #endif
 };
 
@@ -121,26 +161,31 @@ HWB_FN void deblock_mb(const ChunkCtx &c, int pic, int mbx, int mby, DeblockScra
   uint8_t *Y = frame_y(c, pd.frame), *Cb = frame_cb(c, pd.frame), *Cr = frame_cr(c, pd.frame);
   const bool two_lists = pd.has_inter == 2;  // picture contains B slices
 
-  // ---- tile loads first (coherent loads: neighbours were written by other warps of this launch): 4 + 3 words per
-  // lane, all issued before anything waits on them, so that their L2 round trips overlap each other and the
-  // boundary-strength phase below (this stage is bound by load latency on the wavefront's critical path)
-  uint32_t tl[4], tc[3];
+  // ---- tile loads first (coherent loads: neighbours were written by other warps of this launch), all issued before
+  // anything waits on them, so that their L2 round trips overlap each other and the boundary-strength phase below
+  // (this stage is bound by load latency on the wavefront's critical path).  Item i of a plane: row i >> 1, part i & 1:
+  // part 0 = the macroblock's own columns (one 16-byte / 8-byte load), part 1 = the 4 columns to the left (one word).
+  Vec16 tl[2];
+  Vec8 tc[2];
   HWB_LANES(l)
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int i = l + 32 * k, r = i / 5 - 4, cq = i % 5 - 1;  // row -4..15, column quad -1..3
-      const bool ok = i < 100 && !((r < 0 && mby == 0) || (cq < 0 && mbx == 0));
-      tl[k] = ok ? ld_u32_cg((const uint32_t *)(Y + (int64_t)(mby * 16 + r) * wc + mbx * 16 + cq * 4)) : 0u;
+    for (int k = 0; k < 2; ++k) {
+      const int i = l + 32 * k, r = (i >> 1) - 4, left = i & 1;  // rows -4..15
+      const bool ok = i < 40 && !(r < 0 && mby == 0) && !(left && mbx == 0);
+      const uint8_t *p = Y + (int64_t)(mby * 16 + r) * wc + mbx * 16;
+      tl[k].w[0] = tl[k].w[1] = tl[k].w[2] = tl[k].w[3] = 0;
+      if (ok) { if (left) tl[k].w[0] = ld_u32_cg((const uint32_t *)(p - 4)); else tl[k] = ld_v16_cg(p); }
     }
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const int i = l + 32 * k, pl = i / 36, kk = i % 36, r = kk / 3 - 4, cq = kk % 3 - 1;  // row -4..7, quads -1..1
-      const bool ok = i < 72 && !((r < 0 && mby == 0) || (cq < 0 && mbx == 0));
-      tc[k] = ok ? ld_u32_cg((const uint32_t *)((pl ? Cr : Cb) + (int64_t)(mby * 8 + r) * cw + mbx * 8 + cq * 4)) : 0u;
+    for (int k = 0; k < 2; ++k) {
+      const int i = l + 32 * k, pl = i >= 24, j = i - 24 * pl, r = (j >> 1) - 4, left = j & 1;  // rows -4..7 of Cb, then Cr
+      const bool ok = i < 48 && !(r < 0 && mby == 0) && !(left && mbx == 0);
+      const uint8_t *p = (pl ? Cr : Cb) + (int64_t)(mby * 8 + r) * cw + mbx * 8;
+      tc[k].w[0] = tc[k].w[1] = 0;
+      if (ok) { if (left) tc[k].w[0] = ld_u32_cg((const uint32_t *)(p - 4)); else tc[k] = ld_v8_cg(p); }
     }
 #if !HWB_DEVICE_BUILD
-    for (int k = 0; k < 4; ++k) sm->pre_l[l][k] = tl[k];
-    for (int k = 0; k < 3; ++k) sm->pre_c[l][k] = tc[k];
+    for (int k = 0; k < 2; ++k) { sm->pre_l[l][k] = tl[k]; sm->pre_c[l][k] = tc[k]; }
 #endif
   HWB_LANES_END
 
@@ -173,18 +218,23 @@ HWB_FN void deblock_mb(const ChunkCtx &c, int pic, int mbx, int mby, DeblockScra
   // ---- tile to shared memory
   HWB_LANES(l)
 #if !HWB_DEVICE_BUILD
-    for (int k = 0; k < 4; ++k) tl[k] = sm->pre_l[l][k];
-    for (int k = 0; k < 3; ++k) tc[k] = sm->pre_c[l][k];
+    for (int k = 0; k < 2; ++k) { tl[k] = sm->pre_l[l][k]; tc[k] = sm->pre_c[l][k]; }
 #endif
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int i = l + 32 * k, r = i / 5 - 4, cq = i % 5 - 1;
-      if (i < 100 && !((r < 0 && mby == 0) || (cq < 0 && mbx == 0))) *(uint32_t *)(sm->luma + (r + 4) * DL_STRIDE + DL_OFF + cq * 4) = tl[k];
+    for (int k = 0; k < 2; ++k) {
+      const int i = l + 32 * k, r = (i >> 1) - 4, left = i & 1;
+      if (i < 40 && !(r < 0 && mby == 0) && !(left && mbx == 0)) {
+        uint8_t *t = sm->luma + (r + 4) * DL_STRIDE + DL_OFF;
+        if (left) *(uint32_t *)(t - 4) = tl[k].w[0]; else st_v16(t, tl[k]);
+      }
     }
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const int i = l + 32 * k, pl = i / 36, kk = i % 36, r = kk / 3 - 4, cq = kk % 3 - 1;
-      if (i < 72 && !((r < 0 && mby == 0) || (cq < 0 && mbx == 0))) *(uint32_t *)(sm->chroma[pl] + (r + 4) * DC_STRIDE + DC_OFF + cq * 4) = tc[k];
+    for (int k = 0; k < 2; ++k) {
+      const int i = l + 32 * k, pl = i >= 24, j = i - 24 * pl, r = (j >> 1) - 4, left = j & 1;
+      if (i < 48 && !(r < 0 && mby == 0) && !(left && mbx == 0)) {
+        uint8_t *t = sm->chroma[pl] + (r + 4) * DC_STRIDE + DC_OFF;
+        if (left) *(uint32_t *)(t - 4) = tc[k].w[0]; else st_v8(t, tc[k]);
+      }
     }
   HWB_LANES_END
 
@@ -228,22 +278,25 @@ HWB_FN void deblock_mb(const ChunkCtx &c, int pic, int mbx, int mby, DeblockScra
     HWB_LANES_END
   }
 
-  // ---- store rows -3..15 x columns -4..15 (the untouched corner is rewritten with its own value
-  //      only where this macroblock has exclusive access, see DESIGN.md "deblock wavefront")
+  // ---- store rows -3..15 x columns -4..15 (luma) / rows -2..7 x columns -4..7 (chroma).  The corner above-left is not
+  //      touched by this macroblock's filters and is left alone; rows above need a macroblock above, columns to the
+  //      left one to the left.  Own columns: one 16-byte / 8-byte store per row.
   HWB_LANES(l)
 #pragma unroll 1
-    for (int i = l; i < 95; i += 32) {
-      int r = i / 5 - 3, cq = i % 5 - 1;
-      if ((r < 0 && (mby == 0 || cq < 0)) || (cq < 0 && mbx == 0)) continue;
-      *(uint32_t *)(Y + (int64_t)(mby * 16 + r) * wc + mbx * 16 + cq * 4) =
-          *(const uint32_t *)(sm->luma + (r + 4) * DL_STRIDE + DL_OFF + cq * 4);
+    for (int i = l; i < 38; i += 32) {
+      const int r = (i >> 1) - 3, left = i & 1;
+      if ((r < 0 && (mby == 0 || left)) || (left && mbx == 0)) continue;
+      const uint8_t *t = sm->luma + (r + 4) * DL_STRIDE + DL_OFF;
+      uint8_t *p = Y + (int64_t)(mby * 16 + r) * wc + mbx * 16;
+      if (left) *(uint32_t *)(p - 4) = *(const uint32_t *)(t - 4); else st_v16(p, *(const Vec16 *)t);
     }
 #pragma unroll 1
-    for (int i = l; i < 60; i += 32) {
-      int pl = i / 30, k = i % 30, r = k / 3 - 2, cq = k % 3 - 1;
-      if ((r < 0 && (mby == 0 || cq < 0)) || (cq < 0 && mbx == 0)) continue;
-      *(uint32_t *)((pl ? Cr : Cb) + (int64_t)(mby * 8 + r) * cw + mbx * 8 + cq * 4) =
-          *(const uint32_t *)(sm->chroma[pl] + (r + 4) * DC_STRIDE + DC_OFF + cq * 4);
+    for (int i = l; i < 40; i += 32) {
+      const int pl = i >= 20, j = i - 20 * pl, r = (j >> 1) - 2, left = j & 1;
+      if ((r < 0 && (mby == 0 || left)) || (left && mbx == 0)) continue;
+      const uint8_t *t = sm->chroma[pl] + (r + 4) * DC_STRIDE + DC_OFF;
+      uint8_t *p = (pl ? Cr : Cb) + (int64_t)(mby * 8 + r) * cw + mbx * 8;
+      if (left) *(uint32_t *)(p - 4) = *(const uint32_t *)(t - 4); else st_v8(p, *(const Vec8 *)t);
     }
   HWB_LANES_END
 }

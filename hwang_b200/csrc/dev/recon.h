@@ -14,7 +14,7 @@ namespace hwb {
 enum { LT_STRIDE = 48, LT_OFF = 16, CT_STRIDE = 32, CT_OFF = 16 };
 
 // Per-warp scratch ("shared memory" on the device).
-struct ReconScratch {
+struct alignas(16) ReconScratch {
   // luma tile rows -1..15 (row r at (r+1)*LT_STRIDE), column c at LT_OFF + c, c in -1..23
   uint8_t luma[17 * LT_STRIDE];
   // chroma tiles rows -1..7, column c at CT_OFF + c
@@ -745,17 +745,26 @@ HWB_FN void recon_mb(const ChunkCtx &c, int pic, int mbx, int mby, ReconScratch 
       }
     HWB_LANES_END
   }
-  // ---- write back, and keep the right edge as the next macroblock's left border
+  // ---- write back (one 16-byte store per luma row, one 8-byte store per chroma row), and keep the right edge as the
+  //      next macroblock's left border
   HWB_LANES(l)
     if (l < 16) {
-      const uint32_t *s = (const uint32_t *)(sm->luma + (l + 1) * LT_STRIDE + LT_OFF);
-      uint32_t *d = (uint32_t *)(Y + (uint64_t)(mby * 16 + l) * wc + mbx * 16);
-      d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
+      const uint8_t *s = sm->luma + (l + 1) * LT_STRIDE + LT_OFF;
+      uint8_t *d = Y + (uint64_t)(mby * 16 + l) * wc + mbx * 16;
+#if HWB_DEVICE_BUILD
+      *(uint4 *)d = *(const uint4 *)s;
+#else
+      memcpy(d, s, 16);
+#endif
     } else {
       int pl = (l - 16) >> 3, r = l & 7;
-      const uint32_t *s = (const uint32_t *)(sm->chroma[pl] + (r + 1) * CT_STRIDE + CT_OFF);
-      uint32_t *d = (uint32_t *)((pl ? Cr : Cb) + (uint64_t)(mby * 8 + r) * cw + mbx * 8);
-      d[0] = s[0]; d[1] = s[1];
+      const uint8_t *s = sm->chroma[pl] + (r + 1) * CT_STRIDE + CT_OFF;
+      uint8_t *d = (pl ? Cr : Cb) + (uint64_t)(mby * 8 + r) * cw + mbx * 8;
+#if HWB_DEVICE_BUILD
+      *(uint2 *)d = *(const uint2 *)s;
+#else
+      memcpy(d, s, 8);
+#endif
     }
   HWB_LANES_END
   HWB_LANES(l)

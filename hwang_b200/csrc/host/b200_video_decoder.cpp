@@ -24,6 +24,8 @@ const int kMaxChunkPictures = 32767;  // frame indices travel as int16 (SliceDes
 B200VideoDecoder::B200VideoDecoder(int device_id, DeviceType output_type, int) : device_id_(device_id), output_type_(output_type) {
   if (hwb_dev_open(device_id, &dev_) != 0) dev_ = nullptr;
   if (const char *e = getenv("HWB_CHUNK_PICTURES")) { int v = atoi(e); if (v > 0) chunk_target_ = v; }
+  if (const char *e = getenv("HWB_RAMP_FIRST")) { int v = atoi(e); if (v > 0) ramp_first_ = v; }
+  ramp_target_ = ramp_first_;
   if (const char *e = getenv("HWB_GROUP_PICTURES")) { int v = atoi(e); if (v > 0) group_target_ = v; }
   if (const char *e = getenv("HWB_PICTURE_PROFILE")) picture_profile_ = atoi(e) != 0;
   if (const char *e = getenv("HWB_NO_RGB")) no_rgb_ = atoi(e) != 0;  // experiments: no fused RGB24 writeback (frames are converted on demand)
@@ -172,7 +174,9 @@ Result B200VideoDecoder::feed(const uint8_t *encoded_buffer, size_t encoded_size
   const size_t pb = picture_bytes();
   if (cur_ && idr) {
     const size_t n = cur_->pics.size();
-    if ((int)n >= chunk_target_ || (n + 1) * pb > memory_budget_ / 2) {
+    if (queue_.empty()) ramp_target_ = std::min(ramp_first_, chunk_target_);  // cold pipeline: start small again
+    if ((int)n >= std::min(ramp_target_, chunk_target_) || (n + 1) * pb > memory_budget_ / 2) {
+      ramp_target_ = std::min(chunk_target_, ramp_target_ * 2);
       Result r = submit_current();
       if (!r.ok) return r;
     }

@@ -66,7 +66,7 @@ class B200VideoDecoder : public VideoDecoderInterface {
   // Zero-copy variant of get_frame for DeviceType::GPU consumers: the oldest frame's RGB24 in the decoder's own device
   // memory.  The pointer stays valid until the next wait_until_frames_copied() / configure() / destruction.
   Result get_frame_device(uint8_t **device_ptr);
-  void set_chunk_pictures(int n) { chunk_target_ = n < 1 ? 1 : n; }
+  void set_chunk_pictures(int n) { chunk_target_ = n < 1 ? 1 : n; ramp_first_ = chunk_target_; }  // explicit size: no ramp
   // The caller feeds from a thread of its own (DecoderAutomata): feed() may then wait for the consumer to free device
   // memory instead of failing when the in-flight chunks reach the memory budget.
   void set_feeder_may_block(bool v) { feeder_may_block_ = v; }
@@ -131,8 +131,14 @@ class B200VideoDecoder : public VideoDecoderInterface {
   // latency-bound per slice, so a batch must hold many slices; several batches are in flight at once (entropy streams
   // rotate), which overlaps host parsing, entropy decoding of later batches, the picture kernel of earlier ones and the
   // copies to the host.
+  // Batches ramp up: the first batch of a cold pipeline is small (ramp_first_ pictures) so that the first frames leave
+  // early -- every batch costs at least one intra slice's entropy latency before its pictures can be reconstructed --
+  // and each following batch doubles up to chunk_target_ (large batches are the efficient ones).  Measured on the
+  // 3000-frame benchmark clip: first frames on the host after 460 ms with equal batches, with the copy engine the
+  // bottleneck from then on.
   int chunk_target_ = 960;
-  int group_target_ = 300;  // pictures per GOP group inside a batch: groups complete (and their frames leave) one after the other
+  int ramp_first_ = 120, ramp_target_ = 120;
+  int group_target_ = 1 << 30;  // pictures per GOP group inside a batch (work order of the picture kernel); default: one group
   bool feeder_may_block_ = false, defer_submit_ = false, no_rgb_ = false, picture_profile_ = false;
   std::unique_ptr<Chunk> cur_;
   std::deque<std::unique_ptr<Chunk>> queue_;    // submitted chunks, oldest first
