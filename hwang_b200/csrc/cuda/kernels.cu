@@ -88,7 +88,7 @@ union PictureScratch {
   DeblockScratch deblock;
 };
 
-// 6 blocks (24 warps) per SM: 80 registers.  Every warp is a generalist and chooses the kind of its next item when it
+// 64 registers (8 blocks per SM possible; the host picks 5 next to a running entropy kernel, 7 otherwise).  Every warp is a generalist and chooses the kind of its next item when it
 // takes it: the head of the deblocking list if the rows it consumes are already being produced (the reconstruction of
 // the row below has started), otherwise the head of the reconstruction list, otherwise (reconstruction exhausted)
 // the deblocking head whatever its state.  Deblocking first: it completes pictures, which releases the rows of the
@@ -104,13 +104,11 @@ union PictureScratch {
 // chain completes, Z finishes, and its warp picks again.  Either way that pick was not the last one.
 // `split` (HWB_PICTURE_SPLIT, 0 = dynamic) keeps the static assignment for experiments: warps whose global index modulo
 // 5 is below it take deblocking items only until those run out.
-__global__ void __launch_bounds__(kThreads, 6) picture_kernel(const __grid_constant__ ChunkCtx c, int32_t *ticket, int split) {
+__global__ void __launch_bounds__(kThreads, 8) picture_kernel(const __grid_constant__ ChunkCtx c, int32_t *ticket, int split) {
   __shared__ PictureScratch sm[kWarpsPerBlock];
   PictureScratch *my = &sm[threadIdx.x >> 5];
-  // A corrupt or unsupported stream leaves MbInfo / coefficient offsets of the failed slice undefined: the entropy
-  // kernel (complete by now: an event orders the launches) has raised the chunk's error flag, the host reports it
-  // when the chunk's first frame is popped, and nothing may be dereferenced here.
-  if (*((volatile const int32_t *)c.error_flag) != 0) return;
+  // A corrupt or unsupported stream leaves MbInfo / coefficient offsets of the failed slice undefined: the rows check
+  // the batch's error flag once the entropy stage of their picture is complete (csrc/dev/picture.h) and touch nothing then.
   // split > 0: static roles by SM: the SMs whose id falls into the first `split` percent only take deblocking items
   // (until they run out), the others only reconstruction items.  Both stages are bound by instruction fetch; an SM that
   // stays inside one of the two code bodies keeps its instruction caches for it, and the two SMs of a TPC must agree
@@ -200,6 +198,7 @@ __global__ void __launch_bounds__(256) yuv_kernel(ChunkCtx c, int frame, int cro
 struct hwb_dev {
   int device = 0;
   int sms = 148;
+  int entropy_bpsm = 3, picture_bpsm = 6;  // resident blocks per SM (hwb_dev_set_occupancy)
   cudaStream_t streams[HWB_NUM_STREAMS];
   std::string err;
   std::atomic<uint64_t> launches{0};
@@ -303,6 +302,15 @@ static int grid_for(hwb_dev *d, int work_warps, int blocks_per_sm) {
   return blocks < cap ? (blocks < 1 ? 1 : blocks) : cap;
 }
 
+// Blocks per SM of the two kernels.  When the picture kernel of a batch is launched together with its entropy kernel
+// (it waits for the entropy stage picture by picture), both grids must fit an SM at the same time whatever order the
+// hardware places their blocks in -- a picture kernel that filled the machine first would wait for entropy blocks that
+// can never start.  2 entropy blocks (at most 96 registers x 128 threads) + 5 picture blocks (64 x 128) = at most 65536 of the 65536
+// registers of an SM, 19 + 94 KB of shared memory, 28 of 64 warps.
+void hwb_dev_set_occupancy(hwb_dev *d, int entropy_blocks_per_sm, int picture_blocks_per_sm) {
+  d->entropy_bpsm = entropy_blocks_per_sm; d->picture_bpsm = picture_blocks_per_sm;
+}
+
 int hwb_dev_entropy(hwb_dev *d, int s, const ChunkCtx *c, int32_t *ticket, int mode) {
   cudaSetDevice(d->device);
   // Resident warps per SM are capped at 12 (3 blocks of 4 warps): the slice decoder is branchy code larger than the
@@ -310,8 +318,8 @@ int hwb_dev_entropy(hwb_dev *d, int s, const ChunkCtx *c, int32_t *ticket, int m
   // misses, and those misses saturate the GPC-level instruction cache (measured at 20 warps per SM: 67% of the stall
   // cycles are "no instruction", gcc instruction requests at 67% of peak).  Sweep on the 3000-slice benchmark chunk:
   // 1 block/SM 561 ms, 2: 411, 3: 394, 4: 402, 5: 409, 8: 430.  HWB_ENTROPY_BLOCKS_PER_SM overrides.
-  static int bpsm = [] { const char *e = getenv("HWB_ENTROPY_BLOCKS_PER_SM"); int v = e ? atoi(e) : 0; return v > 0 ? v : 3; }();
-  const int grid = grid_for(d, c->num_tickets, bpsm);
+  static int bpsm_env = [] { const char *e = getenv("HWB_ENTROPY_BLOCKS_PER_SM"); int v = e ? atoi(e) : 0; return v; }();
+  const int grid = grid_for(d, c->num_tickets, bpsm_env > 0 ? bpsm_env : d->entropy_bpsm);
   if (mode == 3) entropy_cabac_ip_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);
   else if (mode == 1) entropy_cabac_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);
   else if (mode == 0) entropy_cavlc_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);
@@ -322,7 +330,8 @@ int hwb_dev_entropy(hwb_dev *d, int s, const ChunkCtx *c, int32_t *ticket, int m
 }
 int hwb_dev_picture(hwb_dev *d, int s, const ChunkCtx *c, int32_t *ticket) {
   cudaSetDevice(d->device);
-  static int bpsm = [] { const char *e = getenv("HWB_PICTURE_BLOCKS_PER_SM"); int v = e ? atoi(e) : 0; return v > 0 ? v : 6; }();
+  static int bpsm_env = [] { const char *e = getenv("HWB_PICTURE_BLOCKS_PER_SM"); int v = e ? atoi(e) : 0; return v; }();
+  const int bpsm = bpsm_env > 0 ? bpsm_env : d->picture_bpsm;
   // percent of the SMs that deblock (0 = every warp chooses dynamically, see picture_kernel)
   static int split_pct = [] { const char *e = getenv("HWB_PICTURE_SPLIT"); int v = e ? atoi(e) : -1; return v >= 0 && v <= 90 ? v : 40; }();
   const int items = c->num_recon_items + c->num_deblock_items;

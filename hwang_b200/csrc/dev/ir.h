@@ -93,6 +93,7 @@ struct SliceDesc {
 // a chunk, so frame index == picture index and there are no write-after-read hazards.
 struct ChunkCtx {
   int32_t mb_w, mb_h, nmb;
+  int32_t nmb_stride;  // macroblocks per picture in the per-picture arrays below (>= nmb; a multiple of 32 on the GPU: pictures never share a 128-byte line)
   int32_t wc, hc;  // coded luma size (multiples of 16)
   int32_t num_pics, num_slices;
   uint8_t *frames;         // [frame] planar Y (wc*hc), Cb, Cr (wc/2*hc/2)
@@ -136,18 +137,18 @@ struct ChunkCtx {
 HWB_HD uint8_t *frame_y(const ChunkCtx &c, int f) { return c.frames + (uint64_t)f * c.frame_stride; }
 HWB_HD uint8_t *frame_cb(const ChunkCtx &c, int f) { return frame_y(c, f) + (uint64_t)c.wc * c.hc; }
 HWB_HD uint8_t *frame_cr(const ChunkCtx &c, int f) { return frame_cb(c, f) + (uint64_t)(c.wc >> 1) * (c.hc >> 1); }
-HWB_HD MbInfo *pic_mbinfo(const ChunkCtx &c, int f) { return c.mbinfo + (uint64_t)f * c.nmb; }
+HWB_HD MbInfo *pic_mbinfo(const ChunkCtx &c, int f) { return c.mbinfo + (uint64_t)f * c.nmb_stride; }
 HWB_HD int16_t *pic_mv(const ChunkCtx &c, int f, int list) {
-  return c.mv + ((uint64_t)f * 2 + list) * c.nmb * 32;
+  return c.mv + ((uint64_t)f * 2 + list) * c.nmb_stride * 32;
 }
 HWB_HD int8_t *pic_refidx(const ChunkCtx &c, int f, int list) {
-  return c.refidx + ((uint64_t)f * 2 + list) * c.nmb * 4;
+  return c.refidx + ((uint64_t)f * 2 + list) * c.nmb_stride * 4;
 }
 HWB_HD int16_t *pic_refpic(const ChunkCtx &c, int f, int list) {
-  return c.refpic + ((uint64_t)f * 2 + list) * c.nmb * 4;
+  return c.refpic + ((uint64_t)f * 2 + list) * c.nmb_stride * 4;
 }
 HWB_HD int16_t *pic_coefs(const ChunkCtx &c, int f) {
-  return c.coefs + (uint64_t)f * c.nmb * SLOTS_PER_MB * COEFS_PER_SLOT;
+  return c.coefs + (uint64_t)f * c.nmb_stride * SLOTS_PER_MB * COEFS_PER_SLOT;
 }
 
 }  // namespace hwb

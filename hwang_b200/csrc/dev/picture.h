@@ -110,6 +110,16 @@ HWB_FN void recon_row(const ChunkCtx &c, int pic, int y, ReconScratch *my) {
   // index).  Waiting per macroblock instead of for whole rows lets a picture follow its reference at a distance of a
   // few macroblocks: the pictures of a GOP form one long diagonal wavefront.  Pictures with more references than
   // are tracked here wait for complete rows.
+  // The picture kernel may be launched together with the batch's entropy kernel: a picture is touched only once all
+  // its slices are entropy-decoded (the per-picture arrays are padded so that pictures never share a cache line, which
+  // makes the plain loads of macroblock records, motion and coefficients safe).  A corrupt slice raises the batch's
+  // error flag before it reports completion: nothing of the batch is dereferenced from then on, the rows only
+  // report progress so that nobody waits for them.
+  for (int i = 0; i < pd.num_slices; ++i) {
+    Progress ent = {c.entropy_prog + pd.first_slice + i, -1};
+    wait_progress(ent, c.nmb);
+  }
+  if (ld_u32_cg((const uint32_t *)c.error_flag) != 0) { publish_progress(prog + y, c.mb_w); return; }
   Progress dep[MAX_TRACKED_DEPS];
   int ndep = 0, reach_x = 0;
   if (has_inter) {
@@ -167,7 +177,9 @@ HWB_FN void deblock_row(const ChunkCtx &c, int pic, int y, DeblockScratch *my) {
   Progress below = {rprog + y + 1, last_row ? (1 << 30) : -1};
   Progress above = {prog + y - 1, y > 0 ? -1 : (1 << 30)};
   ProfClock pc(c.prof);
-  for (int x = 0; x < c.mb_w; ++x) {
+  wait_progress(mine, 1);  // the row's reconstruction has started, so the entropy stage of the picture is complete
+  const bool failed = ld_u32_cg((const uint32_t *)c.error_flag) != 0;
+  for (int x = 0; x < c.mb_w && !failed; ++x) {
     const int lag = x + 2 < c.mb_w ? x + 2 : c.mb_w;
     wait_progress(mine, x + 1);
     wait_progress(below, lag);
@@ -192,6 +204,7 @@ HWB_FN void deblock_row(const ChunkCtx &c, int pic, int y, DeblockScratch *my) {
   }
   // picture complete?  Every row's samples and RGB24 were written before its count (fence), so whoever counts the last
   // row may tell the host (system-scope fence: the copy engine reads what the host was promised).
+  if (failed) { publish_progress(prog + y, c.mb_w); return; }  // the host learns about the error when the batch ends
 #if HWB_DEVICE_BUILD
   __syncwarp();
   if ((threadIdx.x & 31) == 0) {

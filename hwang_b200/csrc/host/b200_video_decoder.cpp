@@ -26,6 +26,7 @@ B200VideoDecoder::B200VideoDecoder(int device_id, DeviceType output_type, int) :
   if (const char *e = getenv("HWB_CHUNK_PICTURES")) { int v = atoi(e); if (v > 0) chunk_target_ = v; }
   if (const char *e = getenv("HWB_RAMP_FIRST")) { int v = atoi(e); if (v > 0) ramp_first_ = v; }
   ramp_target_ = ramp_first_;
+  if (const char *e = getenv("HWB_CONCURRENT")) concurrent_ = atoi(e) != 0;
   if (const char *e = getenv("HWB_GROUP_PICTURES")) { int v = atoi(e); if (v > 0) group_target_ = v; }
   if (const char *e = getenv("HWB_PICTURE_PROFILE")) picture_profile_ = atoi(e) != 0;
   if (const char *e = getenv("HWB_NO_RGB")) no_rgb_ = atoi(e) != 0;  // experiments: no fused RGB24 writeback (frames are converted on demand)
@@ -232,6 +233,7 @@ Result B200VideoDecoder::submit_current() {
   if (!ch->seg_first.empty() && ch->seg_first.back() == -1) ch->seg_first.pop_back();
   const int P = (int)ch->pics.size(), S = (int)ch->slices.size();
   const int mb_w = stream_.mb_w(), mb_h = stream_.mb_h(), nmb = mb_w * mb_h;
+  const size_t nmb_s = align_up((size_t)nmb, 32);  // per-picture stride of the macroblock arrays: pictures never share a 128-byte line
   // ---- display order per segment; unrequested non-reference pictures are not decoded at all (their frame buffers stay
   // undefined: nothing references them and the consumer drops them); wanted pictures get an RGB24 slot
   ch->order.resize(P);
@@ -280,9 +282,9 @@ Result B200VideoDecoder::submit_current() {
   const size_t rgb_bytes = (size_t)width_ * height_ * 3;
   size_t off = 0;
   auto take = [&](size_t n) { size_t o = off; off = align_up(off + n, 256); return o; };
-  const size_t o_frames = take(fs * P), o_mbinfo = take((size_t)P * nmb * sizeof(hwb::MbInfo)), o_mv = take((size_t)P * 2 * nmb * 64),
-               o_refidx = take((size_t)P * 2 * nmb * 4), o_refpic = take((size_t)P * 2 * nmb * 8),
-               o_coefs = take((size_t)P * nmb * hwb::SLOTS_PER_MB * 32), o_ectx = take((size_t)S * mb_w * sizeof(hwb::NbCtx)),
+  const size_t o_frames = take(fs * P), o_mbinfo = take((size_t)P * nmb_s * sizeof(hwb::MbInfo)), o_mv = take((size_t)P * 2 * nmb_s * 64),
+               o_refidx = take((size_t)P * 2 * nmb_s * 4), o_refpic = take((size_t)P * 2 * nmb_s * 8),
+               o_coefs = take((size_t)P * nmb_s * hwb::SLOTS_PER_MB * 32), o_ectx = take((size_t)S * mb_w * sizeof(hwb::NbCtx)),
                o_bits = take(ch->bitstream.size() + 64), o_pics = take((size_t)P * sizeof(PicDesc)), o_slices = take((size_t)S * sizeof(SliceDesc)),
                o_ritems = take(recon_items.size() * 4), o_ditems = take(deblock_items.size() * 4), o_order = take((size_t)S * 4),
                o_rgb = take(rgb_bytes * (size_t)nrgb);
@@ -310,7 +312,7 @@ Result B200VideoDecoder::submit_current() {
   uint8_t *b = ch->slab.base;
   ChunkCtx &c = ch->ctx;
   memset(&c, 0, sizeof(c));
-  c.mb_w = mb_w; c.mb_h = mb_h; c.nmb = nmb; c.wc = mb_w * 16; c.hc = mb_h * 16; c.num_pics = P; c.num_slices = S;
+  c.mb_w = mb_w; c.mb_h = mb_h; c.nmb = nmb; c.nmb_stride = (int32_t)nmb_s; c.wc = mb_w * 16; c.hc = mb_h * 16; c.num_pics = P; c.num_slices = S;
   c.frames = b + o_frames; c.frame_stride = fs;
   c.mbinfo = (hwb::MbInfo *)(b + o_mbinfo); c.mv = (int16_t *)(b + o_mv); c.refidx = (int8_t *)(b + o_refidx); c.refpic = (int16_t *)(b + o_refpic);
   c.coefs = (int16_t *)(b + o_coefs); c.ectx = b + o_ectx; c.ectx_stride = (uint64_t)mb_w * sizeof(hwb::NbCtx);
@@ -381,10 +383,18 @@ Result B200VideoDecoder::submit_current() {
     for (auto &sl : ch->slices) has_b |= sl.slice_type == hwb::SLICE_B;
     if (!has_b) mode = 3;
   }
+  // The picture kernel is launched right behind the entropy kernel, on its own stream, and waits for the entropy stage
+  // picture by picture (csrc/dev/picture.h): the GOPs whose slices are done are reconstructed, converted and copied out
+  // while the long intra slices of later GOPs are still being decoded.  Both grids are sized to fit the SMs together
+  // (hwb_dev_set_occupancy).  HWB_CONCURRENT=0: the picture kernel starts when the entropy kernel has finished.
+  hwb_dev_set_occupancy(dev_, concurrent_ ? 2 : 3, concurrent_ ? 5 : 7);
+  hwb_event *ev_inputs = hwb_dev_event_create(dev_);
+  rc |= hwb_dev_event_record(dev_, ev_inputs, st);  // uploads and the zeroed counters
   if (c.num_tickets > 0) rc |= hwb_dev_entropy(dev_, st, &c, tickets, mode);
   rc |= hwb_dev_event_record(dev_, ch->ev_entropy, st);
-  rc |= hwb_dev_stream_wait(dev_, st_pic, ch->ev_entropy);
-  rc |= hwb_dev_event_record(dev_, ch->ev_picture, st_pic);  // previous picture kernel done AND this chunk's entropy done
+  rc |= hwb_dev_stream_wait(dev_, st_pic, concurrent_ ? ev_inputs : ch->ev_entropy);
+  hwb_dev_event_destroy(dev_, ev_inputs);  // the wait already enqueued keeps its own reference
+  rc |= hwb_dev_event_record(dev_, ch->ev_picture, st_pic);  // previous picture kernel done (and, without concurrency, this batch's entropy stage)
   rc |= hwb_dev_picture(dev_, st_pic, &c, tickets + 1);
   rc |= hwb_dev_event_record(dev_, ch->ev_done, st_pic);
   if (rc) { sticky_error_ = std::string("B200 decoder: CUDA launch failed: ") + hwb_dev_error(dev_); return Result(false, sticky_error_); }

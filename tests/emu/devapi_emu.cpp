@@ -35,6 +35,7 @@ int hwb_dev_d2h(hwb_dev *, int, void *dst, const void *src, size_t n) { memcpy(d
 int hwb_dev_d2d(hwb_dev *, int, void *dst, const void *src, size_t n) { memcpy(dst, src, n); return 0; }
 int hwb_dev_memset(hwb_dev *, int, void *dst, int v, size_t n) { memset(dst, v, n); return 0; }
 
+void hwb_dev_set_occupancy(hwb_dev *, int, int) {}
 int hwb_dev_entropy(hwb_dev *d, int, const ChunkCtx *c, int32_t *, int) {
   uint8_t states[1024];
   for (int t = 0; t < c->num_tickets; ++t) { SliceDec sd; decode_slice(*c, c->entropy_order[t], states, &sd); }
@@ -46,7 +47,7 @@ int hwb_dev_entropy(hwb_dev *d, int, const ChunkCtx *c, int32_t *, int) {
 // could deadlock on the GPU, which is reported as a device error.
 int hwb_dev_picture(hwb_dev *d, int, const ChunkCtx *c, int32_t *) {
   d->launches++;
-  if (*c->error_flag) return 0;  // as the CUDA kernel: nothing is dereferenced after an entropy error
+  if (*c->error_flag) return 0;  // as the CUDA kernel's rows: nothing is dereferenced after an entropy error
   PictureScratchEmu *smp = new PictureScratchEmu(); PictureScratchEmu &sm = *smp;
   auto rows_done = [&](const int32_t *prog, int pic, int y) { return y < 0 || y >= c->mb_h || prog[(size_t)pic * c->mb_h + y] >= c->mb_w; };
   auto recon_ready = [&](uint32_t it) {

@@ -218,7 +218,7 @@ struct Encoder {
     pics.resize(NSLOT); slices.resize(NSLOT * MAXSL); prog.resize(NSLOT * (MAXSL + 2 * mb_h));
     ectx.resize((size_t)NSLOT * MAXSL * mb_w * sizeof(NbCtx));
     memset(&c, 0, sizeof(c));
-    c.mb_w = mb_w; c.mb_h = mb_h; c.nmb = nmb; c.wc = wc; c.hc = hc; c.num_pics = NSLOT; c.num_slices = NSLOT * MAXSL;
+    c.mb_w = mb_w; c.mb_h = mb_h; c.nmb = nmb; c.nmb_stride = nmb; c.wc = wc; c.hc = hc; c.num_pics = NSLOT; c.num_slices = NSLOT * MAXSL;
     c.frames = frames.data(); c.frame_stride = fs; c.mbinfo = mbinfo.data(); c.mv = mv.data(); c.refidx = refidx.data();
     c.refpic = refpic.data(); c.coefs = coefs.data(); c.ectx = ectx.data(); c.ectx_stride = (uint64_t)mb_w * sizeof(NbCtx);
     c.bitstream = nullptr; c.pics = pics.data(); c.slices = slices.data(); c.entropy_prog = prog.data();
