@@ -59,6 +59,43 @@ __device__ __forceinline__ int warp_ticket(int32_t *ticket) {
 // One lane per warp walks a slice.  All of its state (neighbour caches, CABAC contexts, scratch) sits in shared
 // memory: thread-local memory is interleaved across the 32 lanes, so a single active lane would touch one cache
 // line per word and thrash L1 (measured: ~4000 cycles per CABAC bin before this change).
+// Ticket hand-out.  Intra slices carry several times the bits of inter slices and every one of them is a single
+// warp's serial work: the intra slices of a batch set the earliest moment its first pictures can be reconstructed.  A
+// warp decodes an intra slice at full speed only while the SM's instruction caches hold the intra path; next to
+// inter-slice warps (a different 30 KB of code) it runs 1.5x slower.  So the SMs [0, intra_sms) are reserved: their
+// warps take the intra tickets (ticket[3]) and nothing else until those are gone, everybody else takes inter tickets
+// (ticket[0]).  Invariant kept from the single-queue version: no inter ticket is handed out before every intra ticket
+// has been taken (a B slice may wait for its co-located picture's slice, which must therefore be running or done).  If
+// the reserved SMs hold no block of this launch (busy device), the others take the intra tickets after a grace period
+// -- no warp ever leaves while a ticket is untaken, so nothing can be stranded.
+__device__ __forceinline__ int take_ticket(int32_t *counter, int limit) {
+  int t = 0;
+  if ((threadIdx.x & 31) == 0) t = atomicAdd(counter, 1);
+  t = __shfl_sync(0xffffffffu, t, 0);
+  return t < limit ? t : -1;
+}
+__device__ __forceinline__ int peek_counter(const int32_t *counter) {
+  int v = 0;
+  if ((threadIdx.x & 31) == 0) asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+  return __shfl_sync(0xffffffffu, v, 0);
+}
+__device__ int next_entropy_ticket(const ChunkCtx &c, int32_t *ticket, bool reserved, long long t_start) {
+  const int n_intra = c.num_intra_tickets, n_inter = c.num_tickets - c.num_intra_tickets;
+  for (;;) {
+    if (n_intra > 0 && peek_counter(ticket + 3) < n_intra) {
+      if (reserved || c.intra_sms == 0 || clock64() - t_start > 100000) {  // ~50 us of grace for the reserved SMs
+        const int t = take_ticket(ticket + 3, n_intra);
+        if (t >= 0) return t;
+      } else {
+        __nanosleep(500);
+      }
+      continue;
+    }
+    const int t = take_ticket(ticket, n_inter);
+    return t >= 0 ? t + n_intra : -1;
+  }
+}
+
 #define HWB_ENTROPY_KERNEL(NAME, NS)                                                                  \
   __global__ void __launch_bounds__(kThreads) NAME(ChunkCtx cparam, int32_t *ticket) {                \
     __shared__ NS::SliceDec sdec[kWarpsPerBlock];                                                     \
@@ -67,9 +104,13 @@ __device__ __forceinline__ int warp_ticket(int32_t *ticket) {
     for (int i = threadIdx.x; i < 256; i += kThreads) hwb_fused_sm[i] = cabac_fused[i];               \
     __syncthreads();                                                                                  \
     const int w = threadIdx.x >> 5;                                                                   \
+    unsigned smid;                                                                                    \
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));                                                          \
+    const bool reserved = (int)smid < c.intra_sms;                                                    \
+    const long long t_start = clock64();                                                              \
     for (;;) {                                                                                        \
-      const int t = warp_ticket(ticket);                                                              \
-      if (t >= c.num_tickets) return;                                                                  \
+      const int t = next_entropy_ticket(c, ticket, reserved, t_start);                                \
+      if (t < 0) return;                                                                              \
       const int s = c.entropy_order[t];                                                               \
       NS::decode_slice(c, s, nullptr, &sdec[w]);                                                      \
       __syncwarp();                                                                                   \
@@ -121,6 +162,10 @@ __global__ void __launch_bounds__(kThreads, 8) picture_kernel(const __grid_const
     unsigned smid, nsmid;
     asm("mov.u32 %0, %%smid;" : "=r"(smid));
     asm("mov.u32 %0, %%nsmid;" : "=r"(nsmid));
+    // the SMs reserved for intra slices (entropy stage of this and later batches) stay free of picture work; the grid is
+    // large (split > 0), so the other SMs hold plenty of blocks
+    if ((int)smid < c.intra_sms) return;
+    smid -= c.intra_sms; nsmid -= c.intra_sms;
     const int mode = split / 1000, pct = split % 1000;  // experiments: how the SMs of the two roles are spread over the chip
     if (mode == 1) fixed_deblock = (int)(smid * 100u / nsmid) < pct;               // one contiguous range of SM ids
     else if (mode == 2) fixed_deblock = (int)(((smid >> 1) * 37u) % 100u) < pct;   // whole TPCs (SM pairs), scattered

@@ -93,7 +93,8 @@ HWB_HD int item_row(uint32_t it) { return (int)((it >> 1) & ((1u << ITEM_ROW_BIT
 // (-1: the row has no inter macroblock).  Rows < reach are final once row `reach` is deblocked (its top-edge filter is
 // the last thing that modifies row reach-1).
 HWB_HD int reference_row_needed(const ChunkCtx &c, int pic, int y) {
-  const int reach = c.mv_reach[(size_t)pic * c.mb_h + y];
+  // ld.global.cg: several pictures share a cache line of this array, and the entropy stage may still be writing the others'
+  const int reach = (int)ld_u32_cg((const uint32_t *)c.mv_reach + (size_t)pic * c.mb_h + y);
   if (reach <= 0) return -1;
   return reach < c.mb_h ? reach : c.mb_h - 1;
 }
@@ -125,7 +126,7 @@ HWB_FN void recon_row(const ChunkCtx &c, int pic, int y, ReconScratch *my) {
   if (has_inter) {
     const int row = reference_row_needed(c, pic, y);
     if (row >= 0) {
-      reach_x = c.mv_reach_x[(size_t)pic * c.mb_h + y];
+      reach_x = (int)ld_u32_cg((const uint32_t *)c.mv_reach_x + (size_t)pic * c.mb_h + y);
       if (pd.num_dep <= MAX_TRACKED_DEPS) {
         ndep = pd.num_dep;
         for (int i = 0; i < MAX_TRACKED_DEPS; ++i)

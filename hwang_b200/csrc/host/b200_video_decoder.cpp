@@ -27,6 +27,7 @@ B200VideoDecoder::B200VideoDecoder(int device_id, DeviceType output_type, int) :
   if (const char *e = getenv("HWB_RAMP_FIRST")) { int v = atoi(e); if (v > 0) ramp_first_ = v; }
   ramp_target_ = ramp_first_;
   if (const char *e = getenv("HWB_CONCURRENT")) concurrent_ = atoi(e) != 0;
+  if (const char *e = getenv("HWB_INTRA_RESERVE")) intra_reserve_ = atoi(e) != 0;
   if (const char *e = getenv("HWB_GROUP_PICTURES")) { int v = atoi(e); if (v > 0) group_target_ = v; }
   if (const char *e = getenv("HWB_PICTURE_PROFILE")) picture_profile_ = atoi(e) != 0;
   if (const char *e = getenv("HWB_NO_RGB")) no_rgb_ = atoi(e) != 0;  // experiments: no fused RGB24 writeback (frames are converted on demand)
@@ -370,6 +371,9 @@ Result B200VideoDecoder::submit_current() {
   if (!order.empty()) rc |= hwb_dev_h2d(dev_, st, b + o_order, order.data(), order.size() * 4);
   c.entropy_order = (const int32_t *)(b + o_order);
   c.num_tickets = (int32_t)order.size();
+  for (int32_t i : order) if (ch->slices[i].slice_type == hwb::SLICE_I) c.num_intra_tickets++;
+  // SMs reserved for the intra slices: 12 warps each (see kernels.cu), at most an eighth of the device
+  if (intra_reserve_ && c.num_intra_tickets > 0 && c.num_intra_tickets < c.num_tickets) c.intra_sms = std::min(18, (c.num_intra_tickets + 11) / 12);
   rc |= hwb_dev_memset(dev_, st, sync, 0, n_sync * 4);
   stats_.h2d_bytes += ch->bitstream.size() + (size_t)P * sizeof(PicDesc) + (size_t)S * sizeof(SliceDesc) + (recon_items.size() * 2 + order.size()) * 4;
   // a copy from pageable memory has been staged by the time cudaMemcpyAsync returns: the buffer can be reused
