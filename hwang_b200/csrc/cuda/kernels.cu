@@ -129,7 +129,7 @@ union PictureScratch {
   DeblockScratch deblock;
 };
 
-// 64 registers (8 blocks per SM possible; the host picks 5 next to a running entropy kernel, 7 otherwise).  Every warp is a generalist and chooses the kind of its next item when it
+// 80 registers, 6 blocks (24 warps) per SM.  Without static roles every warp is a generalist and chooses the kind of its next item when it
 // takes it: the head of the deblocking list if the rows it consumes are already being produced (the reconstruction of
 // the row below has started), otherwise the head of the reconstruction list, otherwise (reconstruction exhausted)
 // the deblocking head whatever its state.  Deblocking first: it completes pictures, which releases the rows of the
@@ -145,7 +145,7 @@ union PictureScratch {
 // chain completes, Z finishes, and its warp picks again.  Either way that pick was not the last one.
 // `split` (HWB_PICTURE_SPLIT, 0 = dynamic) keeps the static assignment for experiments: warps whose global index modulo
 // 5 is below it take deblocking items only until those run out.
-__global__ void __launch_bounds__(kThreads, 8) picture_kernel(const __grid_constant__ ChunkCtx c, int32_t *ticket, int split) {
+__global__ void __launch_bounds__(kThreads, 6) picture_kernel(const __grid_constant__ ChunkCtx c, int32_t *ticket, int split) {
   __shared__ PictureScratch sm[kWarpsPerBlock];
   PictureScratch *my = &sm[threadIdx.x >> 5];
   // A corrupt or unsupported stream leaves MbInfo / coefficient offsets of the failed slice undefined: the rows check
@@ -350,8 +350,8 @@ static int grid_for(hwb_dev *d, int work_warps, int blocks_per_sm) {
 // Blocks per SM of the two kernels.  When the picture kernel of a batch is launched together with its entropy kernel
 // (it waits for the entropy stage picture by picture), both grids must fit an SM at the same time whatever order the
 // hardware places their blocks in -- a picture kernel that filled the machine first would wait for entropy blocks that
-// can never start.  2 entropy blocks (at most 96 registers x 128 threads) + 5 picture blocks (64 x 128) = at most 65536 of the 65536
-// registers of an SM, 19 + 94 KB of shared memory, 28 of 64 warps.
+// can never start.  2 entropy blocks (at most 96 registers x 128 threads) + 4 picture blocks (80 x 128) = 65536 of the 65536
+// registers of an SM, 19 + 75 KB of shared memory, 24 of 64 warps.
 void hwb_dev_set_occupancy(hwb_dev *d, int entropy_blocks_per_sm, int picture_blocks_per_sm) {
   d->entropy_bpsm = entropy_blocks_per_sm; d->picture_bpsm = picture_blocks_per_sm;
 }

@@ -372,7 +372,9 @@ Result B200VideoDecoder::submit_current() {
   c.entropy_order = (const int32_t *)(b + o_order);
   c.num_tickets = (int32_t)order.size();
   for (int32_t i : order) if (ch->slices[i].slice_type == hwb::SLICE_I) c.num_intra_tickets++;
-  // SMs reserved for the intra slices: 12 warps each (see kernels.cu), at most an eighth of the device
+  // HWB_INTRA_RESERVE=1: SMs reserved for the intra slices, 12 warps each (see kernels.cu), at most an eighth of the
+  // device.  Off by default: measured, the intra slices finish no earlier (their fetch misses queue at the GPC-level
+  // instruction cache, which the reservation does not isolate), and the picture kernel loses those SMs.
   if (intra_reserve_ && c.num_intra_tickets > 0 && c.num_intra_tickets < c.num_tickets) c.intra_sms = std::min(18, (c.num_intra_tickets + 11) / 12);
   rc |= hwb_dev_memset(dev_, st, sync, 0, n_sync * 4);
   stats_.h2d_bytes += ch->bitstream.size() + (size_t)P * sizeof(PicDesc) + (size_t)S * sizeof(SliceDesc) + (recon_items.size() * 2 + order.size()) * 4;
@@ -387,11 +389,13 @@ Result B200VideoDecoder::submit_current() {
     for (auto &sl : ch->slices) has_b |= sl.slice_type == hwb::SLICE_B;
     if (!has_b) mode = 3;
   }
-  // The picture kernel is launched right behind the entropy kernel, on its own stream, and waits for the entropy stage
-  // picture by picture (csrc/dev/picture.h): the GOPs whose slices are done are reconstructed, converted and copied out
-  // while the long intra slices of later GOPs are still being decoded.  Both grids are sized to fit the SMs together
-  // (hwb_dev_set_occupancy).  HWB_CONCURRENT=0: the picture kernel starts when the entropy kernel has finished.
-  hwb_dev_set_occupancy(dev_, concurrent_ ? 2 : 3, concurrent_ ? 5 : 7);
+  // Default: the picture kernel starts when the batch's entropy kernel has finished (an event orders them).
+  // HWB_CONCURRENT=1 launches it right behind the entropy kernel instead; it then waits for the entropy stage picture
+  // by picture (csrc/dev/picture.h) and both grids are sized to fit the SMs together (hwb_dev_set_occupancy).  Measured on
+  // the 3000-frame benchmark clip this gains nothing: the first pictures wait for their intra slices either way (a
+  // 1080p intra slice takes 245 ms on a warp of its own and about 350 ms next to 1700 other slices), and the picture
+  // kernel loses a third of its resident warps to the co-residency rule (profiles/r2_experiments.md).
+  hwb_dev_set_occupancy(dev_, concurrent_ ? 2 : 3, concurrent_ ? 4 : 6);
   hwb_event *ev_inputs = hwb_dev_event_create(dev_);
   rc |= hwb_dev_event_record(dev_, ev_inputs, st);  // uploads and the zeroed counters
   if (c.num_tickets > 0) rc |= hwb_dev_entropy(dev_, st, &c, tickets, mode);
