@@ -36,8 +36,8 @@ struct ProfClock {
   long long t;
   __device__ __forceinline__ explicit ProfClock(unsigned long long *p) : out(p), t(0) { if (out) t = clock64(); }
   // charge the cycles since the last mark to `what`
-  __device__ __forceinline__ void mark(int what) {
-    if (!out) return;
+  __device__ __forceinline__ void mark(int what) { if (out) charge(what); }
+  __device__ __noinline__ void charge(int what) {  // out of line: the row loops stay small for the instruction caches
     const long long now = clock64();
     if ((threadIdx.x & 31) == 0) atomicAdd(out + what, (unsigned long long)(now - t));
     t = now;
@@ -53,8 +53,7 @@ struct Progress {  // a counter watched by this warp, with the last value seen (
 };
 
 #if HWB_DEVICE_BUILD
-__device__ __forceinline__ void wait_progress(Progress &g, int need) {
-  if (g.seen >= need) return;
+__device__ __noinline__ void poll_progress(Progress &g, int need) {
   int32_t v = 0;
   if ((threadIdx.x & 31) == 0) {
     for (;;) {  // relaxed GPU-scope poll; the data it guards is read with ld.global.cg (L2) by the callers
@@ -65,6 +64,7 @@ __device__ __forceinline__ void wait_progress(Progress &g, int need) {
   }
   g.seen = __shfl_sync(0xffffffffu, v, 0);
 }
+__device__ __forceinline__ void wait_progress(Progress &g, int need) { if (g.seen < need) poll_progress(g, need); }
 // Release store at GPU scope: orders the warp's earlier writes (made visible to lane 0 by __syncwarp) before the
 // flag.  Unlike __threadfence() + volatile store (MEMBAR.SC + CCTL.IVALL + a system-scope store) it does not
 // invalidate the SM's L1 on every macroblock, which the table and MbInfo loads of the other warps live in.
