@@ -140,6 +140,7 @@ Result B200VideoDecoder::configure(const FrameInfo &metadata, const std::vector<
 void B200VideoDecoder::set_interval_hint(uint64_t start_frame, const std::vector<uint64_t> &wanted) {
   std::lock_guard<std::mutex> lk(mu_);
   hint_valid_ = true; hint_start_ = start_frame; hint_wanted_ = wanted;  // consumed when the next segment opens (feed)
+  hint_span_ = wanted.empty() ? 0 : wanted.back() - start_frame + 1;
 }
 
 B200VideoDecoder::Slab B200VideoDecoder::take_slab(size_t n) {
@@ -173,11 +174,17 @@ Result B200VideoDecoder::feed(const uint8_t *encoded_buffer, size_t encoded_size
   const bool idr = stream_.next_is_idr(encoded_buffer, encoded_size);
   // A chunk is cut at IDR pictures only (nothing refers across), once it holds chunk_target_ pictures or its device
   // footprint reaches half of the memory budget; a single GOP larger than the budget cannot be decoded.
-  const size_t pb = picture_bytes();
+  // A sparse request (a hint that wants less than half of the frames: long-GOP seeks, every n-th frame) is bound by
+  // the latency of its GOP chains, not by throughput: all its GOPs should be in ONE batch (their chains then run side
+  // by side in one picture kernel), nothing is gained by an early small batch, and RGB24 space is needed for the wanted
+  // frames only.
+  const bool sparse = hint_valid_ ? hint_wanted_.size() * 2 < (size_t)std::max<uint64_t>(1, hint_span_) : (cur_ && cur_->sparse);
+  const size_t pb = picture_bytes() - (sparse ? (size_t)width_ * height_ * 3 * 3 / 4 : 0);
   if (cur_ && idr) {
     const size_t n = cur_->pics.size();
     if (queue_.empty()) ramp_target_ = std::min(ramp_first_, chunk_target_);  // cold pipeline: start small again
-    if ((int)n >= std::min(ramp_target_, chunk_target_) || (n + 1) * pb > memory_budget_ / 2) {
+    const int target = cur_->sparse ? 4 * chunk_target_ : std::min(ramp_target_, chunk_target_);
+    if ((int)n >= target || (n + 1) * pb > memory_budget_ / 2) {
       ramp_target_ = std::min(chunk_target_, ramp_target_ * 2);
       Result r = submit_current();
       if (!r.ok) return r;
@@ -195,6 +202,7 @@ Result B200VideoDecoder::feed(const uint8_t *encoded_buffer, size_t encoded_size
     cur_->bitstream.clear();
     cur_->bitstream.reserve(last_chunk_bytes_ + (last_chunk_bytes_ >> 2) + (1 << 20));
     cur_->crop_x = stream_.crop_left(); cur_->crop_y = stream_.crop_top();
+    cur_->sparse = sparse;
     stream_.reset_dpb();
   }
   // open a segment at the first picture after a flush (or of the chunk): it must be an IDR picture
@@ -549,10 +557,9 @@ void B200VideoDecoder::drain_copies() {
     if (staged_[i].busy) { if (staged_[i].user) memcpy(staged_[i].user, stage_pinned_[i], staged_[i].size); staged_[i].busy = false; }
   for (auto &c : retired_) recycle(c, true);
   retired_.clear();
-  // cached slabs beyond two are returned to the driver only when memory is tight (cudaFree synchronises the device)
-  size_t cached = 0;
-  for (auto &s : free_slabs_) cached += s.size;
-  while (free_slabs_.size() > 2 && live_bytes_ > memory_budget_ / 2) { live_bytes_ -= free_slabs_.back().size; hwb_dev_free(dev_, free_slabs_.back().base); free_slabs_.pop_back(); }
+  // cached slabs go back to the driver only when this decoder holds more than its budget (cudaFree synchronises the
+  // device, and a dense pass reuses every slab of the previous one: batches ramp up through the same sizes)
+  while (!free_slabs_.empty() && live_bytes_ > memory_budget_) { live_bytes_ -= free_slabs_.back().size; hwb_dev_free(dev_, free_slabs_.back().base); free_slabs_.pop_back(); }
   memory_cv_.notify_all();
 }
 

@@ -100,6 +100,7 @@ class B200VideoDecoder : public VideoDecoderInterface {
     size_t done_capacity = 0;
     uint64_t alg_bytes = 0;
     int crop_x = 0, crop_y = 0;
+    bool sparse = false;  // opened by a sparse request (see feed)
   };
   struct Staged { uint8_t *user = nullptr; size_t size = 0; hwb_event *done = nullptr; bool busy = false; };
 
@@ -151,7 +152,7 @@ class B200VideoDecoder : public VideoDecoderInterface {
   int next_entropy_stream_ = 0;
   std::vector<uint8_t> spare_bits_;
   bool hint_valid_ = false;
-  uint64_t hint_start_ = 0;
+  uint64_t hint_start_ = 0, hint_span_ = 0;
   std::vector<uint64_t> hint_wanted_;
   hwb_event *interval_begin_ = nullptr;  // ev_begin of the first chunk since the last wall-clock reading
   // output staging for pageable destinations and the planar test output
