@@ -279,16 +279,21 @@ def sparse_section(hw, local):
         dec = hw.Decoder(io.BytesIO(mp4), video_index=index, device_type=hw.DeviceType.GPU, device_id=local)
         dec.retrieve(rows[:2])  # warm-up: allocations, kernels
         best = None
+        st0 = dec._decoder.stats()
         for _ in range(3):
             t = time.perf_counter()
             frames = dec.retrieve(rows)
             dt = (time.perf_counter() - t) * 1000.0 / len(rows)
             best = dt if best is None else min(best, dt)
+        st1 = dec._decoder.stats()
         assert len(frames) == len(rows)
         del frames
         cpu_ms, cpu_n = cpu_sparse_ms_per_frame(mp4, index, rows)
         out[key] = {'workload': spec['name'], 'rows': len(rows), 'frames_in_clip': n, 'intervals': len(hw.slice_into_video_intervals(index, rows)),
-                    'ms_per_returned_frame': round(best, 3), 'cpu_ms_per_returned_frame_1thread': round(cpu_ms, 3), 'cpu_sample_rows': cpu_n,
+                    'ms_per_returned_frame': round(best, 3),
+                    'device_ms_per_request': {k: round((st1[k] - st0[k]) / 3, 1) for k in ('entropy_ms', 'picture_ms', 'wall_ms')},
+                    'pictures_decoded_per_request': (st1['pictures_decoded'] - st0['pictures_decoded']) // 3,
+                    'cpu_ms_per_returned_frame_1thread': round(cpu_ms, 3), 'cpu_sample_rows': cpu_n,
                     'bits_per_frame': round(8 * len(mp4) / n)}
     return out
 

@@ -131,7 +131,7 @@ union PictureScratch {
 
 // 80 registers, 6 blocks (24 warps) per SM.  Without static roles every warp is a generalist and chooses the kind of its next item when it
 // takes it: the head of the deblocking list if the rows it consumes are already being produced (the reconstruction of
-// the row below has started), otherwise the head of the reconstruction list, otherwise (reconstruction exhausted)
+// the row below its band has started), otherwise the head of the reconstruction list, otherwise (reconstruction exhausted)
 // the deblocking head whatever its state.  Deblocking first: it completes pictures, which releases the rows of the
 // next level waiting for their reference and the frames waiting to be copied out.
 // Why this cannot deadlock (see also csrc/dev/picture.h): let X be the earliest unfinished item in the global
@@ -189,7 +189,8 @@ __global__ void __launch_bounds__(kThreads, 6) picture_kernel(const __grid_const
         if (t < c.num_deblock_items) {
           const uint32_t it = c.deblock_items[t];
           const int pic = item_pic(it), y = item_row(it);
-          const int32_t *p = c.recon_prog + (size_t)pic * c.mb_h + (y + 1 < c.mb_h ? y + 1 : y);
+          // the band needs its own rows and the one below reconstructed: the last of them has started => all have been handed out
+          const int32_t *p = c.recon_prog + (size_t)pic * c.mb_h + (y + DEBLOCK_BAND < c.mb_h ? y + DEBLOCK_BAND : c.mb_h - 1);
           int32_t v;
           asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
           ready = v >= 1;
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, 6) picture_kernel(const __grid_const
       if (t >= c.num_deblock_items) { deblock_left = false; continue; }
       const uint32_t it = c.deblock_items[t];
       pick.mark(PROF_PICK);
-      deblock_row(c, item_pic(it), item_row(it), &my->deblock);
+      deblock_band(c, item_pic(it), item_row(it), &my->deblock);
     } else {
       const int t = warp_ticket(ticket);
       if (t >= c.num_recon_items) { recon_left = false; continue; }

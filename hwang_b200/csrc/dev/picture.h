@@ -6,7 +6,7 @@
 //   reconstruct (p,y) at x : intra macroblocks need row y-1 reconstructed up to x+1 (unfiltered top / top-right
 //                            samples); inter rows need the rows of their reference pictures that the entropy stage
 //                            found them to reach (ChunkCtx::mv_reach) completely deblocked;
-//   deblock (p,y) at x     : (x,y) reconstructed; row y+1 reconstructed up to x+1 (its intra macroblocks read the
+//   deblock (p,y) at x     : (rows are handed out in bands of DEBLOCK_BAND, see deblock_band) (x,y) reconstructed; row y+1 reconstructed up to x+1 (its intra macroblocks read the
 //                            UNFILTERED samples of row y, so they must be done before the filter runs in place);
 //                            row y-1 deblocked up to x+1 (H.264 filters in raster order).
 // Both item lists are ordered by (dependency level of the picture, row, picture), so an item only ever waits on
@@ -168,55 +168,71 @@ HWB_FN void recon_row(const ChunkCtx &c, int pic, int y, ReconScratch *my) {
   }
 }
 
-HWB_FN void deblock_row(const ChunkCtx &c, int pic, int y, DeblockScratch *my) {
+// Deblocking work item: a BAND of DEBLOCK_BAND consecutive rows, filtered by one warp in a skewed order (column x of
+// the band's first row, x-2 of the second, x-4 of the third ...: exactly the lag H.264's raster-order filter needs).
+// A deblocking row on its own can only advance at the pace of the reconstruction it follows (its rows are
+// reconstructed side by side, all at the same column), so a warp per row spends most of its life waiting and the
+// resident warps -- not the work -- limit how many pictures of a long GOP chain are in flight; a band does several
+// rows' worth of filtering per step of that pace.
+enum { DEBLOCK_BAND = 4 };
+
+HWB_FN void deblock_band(const ChunkCtx &c, int pic, int y0, DeblockScratch *my) {
   const PicDesc &pd = c.pics[pic];
   int32_t *prog = c.dbl_prog + (size_t)pic * c.mb_h;
   const int32_t *rprog = c.recon_prog + (size_t)pic * c.mb_h;
   uint8_t *rgb = pd.rgb_slot >= 0 ? c.rgb + (uint64_t)pd.rgb_slot * c.rgb_stride : nullptr;
-  const bool last_row = y == c.mb_h - 1;
-  Progress mine = {rprog + y, -1};
-  Progress below = {rprog + y + 1, last_row ? (1 << 30) : -1};
-  Progress above = {prog + y - 1, y > 0 ? -1 : (1 << 30)};
+  const int nb = y0 + DEBLOCK_BAND <= c.mb_h ? DEBLOCK_BAND : c.mb_h - y0;
+  Progress rp[DEBLOCK_BAND + 1];  // reconstruction of rows y0 .. y0+nb
+#pragma unroll
+  for (int k = 0; k <= DEBLOCK_BAND; ++k) { rp[k].p = rprog + y0 + k; rp[k].seen = (k <= nb && y0 + k < c.mb_h) ? -1 : (1 << 30); }
+  Progress above = {prog + y0 - 1, y0 > 0 ? -1 : (1 << 30)};
   ProfClock pc(c.prof);
-  wait_progress(mine, 1);  // the row's reconstruction has started, so the entropy stage of the picture is complete
+  wait_progress(rp[0], 1);  // the row's reconstruction has started, so the entropy stage of the picture is complete
   const bool failed = ld_u32_cg((const uint32_t *)c.error_flag) != 0;
-  for (int x = 0; x < c.mb_w && !failed; ++x) {
-    const int lag = x + 2 < c.mb_w ? x + 2 : c.mb_w;
-    wait_progress(mine, x + 1);
-    wait_progress(below, lag);
-    pc.mark(PROF_WAIT_RECON);
-    wait_progress(above, lag);
-    pc.mark(PROF_WAIT_DEBLOCK_ABOVE);
-    deblock_mb(c, pic, x, y, my);
-    publish_progress(prog + y, x + 1);
-    pc.mark(PROF_DEBLOCK_MB);
-    if (rgb) {
-      // RGB24 writeback fused into this pass: with (x,y) filtered, macroblock (x,y-1) is final (its right edge was
-      // filtered by (x+1,y-1), which the wait above covers; its bottom edge just now), and so is (x-1,y) on the
-      // last row.  Two macroblocks per step: 32 lanes x 16 pixels, three 16-byte stores each.
-      const bool flush = x == c.mb_w - 1;
-      if (y > 0 && ((x & 1) || flush)) rgb24_macroblocks(c, pd.frame, rgb, x & ~1, (x & 1) ? 2 : 1, y - 1);
-      if (last_row) {
-        if (x >= 2 && !(x & 1)) rgb24_macroblocks(c, pd.frame, rgb, x - 2, 2, y);
-        if (flush) rgb24_macroblocks(c, pd.frame, rgb, (x & 1) ? x - 1 : x, (x & 1) ? 2 : 1, y);
+  for (int x = 0; x < c.mb_w + 2 * (nb - 1) && !failed; ++x) {
+#pragma unroll
+    for (int k = 0; k < DEBLOCK_BAND; ++k) {
+      const int xx = x - 2 * k, y = y0 + k;
+      if (k >= nb || xx < 0 || xx >= c.mb_w) continue;
+      const int lag = xx + 2 < c.mb_w ? xx + 2 : c.mb_w;
+      wait_progress(rp[k], xx + 1);
+      wait_progress(rp[k + 1], lag);
+      pc.mark(PROF_WAIT_RECON);
+      if (k == 0) { wait_progress(above, lag); pc.mark(PROF_WAIT_DEBLOCK_ABOVE); }  // rows inside the band: program order
+      deblock_mb(c, pic, xx, y, my);
+      publish_progress(prog + y, xx + 1);
+      pc.mark(PROF_DEBLOCK_MB);
+      if (rgb) {
+        // RGB24 writeback fused into this pass: with (xx,y) filtered, macroblock (xx,y-1) is final (its right edge was
+        // filtered by (xx+1,y-1), which the wait / the skew covers; its bottom edge just now), and so is (xx-1,y) on
+        // the last row.  Two macroblocks per step: 32 lanes x 16 pixels, three 16-byte stores each.
+        const bool flush = xx == c.mb_w - 1, last_row = y == c.mb_h - 1;
+        if (y > 0 && ((xx & 1) || flush)) rgb24_macroblocks(c, pd.frame, rgb, xx & ~1, (xx & 1) ? 2 : 1, y - 1);
+        if (last_row) {
+          if (xx >= 2 && !(xx & 1)) rgb24_macroblocks(c, pd.frame, rgb, xx - 2, 2, y);
+          if (flush) rgb24_macroblocks(c, pd.frame, rgb, (xx & 1) ? xx - 1 : xx, (xx & 1) ? 2 : 1, y);
+        }
+        pc.mark(PROF_RGB);
       }
-      pc.mark(PROF_RGB);
     }
   }
   // picture complete?  Every row's samples and RGB24 were written before its count (fence), so whoever counts the last
-  // row may tell the host (system-scope fence: the copy engine reads what the host was promised).
-  if (failed) { publish_progress(prog + y, c.mb_w); return; }  // the host learns about the error when the batch ends
+  // rows may tell the host (system-scope fence: the copy engine reads what the host was promised).
+  if (failed) {  // the host learns about the error when the batch ends
+    for (int k = 0; k < nb; ++k) publish_progress(prog + y0 + k, c.mb_w);
+    return;
+  }
 #if HWB_DEVICE_BUILD
   __syncwarp();
   if ((threadIdx.x & 31) == 0) {
     __threadfence();
-    if (atomicAdd(c.rows_done + pic, 1) == c.mb_h - 1) {
+    if (atomicAdd(c.rows_done + pic, nb) == c.mb_h - nb) {
       __threadfence_system();
       *((volatile int32_t *)c.pic_done + pic) = 1;
     }
   }
 #else
-  if (++c.rows_done[pic] == c.mb_h) c.pic_done[pic] = 1;
+  if ((c.rows_done[pic] += nb) == c.mb_h) c.pic_done[pic] = 1;
 #endif
 }
 

@@ -281,7 +281,10 @@ Result B200VideoDecoder::submit_current() {
       for (int i = g0; i < g1; ++i) if (!ch->skipped[i]) by_level[ch->pics[i].level].push_back(i);
       for (auto &v : by_level)
         for (int y = 0; y < mb_h; ++y)
-          for (int32_t pic : v) { recon_items.push_back(hwb::make_item(pic, y, 0)); deblock_items.push_back(hwb::make_item(pic, y, 1)); }
+          for (int32_t pic : v) {
+            recon_items.push_back(hwb::make_item(pic, y, 0));
+            if (y % hwb::DEBLOCK_BAND == 0) deblock_items.push_back(hwb::make_item(pic, y, 1));  // one item per band of rows
+          }
       g0 = g1;
     }
   }

@@ -4,6 +4,7 @@
 // test tier can exercise the decode core and the host scheduler bit-exactly against the oracle on
 // machines without a GPU.  It is built into tests/emu/libhwb_emu.so, never into the product library
 // (hwang_b200/libhwang_b200.so links csrc/cuda/kernels.cu instead and fails loudly without a GPU).
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <string>
@@ -60,15 +61,32 @@ int hwb_dev_picture(hwb_dev *d, int, const ChunkCtx *c, int32_t *) {
   };
   auto deblock_ready = [&](uint32_t it) {
     const int pic = item_pic(it), y = item_row(it);
-    return rows_done(c->recon_prog, pic, y) && rows_done(c->recon_prog, pic, y + 1) && rows_done(c->dbl_prog, pic, y - 1);
+    for (int k = 0; k <= DEBLOCK_BAND; ++k) if (!rows_done(c->recon_prog, pic, y + k)) return false;  // the band's rows and the one below
+    return rows_done(c->dbl_prog, pic, y - 1);
   };
+  if (getenv("HWB_EMU_REACH_STATS")) {  // how far inter prediction reaches (what the picture kernel's waits are made of)
+    long hx[8] = {0}, hy[8] = {0}, rows = 0;
+    for (int p = 0; p < c->num_pics; ++p)
+      for (int y = 0; y < c->mb_h; ++y) {
+        const int r = c->mv_reach[(size_t)p * c->mb_h + y], rx = c->mv_reach_x[(size_t)p * c->mb_h + y];
+        if (r <= 0) continue;
+        rows++;
+        int dy = r - 1 - y; dy = dy < 0 ? 0 : (dy > 7 ? 7 : dy);
+        hy[dy]++; hx[rx > 7 ? 7 : rx]++;
+      }
+    fprintf(stderr, "[emu reach] inter rows %ld | rows below own (0..7+):", rows);
+    for (int i = 0; i < 8; ++i) fprintf(stderr, " %ld", hy[i]);
+    fprintf(stderr, " | macroblocks to the right incl. own (0..7+):");
+    for (int i = 0; i < 8; ++i) fprintf(stderr, " %ld", hx[i]);
+    fprintf(stderr, "\n");
+  }
   int ir = 0, id = 0;
   g_unsatisfied_waits = 0;
   g_mc_window.violations = 0;
   while (ir < c->num_recon_items || id < c->num_deblock_items) {
     bool progressed = false;
     while (ir < c->num_recon_items && recon_ready(c->recon_items[ir])) { recon_row(*c, item_pic(c->recon_items[ir]), item_row(c->recon_items[ir]), &sm.recon); ir++; progressed = true; }
-    while (id < c->num_deblock_items && deblock_ready(c->deblock_items[id])) { deblock_row(*c, item_pic(c->deblock_items[id]), item_row(c->deblock_items[id]), &sm.deblock); id++; progressed = true; }
+    while (id < c->num_deblock_items && deblock_ready(c->deblock_items[id])) { deblock_band(*c, item_pic(c->deblock_items[id]), item_row(c->deblock_items[id]), &sm.deblock); id++; progressed = true; }
     if (!progressed) { *c->error_flag = 901; d->err = "emulation: work lists are not in dependency order"; break; }
   }
   if (g_unsatisfied_waits) { *c->error_flag = 902; d->err = "emulation: a wait was not satisfied"; }
