@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(kThreads, 6) picture_kernel(const __grid_const
           const uint32_t it = c.deblock_items[t];
           const int pic = item_pic(it), y = item_row(it);
           // the band needs its own rows and the one below reconstructed: the last of them has started => all have been handed out
-          const int32_t *p = c.recon_prog + (size_t)pic * c.mb_h + (y + DEBLOCK_BAND < c.mb_h ? y + DEBLOCK_BAND : c.mb_h - 1);
+          const int32_t *p = c.recon_prog + (size_t)pic * c.mb_h + (y + c.deblock_band < c.mb_h ? y + c.deblock_band : c.mb_h - 1);
           int32_t v;
           asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
           ready = v >= 1;

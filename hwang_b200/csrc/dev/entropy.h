@@ -523,7 +523,7 @@ HWB_HD int cabac_residual_impl(SliceDec &s, Cabac &cab, const uint8_t *base, uin
   const bool tab = cat == 5 || cat == 3;
   const uint8_t *sig_tab = cat == 5 ? cabac_sig8x8_ctx : ctx_inc_chroma_dc;
   const uint8_t *last_tab = cat == 5 ? cabac_last8x8_ctx : ctx_inc_chroma_dc;
-  uint32_t m[2] = {0, 0};
+  uint32_t m0 = 0, m1 = 0;  // two registers, not an array: a dynamically indexed array lives in local memory
   const int lastc = max_coeff - 1;
   int i = 0;
 #pragma unroll 1
@@ -531,18 +531,18 @@ HWB_HD int cabac_residual_impl(SliceDec &s, Cabac &cab, const uint8_t *base, uin
     int si = i, li = i;
     if (tab) { si = sig_tab[i]; li = last_tab[i]; }
     if (cabac_decision(cab, base, sig_st + si)) {
-      m[i >> 5] |= 1u << (i & 31);
+      if (i < 32) m0 |= 1u << i; else m1 |= 1u << (i - 32);
       if (cabac_decision(cab, base, last_st + li)) break;
     }
   }
-  if (i == lastc) m[i >> 5] |= 1u << (i & 31);
+  if (i == lastc) { if (i < 32) m0 |= 1u << i; else m1 |= 1u << (i - 32); }
   // ---- levels, highest frequency first
   int eq1 = 0, gt1 = 0;
   const int cmax = cat == 3 ? 3 : 4;
   const uint64_t scan_packed = cat == 3 ? HWB_IDENT_PACKED : HWB_ZZ4_PACKED;
 #pragma unroll 1
   for (int half = cat == 5 ? 1 : 0; half >= 0; --half) {
-    uint32_t mask = m[half];
+    uint32_t mask = half ? m1 : m0;
 #pragma unroll 1
     while (mask) {
       const int k = 31 - clz32(mask);
@@ -571,7 +571,7 @@ HWB_HD int cabac_residual_impl(SliceDec &s, Cabac &cab, const uint8_t *base, uin
       s.coef[pos] = (int16_t)(sign ? -absv : absv);
     }
   }
-  return popc32(m[0]) + popc32(m[1]);
+  return popc32(m0) + popc32(m1);
 }
 // ================================================================================ output helpers
 HWB_HD void coef_clear(SliceDec &s, int n) {

@@ -126,6 +126,7 @@ struct ChunkCtx {
   uint8_t *rgb;            // [slot] packed RGB24, out_w * out_h * 3 bytes each (tight)
   uint64_t rgb_stride;
   int32_t crop_x, crop_y, out_w, out_h;  // cropping rectangle of the output frames inside the coded picture
+  int32_t deblock_band;    // rows per deblocking work item (1..DEBLOCK_BAND, picture.h)
   // Completion of single pictures, so that frames travel to the host while the picture kernel is still working on the
   // rest of the batch: rows_done[pic] counts deblocked rows (device memory); the warp that completes the last row of a
   // picture sets pic_done[pic] = 1 in page-locked HOST memory (mapped into the device address space), which the host

@@ -181,7 +181,8 @@ HWB_FN void deblock_band(const ChunkCtx &c, int pic, int y0, DeblockScratch *my)
   int32_t *prog = c.dbl_prog + (size_t)pic * c.mb_h;
   const int32_t *rprog = c.recon_prog + (size_t)pic * c.mb_h;
   uint8_t *rgb = pd.rgb_slot >= 0 ? c.rgb + (uint64_t)pd.rgb_slot * c.rgb_stride : nullptr;
-  const int nb = y0 + DEBLOCK_BAND <= c.mb_h ? DEBLOCK_BAND : c.mb_h - y0;
+  const int band = c.deblock_band >= 1 && c.deblock_band <= DEBLOCK_BAND ? c.deblock_band : DEBLOCK_BAND;
+  const int nb = y0 + band <= c.mb_h ? band : c.mb_h - y0;
   Progress rp[DEBLOCK_BAND + 1];  // reconstruction of rows y0 .. y0+nb
 #pragma unroll
   for (int k = 0; k <= DEBLOCK_BAND; ++k) { rp[k].p = rprog + y0 + k; rp[k].seen = (k <= nb && y0 + k < c.mb_h) ? -1 : (1 << 30); }

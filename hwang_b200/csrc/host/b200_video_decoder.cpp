@@ -26,6 +26,7 @@ B200VideoDecoder::B200VideoDecoder(int device_id, DeviceType output_type, int) :
   if (const char *e = getenv("HWB_CHUNK_PICTURES")) { int v = atoi(e); if (v > 0) chunk_target_ = v; }
   if (const char *e = getenv("HWB_RAMP_FIRST")) { int v = atoi(e); if (v > 0) ramp_first_ = v; }
   ramp_target_ = ramp_first_;
+  if (const char *e = getenv("HWB_DEBLOCK_BAND")) { int v = atoi(e); if (v >= 1 && v <= hwb::DEBLOCK_BAND) deblock_band_ = v; }
   if (const char *e = getenv("HWB_CONCURRENT")) concurrent_ = atoi(e) != 0;
   if (const char *e = getenv("HWB_INTRA_RESERVE")) intra_reserve_ = atoi(e) != 0;
   if (const char *e = getenv("HWB_GROUP_PICTURES")) { int v = atoi(e); if (v > 0) group_target_ = v; }
@@ -266,6 +267,10 @@ Result B200VideoDecoder::submit_current() {
   // group_target_ pictures); inside a group items are ordered (level, row, picture), groups follow one another.  The
   // warps flow from one group into the next without a launch boundary, while the groups -- and with them the frames, in
   // display order -- complete one after the other, so the copies to the host start long before the kernel ends.
+  // Rows per deblocking item: narrow batches (few GOP chains: long-GOP seeks) are limited by resident warps waiting at
+  // the reconstruction's pace, so a warp takes a band of rows; wide batches have work for every warp anyway and run
+  // (measured) a little faster with more, smaller items.
+  const int band = deblock_band_ > 0 ? deblock_band_ : (ch->sparse ? hwb::DEBLOCK_BAND : 1);
   std::vector<uint32_t> recon_items, deblock_items;
   recon_items.reserve((size_t)(P - nskipped) * mb_h);
   deblock_items.reserve((size_t)(P - nskipped) * mb_h);
@@ -283,7 +288,7 @@ Result B200VideoDecoder::submit_current() {
         for (int y = 0; y < mb_h; ++y)
           for (int32_t pic : v) {
             recon_items.push_back(hwb::make_item(pic, y, 0));
-            if (y % hwb::DEBLOCK_BAND == 0) deblock_items.push_back(hwb::make_item(pic, y, 1));  // one item per band of rows
+            if (y % band == 0) deblock_items.push_back(hwb::make_item(pic, y, 1));  // one item per band of rows
           }
       g0 = g1;
     }
@@ -333,6 +338,7 @@ Result B200VideoDecoder::submit_current() {
   c.num_recon_items = (int32_t)recon_items.size(); c.num_deblock_items = (int32_t)deblock_items.size();
   c.rgb = b + o_rgb; c.rgb_stride = rgb_bytes;
   c.crop_x = ch->crop_x; c.crop_y = ch->crop_y; c.out_w = (int32_t)width_; c.out_h = (int32_t)height_;
+  c.deblock_band = band;
   int32_t *sync = (int32_t *)(b + o_sync);
   int32_t *tickets = sync;
   c.entropy_prog = sync + 4;

@@ -61,7 +61,7 @@ int hwb_dev_picture(hwb_dev *d, int, const ChunkCtx *c, int32_t *) {
   };
   auto deblock_ready = [&](uint32_t it) {
     const int pic = item_pic(it), y = item_row(it);
-    for (int k = 0; k <= DEBLOCK_BAND; ++k) if (!rows_done(c->recon_prog, pic, y + k)) return false;  // the band's rows and the one below
+    for (int k = 0; k <= c->deblock_band; ++k) if (!rows_done(c->recon_prog, pic, y + k)) return false;  // the band's rows and the one below
     return rows_done(c->dbl_prog, pic, y - 1);
   };
   if (getenv("HWB_EMU_REACH_STATS")) {  // how far inter prediction reaches (what the picture kernel's waits are made of)
