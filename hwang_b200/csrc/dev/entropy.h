@@ -23,6 +23,14 @@
 #else
 #define HWB_IS_B(slice_type) ((slice_type) == SLICE_B)
 #endif
+// HWB_ENT_NO_T8: a copy for batches whose pictures all have transform_8x8_mode_flag = 0 (Baseline / Main streams): no
+// 8x8 residual category, no Intra8x8, no transform_size_8x8_flag -- less code on the per-macroblock path.
+#undef HWB_T8_ON
+#ifdef HWB_ENT_NO_T8
+#define HWB_T8_ON false
+#else
+#define HWB_T8_ON true
+#endif
 #undef HWB_IS_CABAC
 #if HWB_ENT_MODE == 1
 #define HWB_IS_CABAC(s) true
@@ -520,9 +528,9 @@ HWB_HD int cabac_residual_impl(SliceDec &s, Cabac &cab, const uint8_t *base, uin
   const uint32_t offs = cabac_cat_ctx[cat];  // ctxIdxOffset of significant_coeff_flag | last_... << 10 | coeff_abs_level_minus1 << 20
   uint8_t *sig_st = st + (offs & 1023), *last_st = st + ((offs >> 10) & 1023), *abs_st = st + (offs >> 20);
   // ---- significance map: one loop for all categories (8x8 and chroma DC map scan positions to contexts by table)
-  const bool tab = cat == 5 || cat == 3;
-  const uint8_t *sig_tab = cat == 5 ? cabac_sig8x8_ctx : ctx_inc_chroma_dc;
-  const uint8_t *last_tab = cat == 5 ? cabac_last8x8_ctx : ctx_inc_chroma_dc;
+  const bool tab = (HWB_T8_ON && cat == 5) || cat == 3;
+  const uint8_t *sig_tab = (HWB_T8_ON && cat == 5) ? cabac_sig8x8_ctx : ctx_inc_chroma_dc;
+  const uint8_t *last_tab = (HWB_T8_ON && cat == 5) ? cabac_last8x8_ctx : ctx_inc_chroma_dc;
   uint32_t m0 = 0, m1 = 0;  // two registers, not an array: a dynamically indexed array lives in local memory
   const int lastc = max_coeff - 1;
   int i = 0;
@@ -541,14 +549,14 @@ HWB_HD int cabac_residual_impl(SliceDec &s, Cabac &cab, const uint8_t *base, uin
   const int cmax = cat == 3 ? 3 : 4;
   const uint64_t scan_packed = cat == 3 ? HWB_IDENT_PACKED : HWB_ZZ4_PACKED;
 #pragma unroll 1
-  for (int half = cat == 5 ? 1 : 0; half >= 0; --half) {
+  for (int half = (HWB_T8_ON && cat == 5) ? 1 : 0; half >= 0; --half) {
     uint32_t mask = half ? m1 : m0;
 #pragma unroll 1
     while (mask) {
       const int k = 31 - clz32(mask);
       mask ^= 1u << k;
       // raster position first: the load (8x8) / shift is off the arithmetic decoder's dependency chain
-      const int pos = cat == 5 ? zigzag8x8[32 * half + k] : (int)((scan_packed >> (4 * (start + k))) & 15);
+      const int pos = (HWB_T8_ON && cat == 5) ? zigzag8x8[32 * half + k] : (int)((scan_packed >> (4 * (start + k))) & 15);
       const int ctx0 = gt1 ? 0 : (eq1 < 3 ? 1 + eq1 : 4);
       int absv;
       if (!cabac_decision(cab, base, abs_st + ctx0)) {
@@ -600,7 +608,7 @@ HWB_FN int cabac_blocks(SliceDec &s, int kind, int q, int cat, int arg, int bit0
   Cabac cab = s.cab;
   const uint8_t *base = s.br.base;
   const int nblk = kind == 0 ? 1 : 4;
-  const int maxc = cat == 5 ? 64 : (cat == 3 ? 4 : ((cat == 1 || cat == 4) ? 15 : 16));
+  const int maxc = (HWB_T8_ON && cat == 5) ? 64 : (cat == 3 ? 4 : ((cat == 1 || cat == 4) ? 15 : 16));
   int n = 0;
 #pragma unroll 1
   for (int k = 0; k < nblk; ++k) {
@@ -619,11 +627,11 @@ HWB_FN int cabac_blocks(SliceDec &s, int kind, int q, int cat, int arg, int bit0
     }
     n = 0;
     bool coded = true;
-    if (inc >= 0) coded = cabac_decision(cab, base, s.states + 85 + 4 * (cat == 5 ? 0 : cat) + inc) != 0;
+    if (inc >= 0) coded = cabac_decision(cab, base, s.states + 85 + 4 * ((HWB_T8_ON && cat == 5) ? 0 : cat) + inc) != 0;
     if (coded) {
-      coef_clear(s, cat == 5 ? 64 : 16);
+      coef_clear(s, (HWB_T8_ON && cat == 5) ? 64 : 16);
       n = cabac_residual_impl(s, cab, base, s.states, cat, maxc, (cat == 1 || cat == 4) ? 1 : 0);
-      coef_emit(s, bit, cat == 5 ? 4 : 1);
+      coef_emit(s, bit, (HWB_T8_ON && cat == 5) ? 4 : 1);
     }
     if (nzp) *nzp = (uint8_t)n;
   }
@@ -663,7 +671,7 @@ HWB_FN void decode_residual(SliceDec &s, bool i16, int cbp, bool t8) {
 #pragma unroll 1
   for (int q = 0; q < 4; ++q) {
     if (!((cbp >> q) & 1)) continue;
-    if (t8) {
+    if (HWB_T8_ON && t8) {
       int n = 0;
       if (cabac) {
         n = cabac_block(s, 5, -1, NZ_LUMA0 + q * 4);
@@ -1040,7 +1048,7 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
       bool t8 = false;
       int cbp;
       if (imbt == 0) {
-        if (s.pd->transform8x8_mode) {
+        if (HWB_T8_ON && s.pd->transform8x8_mode) {
           if (HWB_IS_CABAC(s)) {
             int ctx = (s.availA && (s.left.flags & NBF_T8)) + (s.availB && (top_flags(s) & NBF_T8));
             t8 = cabac_bin(s, 399 + ctx) != 0;
@@ -1188,7 +1196,7 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
       else { uint32_t k = s_ue(s); if (k > 47) { sd_fail(s, 56); return; } cbp = golomb_to_inter_cbp[k]; }
       o.cbp = (uint8_t)cbp;
       bool t8 = false;
-      if ((cbp & 15) && s.pd->transform8x8_mode && t8_allowed) {
+      if (HWB_T8_ON && (cbp & 15) && s.pd->transform8x8_mode && t8_allowed) {
         if (HWB_IS_CABAC(s)) {
           int ctx = (s.availA && (s.left.flags & NBF_T8)) + (s.availB && (top_flags(s) & NBF_T8));
           t8 = cabac_bin(s, 399 + ctx) != 0;
