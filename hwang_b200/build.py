@@ -62,11 +62,13 @@ def build_emu(force=False):
     return EMU
 
 
-def build_product(force=False):
+def build_product(force=False, out=None, nvcc_extra=()):
+    """out / nvcc_extra: an experimental build beside the product (A/B runs on one GPU box: HWB_PRODUCT_LIB=out)."""
+    PRODUCT = out or globals()['PRODUCT']
     if not force and not _newer(PRODUCT, _all_sources()):
         return PRODUCT
     nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
-    obj = os.path.join(ROOT, 'build', 'obj')
+    obj = os.path.join(ROOT, 'build', 'obj' if out is None else 'obj_' + os.path.basename(out))
     os.makedirs(obj, exist_ok=True)
     objs = []
     for s in HOST_SRCS:
@@ -75,7 +77,7 @@ def build_product(force=False):
         objs.append(o)
     ko = os.path.join(obj, 'kernels.o')
     _run([nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC',
-          '-Xptxas', '-v', '-c', 'hwang_b200/csrc/cuda/kernels.cu', '-o', ko])
+          '-Xptxas', '-v'] + list(nvcc_extra) + ['-c', 'hwang_b200/csrc/cuda/kernels.cu', '-o', ko])
     objs.append(ko)
     tmp = PRODUCT + '.tmp%d' % os.getpid()
     _run([nvcc, '-shared', '-o', tmp] + objs + ['-lcudart_static', '-lpthread', '-ldl', '-lrt'])
@@ -90,4 +92,8 @@ def build_all(force=False):
 
 
 if __name__ == '__main__':
-    build_all('--force' in sys.argv)
+    if '--variant' in sys.argv:  # python -m hwang_b200.build --variant build/libX.so -DFLAG=1 ...
+        i = sys.argv.index('--variant')
+        build_product(True, os.path.join(ROOT, sys.argv[i + 1]), sys.argv[i + 2:])
+    else:
+        build_all('--force' in sys.argv)

@@ -16,11 +16,6 @@
 #include <atomic>
 #include <string>
 
-// The CABAC engine's fused transition table is read once per bin by the single active lane of every warp: a
-// shared-memory copy (1 KB per CTA, filled at kernel start) keeps that load off the global / constant path.
-__shared__ __align__(8) uint32_t hwb_fused_sm[256];
-#define HWB_CABAC_FUSED hwb_fused_sm
-
 #include "../dev/devapi.h"
 #include "../dev/picture.h"
 #include "../dev/entropy.h"  // generic (runtime entropy_coding_mode): namespace hwb::ent
@@ -39,8 +34,13 @@ __shared__ __align__(8) uint32_t hwb_fused_sm[256];
 #define HWB_ENT_NO_B 1
 #include "../dev/entropy.h"
 #undef HWB_ENT_NS
+#define HWB_ENT_NS ent_cabac_ip4
+#define HWB_ENT_NO_T8 1
+#include "../dev/entropy.h"
+#undef HWB_ENT_NS
 #undef HWB_ENT_MODE
 #undef HWB_ENT_NO_B
+#undef HWB_ENT_NO_T8
 
 using namespace hwb;
 
@@ -101,7 +101,6 @@ __device__ int next_entropy_ticket(const ChunkCtx &c, int32_t *ticket, bool rese
     __shared__ NS::SliceDec sdec[kWarpsPerBlock];                                                     \
     __shared__ ChunkCtx c;                                                                            \
     if (threadIdx.x == 0) c = cparam;                                                                 \
-    for (int i = threadIdx.x; i < 256; i += kThreads) hwb_fused_sm[i] = cabac_fused[i];               \
     __syncthreads();                                                                                  \
     const int w = threadIdx.x >> 5;                                                                   \
     unsigned smid;                                                                                    \
@@ -120,6 +119,7 @@ HWB_ENTROPY_KERNEL(entropy_kernel, hwb::ent)              // pictures of both en
 HWB_ENTROPY_KERNEL(entropy_cabac_kernel, hwb::ent_cabac)  // every picture of the chunk is CABAC
 HWB_ENTROPY_KERNEL(entropy_cavlc_kernel, hwb::ent_cavlc)  // every picture of the chunk is CAVLC
 HWB_ENTROPY_KERNEL(entropy_cabac_ip_kernel, hwb::ent_cabac_ip)  // CABAC, no B slice in the chunk
+HWB_ENTROPY_KERNEL(entropy_cabac_ip4_kernel, hwb::ent_cabac_ip4)  // ... and no picture with the 8x8 transform (Main profile)
 
 // ------------------------------------------------------------------------------------ picture kernel
 // Reconstruction, deblocking and the RGB24 writeback of every picture of a chunk in ONE launch: see csrc/dev/picture.h
@@ -366,7 +366,8 @@ int hwb_dev_entropy(hwb_dev *d, int s, const ChunkCtx *c, int32_t *ticket, int m
   // 1 block/SM 561 ms, 2: 411, 3: 394, 4: 402, 5: 409, 8: 430.  HWB_ENTROPY_BLOCKS_PER_SM overrides.
   static int bpsm_env = [] { const char *e = getenv("HWB_ENTROPY_BLOCKS_PER_SM"); int v = e ? atoi(e) : 0; return v; }();
   const int grid = grid_for(d, c->num_tickets, bpsm_env > 0 ? bpsm_env : d->entropy_bpsm);
-  if (mode == 3) entropy_cabac_ip_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);
+  if (mode == 4) entropy_cabac_ip4_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);
+  else if (mode == 3) entropy_cabac_ip_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);
   else if (mode == 1) entropy_cabac_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);
   else if (mode == 0) entropy_cavlc_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);
   else entropy_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);

@@ -75,11 +75,11 @@ struct SliceDec {
   int slice_num;  // inside picture
   BitReader br;
   Cabac cab;
-  uint8_t *st;  // CABAC context states (== states on the decoder; the stream generator points it at a dummy)
   bool cabac;
   uint32_t stop_bitpos;
   int qp;
   int last_dqp;
+  int pre_mbt;  // CABAC P slices: mb_type as decoded together with mb_skip_flag (cabac_p_header), -1 = not decoded yet
   LeftCtx left;
   uint32_t top_words[4];   // words 0..3 of the top neighbour's line-buffer entry (flags/cbp/cmode/dirmask, cbf, chroma nnz)
   int8_t tl_ref[2];        // top-left macroblock's bottom-right block (saved before its line entry is overwritten)
@@ -117,9 +117,11 @@ struct SliceDec {
   int8_t *o_refidx[2];
   int16_t *o_refpic[2];
   int16_t *o_coefs;
-  // CABAC context states live inside the slice state (shared memory on the GPU), so that the decoder addresses
-  // them as shared-memory offsets instead of through a generic pointer
-  alignas(16) uint8_t states[464];
+  // CABAC contexts (one fused-table entry each, see bits.h CtxE) and a copy of the 128-entry fused table live inside
+  // the slice state (shared memory on the GPU): the decoder addresses both as constant offsets from the one pointer
+  // it holds anyway
+  alignas(16) CtxE ctxe[464];
+  alignas(16) CtxE fused[128];
 };
 
 HWB_HD void sd_fail(SliceDec &s, int code) { if (!s.error) s.error = code; }
@@ -127,9 +129,37 @@ HWB_HD uint32_t top_flags(const SliceDec &s) { return s.top_words[0] & 0xff; }  
 
 // Out-of-line engine access for the macroblock-layer syntax (tens of call sites): keeps the kernel small enough for
 // the instruction cache.  The residual loops use the inlined, register-resident versions instead.
-HWB_FN int cabac_bin(SliceDec &s, int ctx) { Cabac c = s.cab; const int b = cabac_decision(c, s.br.base, s.states + ctx); s.cab = c; return b; }
-HWB_FN int cabac_byp(SliceDec &s) { Cabac c = s.cab; const int b = cabac_bypass(c, s.br.base); s.cab = c; return b; }
-HWB_FN int cabac_term(SliceDec &s) { Cabac c = s.cab; const int b = cabac_terminate(c, s.br.base); s.cab = c; return b; }
+// Syntax elements of more than a bin or two keep the engine in registers for their whole duration instead:
+#define HWB_CAB_ENTER(s) CabReg cab = cab_enter((s).cab); const CtxE *const ft = (s).fused
+#define HWB_CAB_LEAVE(s) cab_leave((s).cab, cab)
+#define HWB_BIN_INL(s, ctx) cabac_decision(cab, (s).cab, (s).ctxe + (ctx), ft)
+#define HWB_BYP(s) cabac_bypass(cab, (s).cab)
+// The decision as a call that takes and returns the engine in registers: the macroblock-layer syntax has some twenty
+// decision sites; inlined (30 instructions each) they were 9 KB of a per-macroblock path that has to fit a 32 KB
+// instruction cache.  Only the residual loops inline the decision.
+#ifndef HWB_BIN_OOL
+#define HWB_BIN_OOL 1
+#endif
+struct BinRet { uint32_t low, range; int32_t nb; int bin; };
+HWB_FN BinRet cabac_bin_reg(uint32_t low, uint32_t range, int32_t nb, SliceDec *s, int ctx) {
+  CabReg c; c.low = low; c.range = range; c.nb = nb;
+  BinRet r;
+  r.bin = cabac_decision(c, s->cab, s->ctxe + ctx, s->fused);
+  r.low = c.low; r.range = c.range; r.nb = c.nb;
+  return r;
+}
+HWB_HD int cabac_bin_call(CabReg &c, SliceDec &s, int ctx) {
+  const BinRet r = cabac_bin_reg(c.low, c.range, c.nb, &s, ctx);
+  c.low = r.low; c.range = r.range; c.nb = r.nb;
+  return r.bin;
+}
+#if HWB_BIN_OOL
+#define HWB_BIN(s, ctx) cabac_bin_call(cab, s, ctx)
+#else
+#define HWB_BIN(s, ctx) HWB_BIN_INL(s, ctx)
+#endif
+HWB_FN int cabac_bin(SliceDec &s, int ctx) { HWB_CAB_ENTER(s); const int b = HWB_BIN_INL(s, ctx); HWB_CAB_LEAVE(s); return b; }
+HWB_FN int cabac_term(SliceDec &s) { CabReg cab = cab_enter(s.cab); const int b = cabac_terminate(cab, s.cab); cab_leave(s.cab, cab); return b; }
 HWB_FN uint32_t s_ue(SliceDec &s) { return br_ue(s.br); }
 HWB_FN int32_t s_se(SliceDec &s) { return br_se(s.br); }
 HWB_FN uint32_t s_get(SliceDec &s, int n) { return br_get(s.br, n); }
@@ -512,7 +542,6 @@ HWB_FN int cavlc_residual(SliceDec &s, int nC, int max_coeff, int start, const u
 }
 
 // ================================================================================ CABAC residual
-HWB_TABLE uint8_t ctx_inc_chroma_dc[4] = {0, 1, 2, 2};
 #define HWB_CAT(sig, last, abs) ((sig) | (last) << 10 | (abs) << 20)
 HWB_CTABLE uint32_t cabac_cat_ctx[6] = {HWB_CAT(105, 166, 227), HWB_CAT(120, 181, 237), HWB_CAT(134, 195, 247),
                                         HWB_CAT(149, 210, 257), HWB_CAT(152, 213, 266), HWB_CAT(402, 417, 426)};
@@ -520,34 +549,84 @@ HWB_CTABLE uint32_t cabac_cat_ctx[6] = {HWB_CAT(105, 166, 227), HWB_CAT(120, 181
 #define HWB_ZZ4_PACKED 0xFEB7ADC963258410ull
 #define HWB_IDENT_PACKED 0xFEDCBA9876543210ull
 
-// cat: 0 I16 DC, 1 I16 AC, 2 luma 4x4, 3 chroma DC, 4 chroma AC, 5 luma 8x8.  The significance map is kept in
-// registers (one bit per scan position).  Returns the number of non-zero coefficients.  Written for a small code
-// footprint (one loop for the map, one for the levels, shared by all categories): with many warps per SM inside
-// different parts of the slice decoder, instruction fetch misses cost more than the few extra selects.
-HWB_HD int cabac_residual_impl(SliceDec &s, Cabac &cab, const uint8_t *base, uint8_t *st, int cat, int max_coeff, int start) {
+// cat: 0 I16 DC, 1 I16 AC, 2 luma 4x4, 3 chroma DC, 4 chroma AC, 5 luma 8x8.
+// Coefficient staging.  Device: lane l of the warp keeps the coefficients at raster positions l and l + 32 of the block
+// being decoded in two registers (every lane runs the same decoder, so a "store" is one predicated move and the block
+// leaves with one coalesced store: no shared-memory staging, no clear / emit barriers).  Host: the staging array in the
+// slice state.
+struct CoefRegs { int lo, hi; };
+HWB_HD void coef_reset(SliceDec &s, CoefRegs &r, bool big) {
+#if HWB_DEVICE_BUILD
+  (void)s; (void)big; r.lo = 0; r.hi = 0;
+#else
+  (void)r; memset(s.coef, 0, big ? 128 : 32);
+#endif
+}
+HWB_HD void coef_put(SliceDec &s, CoefRegs &r, int pos, int v) {
+#if HWB_DEVICE_BUILD
+  (void)s;
+  const int lane = (int)(threadIdx.x & 31);
+  if (lane == (pos & 31)) { if (pos < 32) r.lo = v; else r.hi = v; }
+#else
+  (void)r; s.coef[pos] = (int16_t)v;
+#endif
+}
+// Append the staged block (nslots * 16 coefficients) to the arena and mark item bits [bit, bit+nslots).
+HWB_HD void coef_flush(SliceDec &s, const CoefRegs &r, int bit, int nslots) {
+  int16_t *dst = s.o_coefs + (uint64_t)s.coef_next * 16;
+#if HWB_DEVICE_BUILD
+  const int lane = (int)(threadIdx.x & 31);
+  if (nslots == 1) { if (lane < 16) dst[lane] = (int16_t)r.lo; }
+  else { dst[lane] = (int16_t)r.lo; dst[lane + 32] = (int16_t)r.hi; }
+#else
+  (void)r; memcpy(dst, s.coef, (size_t)nslots * 32);
+#endif
+  s.coef_next += nslots;
+  s.out.nzmask |= ((1u << nslots) - 1u) << bit;
+}
+
+// One residual block: significance map (kept as a bit mask in registers), then the levels, highest frequency first.
+// `sig` / `last` / `abs` point at the category's first context of each kind.  Returns the number of non-zero
+// coefficients.  The 8x8 category maps scan positions to contexts through tables and has its own map loop; the chroma DC
+// increments min(i, 2) equal i for the three positions that are coded, so every other category shares the plain loop.
+HWB_HD int cabac_residual_impl(SliceDec &s, CabReg &cab, CoefRegs &cr, const CtxE *ft, int cat, int max_coeff, int start) {
   const uint32_t offs = cabac_cat_ctx[cat];  // ctxIdxOffset of significant_coeff_flag | last_... << 10 | coeff_abs_level_minus1 << 20
-  uint8_t *sig_st = st + (offs & 1023), *last_st = st + ((offs >> 10) & 1023), *abs_st = st + (offs >> 20);
-  // ---- significance map: one loop for all categories (8x8 and chroma DC map scan positions to contexts by table)
-  const bool tab = (HWB_T8_ON && cat == 5) || cat == 3;
-  const uint8_t *sig_tab = (HWB_T8_ON && cat == 5) ? cabac_sig8x8_ctx : ctx_inc_chroma_dc;
-  const uint8_t *last_tab = (HWB_T8_ON && cat == 5) ? cabac_last8x8_ctx : ctx_inc_chroma_dc;
+  CtxE *sig = s.ctxe + (offs & 1023), *last = s.ctxe + ((offs >> 10) & 1023), *abs_st = s.ctxe + (offs >> 20);
   uint32_t m0 = 0, m1 = 0;  // two registers, not an array: a dynamically indexed array lives in local memory
   const int lastc = max_coeff - 1;
-  int i = 0;
+  if (HWB_T8_ON && cat == 5) {
+    int i = 0;
 #pragma unroll 1
-  for (; i < lastc; ++i) {
-    int si = i, li = i;
-    if (tab) { si = sig_tab[i]; li = last_tab[i]; }
-    if (cabac_decision(cab, base, sig_st + si)) {
-      if (i < 32) m0 |= 1u << i; else m1 |= 1u << (i - 32);
-      if (cabac_decision(cab, base, last_st + li)) break;
+    for (; i < 63; ++i) {
+      if (cabac_decision(cab, s.cab, sig + cabac_sig8x8_ctx[i], ft)) {
+        if (i < 32) m0 |= 1u << i; else m1 |= 1u << (i - 32);
+        if (cabac_decision(cab, s.cab, last + cabac_last8x8_ctx[i], ft)) break;
+      }
     }
+    if (i == 63) m1 |= 1u << 31;
+  } else {
+    uint32_t bit = 1;
+    const uint32_t endbit = 1u << lastc;
+    // Software pipeline: the entries of this position's last-flag context and of the next position's significance
+    // context are loaded before the decision that tells which of them is needed (every position has contexts of its
+    // own, so neither can be stale), which takes the shared-memory latency off the bin-to-bin dependency chain.
+    CtxE e = ctxe_load(sig);
+#pragma unroll 1
+    while (bit != endbit) {
+      const CtxE el = ctxe_load(last);
+      const CtxE en = ctxe_load(sig + 1);  // one past the category's map contexts at the final position: loaded, never used
+      if (cabac_decide(cab, s.cab, e, sig, ft)) {
+        m0 |= bit;
+        if (cabac_decide(cab, s.cab, el, last, ft)) break;
+      }
+      e = en; bit <<= 1; ++sig; ++last;
+    }
+    m0 |= bit;  // the coefficient the map ended on (last flag set, or the final position, which is inferred)
   }
-  if (i == lastc) { if (i < 32) m0 |= 1u << i; else m1 |= 1u << (i - 32); }
-  // ---- levels, highest frequency first
-  int eq1 = 0, gt1 = 0;
+  // ---- levels
+  int eq1 = 1, gt1 = 0;  // eq1: 1 + number of levels equal to 1 so far, capped at 4 (the context increment while gt1 == 0)
   const int cmax = cat == 3 ? 3 : 4;
-  const uint64_t scan_packed = cat == 3 ? HWB_IDENT_PACKED : HWB_ZZ4_PACKED;
+  const uint64_t scan_packed = cat == 3 ? HWB_IDENT_PACKED : (HWB_ZZ4_PACKED >> (4 * start));
 #pragma unroll 1
   for (int half = (HWB_T8_ON && cat == 5) ? 1 : 0; half >= 0; --half) {
     uint32_t mask = half ? m1 : m0;
@@ -556,45 +635,27 @@ HWB_HD int cabac_residual_impl(SliceDec &s, Cabac &cab, const uint8_t *base, uin
       const int k = 31 - clz32(mask);
       mask ^= 1u << k;
       // raster position first: the load (8x8) / shift is off the arithmetic decoder's dependency chain
-      const int pos = (HWB_T8_ON && cat == 5) ? zigzag8x8[32 * half + k] : (int)((scan_packed >> (4 * (start + k))) & 15);
-      const int ctx0 = gt1 ? 0 : (eq1 < 3 ? 1 + eq1 : 4);
-      int absv;
-      if (!cabac_decision(cab, base, abs_st + ctx0)) {
-        absv = 1; eq1++;
+      const int pos = (HWB_T8_ON && cat == 5) ? zigzag8x8[32 * half + k] : (int)((scan_packed >> (4 * k)) & 15);
+      int absv = 1;
+      if (!cabac_decision(cab, s.cab, abs_st + (gt1 ? 0 : eq1), ft)) {
+        eq1 = eq1 < 4 ? eq1 + 1 : 4;
       } else {
-        uint8_t *st1 = abs_st + 5 + (gt1 < cmax ? gt1 : cmax);
+        CtxE *st1 = abs_st + 5 + (gt1 < cmax ? gt1 : cmax);
         absv = 2;
 #pragma unroll 1
-        while (absv < 15 && cabac_decision(cab, base, st1)) absv++;
+        while (absv < 15 && cabac_decision(cab, s.cab, st1, ft)) absv++;
         if (absv >= 15) {
-          int kk = 0;
-#pragma unroll 1
-          while (cabac_bypass(cab, base)) { absv += 1 << kk; kk++; if (kk > 20) { sd_fail(s, 30); return 0; } }
-#pragma unroll 1
-          while (kk--) absv += cabac_bypass(cab, base) << kk;
+          const int esc = cabac_escape(cab, s.cab, 0);
+          if (esc < 0) { sd_fail(s, 30); return 0; }
+          absv += esc;
         }
         gt1++;
       }
-      const int sign = cabac_bypass(cab, base);
-      s.coef[pos] = (int16_t)(sign ? -absv : absv);
+      const int sign = cabac_bypass(cab, s.cab);
+      coef_put(s, cr, pos, sign ? -absv : absv);
     }
   }
   return popc32(m0) + popc32(m1);
-}
-// ================================================================================ output helpers
-HWB_HD void coef_clear(SliceDec &s, int n) {
-  HWB_LANES(l)
-  if (2 * l < n) ((uint32_t *)s.coef)[l] = 0;
-  HWB_LANES_END
-}
-// Append s.coef[0..16*nslots) to the arena and mark item bits [bit, bit+nslots).
-HWB_HD void coef_emit(SliceDec &s, int bit, int nslots) {
-  uint32_t *dst = (uint32_t *)(s.o_coefs + (uint64_t)s.coef_next * 16);
-  HWB_LANES(l)
-  if (l < nslots * 8) dst[l] = ((const uint32_t *)s.coef)[l];
-  HWB_LANES_END
-  s.coef_next += nslots;
-  s.out.nzmask |= ((1u << nslots) - 1u) << bit;
 }
 
 // Residual blocks in CABAC mode with the arithmetic decoder held in registers across the whole group:
@@ -604,38 +665,60 @@ HWB_HD void coef_emit(SliceDec &s, int bit, int nslots) {
 //   kind 4: the four chroma AC blocks of plane q
 //   for kinds 1 and 4 `arg` is the coded_block_flag value assumed for unavailable neighbours; the neighbour
 //   caches (total_coeff per block) are read and updated here.
+// CAVLC staging helpers (the CAVLC decoder scatters levels into s.coef)
+HWB_HD void coef_clear(SliceDec &s, int n) {
+  HWB_LANES(l)
+  if (2 * l < n) ((uint32_t *)s.coef)[l] = 0;
+  HWB_LANES_END
+}
+HWB_HD void coef_emit(SliceDec &s, int bit, int nslots) {
+  uint32_t *dst = (uint32_t *)(s.o_coefs + (uint64_t)s.coef_next * 16);
+  HWB_LANES(l)
+  if (l < nslots * 8) dst[l] = ((const uint32_t *)s.coef)[l];
+  HWB_LANES_END
+  s.coef_next += nslots;
+  s.out.nzmask |= ((1u << nslots) - 1u) << bit;
+}
+// Group tables: byte offset (from the slice state) of each block's entry in its total_coeff cache; the left neighbour
+// is one byte before it, the top neighbour `up` bytes.
+HWB_CTABLE uint16_t blk_nz_off[24] = {
+#define HWB_NZ(bx, by) (uint16_t)(HWB_O(nz_cache) + HWB_CI(bx, by))
+  HWB_NZ(0, 0), HWB_NZ(1, 0), HWB_NZ(0, 1), HWB_NZ(1, 1), HWB_NZ(2, 0), HWB_NZ(3, 0), HWB_NZ(2, 1), HWB_NZ(3, 1),
+  HWB_NZ(0, 2), HWB_NZ(1, 2), HWB_NZ(0, 3), HWB_NZ(1, 3), HWB_NZ(2, 2), HWB_NZ(3, 2), HWB_NZ(2, 3), HWB_NZ(3, 3),
+#undef HWB_NZ
+#define HWB_CNZ(p, bx, by) (uint16_t)(HWB_O(cnz_cache[p]) + ((by) + 1) * 4 + (bx) + 1)
+  HWB_CNZ(0, 0, 0), HWB_CNZ(0, 1, 0), HWB_CNZ(0, 0, 1), HWB_CNZ(0, 1, 1), HWB_CNZ(1, 0, 0), HWB_CNZ(1, 1, 0), HWB_CNZ(1, 0, 1), HWB_CNZ(1, 1, 1)
+#undef HWB_CNZ
+};
 HWB_FN int cabac_blocks(SliceDec &s, int kind, int q, int cat, int arg, int bit0) {
-  Cabac cab = s.cab;
-  const uint8_t *base = s.br.base;
+  HWB_CAB_ENTER(s);
+  CoefRegs cr;
   const int nblk = kind == 0 ? 1 : 4;
-  const int maxc = (HWB_T8_ON && cat == 5) ? 64 : (cat == 3 ? 4 : ((cat == 1 || cat == 4) ? 15 : 16));
+  const bool big = HWB_T8_ON && cat == 5;
+  const int maxc = big ? 64 : (cat == 3 ? 4 : ((cat == 1 || cat == 4) ? 15 : 16));
+  CtxE *cbf = s.ctxe + 85 + 4 * (big ? 0 : cat);
+  const int g = kind == 1 ? q * 4 : 16 + q * 4, up = kind == 1 ? 8 : 4;
+  if (kind != 0) bit0 = kind == 1 ? NZ_LUMA0 + q * 4 : (q ? NZ_CR0 : NZ_CB0);
+  const int unavail_mask = 0x7f | (arg << 7);  // kinds 1 and 4 only
   int n = 0;
 #pragma unroll 1
   for (int k = 0; k < nblk; ++k) {
-    int inc = arg, bit = bit0;
+    int inc = arg;
     uint8_t *nzp = nullptr;
-    if (kind == 1) {
-      const int z = q * 4 + k, ci = HWB_CI(z2x(z), z2y(z));
-      const int na = s.nz_cache[ci - 1], nb = s.nz_cache[ci - 8];
-      inc = (na == 0x80 ? arg : (na != 0)) + 2 * (nb == 0x80 ? arg : (nb != 0));
-      bit = NZ_LUMA0 + z; nzp = s.nz_cache + ci;
-    } else if (kind == 4) {
-      const int bx = k & 1, by = k >> 1;
-      const int na = s.cnz_cache[q][(by + 1) * 4 + bx], nb = s.cnz_cache[q][by * 4 + bx + 1];
-      inc = (na == 0x80 ? arg : (na != 0)) + 2 * (nb == 0x80 ? arg : (nb != 0));
-      bit = (q ? NZ_CR0 : NZ_CB0) + k; nzp = &s.cnz_cache[q][(by + 1) * 4 + bx + 1];
+    if (kind != 0) {
+      nzp = (uint8_t *)&s + blk_nz_off[g + k];
+      // coded flag of a neighbour: its total_coeff (0..16) != 0; 0x80 marks an unavailable one, which counts as `arg`
+      inc = ((nzp[-1] & unavail_mask) != 0) + 2 * ((*(nzp - up) & unavail_mask) != 0);
     }
     n = 0;
-    bool coded = true;
-    if (inc >= 0) coded = cabac_decision(cab, base, s.states + 85 + 4 * ((HWB_T8_ON && cat == 5) ? 0 : cat) + inc) != 0;
-    if (coded) {
-      coef_clear(s, (HWB_T8_ON && cat == 5) ? 64 : 16);
-      n = cabac_residual_impl(s, cab, base, s.states, cat, maxc, (cat == 1 || cat == 4) ? 1 : 0);
-      coef_emit(s, bit, (HWB_T8_ON && cat == 5) ? 4 : 1);
+    if (inc < 0 || cabac_decision(cab, s.cab, cbf + inc, ft)) {
+      coef_reset(s, cr, big);
+      n = cabac_residual_impl(s, cab, cr, ft, cat, maxc, (cat == 1 || cat == 4) ? 1 : 0);
+      coef_flush(s, cr, bit0 + k, big ? 4 : 1);
     }
     if (nzp) *nzp = (uint8_t)n;
   }
-  s.cab = cab;
+  HWB_CAB_LEAVE(s);
   return n;
 }
 // Hides a constant from the compiler's interprocedural constant propagation: with literal `kind` arguments it cloned
@@ -736,23 +819,31 @@ HWB_FN void decode_residual(SliceDec &s, bool i16, int cbp, bool t8) {
 }
 
 // ================================================================================ CABAC syntax elements
-HWB_FN int cabac_intra_mb_type(SliceDec &s, int base, bool islice) {
-  int st = base;
+HWB_FN int cabac_intra_mb_type(SliceDec &s, int ctx_base, bool islice) {
+  int st = ctx_base, first = ctx_base;
   if (islice) {
-    int ctx = 0;
-    if (s.availA && !(s.left.flags & NBF_INXN)) ctx++;
-    if (s.availB && !(top_flags(s) & NBF_INXN)) ctx++;
-    if (!cabac_bin(s, st + ctx)) return 0;
+    if (s.availA && !(s.left.flags & NBF_INXN)) first++;
+    if (s.availB && !(top_flags(s) & NBF_INXN)) first++;
     st += 2;
-  } else {
-    if (!cabac_bin(s, st)) return 0;
   }
-  if (cabac_term(s)) return 25;
-  int t = 1;
-  t += 12 * cabac_bin(s, st + 1);
-  if (cabac_bin(s, st + 2)) t += 4 + 4 * cabac_bin(s, st + 2 + (islice ? 1 : 0));
-  t += 2 * cabac_bin(s, st + 3 + (islice ? 1 : 0));
-  t += cabac_bin(s, st + 3 + (islice ? 2 : 0));
+  HWB_CAB_ENTER(s);
+  int t = 0;
+  if (HWB_BIN(s, first)) {
+    if (cabac_terminate(cab, s.cab)) t = 25;
+    else {
+      // five suffix bins: context (relative to st) and weight, 4 bits each; the third only follows a set second one
+      const uint32_t ctxs = islice ? 0x54321u : 0x33221u, adds = 0x1244Cu;
+      t = 1;
+      int prev = 1;
+#pragma unroll 1
+      for (int i = 0; i < 5; ++i) {
+        if (i == 2 && !prev) continue;
+        prev = HWB_BIN(s, st + (int)((ctxs >> (4 * i)) & 15));
+        if (prev) t += (int)((adds >> (4 * i)) & 15);
+      }
+    }
+  }
+  HWB_CAB_LEAVE(s);
   return t;
 }
 
@@ -795,30 +886,43 @@ HWB_FN int cabac_ref_idx(SliceDec &s, int l, int bx, int by) {
   if (ra > 0 && !s.dir_cache[HWB_CI(bx - 1, by)]) ctx++;
   if (rb > 0 && !s.dir_cache[HWB_CI(bx, by - 1)]) ctx += 2;
   int ref = 0;
+  HWB_CAB_ENTER(s);
 #pragma unroll 1
-  while (cabac_bin(s, 54 + ctx)) {
+  while (HWB_BIN(s, 54 + ctx)) {
     ref++;
     ctx = (ctx >> 2) + 4;
-    if (ref >= 32) { sd_fail(s, 40); return 0; }
+    if (ref >= 32) { sd_fail(s, 40); ref = 0; break; }
   }
+  HWB_CAB_LEAVE(s);
   return ref;
 }
 
-HWB_FN int cabac_mvd(SliceDec &s, int base, int amvd, int &absout) {
-  int inc = amvd < 3 ? 0 : (amvd > 32 ? 2 : 1);
-  if (!cabac_bin(s, base + inc)) { absout = 0; return 0; }
-  int mvd = 1, ctx = base + 3;
+// Both components of a motion vector difference in one call.  sa / sb: sums of the neighbours' absolute differences
+// (context selection); returns the differences and their absolute values capped at 70 (what the neighbours-to-come see).
+struct MvdPair { int dx, dy, ax, ay; };
+HWB_FN MvdPair cabac_mvd_pair(SliceDec &s, int sa, int sb) {
+  HWB_CAB_ENTER(s);
+  MvdPair r; r.dx = r.dy = r.ax = r.ay = 0;
 #pragma unroll 1
-  while (mvd < 9 && cabac_bin(s, ctx)) { if (mvd < 4) ctx++; mvd++; }
-  if (mvd >= 9) {
-    int k = 3;
+  for (int comp = 0; comp < 2; ++comp) {
+    const int amvd = comp ? sb : sa, cb = comp ? 47 : 40;
+    int mvd = 0, absv = 0;
+    if (HWB_BIN(s, cb + (amvd < 3 ? 0 : (amvd > 32 ? 2 : 1)))) {
+      mvd = 1;
+      int ctx = cb + 3;
 #pragma unroll 1
-    while (cabac_byp(s)) { mvd += 1 << k; k++; if (k > 24) { sd_fail(s, 41); return 0; } }
-#pragma unroll 1
-    while (k--) mvd += cabac_byp(s) << k;
+      while (mvd < 9 && HWB_BIN(s, ctx)) { if (mvd < 4) ctx++; mvd++; }
+      if (mvd >= 9) {
+        const int esc = cabac_escape(cab, s.cab, 3);
+        if (esc < 0) sd_fail(s, 41); else mvd += esc;
+      }
+      absv = mvd < 70 ? mvd : 70;
+      if (HWB_BYP(s)) mvd = -mvd;
+    }
+    if (comp) { r.dy = mvd; r.ay = absv; } else { r.dx = mvd; r.ax = absv; }
   }
-  absout = mvd < 70 ? mvd : 70;
-  return cabac_byp(s) ? -mvd : mvd;
+  HWB_CAB_LEAVE(s);
+  return r;
 }
 
 HWB_FN int cabac_cbp(SliceDec &s) {
@@ -827,38 +931,108 @@ HWB_FN int cabac_cbp(SliceDec &s) {
   int cbpa = s.availA ? ((L.flags & NBF_IPCM) ? 0x2F : L.cbp) : 0x0F;
   int cbpb = s.availB ? ((top_flags(s) & NBF_IPCM) ? 0x2F : (int)((s.top_words[0] >> 8) & 0xff)) : 0x0F;
   int cbp = 0;
+  HWB_CAB_ENTER(s);
 #pragma unroll 1
   for (int b8 = 0; b8 < 4; ++b8) {
     int a = (b8 & 1) ? !((cbp >> (b8 - 1)) & 1) : !((cbpa >> (b8 + 1)) & 1);
     int bq = (b8 & 2) ? !((cbp >> (b8 - 2)) & 1) : !((cbpb >> (b8 + 2)) & 1);
-    cbp |= cabac_bin(s, 73 + a + 2 * bq) << b8;
+    cbp |= HWB_BIN(s, 73 + a + 2 * bq) << b8;
   }
   int ca = s.availA ? (cbpa >> 4) & 3 : 0, cb = s.availB ? (cbpb >> 4) & 3 : 0;
-  int ctx = (ca > 0) + 2 * (cb > 0);
-  if (cabac_bin(s, 77 + ctx)) {
-    ctx = 4 + (ca == 2) + 2 * (cb == 2);
-    cbp |= (1 + cabac_bin(s, 77 + ctx)) << 4;
+  // chroma: up to two bins; the second one's contexts sit four further on
+  int ctx = 77 + (ca > 0) + 2 * (cb > 0), val = 0;
+#pragma unroll 1
+  for (int k = 0; k < 2; ++k) {
+    if (!HWB_BIN(s, ctx)) break;
+    val++;
+    ctx = 77 + 4 + (ca == 2) + 2 * (cb == 2);
   }
-  return cbp;
+  HWB_CAB_LEAVE(s);
+  return cbp | (val << 4);
 }
 
 HWB_FN int cabac_dqp(SliceDec &s) {
   int ctx = s.last_dqp != 0, val = 0;
-  while (cabac_bin(s, 60 + ctx)) {
+  HWB_CAB_ENTER(s);
+#pragma unroll 1
+  while (HWB_BIN(s, 60 + ctx)) {
     ctx = 2 + (ctx >> 1);
     val++;
-    if (val > 104) { sd_fail(s, 42); return 0; }
+    if (val > 104) { sd_fail(s, 42); val = 0; break; }
   }
+  HWB_CAB_LEAVE(s);
   return (val & 1) ? (val + 1) >> 1 : -((val + 1) >> 1);
 }
 
 HWB_FN int cabac_chroma_mode(SliceDec &s) {
-  int ctx = 0;
+  int ctx = 64;
   if (s.availA && s.left.cmode != 0) ctx++;
   if (s.availB && ((s.top_words[0] >> 16) & 0xff) != 0) ctx++;
-  if (!cabac_bin(s, 64 + ctx)) return 0;
-  if (!cabac_bin(s, 64 + 3)) return 1;
-  return 2 + cabac_bin(s, 64 + 3);
+  HWB_CAB_ENTER(s);
+  int m = 0;
+#pragma unroll 1
+  for (; m < 3; ++m) {  // truncated unary, maximum 3; every bin after the first uses context 67
+    if (!HWB_BIN(s, ctx)) break;
+    ctx = 64 + 3;
+  }
+  HWB_CAB_LEAVE(s);
+  return m;
+}
+
+// prev_intra4x4/8x8_pred_mode_flag + rem_intra_pred_mode of every block of an I_NxN macroblock, and the mode derivation
+// (8.3.1.1) that goes with them.
+HWB_FN void cabac_intra_modes(SliceDec &s, bool t8) {
+  MbInfo &o = s.out;
+  const int nb = t8 ? 4 : 16;
+  HWB_CAB_ENTER(s);
+#pragma unroll 1
+  for (int k = 0; k < nb; ++k) {
+    const int bx = t8 ? (k & 1) * 2 : z2x(k), by = t8 ? (k >> 1) * 2 : z2y(k);
+    int8_t *im = s.im_cache + HWB_CI(bx, by);
+    const int ma = im[-1], mb_ = im[-8];
+    const int pred = (ma < 0 || mb_ < 0) ? 2 : (ma < mb_ ? ma : mb_);
+    int mode = pred;
+    if (!HWB_BIN(s, 68)) {
+      int rem = 0;
+#pragma unroll 1
+      for (int i = 0; i < 3; ++i) rem |= HWB_BIN(s, 69) << i;
+      mode = rem < pred ? rem : rem + 1;
+    }
+    o.i4modes[k] = (uint8_t)mode;
+    im[0] = (int8_t)mode;
+    if (t8) { im[1] = (int8_t)mode; im[8] = (int8_t)mode; im[9] = (int8_t)mode; }
+  }
+  HWB_CAB_LEAVE(s);
+}
+
+// P slice: mb_skip_flag and, for a coded macroblock, mb_type up to the intra prefix.  Returns -1 (skipped), 0..3
+// (P_L0_16x16, P_L0_L0_16x8, P_L0_L0_8x16, P_8x8) or 5 (intra: the intra mb_type follows).
+HWB_FN int cabac_p_header(SliceDec &s, int skip_ctx) {
+  HWB_CAB_ENTER(s);
+  int r = -1;
+  if (!HWB_BIN(s, 11 + skip_ctx)) {
+    if (HWB_BIN(s, 14)) r = 5;
+    else {
+      const int b1 = HWB_BIN(s, 15);
+      const int b2 = HWB_BIN(s, 16 + b1);
+      r = b1 ? 2 - b2 : 3 * b2;
+    }
+  }
+  HWB_CAB_LEAVE(s);
+  return r;
+}
+// P slice: the four sub_mb_type values of a P_8x8 macroblock, 2 bits each
+HWB_FN int cabac_p_sub_types(SliceDec &s) {
+  HWB_CAB_ENTER(s);
+  int r = 0;
+#pragma unroll 1
+  for (int q = 0; q < 4; ++q) {
+    int t = 0;
+    if (!HWB_BIN(s, 21)) t = !HWB_BIN(s, 22) ? 1 : (HWB_BIN(s, 23) ? 2 : 3);
+    r |= t << (2 * q);
+  }
+  HWB_CAB_LEAVE(s);
+  return r;
 }
 
 // Publish a decoded macroblock: MbInfo, final motion data, and the neighbour context for the macroblocks to come.
@@ -964,8 +1138,8 @@ HWB_FN void read_mvd_and_set(SliceDec &s, int l, int bx, int by, int w, int h, i
   if (HWB_IS_CABAC(s)) {
     int sa = s.mvd_cache[l][HWB_CI(bx - 1, by)][0] + s.mvd_cache[l][HWB_CI(bx, by - 1)][0];
     int sb = s.mvd_cache[l][HWB_CI(bx - 1, by)][1] + s.mvd_cache[l][HWB_CI(bx, by - 1)][1];
-    dx = cabac_mvd(s, 40, sa, ax);
-    dy = cabac_mvd(s, 47, sb, ay);
+    const MvdPair m = cabac_mvd_pair(s, sa, sb);
+    dx = m.dx; dy = m.dy; ax = m.ax; ay = m.ay;
   } else {
     dx = s_se(s); dy = s_se(s);
   }
@@ -1010,10 +1184,8 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
     if (HWB_IS_CABAC(s)) {
       if (st == SLICE_I) mbt = cabac_intra_mb_type(s, 3, true);
       else if (st == SLICE_P) {
-        if (!cabac_bin(s, 14)) {
-          if (!cabac_bin(s, 15)) mbt = 3 * cabac_bin(s, 16);
-          else mbt = 2 - cabac_bin(s, 17);
-        } else mbt = 5 + cabac_intra_mb_type(s, 17, false);
+        mbt = s.pre_mbt;  // decoded with mb_skip_flag (decode_slice)
+        if (mbt == 5) mbt += cabac_intra_mb_type(s, 17, false);
       } else mbt = cabac_b_mb_type(s);
     } else mbt = (int)s_ue(s);
     int imbt = -1;  // intra mb_type 0..25
@@ -1056,29 +1228,22 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
         }
         o.mbtype = t8 ? MB_I8x8 : MB_I4x4;
         if (t8) o.flags |= MBF_T8x8;
-        const int nb = t8 ? 4 : 16;
+        if (HWB_IS_CABAC(s)) cabac_intra_modes(s, t8);
+        else {
+          const int nb = t8 ? 4 : 16;
 #pragma unroll 1
-        for (int k = 0; k < nb; ++k) {
-          int bx = t8 ? (k & 1) * 2 : z2x(k), by = t8 ? (k >> 1) * 2 : z2y(k);
-          int ma = s.im_cache[HWB_CI(bx - 1, by)], mb_ = s.im_cache[HWB_CI(bx, by - 1)];
-          int pred = (ma < 0 || mb_ < 0) ? 2 : (ma < mb_ ? ma : mb_);
-          int mode;
-          if (HWB_IS_CABAC(s)) {
-            if (cabac_bin(s, 68)) mode = pred;
-            else {
-              int rem = cabac_bin(s, 69);
-              rem |= cabac_bin(s, 69) << 1;
-              rem |= cabac_bin(s, 69) << 2;
-              mode = rem < pred ? rem : rem + 1;
-            }
-          } else {
+          for (int k = 0; k < nb; ++k) {
+            int bx = t8 ? (k & 1) * 2 : z2x(k), by = t8 ? (k >> 1) * 2 : z2y(k);
+            int ma = s.im_cache[HWB_CI(bx - 1, by)], mb_ = s.im_cache[HWB_CI(bx, by - 1)];
+            int pred = (ma < 0 || mb_ < 0) ? 2 : (ma < mb_ ? ma : mb_);
+            int mode;
             if (s_get(s, 1)) mode = pred;
             else { int rem = (int)s_get(s, 3); mode = rem < pred ? rem : rem + 1; }
-          }
-          o.i4modes[k] = (uint8_t)mode;
-          int wd = t8 ? 2 : 1;
+            o.i4modes[k] = (uint8_t)mode;
+            int wd = t8 ? 2 : 1;
 #pragma unroll 1
-          for (int y = by; y < by + wd; ++y) for (int x = bx; x < bx + wd; ++x) s.im_cache[HWB_CI(x, y)] = (int8_t)mode;
+            for (int y = by; y < by + wd; ++y) for (int x = bx; x < bx + wd; ++x) s.im_cache[HWB_CI(x, y)] = (int8_t)mode;
+          }
         }
       } else {
         o.mbtype = MB_I16x16;
@@ -1118,12 +1283,13 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
       } else if ((!B && mbt >= 3) || (B && mbt == 22)) {
         // 8x8 with sub-macroblock types.  sub shapes: 0: 8x8, 1: 8x4, 2: 4x8, 3: 4x4; pred flags: 1 L0, 2 L1, 3 Bi
         ng = 4;
+        const int psub = (HWB_IS_CABAC(s) && !B) ? cabac_p_sub_types(s) : 0;
 #pragma unroll 1
         for (int q = 0; q < 4; ++q) {
           int t;
           if (HWB_IS_CABAC(s)) {
             if (B) t = cabac_b_sub_type(s);
-            else t = cabac_bin(s, 21) ? 0 : (!cabac_bin(s, 22) ? 1 : (cabac_bin(s, 23) ? 2 : 3));
+            else t = (psub >> (2 * q)) & 3;
           } else t = (int)s_ue(s);
           if (t > (B ? 12 : 3)) { sd_fail(s, 53); return; }
           int shp = t, f = 1;
@@ -1223,7 +1389,6 @@ HWB_FN void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states
   s.slice_num = slice_idx - s.pd->first_slice;
   s.cabac = s.pd->cabac != 0;
   (void)cabac_states;
-  s.st = s.states;
   s.error = 0;
   const SliceDesc &sd = *s.sd;
   const uint8_t *data = c.bitstream + sd.data_off;
@@ -1243,7 +1408,12 @@ HWB_FN void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states
   // the arena region of a slice starts at its first macroblock's worst-case offset
   s.coef_next = (uint32_t)sd.first_mb * SLOTS_PER_MB;
   if (HWB_IS_CABAC(s)) {
-    cabac_init_states(s.states, sd.slice_type == SLICE_I ? 0 : 1 + sd.cabac_init_idc, sd.qp);
+    const int table = sd.slice_type == SLICE_I ? 0 : 1 + sd.cabac_init_idc;
+    const CtxE *ft = (const CtxE *)cabac_fused;
+    HWB_LANES(l)
+    for (int i = l; i < 128; i += 32) ctxe_store(s.fused + i, ctxe_load(ft + i));
+    for (int i = l; i < HWB_CABAC_NCTX; i += 32) ctxe_store(s.ctxe + i, ctxe_load(ft + cabac_init_state(table, sd.qp, i)));
+    HWB_LANES_END
     cabac_start(s.cab, data, (sd.bit_off + 7) >> 3);  // cabac_alignment_one_bits, then 9 bits of codIOffset
   }
   const int first = sd.first_mb;
@@ -1265,7 +1435,8 @@ HWB_FN void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states
     if (sd.slice_type != SLICE_I) {
       if (HWB_IS_CABAC(s)) {
         int ctx = (s.availA && !(s.left.flags & NBF_SKIP)) + (s.availB && !(top_flags(s) & NBF_SKIP));
-        skipped = cabac_bin(s, (HWB_IS_B(sd.slice_type) ? 24 : 11) + ctx) != 0;
+        if (HWB_IS_B(sd.slice_type)) skipped = cabac_bin(s, 24 + ctx) != 0;
+        else { s.pre_mbt = cabac_p_header(s, ctx); skipped = s.pre_mbt < 0; }
       } else {
         if (run < 0) {
           run = (int)s_ue(s);

@@ -404,7 +404,12 @@ Result B200VideoDecoder::submit_current() {
   if (mode == 1) {  // CABAC throughout: the copy of the kernel without B-slice support when the chunk has none
     bool has_b = false;
     for (auto &sl : ch->slices) has_b |= sl.slice_type == hwb::SLICE_B;
-    if (!has_b) mode = 3;
+    if (!has_b) {
+      bool t8 = false;  // ... and the copy without the 8x8 transform either when no picture enables it (Baseline / Main streams)
+      for (auto &p : ch->pics) t8 |= p.transform8x8_mode != 0;
+      static const bool no_ip4 = getenv("HWB_NO_IP4") != nullptr;
+      mode = (t8 || no_ip4) ? 3 : 4;
+    }
   }
   // Default: the picture kernel starts when the batch's entropy kernel has finished (an event orders them).
   // HWB_CONCURRENT=1 launches it right behind the entropy kernel instead; it then waits for the entropy stage picture

@@ -41,6 +41,21 @@ int hwb_dev_entropy(hwb_dev *d, int, const ChunkCtx *c, int32_t *, int) {
   uint8_t states[1024];
   for (int t = 0; t < c->num_tickets; ++t) { SliceDec sd; decode_slice(*c, c->entropy_order[t], states, &sd); }
   d->launches++;
+  if (getenv("HWB_EMU_MBSTATS")) {  // macroblock mix of the batch per picture kind (development aid)
+    long hist[2][8] = {}, nzb[2] = {}, n[2] = {};
+    for (int p = 0; p < c->num_pics; ++p) {
+      const int intra = !c->pics[p].has_inter;
+      const MbInfo *mi = pic_mbinfo(*c, c->pics[p].frame);
+      for (int m = 0; m < c->nmb; ++m) {
+        int k = mi[m].mbtype;
+        if (k == MB_INTER) k = (mi[m].flags & MBF_SKIP) ? 5 : (mi[m].cbp ? 6 : 4);
+        hist[intra][k]++; nzb[intra] += __builtin_popcount(mi[m].nzmask); n[intra]++;
+      }
+    }
+    for (int i = 0; i < 2; ++i)
+      fprintf(stderr, "[mbstats] %s pictures: mbs %ld  I4x4 %ld I8x8 %ld I16 %ld PCM %ld inter-nocbp %ld skip %ld inter-cbp %ld  coded blocks/mb %.2f\n",
+              i ? "intra" : "inter", n[i], hist[i][0], hist[i][1], hist[i][2], hist[i][3], hist[i][4], hist[i][5], hist[i][6], n[i] ? (double)nzb[i] / n[i] : 0.0);
+  }
   return 0;
 }
 // The picture kernel's two work lists, executed serially: an item runs once everything it waits for is complete
@@ -148,18 +163,22 @@ struct SpecCabac {
   }
 };
 int hwb_emu_cabac_selftest(const uint8_t *data, size_t n, size_t start_byte, const uint8_t *ops, size_t nops, int nctx) {
-  uint8_t st_a[128], st_b[128];
-  for (int i = 0; i < 128; ++i) st_a[i] = st_b[i] = (uint8_t)((i * 37 + 11) & 127);
-  Cabac c; cabac_start(c, data, (uint32_t)start_byte);
+  const CtxE *ft = (const CtxE *)cabac_fused;
+  CtxE st_a[128];
+  uint8_t st_b[128];
+  for (int i = 0; i < 128; ++i) { st_b[i] = (uint8_t)((i * 37 + 11) & 127); st_a[i] = ft[st_b[i]]; }
+  Cabac home; cabac_start(home, data, (uint32_t)start_byte);
+  CabReg c = cab_enter(home);
   SpecCabac r; r.d = data; r.n = n; r.start(start_byte);
   for (size_t i = 0; i < nops; ++i) {
     int a, b;
-    if (ops[i] < 128) { const int k = ops[i] % nctx; a = cabac_decision(c, data, st_a + k); b = r.decision(st_b[k]); if (st_a[k] != st_b[k]) return (int)i; }
-    else if (ops[i] == 128) { a = cabac_bypass(c, data); b = r.bypass(); }
-    else { a = cabac_terminate(c, data); b = r.terminate(); if (a != b) return (int)i; if (a) return -1; }
+    if (ops[i] < 128) { const int k = ops[i] % nctx; a = cabac_decision(c, home, st_a + k, ft); b = r.decision(st_b[k]); if (ctxe_state(st_a[k]) != st_b[k]) return (int)i; }
+    else if (ops[i] == 128) { a = cabac_bypass(c, home); b = r.bypass(); }
+    else { a = cabac_terminate(c, home); b = r.terminate(); if (a != b) return (int)i; if (a) return -1; }
     if (a != b) return (int)i;
-    if (cabac_bitpos(c) != r.bitpos) return (int)i;  // bits consumed: 9 at start + one per renormalisation shift
-    if ((size_t)c.pos + 4 > n) return -1;            // ran out of test data
+    cab_leave(home, c);
+    if (cabac_bitpos(home) != r.bitpos) return (int)i;  // bits consumed: 9 at start + one per renormalisation shift
+    if ((size_t)home.pos + 4 > n) return -1;            // ran out of test data
   }
   return -1;
 }

@@ -4,7 +4,7 @@ import re
 import subprocess
 import sys
 
-out = subprocess.run(['cuobjdump', '-elf', 'hwang_b200/libhwang_b200.so'], capture_output=True, text=True).stdout
+out = subprocess.run(['cuobjdump', '-elf', __import__('os').environ.get('HWB_PRODUCT_LIB', 'hwang_b200/libhwang_b200.so')], capture_output=True, text=True).stdout
 pat = sys.argv[1] if len(sys.argv) > 1 else ''
 rows = []
 for line in out.splitlines():

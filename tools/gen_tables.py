@@ -97,8 +97,9 @@ assert trans_mps.tolist() == [min(p + 1, 62) for p in range(63)] + [63]
 emit('cabac_trans_lps', trans_lps, const=True)
 # fused table for the branch-free decoder, two 32-bit words per state (state = pStateIdx << 1 | valMPS):
 #   word 0 = rangeLPS for qCodIRangeIdx 0..3, one byte each (byte q)
-#   word 1 = next state after an MPS | next state after an LPS << 8
-# Both words depend on the context state only, so the decoder can fetch them before codIRange is known.
+#   word 1 = next state after an MPS | next state after an LPS << 8 | the state itself << 16 (bit 16 = valMPS)
+# Both words depend on the context state only: the decoder keeps this 8-byte entry per context (one load on the
+# decision's dependency chain) and replaces it by the successor's entry after the decision.
 fused = np.zeros((128, 2), np.uint32)
 for p in range(64):
     for mps in range(2):
@@ -106,8 +107,8 @@ for p in range(64):
         nm = (min(p + 1, 62) << 1 | mps) if p < 63 else (63 << 1 | mps)
         if p == 62: nm = (62 << 1) | mps
         fused[(p << 1) | mps, 0] = sum(int(range_lps[p, q]) << (8 * q) for q in range(4))
-        fused[(p << 1) | mps, 1] = nm | (nl << 8)
-emit('cabac_fused', fused, 'uint32_t', 8, const=True)
+        fused[(p << 1) | mps, 1] = nm | (nl << 8) | (((p << 1) | mps) << 16)
+emit('cabac_fused', fused, 'uint32_t', 8)  # copied into every slice state at slice start (lane-parallel reads: not __constant__)
 
 sig8 = u8(find([0, 1, 2, 3, 4, 5, 5, 4, 4, 3, 3, 4, 4, 4, 5, 5, 4, 4, 4, 4, 3, 3, 6, 7, 7, 7, 8, 9, 10, 9, 8, 7], 0, 1), 63)
 assert sig8[-1] == 12 or True

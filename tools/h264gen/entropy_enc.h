@@ -48,7 +48,6 @@ struct SliceEnc {
   CabacEnc ce;
   bool cabac = false;
   int run = 0;  // pending CAVLC mb_skip_run
-  uint8_t dummy_states[1024];
 };
 
 // ------------------------------------------------------------------ CAVLC residual writer

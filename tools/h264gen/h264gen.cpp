@@ -774,7 +774,7 @@ struct Encoder {
       e.cabac = cabac;
       write_slice_header(e.bw, ps, sd, first_mb, nal_type, idr_id, nrefs_total);
       SliceDec &s = e.s;
-      s.c = &c; s.pd = &pd; s.sd = &sd; s.slice_num = sl; s.cabac = cabac; s.st = e.dummy_states; s.error = 0;
+      s.c = &c; s.pd = &pd; s.sd = &sd; s.slice_num = sl; s.cabac = cabac; s.error = 0;
       s.qp = sd.qp; s.last_dqp = 0;
       s.line = (NbCtx *)(c.ectx + (uint64_t)(slot * MAXSL + sl) * c.ectx_stride);
       s.coef_next = (uint32_t)first_mb * SLOTS_PER_MB;

@@ -9,6 +9,7 @@ gives every callee's offset and size inside the kernel's .text section, so offse
 The report must have been taken from the library as it is built now.
 """
 import csv
+import os
 import re
 import subprocess
 import sys
@@ -20,7 +21,7 @@ if '--hot' in sys.argv:
 path, kernel = args[0], args[1]
 units = float(args[2]) if len(args) > 2 else 0.0
 
-elf = subprocess.run(['cuobjdump', '-elf', 'hwang_b200/libhwang_b200.so'], capture_output=True, text=True).stdout
+elf = subprocess.run(['cuobjdump', '-elf', os.environ.get('HWB_PRODUCT_LIB', 'hwang_b200/libhwang_b200.so')], capture_output=True, text=True).stdout
 funcs = []  # (offset, size, name)
 ksize = 0
 for line in elf.splitlines():
@@ -60,12 +61,16 @@ tot_smp = sum(i[3] for i in inst)
 agg = {}
 for a, src, ex, smp in inst:
     f = owner(a - base)
-    e = agg.setdefault(f, [0, 0, 0])
+    e = agg.setdefault(f, [0, 0, 0, 0])
     e[0] += ex; e[1] += smp; e[2] += 1
-print('%-28s %8s %7s %7s %9s %s' % ('function', 'instr', 'exec%', 'smp%', 'cyc/inst', 'exec/unit' if units else ''))
-for f, (ex, smp, n) in sorted(agg.items(), key=lambda x: -x[1][0]):
+    if units and ex >= 0.25 * units:
+        e[3] += 16  # bytes of code executed at least once per four units: what the instruction caches have to hold
+print('%-28s %8s %7s %7s %9s %s' % ('function', 'instr', 'exec%', 'smp%', 'cyc/inst', 'exec/unit  hot bytes' if units else ''))
+for f, (ex, smp, n, hb) in sorted(agg.items(), key=lambda x: -x[1][0]):
     print('%-28s %8d %7.2f %7.2f %9.2f %s' % (f, n, 100.0 * ex / tot_ex, 100.0 * smp / max(1, tot_smp),
-                                              (smp / max(1, tot_smp)) / max(1e-12, ex / tot_ex), ('%.1f' % (ex / units)) if units else ''))
+                                              (smp / max(1, tot_smp)) / max(1e-12, ex / tot_ex), ('%9.1f %6d' % (ex / units, hb)) if units else ''))
+if units:
+    print('hot code (executed >= 0.25 times per unit): %d bytes' % sum(v[3] for v in agg.values()))
 print('total warp instructions executed: %d%s' % (tot_ex, (' = %.1f per unit' % (tot_ex / units)) if units else ''))
 if hot:
     print('\nhottest instructions:')
