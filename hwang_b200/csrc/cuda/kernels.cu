@@ -19,28 +19,31 @@
 #include "../dev/devapi.h"
 #include "../dev/picture.h"
 #include "../dev/entropy.h"  // generic (runtime entropy_coding_mode): namespace hwb::ent
-#define HWB_ENT_NS ent_cabac
-#define HWB_ENT_MODE 1
-#include "../dev/entropy.h"
-#undef HWB_ENT_NS
-#undef HWB_ENT_MODE
-#define HWB_ENT_NS ent_cavlc
+// Specialised copies of the slice decoder (the per-macroblock path has to fit the SM's instruction cache):
+// MODE 1 / 0 = CABAC / CAVLC only, NO_B = no B-slice support, NO_T8 = no 8x8 transform.
 #define HWB_ENT_MODE 0
+#define HWB_ENT_NS ent_cavlc
 #include "../dev/entropy.h"
 #undef HWB_ENT_NS
 #undef HWB_ENT_MODE
-#define HWB_ENT_NS ent_cabac_ip
 #define HWB_ENT_MODE 1
-#define HWB_ENT_NO_B 1
+#define HWB_ENT_NS ent_cabac
 #include "../dev/entropy.h"
 #undef HWB_ENT_NS
-#define HWB_ENT_NS ent_cabac_ip4
 #define HWB_ENT_NO_T8 1
+#define HWB_ENT_NS ent_cabac4
 #include "../dev/entropy.h"
 #undef HWB_ENT_NS
-#undef HWB_ENT_MODE
-#undef HWB_ENT_NO_B
+#define HWB_ENT_NO_B 1
+#define HWB_ENT_NS ent_cabac_ip4
+#include "../dev/entropy.h"
+#undef HWB_ENT_NS
 #undef HWB_ENT_NO_T8
+#define HWB_ENT_NS ent_cabac_ip
+#include "../dev/entropy.h"
+#undef HWB_ENT_NS
+#undef HWB_ENT_NO_B
+#undef HWB_ENT_MODE
 
 using namespace hwb;
 
@@ -96,6 +99,9 @@ __device__ int next_entropy_ticket(const ChunkCtx &c, int32_t *ticket, bool rese
   }
 }
 
+// (Tried and dropped: a second copy of the decoder for inter slices with every decision out of line, intra slices
+// keeping the inlined one -- two copies in one launch took 357 ms per 3000 slices instead of 286: what the SMs miss in
+// their own instruction caches they fetch from a cache shared by the GPC, and twice the code thrashes that one.)
 #define HWB_ENTROPY_KERNEL(NAME, NS)                                                                  \
   __global__ void __launch_bounds__(kThreads) NAME(ChunkCtx cparam, int32_t *ticket) {                \
     __shared__ NS::SliceDec sdec[kWarpsPerBlock];                                                     \
@@ -115,11 +121,12 @@ __device__ int next_entropy_ticket(const ChunkCtx &c, int32_t *ticket, bool rese
       __syncwarp();                                                                                   \
     }                                                                                                 \
   }
-HWB_ENTROPY_KERNEL(entropy_kernel, hwb::ent)              // pictures of both entropy modes in one chunk
-HWB_ENTROPY_KERNEL(entropy_cabac_kernel, hwb::ent_cabac)  // every picture of the chunk is CABAC
-HWB_ENTROPY_KERNEL(entropy_cavlc_kernel, hwb::ent_cavlc)  // every picture of the chunk is CAVLC
+HWB_ENTROPY_KERNEL(entropy_kernel, hwb::ent)                    // pictures of both entropy modes in one chunk
+HWB_ENTROPY_KERNEL(entropy_cavlc_kernel, hwb::ent_cavlc)        // every picture of the chunk is CAVLC
+HWB_ENTROPY_KERNEL(entropy_cabac_kernel, hwb::ent_cabac)        // every picture of the chunk is CABAC
+HWB_ENTROPY_KERNEL(entropy_cabac4_kernel, hwb::ent_cabac4)      // ... and none uses the 8x8 transform
 HWB_ENTROPY_KERNEL(entropy_cabac_ip_kernel, hwb::ent_cabac_ip)  // CABAC, no B slice in the chunk
-HWB_ENTROPY_KERNEL(entropy_cabac_ip4_kernel, hwb::ent_cabac_ip4)  // ... and no picture with the 8x8 transform (Main profile)
+HWB_ENTROPY_KERNEL(entropy_cabac_ip4_kernel, hwb::ent_cabac_ip4)  // ... and no 8x8 transform (Main profile)
 
 // ------------------------------------------------------------------------------------ picture kernel
 // Reconstruction, deblocking and the RGB24 writeback of every picture of a chunk in ONE launch: see csrc/dev/picture.h
@@ -367,6 +374,7 @@ int hwb_dev_entropy(hwb_dev *d, int s, const ChunkCtx *c, int32_t *ticket, int m
   static int bpsm_env = [] { const char *e = getenv("HWB_ENTROPY_BLOCKS_PER_SM"); int v = e ? atoi(e) : 0; return v; }();
   const int grid = grid_for(d, c->num_tickets, bpsm_env > 0 ? bpsm_env : d->entropy_bpsm);
   if (mode == 4) entropy_cabac_ip4_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);
+  else if (mode == 5) entropy_cabac4_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);
   else if (mode == 3) entropy_cabac_ip_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);
   else if (mode == 1) entropy_cabac_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);
   else if (mode == 0) entropy_cavlc_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);

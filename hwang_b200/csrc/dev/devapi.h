@@ -43,7 +43,8 @@ int hwb_dev_memset(hwb_dev *d, int stream, void *dst, int value, size_t n);
 
 // Decode stages.  `c` is a host copy of the chunk context (its pointers are device pointers).
 // ticket: device int32[1] (entropy) / int32[2] (picture kernel) zeroed by the caller, used for ordered work distribution.
-// mode: 1 = every picture of the chunk is CABAC, 3 = CABAC and no B slice, 0 = every picture is CAVLC, -1 = mixed (generic kernel)
+// mode: 1 = every picture of the chunk is CABAC, 3 = CABAC and no B slice, 4 = 3 and no 8x8 transform, 5 = CABAC with B slices and no 8x8
+// transform, 0 = every picture is CAVLC, -1 = mixed (generic kernel)
 int hwb_dev_entropy(hwb_dev *d, int stream, const hwb::ChunkCtx *c, int32_t *ticket, int mode);
 // resident blocks per SM of the entropy / picture kernels launched from now on (see kernels.cu)
 void hwb_dev_set_occupancy(hwb_dev *d, int entropy_blocks_per_sm, int picture_blocks_per_sm);

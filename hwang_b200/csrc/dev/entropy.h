@@ -122,6 +122,10 @@ struct SliceDec {
   // it holds anyway
   alignas(16) CtxE ctxe[464];
   alignas(16) CtxE fused[128];
+  // per-lane move tables of the cache maintenance (fill_tab_a/b, top_dflt, line_tab, fill_dflt_a below), copied here once
+  // per slice: read as constant offsets from the slice state instead of through 64-bit global addresses
+  uint32_t t_a[32], t_b[28], t_topd[20], t_line[20];
+  uint8_t t_da[24];
 };
 
 HWB_HD void sd_fail(SliceDec &s, int code) { if (!s.error) s.error = code; }
@@ -236,6 +240,15 @@ HWB_TABLE uint32_t fill_tab_b[28] = {HWB_LINE_WORDS(HWB_TOPROW), HWB_ROWS4(HWB_O
 HWB_TABLE uint32_t top_dflt[20] = {0, 0, 0x80808080u, 0, 0x80808080u, 0xFFFFFFFFu, 0xFEFEFEFEu, 0xFEFEFEFEu, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 // finish_mb: source of word l of the line-buffer entry (the bottom row of the caches; words 0..3 staged in s.top_words)
 HWB_TABLE uint32_t line_tab[20] = {HWB_LINE_WORDS(HWB_BOTROW)};
+// Once per slice, with init_caches: the tables' copies inside the slice state.
+HWB_HD void init_lane_tables(SliceDec &s) {
+  HWB_LANES(l)
+  s.t_a[l] = fill_tab_a[l];
+  if (l < 28) s.t_b[l] = fill_tab_b[l];
+  if (l < 20) { s.t_topd[l] = top_dflt[l]; s.t_line[l] = line_tab[l]; }
+  if (l < 24) s.t_da[l] = fill_dflt_a[l];
+  HWB_LANES_END
+}
 
 // Per macroblock: the left column is the previous macroblock's right column (still in the caches), the top row
 // comes from the slice's line buffer, the interior is reset.
@@ -249,16 +262,16 @@ HWB_FN void fill_caches(SliceDec &s, bool unused) {
   // ---- phase 1: left column, top row (one line-buffer word per lane), corners
   HWB_LANES(l)
   {
-    const uint32_t e = fill_tab_a[l];
+    const uint32_t e = s.t_a[l];
     uint8_t *d = sb + (e >> 16);
     const uint8_t *f = sb + (e & 0xffff);
-    if (l < 24) *d = availA ? *f : fill_dflt_a[l];
+    if (l < 24) *d = availA ? *f : s.t_da[l];
     else *(uint16_t *)d = availA ? *(const uint16_t *)f : (uint16_t)0;
   }
   if (l < 20) {
-    *(uint32_t *)(sb + fill_tab_b[l]) = availB ? ((const uint32_t *)T)[l] : top_dflt[l];
+    *(uint32_t *)(sb + s.t_b[l]) = availB ? ((const uint32_t *)T)[l] : s.t_topd[l];
   } else if (l < 28) {
-    const uint32_t e = fill_tab_b[l];
+    const uint32_t e = s.t_b[l];
     *(uint32_t *)(sb + (e >> 16)) = availA ? *(const uint32_t *)(sb + (e & 0xffff)) : 0u;
   } else {
     // corners: lanes 28,29 = top-right of list 0,1; lanes 30,31 = top-left
@@ -589,6 +602,10 @@ HWB_HD void coef_flush(SliceDec &s, const CoefRegs &r, int bit, int nslots) {
 // `sig` / `last` / `abs` point at the category's first context of each kind.  Returns the number of non-zero
 // coefficients.  The 8x8 category maps scan positions to contexts through tables and has its own map loop; the chroma DC
 // increments min(i, 2) equal i for the three positions that are coded, so every other category shares the plain loop.
+// The residual loops inline the decision (measured: as calls, 3000 slices took 330 ms instead of 286 and an intra
+// slice 250 ms instead of 200).
+#undef HWB_RBIN
+#define HWB_RBIN(ptr) cabac_decision(cab, s.cab, ptr, ft)
 HWB_HD int cabac_residual_impl(SliceDec &s, CabReg &cab, CoefRegs &cr, const CtxE *ft, int cat, int max_coeff, int start) {
   const uint32_t offs = cabac_cat_ctx[cat];  // ctxIdxOffset of significant_coeff_flag | last_... << 10 | coeff_abs_level_minus1 << 20
   CtxE *sig = s.ctxe + (offs & 1023), *last = s.ctxe + ((offs >> 10) & 1023), *abs_st = s.ctxe + (offs >> 20);
@@ -598,9 +615,9 @@ HWB_HD int cabac_residual_impl(SliceDec &s, CabReg &cab, CoefRegs &cr, const Ctx
     int i = 0;
 #pragma unroll 1
     for (; i < 63; ++i) {
-      if (cabac_decision(cab, s.cab, sig + cabac_sig8x8_ctx[i], ft)) {
+      if (HWB_RBIN(sig + cabac_sig8x8_ctx[i])) {
         if (i < 32) m0 |= 1u << i; else m1 |= 1u << (i - 32);
-        if (cabac_decision(cab, s.cab, last + cabac_last8x8_ctx[i], ft)) break;
+        if (HWB_RBIN(last + cabac_last8x8_ctx[i])) break;
       }
     }
     if (i == 63) m1 |= 1u << 31;
@@ -637,13 +654,13 @@ HWB_HD int cabac_residual_impl(SliceDec &s, CabReg &cab, CoefRegs &cr, const Ctx
       // raster position first: the load (8x8) / shift is off the arithmetic decoder's dependency chain
       const int pos = (HWB_T8_ON && cat == 5) ? zigzag8x8[32 * half + k] : (int)((scan_packed >> (4 * k)) & 15);
       int absv = 1;
-      if (!cabac_decision(cab, s.cab, abs_st + (gt1 ? 0 : eq1), ft)) {
+      if (!HWB_RBIN(abs_st + (gt1 ? 0 : eq1))) {
         eq1 = eq1 < 4 ? eq1 + 1 : 4;
       } else {
         CtxE *st1 = abs_st + 5 + (gt1 < cmax ? gt1 : cmax);
         absv = 2;
 #pragma unroll 1
-        while (absv < 15 && cabac_decision(cab, s.cab, st1, ft)) absv++;
+        while (absv < 15 && HWB_RBIN(st1)) absv++;
         if (absv >= 15) {
           const int esc = cabac_escape(cab, s.cab, 0);
           if (esc < 0) { sd_fail(s, 30); return 0; }
@@ -711,7 +728,7 @@ HWB_FN int cabac_blocks(SliceDec &s, int kind, int q, int cat, int arg, int bit0
       inc = ((nzp[-1] & unavail_mask) != 0) + 2 * ((*(nzp - up) & unavail_mask) != 0);
     }
     n = 0;
-    if (inc < 0 || cabac_decision(cab, s.cab, cbf + inc, ft)) {
+    if (inc < 0 || HWB_RBIN(cbf + inc)) {
       coef_reset(s, cr, big);
       n = cabac_residual_impl(s, cab, cr, ft, cat, maxc, (cat == 1 || cat == 4) ? 1 : 0);
       coef_flush(s, cr, bit0 + k, big ? 4 : 1);
@@ -847,36 +864,52 @@ HWB_FN int cabac_intra_mb_type(SliceDec &s, int ctx_base, bool islice) {
   return t;
 }
 
-HWB_FN int cabac_b_mb_type(SliceDec &s) {
+// B slice: mb_skip_flag and mb_type in one engine session.  Returns -1 (B_Skip), 0..22, or 23 (intra: the intra mb_type
+// follows, decoded by the caller).
+HWB_FN int cabac_b_header(SliceDec &s, int skip_ctx) {
   int ctx = 0;
   if (s.availA && !(s.left.flags & NBF_DIRECT16)) ctx++;
   if (s.availB && !(top_flags(s) & NBF_DIRECT16)) ctx++;
   const int st = 27;
-  if (!cabac_bin(s, st + ctx)) return 0;
-  if (!cabac_bin(s, st + 3)) return 1 + cabac_bin(s, st + 5);
-  int bits = cabac_bin(s, st + 4) << 3;
-  bits |= cabac_bin(s, st + 5) << 2;
-  bits |= cabac_bin(s, st + 5) << 1;
-  bits |= cabac_bin(s, st + 5);
-  if (bits < 8) return bits + 3;
-  if (bits == 13) return 23 + cabac_intra_mb_type(s, 32, false);
-  if (bits == 14) return 11;
-  if (bits == 15) return 22;
-  bits = (bits << 1) | cabac_bin(s, st + 5);
-  return bits - 4;
+  HWB_CAB_ENTER(s);
+  int r = -1;
+  if (!HWB_BIN(s, 24 + skip_ctx)) {
+    r = 0;
+    if (HWB_BIN(s, st + ctx)) {
+      if (!HWB_BIN(s, st + 3)) r = 1 + HWB_BIN(s, st + 5);
+      else {
+        int bits = HWB_BIN(s, st + 4);
+#pragma unroll 1
+        for (int i = 0; i < 3; ++i) bits = (bits << 1) | HWB_BIN(s, st + 5);
+        if (bits < 8) r = bits + 3;
+        else if (bits == 13) r = 23;
+        else if (bits == 14) r = 11;
+        else if (bits == 15) r = 22;
+        else r = ((bits << 1) | HWB_BIN(s, st + 5)) - 4;
+      }
+    }
+  }
+  HWB_CAB_LEAVE(s);
+  return r;
 }
 
 HWB_FN int cabac_b_sub_type(SliceDec &s) {
   const int st = 36;
-  if (!cabac_bin(s, st)) return 0;
-  if (!cabac_bin(s, st + 1)) return 1 + cabac_bin(s, st + 3);
-  int t = 3;
-  if (cabac_bin(s, st + 2)) {
-    if (cabac_bin(s, st + 3)) return 11 + cabac_bin(s, st + 3);
-    t += 4;
+  HWB_CAB_ENTER(s);
+  int t = 0;
+  if (HWB_BIN(s, st)) {
+    if (!HWB_BIN(s, st + 1)) t = 1 + HWB_BIN(s, st + 3);
+    else {
+      t = 3;
+      bool two = true;
+      if (HWB_BIN(s, st + 2)) {
+        if (HWB_BIN(s, st + 3)) { t = 11 + HWB_BIN(s, st + 3); two = false; }
+        else t += 4;
+      }
+      if (two) { t += 2 * HWB_BIN(s, st + 3); t += HWB_BIN(s, st + 3); }
+    }
   }
-  t += 2 * cabac_bin(s, st + 3);
-  t += cabac_bin(s, st + 3);
+  HWB_CAB_LEAVE(s);
   return t;
 }
 
@@ -1073,8 +1106,8 @@ HWB_FN void finish_mb(SliceDec &s, bool skipped, bool direct16, bool is_pcm) {
   }
   HWB_LANES_END
   // ---- phase 2: motion out (lane = 4x4 block, lanes 0..15 list 0, 16..31 list 1), line entry (lane = word), left context
-  uint32_t dm = 0;
-  for (int x = 0; x < 4; ++x) if (s.dir_cache[bot + x]) dm |= 1u << x;
+  uint32_t dm = 0;  // direct-mode flags of the bottom row: only B slices ever set any
+  if (B) for (int x = 0; x < 4; ++x) if (s.dir_cache[bot + x]) dm |= 1u << x;
   // words 0..3 of the line entry are staged where fill_caches keeps the top neighbour's (no longer needed)
   s.top_words[0] = flags | ((uint32_t)o.cbp << 8) | ((uint32_t)o.cmode << 16) | (dm << 24);
   s.top_words[1] = cbf;
@@ -1106,7 +1139,7 @@ HWB_FN void finish_mb(SliceDec &s, bool skipped, bool direct16, bool is_pcm) {
       s.o_refpic[1][(uint64_t)s.mbaddr * 4 + i] = -1;
     }
   }
-  if (l < 20) ((uint32_t *)n)[l] = *(const uint32_t *)((const uint8_t *)&s + line_tab[l]);
+  if (l < 20) ((uint32_t *)n)[l] = *(const uint32_t *)((const uint8_t *)&s + s.t_line[l]);
   HWB_LANES_END
   if (inter) {
 #if HWB_DEVICE_BUILD
@@ -1186,7 +1219,10 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
       else if (st == SLICE_P) {
         mbt = s.pre_mbt;  // decoded with mb_skip_flag (decode_slice)
         if (mbt == 5) mbt += cabac_intra_mb_type(s, 17, false);
-      } else mbt = cabac_b_mb_type(s);
+      } else {
+        mbt = s.pre_mbt;
+        if (mbt == 23) mbt += cabac_intra_mb_type(s, 32, false);
+      }
     } else mbt = (int)s_ue(s);
     int imbt = -1;  // intra mb_type 0..25
     if (st == SLICE_I) imbt = mbt;
@@ -1334,12 +1370,12 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
               if (r >= sd.num_ref[l]) { sd_fail(s, 54); return; }
             }
             refs[l][g] = (int8_t)r;
-            set_refs(s, l, bx, by, w, h, r >= 0 ? r : REF_NONE);
+            if (ng > 1) set_refs(s, l, bx, by, w, h, r >= 0 ? r : REF_NONE);  // a single 16x16 partition: nothing inside the macroblock looks at it
           }
         // motion vectors; references of not-yet-decoded groups must look unavailable for C-neighbour lookups
 #pragma unroll 1
         for (int l = 0; l < nl; ++l) {
-          set_refs(s, l, 0, 0, 4, 4, REF_UNAVAIL);
+          if (ng > 1) set_refs(s, l, 0, 0, 4, 4, REF_UNAVAIL);
 #pragma unroll 1
           for (int g = 0; g < ng; ++g) {
             const int e = s.grp[g], bx = e & 3, by = (e >> 2) & 3, w = ((e >> 4) & 3) + 1, h = ((e >> 6) & 3) + 1;
@@ -1404,6 +1440,7 @@ HWB_FN void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states
   }
   s.qp = sd.qp; s.last_dqp = 0; s.row_reach = 0; s.row_reach_x = 0;
   init_caches(s);
+  init_lane_tables(s);
   s.line = (NbCtx *)(c.ectx + (uint64_t)slice_idx * c.ectx_stride);
   // the arena region of a slice starts at its first macroblock's worst-case offset
   s.coef_next = (uint32_t)sd.first_mb * SLOTS_PER_MB;
@@ -1435,8 +1472,8 @@ HWB_FN void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states
     if (sd.slice_type != SLICE_I) {
       if (HWB_IS_CABAC(s)) {
         int ctx = (s.availA && !(s.left.flags & NBF_SKIP)) + (s.availB && !(top_flags(s) & NBF_SKIP));
-        if (HWB_IS_B(sd.slice_type)) skipped = cabac_bin(s, 24 + ctx) != 0;
-        else { s.pre_mbt = cabac_p_header(s, ctx); skipped = s.pre_mbt < 0; }
+        s.pre_mbt = HWB_IS_B(sd.slice_type) ? cabac_b_header(s, ctx) : cabac_p_header(s, ctx);
+        skipped = s.pre_mbt < 0;
       } else {
         if (run < 0) {
           run = (int)s_ue(s);

@@ -401,15 +401,13 @@ Result B200VideoDecoder::submit_current() {
   if (!interval_begin_) { interval_begin_ = hwb_dev_event_create(dev_); if (interval_begin_) rc |= hwb_dev_event_record(dev_, interval_begin_, st); }  // a busy period of the device starts
   int mode = ch->pics[0].cabac ? 1 : 0;
   for (auto &p : ch->pics) if ((p.cabac ? 1 : 0) != mode) mode = -1;
-  if (mode == 1) {  // CABAC throughout: the copy of the kernel without B-slice support when the chunk has none
-    bool has_b = false;
+  if (mode == 1) {  // CABAC throughout: copies of the kernel without B-slice support / without the 8x8 transform when the chunk has none
+    bool has_b = false, t8 = false;  // (the per-macroblock path has to fit the SM's instruction cache: DESIGN.md 4a)
     for (auto &sl : ch->slices) has_b |= sl.slice_type == hwb::SLICE_B;
-    if (!has_b) {
-      bool t8 = false;  // ... and the copy without the 8x8 transform either when no picture enables it (Baseline / Main streams)
-      for (auto &p : ch->pics) t8 |= p.transform8x8_mode != 0;
-      static const bool no_ip4 = getenv("HWB_NO_IP4") != nullptr;
-      mode = (t8 || no_ip4) ? 3 : 4;
-    }
+    for (auto &p : ch->pics) t8 |= p.transform8x8_mode != 0;
+    static const bool no_4 = getenv("HWB_NO_IP4") != nullptr;
+    if (no_4) t8 = true;
+    mode = has_b ? (t8 ? 1 : 5) : (t8 ? 3 : 4);
   }
   // Default: the picture kernel starts when the batch's entropy kernel has finished (an event orders them).
   // HWB_CONCURRENT=1 launches it right behind the entropy kernel instead; it then waits for the entropy stage picture

@@ -141,7 +141,7 @@ class B200VideoDecoder : public VideoDecoderInterface {
   int ramp_first_ = 120, ramp_target_ = 120;
   int deblock_band_ = 0;  // 0 = by batch kind (see submit_current)
   int group_target_ = 1 << 30;  // pictures per GOP group inside a batch (work order of the picture kernel); default: one group
-  bool feeder_may_block_ = false, defer_submit_ = false, no_rgb_ = false, picture_profile_ = false, concurrent_ = false, intra_reserve_ = false;
+  bool feeder_may_block_ = false, defer_submit_ = false, no_rgb_ = false, picture_profile_ = false, concurrent_ = false, intra_reserve_ = true;
   std::unique_ptr<Chunk> cur_;
   std::deque<std::unique_ptr<Chunk>> queue_;    // submitted chunks, oldest first
   std::vector<std::unique_ptr<Chunk>> retired_;  // fully popped, slab reusable after the next copy-stream sync

@@ -778,7 +778,7 @@ struct Encoder {
       s.qp = sd.qp; s.last_dqp = 0;
       s.line = (NbCtx *)(c.ectx + (uint64_t)(slot * MAXSL + sl) * c.ectx_stride);
       s.coef_next = (uint32_t)first_mb * SLOTS_PER_MB;
-      init_caches(s);
+      init_caches(s); init_lane_tables(s);
       if (cabac) {
         while (!e.bw.aligned()) e.bw.put1(1);
         cabac_init_states(e.ce.st, ps.type == SLICE_I ? 0 : 1 + sd.cabac_init_idc, sd.qp);
