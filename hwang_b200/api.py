@@ -1,5 +1,6 @@
 import ctypes
 import os
+import threading
 
 import numpy as np
 
@@ -187,21 +188,80 @@ class EncodedData:  # DecoderAutomata::EncodedData, hwang/decoder_automata.h:43-
         self.valid_frames = []
 
 
+# Page-locked allocations are slow (cudaHostAlloc pins page by page: a few GB/s), and a sparse request returns a gigabyte
+# of frames: released buffers are kept for the next request instead of being unpinned.  HWB_PINNED_POOL_MB bounds what
+# the pool may hold (default 6144; 0 = no pool).
+_pool_lock = threading.Lock()
+_pool = []  # (capacity, ptr), idle buffers
+_pool_bytes = 0
+_POOL_MAX = int(os.environ.get('HWB_PINNED_POOL_MB', '6144')) << 20
+_POOL_GRAIN = 8 << 20
+
+
+def _pool_take(nbytes):
+    global _pool_bytes
+    with _pool_lock:
+        best = None
+        for i, (cap, ptr) in enumerate(_pool):
+            if cap >= nbytes and cap <= 2 * nbytes + _POOL_GRAIN and (best is None or cap < _pool[best][0]):
+                best = i
+        if best is None:
+            return None
+        cap, ptr = _pool.pop(best)
+        _pool_bytes -= cap
+        return cap, ptr
+
+
+def _pool_give(cap, ptr):
+    """-> list of pointers the caller has to free (the buffer itself if the pool is off, evicted ones otherwise)."""
+    global _pool_bytes
+    if _POOL_MAX <= 0 or cap > _POOL_MAX:
+        return [ptr]
+    evict = []
+    with _pool_lock:
+        _pool.append((cap, ptr))
+        _pool_bytes += cap
+        while _pool_bytes > _POOL_MAX:  # oldest first
+            c, p = _pool.pop(0)
+            _pool_bytes -= c
+            evict.append(p)
+    return evict
+
+
+def release_pinned_pool():
+    """Unpin every idle buffer of the pool."""
+    global _pool_bytes
+    with _pool_lock:
+        idle, _pool[:] = list(_pool), []
+        _pool_bytes = 0
+    for _, p in idle:
+        _lib.lib().hwb_free_pinned(p)
+
+
 class PinnedBuffer:
     """Page-locked host memory exposed as a numpy array; output frames are views into it."""
 
     def __init__(self, nbytes):
         self.nbytes = nbytes
-        self.ptr = _lib.lib().hwb_alloc_pinned(nbytes)
-        if not self.ptr:
-            raise MemoryError('hwb_alloc_pinned(%d) failed' % nbytes)
+        got = _pool_take(nbytes) if _POOL_MAX > 0 else None
+        if got:
+            self.capacity, self.ptr = got
+        else:
+            self.capacity = (nbytes + _POOL_GRAIN - 1) // _POOL_GRAIN * _POOL_GRAIN
+            self.ptr = _lib.lib().hwb_alloc_pinned(self.capacity)
+            if not self.ptr:
+                release_pinned_pool()  # the idle buffers may be what is in the way
+                self.ptr = _lib.lib().hwb_alloc_pinned(self.capacity)
+            if not self.ptr:
+                raise MemoryError('hwb_alloc_pinned(%d) failed' % self.capacity)
         self.array = np.ctypeslib.as_array((ctypes.c_uint8 * nbytes).from_address(self.ptr))
 
     def __del__(self):
         try:
             if self.ptr:
-                _lib.lib().hwb_free_pinned(self.ptr)
-                self.ptr = None
+                ptr, self.ptr = self.ptr, None
+                for p in _pool_give(self.capacity, ptr):
+                    _lib.lib().hwb_free_pinned(p)
         except Exception:
             pass
 

@@ -65,7 +65,7 @@ __device__ __forceinline__ int warp_ticket(int32_t *ticket) {
 // Ticket hand-out.  Intra slices carry several times the bits of inter slices and every one of them is a single
 // warp's serial work: the intra slices of a batch set the earliest moment its first pictures can be reconstructed.  A
 // warp decodes an intra slice at full speed only while the SM's instruction caches hold the intra path; next to
-// inter-slice warps (a different 30 KB of code) it runs 1.5x slower.  So the SMs [0, intra_sms) are reserved: their
+// inter-slice warps (a different 30 KB of code) it runs 1.5x slower.  So the SMs [intra_sm_base, intra_sm_base + intra_sms) are reserved: their
 // warps take the intra tickets (ticket[3]) and nothing else until those are gone, everybody else takes inter tickets
 // (ticket[0]).  Invariant kept from the single-queue version: no inter ticket is handed out before every intra ticket
 // has been taken (a B slice may wait for its co-located picture's slice, which must therefore be running or done).  If
@@ -111,7 +111,7 @@ __device__ int next_entropy_ticket(const ChunkCtx &c, int32_t *ticket, bool rese
     const int w = threadIdx.x >> 5;                                                                   \
     unsigned smid;                                                                                    \
     asm("mov.u32 %0, %%smid;" : "=r"(smid));                                                          \
-    const bool reserved = (int)smid < c.intra_sms;                                                    \
+    const bool reserved = smid - (unsigned)c.intra_sm_base < (unsigned)c.intra_sms;                   \
     const long long t_start = clock64();                                                              \
     for (;;) {                                                                                        \
       const int t = next_entropy_ticket(c, ticket, reserved, t_start);                                \
@@ -169,10 +169,6 @@ __global__ void __launch_bounds__(kThreads, 6) picture_kernel(const __grid_const
     unsigned smid, nsmid;
     asm("mov.u32 %0, %%smid;" : "=r"(smid));
     asm("mov.u32 %0, %%nsmid;" : "=r"(nsmid));
-    // the SMs reserved for intra slices (entropy stage of this and later batches) stay free of picture work; the grid is
-    // large (split > 0), so the other SMs hold plenty of blocks
-    if ((int)smid < c.intra_sms) return;
-    smid -= c.intra_sms; nsmid -= c.intra_sms;
     const int mode = split / 1000, pct = split % 1000;  // experiments: how the SMs of the two roles are spread over the chip
     if (mode == 1) fixed_deblock = (int)(smid * 100u / nsmid) < pct;               // one contiguous range of SM ids
     else if (mode == 2) fixed_deblock = (int)(((smid >> 1) * 37u) % 100u) < pct;   // whole TPCs (SM pairs), scattered
@@ -251,6 +247,7 @@ __global__ void __launch_bounds__(256) yuv_kernel(ChunkCtx c, int frame, int cro
 struct hwb_dev {
   int device = 0;
   int sms = 148;
+  int smem_per_sm = 228 * 1024, smem_optin = 227 * 1024;
   int entropy_bpsm = 3, picture_bpsm = 6;  // resident blocks per SM (hwb_dev_set_occupancy)
   cudaStream_t streams[HWB_NUM_STREAMS];
   std::string err;
@@ -280,6 +277,8 @@ int hwb_dev_open(int device, hwb_dev **out) {
   hwb_dev *d = new hwb_dev();
   d->device = device;
   cudaDeviceGetAttribute(&d->sms, cudaDevAttrMultiProcessorCount, device);
+  cudaDeviceGetAttribute(&d->smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
+  cudaDeviceGetAttribute(&d->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   // Priorities, highest first: copies to the host, then the picture kernel (a chunk finishes -- and its frames start
   // travelling to the host -- while later chunks are still being entropy-decoded), then entropy decoding
   int least = 0, greatest = 0;
@@ -372,13 +371,34 @@ int hwb_dev_entropy(hwb_dev *d, int s, const ChunkCtx *c, int32_t *ticket, int m
   // cycles are "no instruction", gcc instruction requests at 67% of peak).  Sweep on the 3000-slice benchmark chunk:
   // 1 block/SM 561 ms, 2: 411, 3: 394, 4: 402, 5: 409, 8: 430.  HWB_ENTROPY_BLOCKS_PER_SM overrides.
   static int bpsm_env = [] { const char *e = getenv("HWB_ENTROPY_BLOCKS_PER_SM"); int v = e ? atoi(e) : 0; return v; }();
-  const int grid = grid_for(d, c->num_tickets, bpsm_env > 0 ? bpsm_env : d->entropy_bpsm);
-  if (mode == 4) entropy_cabac_ip4_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);
-  else if (mode == 5) entropy_cabac4_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);
-  else if (mode == 3) entropy_cabac_ip_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);
-  else if (mode == 1) entropy_cabac_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);
-  else if (mode == 0) entropy_cavlc_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);
-  else entropy_kernel<<<grid, kThreads, 0, d->streams[s]>>>(*c, ticket);
+  const int bpsm = bpsm_env > 0 ? bpsm_env : d->entropy_bpsm;
+  const int grid = grid_for(d, c->num_tickets, bpsm);
+  // The cap has to hold across launches too: the entropy kernels of all batches of a request are in flight together, and
+  // the block scheduler would pack seven of their blocks (28 warps) onto an SM.  Unused dynamic shared memory makes a
+  // block as large as 1/bpsm of what entropy blocks may take of an SM (all but 54 KB, which stay for two blocks of the
+  // picture kernel), so that at most bpsm of them are resident whichever launches they come from -- earlier batches
+  // first, which is the order their frames are due in.  HWB_ENTROPY_SMEM_CAP=0 turns it off.
+  static const bool cap = [] { const char *e = getenv("HWB_ENTROPY_SMEM_CAP"); return !e || atoi(e) != 0; }();
+  size_t pad = 0;
+  auto launch = [&](auto kernel) {
+    if (cap) {
+      cudaFuncAttributes fa;
+      if (cudaFuncGetAttributes(&fa, kernel) == cudaSuccess) {
+        const size_t per_block = ((size_t)d->smem_per_sm - 54 * 1024) / (size_t)bpsm - 1024;  // 1 KB per block is the system's
+        if (per_block > fa.sharedSizeBytes && per_block <= (size_t)d->smem_optin) {
+          pad = per_block - fa.sharedSizeBytes;
+          cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+        }
+      }
+    }
+    kernel<<<grid, kThreads, pad, d->streams[s]>>>(*c, ticket);
+  };
+  if (mode == 4) launch(entropy_cabac_ip4_kernel);
+  else if (mode == 5) launch(entropy_cabac4_kernel);
+  else if (mode == 3) launch(entropy_cabac_ip_kernel);
+  else if (mode == 1) launch(entropy_cabac_kernel);
+  else if (mode == 0) launch(entropy_cavlc_kernel);
+  else launch(entropy_kernel);
   HWB_CUDA(d, cudaGetLastError());
   d->launches++;
   return 0;

@@ -389,10 +389,16 @@ Result B200VideoDecoder::submit_current() {
   c.entropy_order = (const int32_t *)(b + o_order);
   c.num_tickets = (int32_t)order.size();
   for (int32_t i : order) if (ch->slices[i].slice_type == hwb::SLICE_I) c.num_intra_tickets++;
-  // HWB_INTRA_RESERVE=1: SMs reserved for the intra slices, 12 warps each (see kernels.cu), at most an eighth of the
-  // device.  Off by default: measured, the intra slices finish no earlier (their fetch misses queue at the GPC-level
-  // instruction cache, which the reservation does not isolate), and the picture kernel loses those SMs.
-  if (intra_reserve_ && c.num_intra_tickets > 0 && c.num_intra_tickets < c.num_tickets) c.intra_sms = std::min(18, (c.num_intra_tickets + 11) / 12);
+  // SMs reserved for the intra slices (see kernels.cu; HWB_INTRA_RESERVE=0 turns it off): an intra slice is a warp's
+  // serial work for a fifth of a second, and it runs faster on an SM whose instruction caches hold the intra path only.
+  // Measured on the 3000-slice benchmark batch: 272 ms with the reservation, 293 without.  HWB_INTRA_WARPS_PER_SM (12) is
+  // how many intra slices share a reserved SM.
+  static const int intra_per_sm = [] { const char *e = getenv("HWB_INTRA_WARPS_PER_SM"); const int v = e ? atoi(e) : 12; return v > 0 ? v : 12; }();
+  if (intra_reserve_ && c.num_intra_tickets > 0 && c.num_intra_tickets < c.num_tickets) {
+    c.intra_sms = std::min(37, (c.num_intra_tickets + intra_per_sm - 1) / intra_per_sm);
+    c.intra_sm_base = intra_sm_next_;  // batches in flight together reserve different SMs
+    intra_sm_next_ = (intra_sm_next_ + c.intra_sms) % 96;  // base + 37 stays below the SM count of any device this targets (148)
+  }
   rc |= hwb_dev_memset(dev_, st, sync, 0, n_sync * 4);
   stats_.h2d_bytes += ch->bitstream.size() + (size_t)P * sizeof(PicDesc) + (size_t)S * sizeof(SliceDesc) + (recon_items.size() * 2 + order.size()) * 4;
   // a copy from pageable memory has been staged by the time cudaMemcpyAsync returns: the buffer can be reused
@@ -453,6 +459,13 @@ Result B200VideoDecoder::finish_chunk(Chunk &c) {
   hwb_dev_d2h(dev_, HWB_STREAM_AUX, &flag, c.error_dev, 4);
   hwb_dev_stream_sync(dev_, HWB_STREAM_AUX);
   float ms = 0;
+  static const bool trace = getenv("HWB_TRACE_BATCHES") != nullptr;  // device timeline of every batch, relative to the busy period's start
+  if (trace && interval_begin_) {
+    float b = 0, e = 0, p = 0, d = 0;
+    hwb_dev_event_elapsed(dev_, interval_begin_, c.ev_begin, &b); hwb_dev_event_elapsed(dev_, interval_begin_, c.ev_entropy, &e);
+    hwb_dev_event_elapsed(dev_, interval_begin_, c.ev_picture, &p); hwb_dev_event_elapsed(dev_, interval_begin_, c.ev_done, &d);
+    fprintf(stderr, "[batch] pictures %4d  inputs resident %7.1f  entropy done %7.1f  picture kernel %7.1f .. %7.1f ms\n", (int)c.pics.size(), b, e, p, d);
+  }
   if (profile_) {
     if (hwb_dev_event_elapsed(dev_, c.ev_begin, c.ev_entropy, &ms) == 0) { stats_.entropy_ms += ms; stats_.entropy_launches++; }
     if (hwb_dev_event_elapsed(dev_, c.ev_picture, c.ev_done, &ms) == 0) { stats_.picture_ms += ms; stats_.picture_launches++; }
