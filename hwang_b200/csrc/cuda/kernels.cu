@@ -94,6 +94,13 @@ __device__ int next_entropy_ticket(const ChunkCtx &c, int32_t *ticket, bool rese
       }
       continue;
     }
+    // every intra ticket has been taken; while some of those slices are still running only the first
+    // c.inter_throttle warps of a block decode inter slices, the others wait
+    if (c.inter_throttle > 0 && (int)(threadIdx.x >> 5) >= c.inter_throttle && peek_counter(c.intra_done) < n_intra) {
+      if (peek_counter(ticket) >= n_inter) return -1;  // nothing left to wait for
+      __nanosleep(4000);
+      continue;
+    }
     const int t = take_ticket(ticket, n_inter);
     return t >= 0 ? t + n_intra : -1;
   }
@@ -119,6 +126,7 @@ __device__ int next_entropy_ticket(const ChunkCtx &c, int32_t *ticket, bool rese
       const int s = c.entropy_order[t];                                                               \
       NS::decode_slice(c, s, nullptr, &sdec[w]);                                                      \
       __syncwarp();                                                                                   \
+      if (t < c.num_intra_tickets && (threadIdx.x & 31) == 0) atomicAdd(c.intra_done, 1);             \
     }                                                                                                 \
   }
 HWB_ENTROPY_KERNEL(entropy_kernel, hwb::ent)                    // pictures of both entropy modes in one chunk
