@@ -80,6 +80,9 @@ struct SliceDec {
   int qp;
   int last_dqp;
   int pre_mbt;  // CABAC P slices: mb_type as decoded together with mb_skip_flag (cabac_p_header), -1 = not decoded yet
+  // macroblock loop state (slice_begin / slice_step / slice_end)
+  int it_slice, it_first, it_addr, it_end_mb, it_run;
+  bool it_end;
   LeftCtx left;
   uint32_t top_words[4];   // words 0..3 of the top neighbour's line-buffer entry (flags/cbp/cmode/dirmask, cbf, chroma nnz)
   int8_t tl_ref[2];        // top-left macroblock's bottom-right block (saved before its line entry is overwritten)
@@ -1419,12 +1422,14 @@ HWB_FN void decode_mb(SliceDec &s, bool skipped) {
 }
 
 // ================================================================================ slice
-HWB_FN void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states, SliceDec *state) {
+// A slice is decoded in three steps so that the CUDA kernels can interleave the macroblocks of the warps of a block
+// (kernels.cu, "lockstep"): slice_begin, slice_step once per macroblock until it returns false, slice_end.  The loop's
+// state lives in the slice state (s.it_*).
+HWB_FN void slice_begin(const ChunkCtx &c, int slice_idx, SliceDec *state) {
   SliceDec &s = *state;
   s.c = &c; s.sd = &c.slices[slice_idx]; s.pd = &c.pics[s.sd->pic];
   s.slice_num = slice_idx - s.pd->first_slice;
   s.cabac = s.pd->cabac != 0;
-  (void)cabac_states;
   s.error = 0;
   const SliceDesc &sd = *s.sd;
   const uint8_t *data = c.bitstream + sd.data_off;
@@ -1453,72 +1458,95 @@ HWB_FN void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states
     HWB_LANES_END
     cabac_start(s.cab, data, (sd.bit_off + 7) >> 3);  // cabac_alignment_one_bits, then 9 bits of codIOffset
   }
-  const int first = sd.first_mb;
-  int addr = first;
-  int mbx = first % c.mb_w, mby = first / c.mb_w;
-  bool end = false;
+  s.it_slice = slice_idx;
+  s.it_first = sd.first_mb;
+  s.it_addr = sd.first_mb;
+  s.mbx = sd.first_mb % c.mb_w; s.mby = sd.first_mb / c.mb_w;
+  s.it_end = false;
   // CAVLC mb_skip_run state: -1 = read a new run before the next macroblock, 0 = the next
   // macroblock is coded, >0 = macroblocks still to skip
-  int run = -1;
-  const int end_mb = sd.end_mb < c.nmb ? sd.end_mb : c.nmb;  // the slice must cover [first_mb, end_mb) exactly
-  while (!end && addr < end_mb) {
-    s.mbaddr = addr; s.mbx = mbx; s.mby = mby;
-    s.availA = s.mbx > 0 && addr - 1 >= first;
-    s.availB = addr - c.mb_w >= first;
-    s.availC = s.mbx < c.mb_w - 1 && addr - c.mb_w + 1 >= first;
-    s.availD = s.mbx > 0 && addr - c.mb_w - 1 >= first;
-    fill_caches(s, false);  // also brings the top neighbour's flags into the slice state (mb_skip_flag context)
-    bool skipped = false;
-    if (sd.slice_type != SLICE_I) {
-      if (HWB_IS_CABAC(s)) {
-        int ctx = (s.availA && !(s.left.flags & NBF_SKIP)) + (s.availB && !(top_flags(s) & NBF_SKIP));
-        s.pre_mbt = HWB_IS_B(sd.slice_type) ? cabac_b_header(s, ctx) : cabac_p_header(s, ctx);
-        skipped = s.pre_mbt < 0;
-      } else {
-        if (run < 0) {
-          run = (int)s_ue(s);
-          if (run > end_mb - addr) { sd_fail(s, 60); break; }
-        }
-        if (run > 0) { skipped = true; run--; }
-      }
-    }
-    decode_mb(s, skipped);
-    if (HWB_IS_CABAC(s) && s.cab.pos > sd.data_size + 8) s.br.overrun = true;  // the engine legitimately reads a few bytes ahead
-    if (s.error || s.br.overrun) break;
+  s.it_run = -1;
+  s.it_end_mb = sd.end_mb < c.nmb ? sd.end_mb : c.nmb;  // the slice must cover [first_mb, end_mb) exactly
+}
+
+// One macroblock.  Returns false when the slice is over (end of slice, error, or its last macroblock done).
+HWB_FN bool slice_step(SliceDec *state) {
+  SliceDec &s = *state;
+  const ChunkCtx &c = *s.c;
+  const SliceDesc &sd = *s.sd;
+  const int first = s.it_first, end_mb = s.it_end_mb;
+  int addr = s.it_addr;
+  if (s.it_end || addr >= end_mb) return false;
+  s.mbaddr = addr;
+  s.availA = s.mbx > 0 && addr - 1 >= first;
+  s.availB = addr - c.mb_w >= first;
+  s.availC = s.mbx < c.mb_w - 1 && addr - c.mb_w + 1 >= first;
+  s.availD = s.mbx > 0 && addr - c.mb_w - 1 >= first;
+  fill_caches(s, false);  // also brings the top neighbour's flags into the slice state (mb_skip_flag context)
+  bool skipped = false;
+  if (sd.slice_type != SLICE_I) {
     if (HWB_IS_CABAC(s)) {
-      end = cabac_term(s) != 0;
-    } else if (skipped) {
-      if (run == 0 && !br_more_rbsp_data(s.br, s.stop_bitpos)) end = true;
+      int ctx = (s.availA && !(s.left.flags & NBF_SKIP)) + (s.availB && !(top_flags(s) & NBF_SKIP));
+      s.pre_mbt = HWB_IS_B(sd.slice_type) ? cabac_b_header(s, ctx) : cabac_p_header(s, ctx);
+      skipped = s.pre_mbt < 0;
     } else {
-      run = -1;
-      if (!br_more_rbsp_data(s.br, s.stop_bitpos)) end = true;
-    }
-    addr++;
-    if (++mbx == c.mb_w) { mbx = 0; ++mby; }
-    if (mbx == 0 || end || addr == end_mb) {
-      // the row just completed (or the part of it this slice covers): what the picture kernel must wait for in the
-      // reference pictures before it predicts this row; several slices may share a row, hence the atomic maximum
-      int32_t *rr = c.mv_reach + (size_t)sd.pic * c.mb_h + (addr - 1) / c.mb_w;
-      int32_t *rx = c.mv_reach_x + (size_t)sd.pic * c.mb_h + (addr - 1) / c.mb_w;
-#if HWB_DEVICE_BUILD
-      __syncwarp();
-      if ((threadIdx.x & 31) == 0) {  // release store: no L1 invalidation (see publish_progress in kernels.cu)
-        if (s.row_reach) { atomicMax(rr, s.row_reach); atomicMax(rx, s.row_reach_x); }
-        const int32_t v = (end || addr == end_mb) ? c.nmb : addr;
-        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(c.entropy_prog + slice_idx), "r"(v) : "memory");
+      if (s.it_run < 0) {
+        s.it_run = (int)s_ue(s);
+        if (s.it_run > end_mb - addr) { sd_fail(s, 60); return false; }
       }
-#else
-      if (s.row_reach > *rr) *rr = s.row_reach;
-      if (s.row_reach_x > *rx) *rx = s.row_reach_x;
-      c.entropy_prog[slice_idx] = (end || addr == end_mb) ? c.nmb : addr;
-#endif
-      s.row_reach = 0; s.row_reach_x = 0;
+      if (s.it_run > 0) { skipped = true; s.it_run--; }
     }
   }
+  decode_mb(s, skipped);
+  if (HWB_IS_CABAC(s) && s.cab.pos > sd.data_size + 8) s.br.overrun = true;  // the engine legitimately reads a few bytes ahead
+  if (s.error || s.br.overrun) return false;
+  bool end = false;
+  if (HWB_IS_CABAC(s)) {
+    end = cabac_term(s) != 0;
+  } else if (skipped) {
+    if (s.it_run == 0 && !br_more_rbsp_data(s.br, s.stop_bitpos)) end = true;
+  } else {
+    s.it_run = -1;
+    if (!br_more_rbsp_data(s.br, s.stop_bitpos)) end = true;
+  }
+  s.it_end = end;
+  addr++;
+  s.it_addr = addr;
+  int mbx = s.mbx + 1;
+  if (mbx == c.mb_w) { mbx = 0; s.mby++; }
+  s.mbx = mbx;
+  if (mbx == 0 || end || addr == end_mb) {
+    // the row just completed (or the part of it this slice covers): what the picture kernel must wait for in the
+    // reference pictures before it predicts this row; several slices may share a row, hence the atomic maximum
+    const int slice_idx = s.it_slice;
+    int32_t *rr = c.mv_reach + (size_t)sd.pic * c.mb_h + (addr - 1) / c.mb_w;
+    int32_t *rx = c.mv_reach_x + (size_t)sd.pic * c.mb_h + (addr - 1) / c.mb_w;
+#if HWB_DEVICE_BUILD
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {  // release store: no L1 invalidation (see publish_progress in kernels.cu)
+      if (s.row_reach) { atomicMax(rr, s.row_reach); atomicMax(rx, s.row_reach_x); }
+      const int32_t v = (end || addr == end_mb) ? c.nmb : addr;
+      asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(c.entropy_prog + slice_idx), "r"(v) : "memory");
+    }
+    __syncwarp();
+#else
+    if (s.row_reach > *rr) *rr = s.row_reach;
+    if (s.row_reach_x > *rx) *rx = s.row_reach_x;
+    c.entropy_prog[slice_idx] = (end || addr == end_mb) ? c.nmb : addr;
+#endif
+    s.row_reach = 0; s.row_reach_x = 0;
+  }
+  return !end && addr < end_mb;
+}
+
+HWB_FN void slice_end(SliceDec *state) {
+  SliceDec &s = *state;
+  const ChunkCtx &c = *s.c;
+  const int slice_idx = s.it_slice;
   // A slice that stops before the next slice's first macroblock (or runs out of data at it without its end flag)
   // would leave macroblock records of the picture undefined: the picture is refused (error 61), nothing of the chunk
   // is reconstructed.  In CABAC mode end_of_slice_flag must also have been seen at the last macroblock.
-  if (!s.error && !s.br.overrun && (addr != end_mb || (HWB_IS_CABAC(s) && !end))) s.error = 61;
+  if (!s.error && !s.br.overrun && (s.it_addr != s.it_end_mb || (HWB_IS_CABAC(s) && !s.it_end))) s.error = 61;
   if (s.error || s.br.overrun) {
 #if HWB_DEVICE_BUILD
     __syncwarp();
@@ -1532,6 +1560,14 @@ HWB_FN void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states
     c.entropy_prog[slice_idx] = c.nmb;
 #endif
   }
+}
+
+HWB_HD void decode_slice(const ChunkCtx &c, int slice_idx, uint8_t *cabac_states, SliceDec *state) {
+  (void)cabac_states;
+  slice_begin(c, slice_idx, state);
+#pragma unroll 1
+  while (slice_step(state)) {}
+  slice_end(state);
 }
 
 }  // namespace HWB_ENT_NS

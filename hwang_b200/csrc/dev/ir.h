@@ -111,8 +111,6 @@ struct ChunkCtx {
   const int32_t *entropy_order;  // [num_tickets] ticket -> slice index: I slices first (longest, no dependencies), then decode order
   int32_t num_tickets;           // slices to entropy-decode (slices of skipped pictures hold no ticket)
   int32_t num_intra_tickets;     // the first num_intra_tickets of them are intra slices
-  int32_t inter_throttle;        // while intra slices of this launch are running, only this many warps of a block (of 4) decode inter slices; 0 / 4 = no throttle
-  int32_t *intra_done;           // intra slices finished (zeroed per chunk)
   int32_t intra_sms;             // SMs [intra_sm_base, intra_sm_base + intra_sms) decode the intra slices (see kernels.cu); 0 = no reservation
   int32_t intra_sm_base;         // rotates from batch to batch: the intra slices of batches in flight together do not pile up on the same SMs
   int32_t *entropy_prog;   // [slice] first macroblock address not yet entropy-decoded (B direct col dependency)

@@ -55,9 +55,10 @@ struct Progress {  // a counter watched by this warp, with the last value seen (
 #if HWB_DEVICE_BUILD
 __device__ __noinline__ void poll_progress(Progress &g, int need) {
   int32_t v = 0;
+  const int32_t *const p = g.p;  // a register copy: the asm's memory clobber made the loop reload it from the caller's frame every turn
   if ((threadIdx.x & 31) == 0) {
     for (;;) {  // relaxed GPU-scope poll; the data it guards is read with ld.global.cg (L2) by the callers
-      asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(g.p) : "memory");
+      asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
       if (v >= need) break;
       __nanosleep(64);
     }

@@ -217,8 +217,13 @@ HWB_FN void mc_partition(const ChunkCtx &c, int rf, int x0, int y0, int w, int h
       const int k = l & 7;
       const uint8_t *base = ref + (int64_t)oy * W + (ox - sh) + 4 * k;
       if (k < nw) {
-#pragma unroll 1
-        for (int r = l >> 3; r < rows; r += 4) *(uint32_t *)(sm->mc_luma + r * MC_LS + 4 * k) = ld_u32_cg((const uint32_t *)(base + (int64_t)r * W));
+        // all of a lane's loads (rows l>>3, +4, ...: at most 6 of the <= 21) are issued before the first store: they go
+        // to L2 (ld.global.cg), and one at a time their latency was a quarter of the macroblock's time
+        uint32_t v[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { const int r = (l >> 3) + 4 * i; if (r < rows) v[i] = ld_u32_cg((const uint32_t *)(base + (int64_t)r * W)); }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { const int r = (l >> 3) + 4 * i; if (r < rows) *(uint32_t *)(sm->mc_luma + r * MC_LS + 4 * k) = v[i]; }
       }
     } else if (l < cols) {  // window crosses the picture edge: one (clamped) column per lane
       const uint8_t *col = ref + clip3(0, W - 1, ox + l);
@@ -231,9 +236,11 @@ HWB_FN void mc_partition(const ChunkCtx &c, int rf, int x0, int y0, int w, int h
       if (cinside) {
         const int nw = (csh + ccols + 3) >> 2, k = l & 3;  // <= 3 words
         if (k < nw) {
-#pragma unroll 1
-          for (int r = (l >> 2) & 3; r < crows; r += 4)
-            *(uint32_t *)(sm->mc_chroma[pl] + r * MC_CS + 4 * k) = ld_u32_cg((const uint32_t *)(P + (int64_t)(cy + r) * cw + (cx - csh)) + k);
+          uint32_t v[3];  // rows (l>>2)&3, +4, +8 of the <= 9
+#pragma unroll
+          for (int i = 0; i < 3; ++i) { const int r = ((l >> 2) & 3) + 4 * i; if (r < crows) v[i] = ld_u32_cg((const uint32_t *)(P + (int64_t)(cy + r) * cw + (cx - csh)) + k); }
+#pragma unroll
+          for (int i = 0; i < 3; ++i) { const int r = ((l >> 2) & 3) + 4 * i; if (r < crows) *(uint32_t *)(sm->mc_chroma[pl] + r * MC_CS + 4 * k) = v[i]; }
         }
       } else if ((l & 15) < ccols) {
         const uint8_t *col = P + clip3(0, cw - 1, cx + (l & 15));
@@ -341,10 +348,15 @@ HWB_FN void mc_list(const ChunkCtx &c, const SliceDesc &sd, int list, const int1
   const int r0 = ri[0];
   bool uni = r0 >= 0 && ri[1] == r0 && ri[2] == r0 && ri[3] == r0;
   const uint32_t m0 = mw[0];
+#if HWB_DEVICE_BUILD
+  // one load per lane and a vote instead of fifteen dependent loads by every lane
+  uni = __all_sync(0xffffffffu, uni && mw[threadIdx.x & 15] == m0);
+#else
   if (uni) {
 #pragma unroll 1
     for (int i = 1; i < 16; ++i) uni &= mw[i] == m0;
   }
+#endif
   if (uni) {
     mc_partition(c, sd.ref_frame[list][r0], mbx * 16, mby * 16, 16, 16, (int16_t)(m0 & 0xffff), (int16_t)(m0 >> 16), dst_y, ds_y, dst_cb, dst_cr, ds_c, sm);
     return;

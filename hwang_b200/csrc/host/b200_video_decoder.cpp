@@ -306,7 +306,7 @@ Result B200VideoDecoder::submit_current() {
                o_ritems = take(recon_items.size() * 4), o_ditems = take(deblock_items.size() * 4), o_order = take((size_t)S * 4),
                o_rgb = take(rgb_bytes * (size_t)nrgb);
   // counters zeroed per chunk: tickets (entropy, recon, deblock) + per-slice entropy progress + per-row progress x2 + mv reach + error flag
-  const size_t n_sync = 4 + (size_t)S + 4 * (size_t)P * mb_h + (size_t)P + 4 + 2 * hwb::PROF_COUNTERS + 2 + 4;
+  const size_t n_sync = 4 + (size_t)S + 4 * (size_t)P * mb_h + (size_t)P + 4 + 2 * hwb::PROF_COUNTERS + 2;
   const size_t o_sync = take(n_sync * 4);
   if (feeder_may_block_ && memory_budget_) {
     // Back-pressure in bytes: wait for the consumer to retire chunks instead of running the device out of memory.
@@ -349,7 +349,6 @@ Result B200VideoDecoder::submit_current() {
   c.rows_done = c.mv_reach_x + (size_t)P * mb_h;
   c.error_flag = c.rows_done + P;
   ch->error_dev = c.error_flag;
-  c.intra_done = sync + n_sync - 4;
   // completion flags in page-locked host memory (recycled between chunks)
   for (size_t i = 0; i < free_flags_.size(); ++i)
     if (free_flags_[i].second >= (size_t)P) { ch->done_host = free_flags_[i].first; ch->done_capacity = free_flags_[i].second; free_flags_.erase(free_flags_.begin() + i); break; }
@@ -400,11 +399,9 @@ Result B200VideoDecoder::submit_current() {
     c.intra_sm_base = intra_sm_next_;  // batches in flight together reserve different SMs
     intra_sm_next_ = (intra_sm_next_ + c.intra_sms) % 96;  // base + 37 stays below the SM count of any device this targets (148)
   }
-  // Experiment, off by default (HWB_INTER_THROTTLE=n: while intra slices of the launch are running only n of the 4 warps
-  // of a block decode inter slices): meant to let the intra slices run at the speed they have on an idle GPU; measured,
-  // they finish no earlier and the batch takes 391 ms instead of 281 (profiles/r2_runs/r2ah_ab.txt).
-  static const int throttle = [] { const char *e = getenv("HWB_INTER_THROTTLE"); const int v = e ? atoi(e) : 0; return v; }();
-  c.inter_throttle = (c.num_intra_tickets > 0 && c.num_intra_tickets < c.num_tickets) ? throttle : 0;
+  // (Tried and removed: while intra slices of the launch are running only one or two of the four warps of a block decode
+  // inter slices, so that the intra slices run at the speed they have on an idle GPU.  They finished no earlier, and the
+  // batch took 391 ms instead of 281: profiles/r2_runs/r2ah_ab.txt.)
   rc |= hwb_dev_memset(dev_, st, sync, 0, n_sync * 4);
   stats_.h2d_bytes += ch->bitstream.size() + (size_t)P * sizeof(PicDesc) + (size_t)S * sizeof(SliceDesc) + (recon_items.size() * 2 + order.size()) * 4;
   // a copy from pageable memory has been staged by the time cudaMemcpyAsync returns: the buffer can be reused
