@@ -423,7 +423,7 @@ Result B200VideoDecoder::submit_current() {
   // by picture (csrc/dev/picture.h) and both grids are sized to fit the SMs together (hwb_dev_set_occupancy).  Measured on
   // the 3000-frame benchmark clip this gains nothing: the first pictures wait for their intra slices either way (a
   // 1080p intra slice takes 245 ms on a warp of its own and about 350 ms next to 1700 other slices), and the picture
-  // kernel loses a third of its resident warps to the co-residency rule (profiles/r2_experiments.md).
+  // kernel loses a third of its resident warps to the co-residency rule (profiles/r2_runs/r2l_sweep.jsonl).
   hwb_dev_set_occupancy(dev_, concurrent_ ? 2 : 3, concurrent_ ? 4 : 6);
   hwb_event *ev_inputs = hwb_dev_event_create(dev_);
   rc |= hwb_dev_event_record(dev_, ev_inputs, st);  // uploads and the zeroed counters

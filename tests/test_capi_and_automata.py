@@ -327,3 +327,35 @@ def test_batch_retrieval_collects_clips_into_common_batches(emu, built):
     for frames, ref in zip(got, refs):
         for r, f in zip([1, 6, 9, 15], frames):
             assert np.array_equal(np.asarray(f), fo.yuv420_to_rgb24(*ref[r]))
+
+
+def test_pinned_buffer_pool_reuses_and_bounds(emu):
+    """api.PinnedBuffer: a released buffer serves the next request of a similar size, the pool is bounded, and
+    release_pinned_pool() hands everything back (the emulation's 'page-locked' allocator is malloc)."""
+    from hwang_b200 import api
+    api.release_pinned_pool()
+    a = api.PinnedBuffer(3 << 20)
+    pa, cap = a.ptr, a.capacity
+    assert cap >= 3 << 20 and len(a.array) == 3 << 20
+    a.array[:16] = 7
+    del a
+    assert api._pool_bytes == cap
+    b = api.PinnedBuffer((3 << 20) - 4096)  # similar size: reused
+    assert b.ptr == pa and api._pool_bytes == 0
+    c = api.PinnedBuffer(64 << 20)          # much larger: a new allocation
+    assert c.ptr != pa
+    del b, c
+    assert api._pool_bytes == cap + (64 << 20)
+    small = api.PinnedBuffer(1 << 10)       # far smaller than anything idle: not served from a 64 MB buffer
+    assert small.capacity <= 2 * (1 << 10) + api._POOL_GRAIN
+    del small
+    old_max = api._POOL_MAX
+    try:
+        api._POOL_MAX = 16 << 20            # shrink the bound: the next release evicts the oldest buffers
+        d = api.PinnedBuffer(5 << 20)
+        del d
+        assert api._pool_bytes <= 16 << 20
+    finally:
+        api._POOL_MAX = old_max
+    api.release_pinned_pool()
+    assert api._pool_bytes == 0 and not api._pool
