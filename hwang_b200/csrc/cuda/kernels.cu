@@ -94,6 +94,9 @@ __device__ int next_entropy_ticket(const ChunkCtx &c, int32_t *ticket, bool rese
       }
       continue;
     }
+    // (Tried and dropped: the warps of a reserved SM idle instead of going on with inter slices.  The first batch's intra
+    // slices finish no earlier than with every launch reserving the same SMs, which is what made the difference: 234 ms
+    // instead of 296, profiles/r2_runs/r2al_*.)
     const int t = take_ticket(ticket, n_inter);
     return t >= 0 ? t + n_intra : -1;
   }

@@ -112,7 +112,7 @@ struct ChunkCtx {
   int32_t num_tickets;           // slices to entropy-decode (slices of skipped pictures hold no ticket)
   int32_t num_intra_tickets;     // the first num_intra_tickets of them are intra slices
   int32_t intra_sms;             // SMs [intra_sm_base, intra_sm_base + intra_sms) decode the intra slices (see kernels.cu); 0 = no reservation
-  int32_t intra_sm_base;         // rotates from batch to batch: the intra slices of batches in flight together do not pile up on the same SMs
+  int32_t intra_sm_base;         // first reserved SM (0: every launch reserves SMs from the same end of the device, so that the intra slices of batches in flight together share SMs with each other rather than with inter slices)
   int32_t *entropy_prog;   // [slice] first macroblock address not yet entropy-decoded (B direct col dependency)
   int32_t *recon_prog;     // [pic][mb_h] macroblocks reconstructed per row
   int32_t *dbl_prog;       // [pic][mb_h] macroblocks deblocked per row

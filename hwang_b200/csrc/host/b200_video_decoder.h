@@ -139,7 +139,6 @@ class B200VideoDecoder : public VideoDecoderInterface {
   // bottleneck from then on.
   int chunk_target_ = 960;
   int ramp_first_ = 120, ramp_target_ = 120;
-  int intra_sm_next_ = 0;  // first SM the next batch reserves for its intra slices (ChunkCtx::intra_sm_base)
   int deblock_band_ = 0;  // 0 = by batch kind (see submit_current)
   int group_target_ = 1 << 30;  // pictures per GOP group inside a batch (work order of the picture kernel); default: one group
   bool feeder_may_block_ = false, defer_submit_ = false, no_rgb_ = false, picture_profile_ = false, concurrent_ = false, intra_reserve_ = true;
