@@ -134,9 +134,8 @@ struct SliceDec {
 HWB_HD void sd_fail(SliceDec &s, int code) { if (!s.error) s.error = code; }
 HWB_HD uint32_t top_flags(const SliceDec &s) { return s.top_words[0] & 0xff; }  // valid when availB
 
-// Out-of-line engine access for the macroblock-layer syntax (tens of call sites): keeps the kernel small enough for
-// the instruction cache.  The residual loops use the inlined, register-resident versions instead.
-// Syntax elements of more than a bin or two keep the engine in registers for their whole duration instead:
+// Engine access for the macroblock-layer syntax.  A syntax element loads the engine into registers once (HWB_CAB_ENTER),
+// decodes its bins (HWB_BIN / HWB_BYP) and stores it back (HWB_CAB_LEAVE); single flags go through cabac_bin.
 #define HWB_CAB_ENTER(s) CabReg cab = cab_enter((s).cab); const CtxE *const ft = (s).fused
 #define HWB_CAB_LEAVE(s) cab_leave((s).cab, cab)
 #define HWB_BIN_INL(s, ctx) cabac_decision(cab, (s).cab, (s).ctxe + (ctx), ft)
