@@ -493,7 +493,7 @@ def run_ours(args):
                      'launches_per_step': {k: v[1] / args.steps for k, v in stage.items()},
                      'summed_launch_ms_per_step': {k: v[0] / args.steps for k, v in stage.items()},
                      'device_wall_ms_per_step': d['wall_ms'] / args.steps,
-                     'note': 'both kernels are bound by instruction issue / per-slice latency, not by HBM (profiles/); batches overlap on the device, '
+                     'note': 'both kernels are bound by instruction-cache misses (GPC-level instruction cache at 90 % of its peak request rate: profiles/r2_entropy_3000_ncu_summary.json) and per-slice latency, not by HBM; batches overlap on the device, '
                              'so summed launch times exceed the device wall clock'},
         'cpu_baseline': cpu,
         'clocks': sampler.result(),
