@@ -405,10 +405,21 @@ void H264Stream::build_ref_lists(const Sps &sps, const SliceHeader &sh, int cur_
       if (same) std::swap(lists[1][0], lists[1][1]);
     }
   }
+  // A slice may name more active entries than there are reference pictures (encoders that rely on the PPS default do
+  // so for the first pictures of a GOP).  The standard gives such entries "no reference picture"; libavcodec, which the
+  // reference delegates to, lets them stand for the initial list's first entry (h264_refs.c: default_ref), and so do we:
+  // a stream that uses them decodes to the same samples.  A list with no picture at all stays short (refused by the caller).
   for (int l = 0; l < 2; ++l) {
     const int nact = sh.num_ref[l];
+    const bool have_dflt = !lists[l].empty();
+    const DpbEntry dflt = have_dflt ? lists[l][0] : DpbEntry{};
+    auto pad = [&]() {
+      if (!have_dflt) return;
+      if ((int)lists[l].size() < nact) lists[l].resize(nact, dflt);
+      for (auto &e : lists[l]) if (e.frame < 0) e = dflt;
+    };
     if ((int)lists[l].size() > nact) lists[l].resize(nact);
-    if (sh.mods[l].empty()) continue;
+    if (sh.mods[l].empty()) { pad(); continue; }
     // 8.2.4.3: the list temporarily holds one extra entry
     std::vector<DpbEntry> &L = lists[l];
     DpbEntry none{}; none.frame = -1; none.pic_num = INT32_MIN; none.long_term = false;
@@ -438,6 +449,7 @@ void H264Stream::build_ref_lists(const Sps &sps, const SliceHeader &sh, int cur_
         if (!(L[c].frame >= 0 && L[c].long_term == want_long && L[c].pic_num == target)) L[nidx++] = L[c];
     }
     L.resize(nact);
+    pad();
   }
 }
 

@@ -96,6 +96,12 @@ SYNTAX_CLIPS = {
     'poc_type1_b_pyramid': dict(frames=26, gop=13, width=176, height=144, profile=2, seed=109, num_ref=3, bframes=3, b_pyramid=1, poc_type=1),
     'poc_type1_mmco5': dict(frames=40, gop=20, width=176, height=144, profile=1, seed=110, num_ref=3, poc_type=1, mmco=1),
     'poc_type2_mmco5': dict(frames=40, gop=20, width=176, height=144, profile=0, seed=111, num_ref=3, poc_type=2, mmco=1),
+    # num_ref_idx_active larger than the number of reference pictures that exist (the first pictures of every GOP): libavcodec
+    # lets the missing entries stand for the initial list's first entry, macroblocks refer to them
+    'short_ref_lists_p': dict(frames=20, gop=10, width=176, height=144, profile=1, seed=113, num_ref=4, pad_refs=1, weighted=1),
+    'short_ref_lists_cavlc_rplm': dict(frames=20, gop=10, width=176, height=144, profile=0, seed=114, num_ref=3, pad_refs=1, rplm_pct=60, slices=2),
+    'short_ref_lists_b_temporal_pyramid': dict(frames=26, gop=13, width=176, height=144, profile=2, seed=115, num_ref=4, bframes=3, b_pyramid=1,
+                                               pad_refs=1, direct_spatial=0, weighted=2),
     'everything_weighted_p_pyramid': dict(frames=34, gop=17, width=176, height=144, profile=2, seed=112, num_ref=4, bframes=3, b_pyramid=1, mmco=1,
                                           rplm_pct=40, weighted=2, slices=2, qp_jitter=2, intra_in_p_pct=6, scaling_lists=1),
 }

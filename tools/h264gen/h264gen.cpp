@@ -706,6 +706,9 @@ struct Encoder {
         if (same) std::swap(l1[0], l1[1]);
       }
     }
+    // pad_refs: what stands in for a list entry without a reference picture (libavcodec: the initial list's first entry)
+    const bool pad0 = P.pad_refs && !l0.empty(), pad1 = P.pad_refs && !l1.empty();
+    const RefEntry dflt0 = pad0 ? l0[0] : RefEntry(), dflt1 = pad1 ? l1[0] : RefEntry();
     rplm_ops[0].clear(); rplm_ops[1].clear();
     if (ps.rplm) {
       const int active[2] = {std::min<int>((int)l0.size(), P.num_ref), std::min<int>((int)l1.size(), 2)};
@@ -734,6 +737,8 @@ struct Encoder {
         }
       }
     }
+    if (pad0) while ((int)l0.size() < P.num_ref) l0.push_back(dflt0);
+    if (pad1) while ((int)l1.size() < 2) l1.push_back(dflt1);
     int nrefs_total[2] = {(int)l0.size(), (int)l1.size()};
 
     std::vector<uint8_t> sample;

@@ -36,7 +36,10 @@ typedef struct hwgen_params {
   int32_t b_pyramid;       // 1: the middle B picture of every run of B pictures is a reference picture (one B-reference level)
   int32_t rplm_pct;        // percent of P/B pictures whose slices carry ref_pic_list_modification (reorders list 0 / list 1)
   int32_t mmco;            // 1: adaptive reference marking (MMCO 1-4, 6, long-term IDR; MMCO 5 when bframes == 0) on some reference pictures
-  int32_t reserved[5];
+  int32_t pad_refs;        // 1: P / B slices declare num_ref_idx_active = num_ref (2 for list 1) even while fewer reference pictures exist (the
+                           //    first pictures of a GOP), as encoders that rely on the PPS default do; the missing entries stand for the
+                           //    initial list's first entry (how libavcodec resolves them) and macroblocks do refer to them
+  int32_t reserved[4];
 } hwgen_params;
 
 void hwgen_default_params(hwgen_params *p);
