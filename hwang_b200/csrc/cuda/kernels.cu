@@ -184,7 +184,10 @@ union PictureScratch {
 // chain completes, Z finishes, and its warp picks again.  Either way that pick was not the last one.
 // `split` (HWB_PICTURE_SPLIT, 0 = dynamic) keeps the static assignment for experiments: warps whose global index modulo
 // 5 is below it take deblocking items only until those run out.
-__global__ void __launch_bounds__(kThreads, 6) picture_kernel(const __grid_constant__ ChunkCtx c, int32_t *ticket, int split) {
+#ifndef HWB_PICTURE_MIN_BLOCKS
+#define HWB_PICTURE_MIN_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(kThreads, HWB_PICTURE_MIN_BLOCKS) picture_kernel(const __grid_constant__ ChunkCtx c, int32_t *ticket, int split) {
   __shared__ PictureScratch sm[kWarpsPerBlock];
   PictureScratch *my = &sm[threadIdx.x >> 5];
   // A corrupt or unsupported stream leaves MbInfo / coefficient offsets of the failed slice undefined: the rows check

@@ -59,23 +59,24 @@ struct alignas(16) DeblockScratch {
 #endif
 };
 
-HWB_HD bool mv_far(const int16_t *a, const int16_t *b) {
-  return iabs(a[0] - b[0]) >= 4 || iabs(a[1] - b[1]) >= 4;
+// Motion vectors travel as one word (x | y << 16), as they are stored.
+HWB_HD bool mv_far(uint32_t a, uint32_t b) {
+  return iabs((int)(int16_t)(a & 0xffff) - (int)(int16_t)(b & 0xffff)) >= 4 || iabs((int)(int16_t)(a >> 16) - (int)(int16_t)(b >> 16)) >= 4;
 }
 
-struct BlkMotion {
-  int r0, r1;             // referenced frame per list, -1 = unused
-  const int16_t *m0, *m1;
+struct BlkMotion {  // by value: as pointers into the motion arrays the structure ended up in thread-local memory
+  int r0, r1;       // referenced frame per list, -1 = unused
+  uint32_t m0, m1;
 };
 
 HWB_HD BlkMotion blk_motion(const ChunkCtx &c, int frame, bool two_lists, int mbaddr, int bx, int by) {
   BlkMotion m;
   int q = (by >> 1) * 2 + (bx >> 1), br = by * 4 + bx;
   m.r0 = pic_refpic(c, frame, 0)[(uint64_t)mbaddr * 4 + q];
-  m.m0 = pic_mv(c, frame, 0) + (uint64_t)mbaddr * 32 + br * 2;
+  m.m0 = ((const uint32_t *)(pic_mv(c, frame, 0) + (uint64_t)mbaddr * 32))[br];
   if (two_lists) {
     m.r1 = pic_refpic(c, frame, 1)[(uint64_t)mbaddr * 4 + q];
-    m.m1 = pic_mv(c, frame, 1) + (uint64_t)mbaddr * 32 + br * 2;
+    m.m1 = ((const uint32_t *)(pic_mv(c, frame, 1) + (uint64_t)mbaddr * 32))[br];
   } else {
     m.r1 = -1; m.m1 = m.m0;
   }

@@ -30,21 +30,32 @@ namespace hwb {
 // memory, so this is the profile that explains it.
 enum { PROF_RECON_MB = 0, PROF_DEBLOCK_MB, PROF_RGB, PROF_WAIT_REF, PROF_WAIT_INTRA, PROF_WAIT_RECON, PROF_WAIT_DEBLOCK_ABOVE, PROF_PICK, PROF_LIFETIME,
        PROF_POLLS, PROF_COUNTERS = 16 };
-#if HWB_DEVICE_BUILD
+// Compiled in only with -DHWB_PROFILE_BUILD=1 (python -m hwang_b200.build --variant ... -DHWB_PROFILE_BUILD=1): the clock
+// and the counter pointer are live across the whole row loop, and the picture kernel is short of registers (80).
+#ifndef HWB_PROFILE_BUILD
+#define HWB_PROFILE_BUILD 0
+#endif
+#if HWB_DEVICE_BUILD && HWB_PROFILE_BUILD
 struct ProfClock {
   unsigned long long *out;
   long long t;
   __device__ __forceinline__ explicit ProfClock(unsigned long long *p) : out(p), t(0) { if (out) t = clock64(); }
   // charge the cycles since the last mark to `what`
-  __device__ __forceinline__ void mark(int what) { if (out) charge(what); }
-  __device__ __noinline__ void charge(int what) {  // out of line: the row loops stay small for the instruction caches
+  __device__ __forceinline__ void mark(int what) { if (out) t = charge(out, what, t); }
+  // out of line: the row loops stay small for the instruction caches; static and by value, so that the object itself
+  // never has its address taken (as a member function it kept `out` and `t` in thread-local memory)
+  static __device__ __noinline__ long long charge(unsigned long long *out, int what, long long t) {
     const long long now = clock64();
     if ((threadIdx.x & 31) == 0) atomicAdd(out + what, (unsigned long long)(now - t));
-    t = now;
+    return now;
   }
 };
 #else
+#if HWB_DEVICE_BUILD
+struct ProfClock { __device__ __forceinline__ explicit ProfClock(unsigned long long *) {} __device__ __forceinline__ void mark(int) {} };
+#else
 struct ProfClock { explicit ProfClock(unsigned long long *) {} void mark(int) {} };
+#endif
 #endif
 
 struct Progress {  // a counter watched by this warp, with the last value seen (counters only grow)
@@ -53,9 +64,11 @@ struct Progress {  // a counter watched by this warp, with the last value seen (
 };
 
 #if HWB_DEVICE_BUILD
-__device__ __noinline__ void poll_progress(Progress &g, int need) {
+// The poll takes the counter's address and returns what it saw: a Progress never has its address taken and lives in
+// registers (passed by reference it sat in the caller's stack frame, one thread-local load per wait_progress check:
+// 218 -> 201 ms per 3000 pictures together with the other thread-local-memory removals, profiles/r2_runs/r2aq_ab.txt).
+__device__ __noinline__ int poll_progress(const int32_t *p, int need) {
   int32_t v = 0;
-  const int32_t *const p = g.p;  // a register copy: the asm's memory clobber made the loop reload it from the caller's frame every turn
   if ((threadIdx.x & 31) == 0) {
     for (;;) {  // relaxed GPU-scope poll; the data it guards is read with ld.global.cg (L2) by the callers
       asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -63,9 +76,9 @@ __device__ __noinline__ void poll_progress(Progress &g, int need) {
       __nanosleep(64);
     }
   }
-  g.seen = __shfl_sync(0xffffffffu, v, 0);
+  return __shfl_sync(0xffffffffu, v, 0);
 }
-__device__ __forceinline__ void wait_progress(Progress &g, int need) { if (g.seen < need) poll_progress(g, need); }
+__device__ __forceinline__ void wait_progress(Progress &g, int need) { if (g.seen < need) g.seen = poll_progress(g.p, need); }
 // Release store at GPU scope: orders the warp's earlier writes (made visible to lane 0 by __syncwarp) before the
 // flag.  Unlike __threadfence() + volatile store (MEMBAR.SC + CCTL.IVALL + a system-scope store) it does not
 // invalidate the SM's L1 on every macroblock, which the table and MbInfo loads of the other warps live in.

@@ -20,30 +20,53 @@ HWB_HD void yuv_to_rgb(int Y, int U, int V, uint8_t *rgb) {
 // Yp / Up / Vp point at the first sample, o at the first output byte.  The vector path (one 16-byte and two 8-byte
 // loads, three 16-byte streaming stores) needs n == 16 and aligned pointers.  Loads go to L2 (ld.global.cg): inside the
 // picture kernel the samples were written moments ago by a warp of the same launch, possibly on another SM.
+// One pixel as R | G << 8 | B << 16; the chroma terms of a pixel pair are computed once (chroma is shared by two pixels).
+HWB_HD uint32_t rgb_pack(int Y, int rv, int gv, int bv) {
+  const int y = ((Y * 8 - 128) * 9539) >> 16;
+  return (uint32_t)clip8(y + rv) | ((uint32_t)clip8(y + gv) << 8) | ((uint32_t)clip8(y + bv) << 16);
+}
 HWB_HD void rgb24_segment(const uint8_t *Yp, const uint8_t *Up, const uint8_t *Vp, uint8_t *o, int n) {
-  alignas(16) uint8_t yy[16], uu[8], vv[8], out[48];
-#if HWB_DEVICE_BUILD
   const bool vec = n == 16 && ((((uintptr_t)Yp) & 15) == 0) && ((((uintptr_t)Up) & 7) == 0) && ((((uintptr_t)Vp) & 7) == 0) && ((((uintptr_t)o) & 15) == 0);
   if (vec) {
-    *(uint4 *)yy = __ldcg((const uint4 *)Yp);
-    *(uint2 *)uu = __ldcg((const uint2 *)Up);
-    *(uint2 *)vv = __ldcg((const uint2 *)Vp);
-  } else
-#endif
-  {
-    for (int i = 0; i < n; ++i) { yy[i] = ld_u8_cg(Yp + i); uu[i >> 1] = ld_u8_cg(Up + (i >> 1)); vv[i >> 1] = ld_u8_cg(Vp + (i >> 1)); }
-  }
-#pragma unroll
-  for (int i = 0; i < 16; ++i) yuv_to_rgb(yy[i], uu[i >> 1], vv[i >> 1], out + 3 * i);
+    // registers only: 16 + 8 + 8 sample bytes in 8 words, 48 output bytes in 12 (byte arrays indexed at run time by the
+    // edge path used to put both paths' samples and output into thread-local memory: 80 bytes through L1 per segment)
+    uint32_t yw[4], uw[2], vw[2], ow[12];
 #if HWB_DEVICE_BUILD
-  if (vec) {
-    uint4 *o4 = (uint4 *)o;
-    const uint4 *s4 = (const uint4 *)out;
-    __stcs(o4, s4[0]); __stcs(o4 + 1, s4[1]); __stcs(o4 + 2, s4[2]);
-  } else
+    { const uint4 t = __ldcg((const uint4 *)Yp); yw[0] = t.x; yw[1] = t.y; yw[2] = t.z; yw[3] = t.w; }
+    { const uint2 t = __ldcg((const uint2 *)Up); uw[0] = t.x; uw[1] = t.y; }
+    { const uint2 t = __ldcg((const uint2 *)Vp); vw[0] = t.x; vw[1] = t.y; }
+#else
+    memcpy(yw, Yp, 16); memcpy(uw, Up, 8); memcpy(vw, Vp, 8);
 #endif
-  {
-    for (int i = 0; i < n * 3; ++i) o[i] = out[i];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {  // four pixels = two chroma samples -> three output words
+      uint32_t px[4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int ci = 2 * g + h;  // chroma sample index 0..7
+        const int u = ((int)((uw[ci >> 2] >> (8 * (ci & 3))) & 0xff) - 128) * 8, v = ((int)((vw[ci >> 2] >> (8 * (ci & 3))) & 0xff) - 128) * 8;
+        const int rv = (v * 13075) >> 16, gv = ((u * -3209) >> 16) + ((v * -6660) >> 16), bv = (u * 16525) >> 16;
+        px[2 * h] = rgb_pack((int)((yw[g] >> (16 * h)) & 0xff), rv, gv, bv);
+        px[2 * h + 1] = rgb_pack((int)((yw[g] >> (16 * h + 8)) & 0xff), rv, gv, bv);
+      }
+      ow[3 * g] = px[0] | (px[1] << 24);
+      ow[3 * g + 1] = (px[1] >> 8) | (px[2] << 16);
+      ow[3 * g + 2] = (px[2] >> 16) | (px[3] << 8);
+    }
+#if HWB_DEVICE_BUILD
+    uint4 *o4 = (uint4 *)o;
+    __stcs(o4, make_uint4(ow[0], ow[1], ow[2], ow[3])); __stcs(o4 + 1, make_uint4(ow[4], ow[5], ow[6], ow[7])); __stcs(o4 + 2, make_uint4(ow[8], ow[9], ow[10], ow[11]));
+#else
+    memcpy(o, ow, 48);
+#endif
+    return;
+  }
+  // edge path (right edge of a picture whose width is not a multiple of 16, unaligned crop): byte by byte
+#pragma unroll 1
+  for (int i = 0; i < n; ++i) {
+    uint8_t px[3];
+    yuv_to_rgb(ld_u8_cg(Yp + i), ld_u8_cg(Up + (i >> 1)), ld_u8_cg(Vp + (i >> 1)), px);
+    o[3 * i] = px[0]; o[3 * i + 1] = px[1]; o[3 * i + 2] = px[2];
   }
 }
 
