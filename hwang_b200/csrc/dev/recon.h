@@ -272,9 +272,11 @@ HWB_FN void mc_partition(const ChunkCtx &c, int rf, int x0, int y0, int w, int h
       }
     HWB_LANES_END
   }
+  // lane -> `ppl` consecutive samples of row y: 16x16: 8 samples, 2 lanes per row; 8x8: 2 and 4; 4x4: 1 and 4 (16 lanes)
+  const int lg_ppl = w == 16 ? 3 : (w == 8 ? 1 : 0), lg_lpr = w == 16 ? 1 : 2;
+  // (Tried and dropped: a copy-only path for integer-sample vectors -- no gain on the bench clip: 637 vs 633 ms per
+  // 9000 pictures, profiles/r2_runs/r2ar_ab.txt.)
   {
-    // lane -> `ppl` consecutive samples of row y: 16x16: 8 samples, 2 lanes per row; 8x8: 2 and 4; 4x4: 1 and 4 (16 lanes)
-    const int lg_ppl = w == 16 ? 3 : (w == 8 ? 1 : 0), lg_lpr = w == 16 ? 1 : 2;
     const bool use_b = fx != 0 && !need_j;                // rounded horizontal half sample, from window row rb
     const bool use_v = fy != 0 && !(need_j && fx == 2);   // rounded vertical half sample, from window column x + cv
     const int cv = 2 + ((fx == 3) ? 1 : 0);
@@ -489,6 +491,13 @@ HWB_FN void recon_mb(const ChunkCtx &c, int pic, int mbx, int mby, ReconScratch 
     }
     // ---- block phase: residuals
     const bool t8 = (mb.flags & MBF_T8x8) != 0;
+    if (nz == 0 && mb.mbtype != MB_I16x16) {
+      // nothing coded (skipped macroblocks, and most others at the bit rates inter pictures run at): no transform phase
+      // (2 % of the picture kernel's time on the bench clip, profiles/r2_runs/r2ar_ab.txt)
+      HWB_LANES(l)
+        if (l == 0) sm->has_res = 0;
+      HWB_LANES_END
+    } else {
     const int qpc0 = chroma_qp(mb.qp, pd.chroma_qp_offset[0]), qpc1 = chroma_qp(mb.qp, pd.chroma_qp_offset[1]);
     const int sl = intra ? 0 : 3;
     HWB_LANES(l)
@@ -539,6 +548,7 @@ HWB_FN void recon_mb(const ChunkCtx &c, int pic, int mbx, int mby, ReconScratch 
       sm->has_res |= got;
 #endif
     HWB_LANES_END
+    }
 
     if (!intra) {
       // ---- inter prediction.  One list and no weights (almost every P macroblock): the partitions are predicted
