@@ -443,7 +443,7 @@ int hwb_dev_picture(hwb_dev *d, int s, const ChunkCtx *c, int32_t *ticket) {
   static int bpsm_env = [] { const char *e = getenv("HWB_PICTURE_BLOCKS_PER_SM"); int v = e ? atoi(e) : 0; return v; }();
   const int bpsm = bpsm_env > 0 ? bpsm_env : d->picture_bpsm;
   // percent of the SMs that deblock (0 = every warp chooses dynamically, see picture_kernel)
-  static int split_pct = [] { const char *e = getenv("HWB_PICTURE_SPLIT"); int v = e ? atoi(e) : -1; return v >= 0 && v <= 90 ? v : 40; }();
+  static int split_pct = [] { const char *e = getenv("HWB_PICTURE_SPLIT"); int v = e ? atoi(e) : -1; return v >= 0 && v <= 90 ? v : 35; }();
   const int items = c->num_recon_items + c->num_deblock_items;
   if (items == 0) return 0;
   const int grid = grid_for(d, items, bpsm);
