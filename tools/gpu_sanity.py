@@ -12,3 +12,17 @@ for kw in (dict(frames=6, gop=3, width=64, height=48, profile=1, bframes=1, seed
            dict(frames=5, gop=5, width=64, height=48, profile=2, seed=9)):   # High, I/P only: entropy_cabac_ip_kernel
     util.assert_yuv_parity(kw)
     print('ok', kw, flush=True)
+
+# RGB24 through the picture kernel's fused writeback: a width whose rows are 16-byte aligned (vector path) and one whose
+# rows are not (byte path), every frame against the oracle's swscale arithmetic
+import io
+import numpy as np
+import hwang_b200 as hw
+from oracle import ffmpeg_oracle as fo
+for kw in (dict(frames=6, gop=3, width=64, height=48, profile=1, seed=10), dict(frames=6, gop=3, width=72, height=48, profile=2, bframes=1, seed=11)):
+    mp4, index, samples, kf = util.make_clip(**kw)
+    ref = util.oracle_frames(index, samples, kf)
+    frames = hw.Decoder(io.BytesIO(mp4), video_index=index).retrieve(list(range(kw['frames'])))
+    for r, f in enumerate(frames):
+        assert np.array_equal(np.asarray(f), fo.yuv420_to_rgb24(*ref[r])), 'rgb frame %d of %s' % (r, kw)
+    print('ok rgb', kw, flush=True)
