@@ -45,6 +45,21 @@ def decode(width, height, fmt, avcc, samples, kf, limit_s=20):
         return 'error: ' + str(e)[:70]
 
 
+def retrieve(mp4, rows, limit_s=30):
+    """The python API (index + DecoderAutomata.get_frames) on a damaged file, in a thread so that a hang is seen as one."""
+    import threading
+    res = {}
+    def run():
+        try:
+            frames = hw.Decoder(io.BytesIO(mp4)).retrieve(rows)
+            res['out'] = 'frames' if len(frames) == len(rows) else 'error: %d of %d frames' % (len(frames), len(rows))
+        except Exception as e:
+            res['out'] = 'error: ' + str(e)[:70]
+    t = threading.Thread(target=run, daemon=True)
+    t.start(); t.join(limit_s)
+    return res.get('out', 'TIMEOUT')
+
+
 def flip(b, rng, lo, hi, n):
     b = bytearray(b)
     hi = min(hi, len(b))
@@ -63,10 +78,17 @@ for it in range(ITER):
     ci = rng.randrange(len(CLIPS))
     kw = CLIPS[ci]
     mp4, index, samples, kf = made[ci]
-    mode = rng.choice(['mp4', 'avcc', 'header', 'payload', 'truncate', 'drop', 'lenfield', 'swap'])
+    mode = rng.choice(['mp4', 'avcc', 'header', 'payload', 'truncate', 'drop', 'lenfield', 'swap', 'retrieve', 'retrieve'])
     W, H, fmt, avcc = kw['width'], kw['height'], index.format(), index.metadata_bytes()
     samples = list(samples); kf = list(kf)
-    if mode == 'mp4':
+    if mode == 'retrieve':
+        # the whole python path on a file whose media data (and sometimes boxes) are damaged: sparse or dense rows
+        offs = index.sample_offsets()
+        lo = offs[0] if rng.random() < 0.8 else 0
+        bad = flip(mp4, rng, lo, len(mp4), rng.randrange(1, 12))
+        rows = sorted(rng.sample(range(kw['frames']), rng.randrange(1, kw['frames'] + 1)))
+        out = retrieve(bad, rows)
+    elif mode == 'mp4':
         # container: corrupt the boxes (not the media data), then index and decode whatever the index says
         bad = flip(mp4, rng, 0, min(len(mp4), 4096), rng.randrange(1, 6))
         try:
