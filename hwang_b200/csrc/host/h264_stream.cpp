@@ -242,7 +242,8 @@ bool H264Stream::next_is_idr(const uint8_t *data, size_t n) const {
     size_t len = 0;
     for (int i = 0; i < nal_length_size_; ++i) len = (len << 8) | data[off + i];
     off += nal_length_size_;
-    if (len == 0 || off + len > n) break;
+    if (len == 0) continue;  // an empty NAL unit is skipped, as parse_sample skips it
+    if (off + len > n) break;
     int t = data[off] & 31;
     if (t == 5) return true;
     if (t == 1) return false;
