@@ -106,6 +106,18 @@ SYNTAX_CLIPS = {
                                           rplm_pct=40, weighted=2, slices=2, qp_jitter=2, intra_in_p_pct=6, scaling_lists=1),
 }
 
+# The same kind of clips, added after the last GPU run of round 2: the CPU tier decodes them through the emulation; the GPU
+# tier's parameter list (SYNTAX_CLIPS) is left as it was verified on hardware.
+CPU_SYNTAX_CLIPS = {
+    # I slices inside P / B pictures (intra refresh by slice): slice_type 0..2 instead of 5..7, pictures whose slices differ in type
+    'mixed_slice_types_p_cabac': dict(frames=20, gop=10, width=176, height=144, profile=1, seed=116, num_ref=3, slices=3, mixed_slices=1),
+    'mixed_slice_types_p_cavlc': dict(frames=20, gop=10, width=176, height=144, profile=0, seed=117, num_ref=2, slices=4, mixed_slices=1, deblock=2),
+    'mixed_slice_types_b_temporal_pyramid': dict(frames=26, gop=13, width=176, height=144, profile=2, seed=118, num_ref=4, bframes=3, b_pyramid=1,
+                                                 slices=3, mixed_slices=1, direct_spatial=0, weighted=2),
+    'mixed_slice_types_b_spatial_cavlc_constrained': dict(frames=24, gop=12, width=176, height=144, profile=2, seed=119, num_ref=3, bframes=2,
+                                                          slices=2, mixed_slices=1, cabac=0, constrained_intra=1, weighted=2),
+}
+
 
 def decode_corrupted_then_clean(seed_list=(1, 2, 3)):
     """Flip bytes inside slice payloads: the decoder must either report an error or return frames, never hang or

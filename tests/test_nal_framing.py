@@ -79,3 +79,59 @@ def test_aud_sei_filler_empty_and_inband_parameter_sets(emu):
         post = [filler] if i % 2 else []
         re.append(_frame(pre + nals + post, 4))
     _decode_both(index, avcc, re, kf)
+
+
+class _Bits:
+    def __init__(self): self.bits = []
+    def u(self, v, n): self.bits += [(v >> (n - 1 - i)) & 1 for i in range(n)]
+    def ue(self, v):
+        v += 1; n = v.bit_length()
+        self.u(0, n - 1); self.u(v, n)
+    def se(self, v): self.ue(2 * v - 1 if v > 0 else -2 * v)
+    def rbsp(self):
+        b = self.bits + [1]
+        b += [0] * (-len(b) % 8)
+        raw = bytes(int(''.join(map(str, b[i:i + 8])), 2) for i in range(0, len(b), 8))
+        out, zeros = bytearray(), 0
+        for x in raw:  # emulation prevention
+            if zeros >= 2 and x <= 3:
+                out.append(3); zeros = 0
+            out.append(x)
+            zeros = zeros + 1 if x == 0 else 0
+        return bytes(out)
+
+
+def test_sps_with_full_vui_hrd_and_timing(emu):
+    """The sequence parameter set as x264 --nal-hrd / hardware encoders write it: sample aspect ratio, overscan, video
+    signal type with colour description, chroma location, timing info, NAL and VCL HRD parameters, bitstream
+    restriction -- everything ahead of the fields a decoder needs must be skipped bit-exactly."""
+    kw = dict(frames=12, gop=6, width=96, height=72, profile=1, seed=62, num_ref=2, bframes=2)  # 72 = 80 - 8: cropping too
+    mp4, index, samples, kf = util.make_clip(**kw)
+    avcc = index.metadata_bytes()
+    nls, sps_list, pps_list = fo.parse_avcc(avcc)
+    mb_w, mb_h = 6, 5
+    b = _Bits()
+    b.u(77, 8); b.u(0x40, 8); b.u(30, 8)            # Main, constraint_set1, level 3.0 (as tools/h264gen writes them)
+    b.ue(0)                                         # sps id
+    b.ue(0)                                         # log2_max_frame_num_minus4
+    b.ue(0); b.ue(4)                                # poc type 0, 8-bit lsb
+    b.ue(2); b.u(0, 1)                              # max_num_ref_frames, gaps
+    b.ue(mb_w - 1); b.ue(mb_h - 1); b.u(1, 1); b.u(1, 1)
+    b.u(1, 1); b.ue(0); b.ue(0); b.ue(0); b.ue(4)   # crop bottom 8 rows
+    b.u(1, 1)                                       # vui_parameters_present
+    b.u(1, 1); b.u(255, 8); b.u(4, 16); b.u(3, 16)  # aspect_ratio: Extended_SAR 4:3
+    b.u(1, 1); b.u(1, 1)                            # overscan info
+    b.u(1, 1); b.u(5, 3); b.u(0, 1); b.u(1, 1); b.u(1, 8); b.u(1, 8); b.u(1, 8)  # video signal type + colour description
+    b.u(1, 1); b.ue(0); b.ue(0)                     # chroma loc
+    b.u(1, 1); b.u(1001, 32); b.u(60000, 32); b.u(1, 1)  # timing info (contains 00 00 01/03 patterns: emulation prevention)
+    for _ in range(2):                              # nal_hrd, vcl_hrd
+        b.u(1, 1); b.ue(1); b.u(4, 4); b.u(6, 4)
+        for _ in range(2): b.ue(7811); b.ue(1561); b.u(0, 1)
+        b.u(23, 5); b.u(23, 5); b.u(23, 5); b.u(24, 5)
+    b.u(0, 1)                                       # low_delay_hrd
+    b.u(0, 1)                                       # pic_struct_present
+    b.u(1, 1); b.u(1, 1); b.ue(0); b.ue(0); b.ue(11); b.ue(11); b.ue(1); b.ue(3)  # bitstream restriction: 1 reorder frame
+    sps = bytes([0x67]) + b.rbsp()
+    new_avcc = bytes(avcc[:5]) + bytes([0xE1]) + struct.pack('>H', len(sps)) + sps + bytes([len(pps_list)]) + \
+        b''.join(struct.pack('>H', len(p)) + p for p in pps_list)
+    _decode_both(index, new_avcc, samples, kf)

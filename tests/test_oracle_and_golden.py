@@ -85,12 +85,12 @@ def test_decode_core_emulation_feature_clips(emu, name):
     util.assert_yuv_parity(kw)
 
 
-@pytest.mark.parametrize('name', sorted(util.SYNTAX_CLIPS))
+@pytest.mark.parametrize('name', sorted(util.SYNTAX_CLIPS) + sorted(util.CPU_SYNTAX_CLIPS))
 def test_real_encoder_syntax_generator_and_decode_core_match_libavcodec(emu, name):
     """Reference B pictures, ref_pic_list_modification, MMCO 1-6 / long-term references, POC types 1 and 2 with MMCO 5:
     the generator's own reconstruction equals libavcodec's output (so the stream means what the generator thinks it
     means) and the decode core (host parser + emulated device) equals libavcodec frame by frame, in display order."""
-    kw = util.SYNTAX_CLIPS[name]
+    kw = util.SYNTAX_CLIPS.get(name) or util.CPU_SYNTAX_CLIPS[name]
     mp4, recon = streamgen.generate(want_recon=True, **kw)
     index = hw.index_video(io.BytesIO(mp4))
     offs, sizes, kfs = index.sample_offsets(), index.sample_sizes(), set(index.keyframe_indices())

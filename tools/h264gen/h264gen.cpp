@@ -624,7 +624,9 @@ struct Encoder {
                           int nrefs_total[2]) {
     (void)nrefs_total;
     b.ue((uint32_t)first_mb);
-    b.ue((uint32_t)(sd.slice_type == SLICE_P ? 5 : sd.slice_type == SLICE_B ? 6 : 7));
+    // 5..7 promise that every slice of the picture has this type; a picture that mixes I slices in says 0..2
+    const bool mixed = P.mixed_slices && P.slices >= 2 && ps.type != SLICE_I;
+    b.ue((uint32_t)((sd.slice_type == SLICE_P ? 0 : sd.slice_type == SLICE_B ? 1 : 2) + (mixed ? 0 : 5)));
     b.ue(0);
     b.put((uint32_t)(ps.frame_num & 15), 4);
     if (nal_type == 5) b.ue((uint32_t)idr_id);
@@ -748,14 +750,16 @@ struct Encoder {
       const int first_mb = (int)((int64_t)sl * nmb / P.slices), end_mb = (int)((int64_t)(sl + 1) * nmb / P.slices);
       SliceDesc &sd = slices[slot * MAXSL + sl];
       memset(&sd, 0, sizeof(sd));
-      sd.pic = slot; sd.first_mb = first_mb; sd.slice_type = (uint8_t)ps.type;
-      sd.qp = (uint8_t)clip3(10, 44, P.qp + (ps.type == SLICE_B ? 2 : (ps.type == SLICE_I ? -2 : 0)) + (P.qp_jitter ? rng.range(-1, 1) : 0));
+      // mixed_slices: every third slice of an inter picture is an I slice
+      const int stype = (P.mixed_slices && P.slices >= 2 && ps.type != SLICE_I && (sl + ps.t) % 3 == 1) ? (int)SLICE_I : (int)ps.type;
+      sd.pic = slot; sd.first_mb = first_mb; sd.slice_type = (uint8_t)stype;
+      sd.qp = (uint8_t)clip3(10, 44, P.qp + (stype == SLICE_B ? 2 : (stype == SLICE_I ? -2 : 0)) + (P.qp_jitter ? rng.range(-1, 1) : 0));
       sd.cabac_init_idc = (uint8_t)(P.cabac_init_idc >= 0 ? P.cabac_init_idc : rng.below(3));
       sd.disable_deblock = (uint8_t)(P.deblock == 1 ? 1 : (P.deblock == 2 ? 2 : 0));
       if (P.deblock == 3) { sd.alpha_off = (int8_t)(rng.range(-3, 3) * 2); sd.beta_off = (int8_t)(rng.range(-3, 3) * 2); if (rng.pct(15)) sd.disable_deblock = (uint8_t)rng.range(1, 2); }
       sd.direct_spatial = (uint8_t)P.direct_spatial;
-      sd.num_ref[0] = (uint8_t)std::min<int>((int)l0.size(), P.num_ref);
-      sd.num_ref[1] = (uint8_t)std::min<int>((int)l1.size(), 2);
+      sd.num_ref[0] = stype == SLICE_I ? 0 : (uint8_t)std::min<int>((int)l0.size(), P.num_ref);
+      sd.num_ref[1] = stype != SLICE_B ? 0 : (uint8_t)std::min<int>((int)l1.size(), 2);
       for (int l = 0; l < 2; ++l) {
         const auto &lst = l ? l1 : l0;
         for (int i = 0; i < sd.num_ref[l]; ++i) {
@@ -766,14 +770,14 @@ struct Encoder {
       sd.luma_log2_denom = 5; sd.chroma_log2_denom = 5;
       for (int l = 0; l < 2; ++l) for (int i = 0; i < 32; ++i) { sd.luma_w[l][i] = 32; sd.chroma_w[l][i][0] = sd.chroma_w[l][i][1] = 32; }
       sd.use_weights = 0;
-      if (ps.type == SLICE_P && P.weighted >= 1) {
+      if (stype == SLICE_P && P.weighted >= 1) {
         sd.use_weights = 1;
         for (int i = 0; i < sd.num_ref[0]; ++i) {
           int diff = content->fade_add(ps.t) - content->fade_add(l0[i].t);
           sd.luma_o[0][i] = (int16_t)clip3(-128, 127, diff);
           if (i == 1) { sd.luma_w[0][i] = 31; sd.chroma_w[0][i][0] = 33; sd.chroma_o[0][i][1] = 1; }
         }
-      } else if (ps.type == SLICE_B && P.weighted >= 2) sd.use_weights = 2;
+      } else if (stype == SLICE_B && P.weighted >= 2) sd.use_weights = 2;
 
       SliceEnc e;
       e.cabac = cabac;
@@ -786,7 +790,7 @@ struct Encoder {
       init_caches(s); init_lane_tables(s);
       if (cabac) {
         while (!e.bw.aligned()) e.bw.put1(1);
-        cabac_init_states(e.ce.st, ps.type == SLICE_I ? 0 : 1 + sd.cabac_init_idc, sd.qp);
+        cabac_init_states(e.ce.st, stype == SLICE_I ? 0 : 1 + sd.cabac_init_idc, sd.qp);
         e.ce.start(&e.bw);
       }
       for (int addr = first_mb; addr < end_mb; ++addr) {
@@ -820,10 +824,11 @@ struct Encoder {
     for (int i = 0; i < 16; ++i) { o.i4modes[i] = 2; m.i4modes[i] = 2; }
     for (int l = 0; l < 2; ++l) { for (int q = 0; q < 4; ++q) m.ref[l][q] = -1; for (int i = 0; i < 16; ++i) m.mv[l][i][0] = m.mv[l][i][1] = 0; }
     MbInfo *mbs = pic_mbinfo(c, slot);
-    const bool B = ps.type == SLICE_B;
+    const int stype = sd.slice_type;  // the slice's type (a picture may mix I slices in)
+    const bool B = stype == SLICE_B;
     int want_qp = s.qp;
     if (P.qp_jitter && rng.pct(20)) want_qp = clip3(8, 46, s.qp + rng.range(-P.qp_jitter, P.qp_jitter));
-    bool intra = ps.type == SLICE_I || rng.pct(P.intra_in_p_pct);
+    bool intra = stype == SLICE_I || rng.pct(P.intra_in_p_pct);
     Levels L;
     memset(&L, 0, sizeof(L));
     int ry[256], ru[64], rv[64];
@@ -831,7 +836,7 @@ struct Encoder {
 
     if (intra && P.ipcm_per_100k > 0 && rng.below(100000) < P.ipcm_per_100k) {
       // ---------------- I_PCM
-      m.imbt = 25; m.mbt = ps.type == SLICE_I ? 25 : (ps.type == SLICE_P ? 30 : 48);
+      m.imbt = 25; m.mbt = stype == SLICE_I ? 25 : (stype == SLICE_P ? 30 : 48);
       o.mbtype = MB_IPCM; o.qp = 0; o.cbp = 0x2F; o.nzmask = 0xFFF;
       uint8_t *dst = (uint8_t *)(pic_coefs(c, slot) + (uint64_t)s.coef_next * 16);
       for (int i = 0; i < 256; ++i) m.pcm[i] = srcY[(size_t)(mby * 16 + (i >> 4)) * wc + mbx * 16 + (i & 15)];
@@ -883,7 +888,7 @@ struct Encoder {
         int cbp = o.cbp;
         m.imbt = 1 + o.imode + 4 * (cbp >> 4) + ((cbp & 15) ? 12 : 0);
       }
-      m.mbt = m.imbt + (ps.type == SLICE_I ? 0 : (ps.type == SLICE_P ? 5 : 23));
+      m.mbt = m.imbt + (stype == SLICE_I ? 0 : (stype == SLICE_P ? 5 : 23));
       m.cbp = o.cbp;
       if (o.cbp || !nxn) { m.dqp = want_qp - s.qp; o.qp = (uint8_t)want_qp; }
       else { m.dqp = 0; o.qp = (uint8_t)s.qp; }

@@ -39,7 +39,9 @@ typedef struct hwgen_params {
   int32_t pad_refs;        // 1: P / B slices declare num_ref_idx_active = num_ref (2 for list 1) even while fewer reference pictures exist (the
                            //    first pictures of a GOP), as encoders that rely on the PPS default do; the missing entries stand for the
                            //    initial list's first entry (how libavcodec resolves them) and macroblocks do refer to them
-  int32_t reserved[4];
+  int32_t mixed_slices;    // 1 (needs slices >= 2): every third slice of a P / B picture is an I slice (intra refresh by slice, as some
+                           //    hardware encoders do); such pictures write slice_type 0..2 instead of 5..7
+  int32_t reserved[3];
 } hwgen_params;
 
 void hwgen_default_params(hwgen_params *p);
