@@ -114,6 +114,14 @@ CPU_SYNTAX_CLIPS = {
     'mixed_slice_types_p_cavlc': dict(frames=20, gop=10, width=176, height=144, profile=0, seed=117, num_ref=2, slices=4, mixed_slices=1, deblock=2),
     'mixed_slice_types_b_temporal_pyramid': dict(frames=26, gop=13, width=176, height=144, profile=2, seed=118, num_ref=4, bframes=3, b_pyramid=1,
                                                  slices=3, mixed_slices=1, direct_spatial=0, weighted=2),
+    # explicit weighted prediction in B slices (weighted_bipred_idc = 1): weights and offsets per list and reference
+    'explicit_weights_in_b': dict(frames=24, gop=12, width=176, height=144, profile=2, seed=120, num_ref=3, bframes=2, slices=2, weighted=3),
+    # headers as other encoders write them: parameter-set ids 3 / 7, pic_init_qp_minus26 = -4, num_ref_idx_default_active = 2
+    'header_variant_p': dict(frames=20, gop=10, width=176, height=144, profile=1, seed=121, num_ref=3, header_variant=1, qp_jitter=2),
+    'header_variant_b_cavlc_mmco': dict(frames=24, gop=12, width=176, height=144, profile=2, seed=122, num_ref=4, bframes=2, header_variant=1, cabac=0,
+                                        weighted=3, rplm_pct=40, mmco=1),
+    'header_variant_b_pyramid_mixed_slices': dict(frames=26, gop=13, width=176, height=144, profile=2, seed=123, num_ref=4, bframes=3, b_pyramid=1,
+                                                  header_variant=1, weighted=3, direct_spatial=0, slices=2, mixed_slices=1),
     'mixed_slice_types_b_spatial_cavlc_constrained': dict(frames=24, gop=12, width=176, height=144, profile=2, seed=119, num_ref=3, bframes=2,
                                                           slices=2, mixed_slices=1, cabac=0, constrained_intra=1, weighted=2),
 }

@@ -242,7 +242,7 @@ struct Encoder {
     b.put(P.profile == 0 ? 0xC0 : (P.profile == 1 ? 0x40 : 0x00), 8);
     int level = (wc * hc <= 720 * 576) ? 30 : (wc * hc <= 1280 * 720 ? 31 : (wc * hc <= 1920 * 1088 ? 40 : 51));
     b.put((uint32_t)level, 8);
-    b.ue(0);
+    b.ue(P.header_variant ? 3 : 0);  // seq_parameter_set_id
     if (prof == 100) { b.ue(1); b.ue(0); b.ue(0); b.put1(0); b.put1(0); }
     b.ue(0);  // log2_max_frame_num_minus4
     b.ue((uint32_t)P.poc_type);
@@ -287,14 +287,14 @@ struct Encoder {
   }
   std::vector<uint8_t> pps_rbsp() const {
     BitWriter b;
-    b.ue(0); b.ue(0);
+    b.ue(P.header_variant ? 7 : 0); b.ue(P.header_variant ? 3 : 0);  // pic_parameter_set_id, seq_parameter_set_id
     b.put1(cabac);
     b.put1(0);
     b.ue(0);
-    b.ue(0); b.ue(0);  // num_ref_idx_default_active_minus1
+    b.ue(P.header_variant ? 1 : 0); b.ue(P.header_variant ? 1 : 0);  // num_ref_idx_default_active_minus1
     b.put1(P.weighted >= 1);
-    b.put(P.weighted >= 2 ? 2 : 0, 2);
-    b.se(0); b.se(0);
+    b.put(P.weighted == 3 ? 1 : (P.weighted == 2 ? 2 : 0), 2);
+    b.se(P.header_variant ? -4 : 0); b.se(0);  // pic_init_qp_minus26, pic_init_qs_minus26
     b.se(P.chroma_qp_offset);
     b.put1(1);  // deblocking_filter_control_present
     b.put1(P.constrained_intra != 0);
@@ -627,14 +627,15 @@ struct Encoder {
     // 5..7 promise that every slice of the picture has this type; a picture that mixes I slices in says 0..2
     const bool mixed = P.mixed_slices && P.slices >= 2 && ps.type != SLICE_I;
     b.ue((uint32_t)((sd.slice_type == SLICE_P ? 0 : sd.slice_type == SLICE_B ? 1 : 2) + (mixed ? 0 : 5)));
-    b.ue(0);
+    b.ue(P.header_variant ? 7 : 0);  // pic_parameter_set_id
     b.put((uint32_t)(ps.frame_num & 15), 4);
     if (nal_type == 5) b.ue((uint32_t)idr_id);
     if (P.poc_type == 0) b.put((uint32_t)(ps.poc & 255), 8);
     if (P.poc_type == 1 && P.bframes != 0) b.se(ps.delta_poc);
     if (sd.slice_type == SLICE_B) b.put1(sd.direct_spatial);
     if (sd.slice_type != SLICE_I) {
-      bool ovr = sd.num_ref[0] != 1 || (sd.slice_type == SLICE_B && sd.num_ref[1] != 1);
+      const int dflt = P.header_variant ? 2 : 1;  // the PPS's num_ref_idx_default_active
+      bool ovr = sd.num_ref[0] != dflt || (sd.slice_type == SLICE_B && sd.num_ref[1] != dflt);
       b.put1(ovr);
       if (ovr) { b.ue((uint32_t)(sd.num_ref[0] - 1)); if (sd.slice_type == SLICE_B) b.ue((uint32_t)(sd.num_ref[1] - 1)); }
       for (int l = 0; l < (sd.slice_type == SLICE_B ? 2 : 1); ++l) {
@@ -669,7 +670,7 @@ struct Encoder {
       }
     }
     if (cabac && sd.slice_type != SLICE_I) b.ue(sd.cabac_init_idc);
-    b.se((int)sd.qp - 26);
+    b.se((int)sd.qp - 26 - (P.header_variant ? -4 : 0));  // slice_qp_delta against pic_init_qp
     b.ue(sd.disable_deblock);
     if (sd.disable_deblock != 1) { b.se(sd.alpha_off / 2); b.se(sd.beta_off / 2); }
   }
@@ -777,6 +778,15 @@ struct Encoder {
           sd.luma_o[0][i] = (int16_t)clip3(-128, 127, diff);
           if (i == 1) { sd.luma_w[0][i] = 31; sd.chroma_w[0][i][0] = 33; sd.chroma_o[0][i][1] = 1; }
         }
+      } else if (stype == SLICE_B && P.weighted == 3) {
+        // explicit weights in a B slice (weighted_bipred_idc = 1): per list and reference, luma and chroma, with offsets
+        sd.use_weights = 1;
+        for (int l = 0; l < 2; ++l)
+          for (int i = 0; i < sd.num_ref[l]; ++i) {
+            const auto &lst = l ? l1 : l0;
+            sd.luma_o[l][i] = (int16_t)clip3(-128, 127, content->fade_add(ps.t) - content->fade_add(lst[i].t));
+            sd.luma_w[l][i] = (int16_t)(32 + (l ? -3 : 2) + i); sd.chroma_w[l][i][0] = (int16_t)(31 + i); sd.chroma_w[l][i][1] = (int16_t)(33 - l); sd.chroma_o[l][i][l] = (int16_t)(l ? -2 : 1);
+          }
       } else if (stype == SLICE_B && P.weighted >= 2) sd.use_weights = 2;
 
       SliceEnc e;

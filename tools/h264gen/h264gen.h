@@ -20,7 +20,7 @@ typedef struct hwgen_params {
   int32_t qp;              // base QP
   int32_t slices;          // slices per picture (>=1)
   uint32_t seed;
-  int32_t weighted;        // 0 none; 1 explicit weighted prediction in P (fade); 2 also implicit bi-pred in B
+  int32_t weighted;        // 0 none; 1 explicit weighted prediction in P (fade); 2 also implicit bi-pred in B; 3 explicit in P and in B
   int32_t direct_spatial;  // B direct mode: 1 spatial, 0 temporal
   int32_t deblock;         // 0 on; 1 off; 2 on except slice edges; 3 on with random per-slice offsets
   int32_t constrained_intra;
@@ -41,7 +41,9 @@ typedef struct hwgen_params {
                            //    initial list's first entry (how libavcodec resolves them) and macroblocks do refer to them
   int32_t mixed_slices;    // 1 (needs slices >= 2): every third slice of a P / B picture is an I slice (intra refresh by slice, as some
                            //    hardware encoders do); such pictures write slice_type 0..2 instead of 5..7
-  int32_t reserved[3];
+  int32_t header_variant;  // 1: parameter-set ids other than 0 (sps 3, pps 7), pic_init_qp_minus26 = -4, num_ref_idx_default_active = 2 / 2 in
+                           //    the PPS (slices override only when they differ), as encoders other than this one write their headers
+  int32_t reserved[2];
 } hwgen_params;
 
 void hwgen_default_params(hwgen_params *p);
