@@ -117,8 +117,9 @@ CPU_SYNTAX_CLIPS = {
     # explicit weighted prediction in B slices (weighted_bipred_idc = 1): weights and offsets per list and reference
     'explicit_weights_in_b': dict(frames=24, gop=12, width=176, height=144, profile=2, seed=120, num_ref=3, bframes=2, slices=2, weighted=3),
     # headers as other encoders write them: parameter-set ids 3 / 7, pic_init_qp_minus26 = -4, num_ref_idx_default_active = 2
-    'header_variant_p': dict(frames=20, gop=10, width=176, height=144, profile=1, seed=121, num_ref=3, header_variant=1, qp_jitter=2),
-    'header_variant_b_cavlc_mmco': dict(frames=24, gop=12, width=176, height=144, profile=2, seed=122, num_ref=4, bframes=2, header_variant=1, cabac=0,
+    # ... and 6-bit frame_num / 5-bit pic_order_cnt_lsb: both wrap inside the 75-picture GOPs of the first clip
+    'header_variant_p': dict(frames=150, gop=75, width=96, height=80, profile=1, seed=121, num_ref=3, header_variant=1, qp_jitter=2, rplm_pct=30, mmco=1),
+    'header_variant_b_cavlc_mmco': dict(frames=72, gop=36, width=176, height=144, profile=2, seed=122, num_ref=4, bframes=2, header_variant=1, cabac=0,
                                         weighted=3, rplm_pct=40, mmco=1),
     'header_variant_b_pyramid_mixed_slices': dict(frames=26, gop=13, width=176, height=144, profile=2, seed=123, num_ref=4, bframes=3, b_pyramid=1,
                                                   header_variant=1, weighted=3, direct_spatial=0, slices=2, mixed_slices=1),

@@ -186,6 +186,9 @@ struct MmcoOp { int op, a; };
 
 struct Encoder {
   hwgen_params P;
+  // bits of frame_num and of pic_order_cnt_lsb (header_variant: 6 and 5, so that both wrap inside a GOP)
+  int fn_bits() const { return P.header_variant ? 6 : 4; }
+  int poc_bits() const { return P.header_variant ? 5 : 8; }
   int W, H, wc, hc, mb_w, mb_h, nmb;
   bool cabac, high;
   const Content *content;
@@ -244,9 +247,9 @@ struct Encoder {
     b.put((uint32_t)level, 8);
     b.ue(P.header_variant ? 3 : 0);  // seq_parameter_set_id
     if (prof == 100) { b.ue(1); b.ue(0); b.ue(0); b.put1(0); b.put1(0); }
-    b.ue(0);  // log2_max_frame_num_minus4
+    b.ue((uint32_t)(fn_bits() - 4));  // log2_max_frame_num_minus4
     b.ue((uint32_t)P.poc_type);
-    if (P.poc_type == 0) b.ue(4);  // log2_max_pic_order_cnt_lsb_minus4 -> 8 bits
+    if (P.poc_type == 0) b.ue((uint32_t)(poc_bits() - 4));  // log2_max_pic_order_cnt_lsb_minus4
     if (P.poc_type == 1) {
       // delta_pic_order_always_zero_flag (only legal here when POC follows decode order), offset_for_non_ref_pic,
       // offset_for_top_to_bottom_field, one-entry cycle: a reference frame advances the expected POC by 2
@@ -628,9 +631,9 @@ struct Encoder {
     const bool mixed = P.mixed_slices && P.slices >= 2 && ps.type != SLICE_I;
     b.ue((uint32_t)((sd.slice_type == SLICE_P ? 0 : sd.slice_type == SLICE_B ? 1 : 2) + (mixed ? 0 : 5)));
     b.ue(P.header_variant ? 7 : 0);  // pic_parameter_set_id
-    b.put((uint32_t)(ps.frame_num & 15), 4);
+    b.put((uint32_t)(ps.frame_num & ((1 << fn_bits()) - 1)), fn_bits());
     if (nal_type == 5) b.ue((uint32_t)idr_id);
-    if (P.poc_type == 0) b.put((uint32_t)(ps.poc & 255), 8);
+    if (P.poc_type == 0) b.put((uint32_t)(ps.poc & ((1 << poc_bits()) - 1)), poc_bits());
     if (P.poc_type == 1 && P.bframes != 0) b.se(ps.delta_poc);
     if (sd.slice_type == SLICE_B) b.put1(sd.direct_spatial);
     if (sd.slice_type != SLICE_I) {
@@ -721,7 +724,7 @@ struct Encoder {
         lst.resize(active[l]);  // entries beyond num_ref_idx_active are dropped before the modification
         // move one or two entries to the front.  picNumPred starts at CurrPicNum; a short-term target is named by the
         // difference to the prediction (idc 0 subtract / 1 add), a long-term one by its LongTermPicNum (idc 2)
-        auto pic_num = [&](const RefEntry &r) { return r.frame_num > ps.frame_num ? r.frame_num - 16 : r.frame_num; };
+        auto pic_num = [&](const RefEntry &r) { return r.frame_num > ps.frame_num ? r.frame_num - (1 << fn_bits()) : r.frame_num; };
         int pred = ps.frame_num;
         const int nops = 1 + (active[l] > 2 && rng.pct(50));
         for (int k = 0; k < nops; ++k) {
@@ -732,7 +735,7 @@ struct Encoder {
             const int pn = pic_num(tgt);
             if (pn < pred) rplm_ops[l].push_back({0, pred - pn - 1});
             else if (pn > pred) rplm_ops[l].push_back({1, pn - pred - 1});
-            else { rplm_ops[l].push_back({0, 15}); }  // same picture again: a full wrap (MaxPicNum = 16)
+            else { rplm_ops[l].push_back({0, (1 << fn_bits()) - 1}); }  // same picture again: a full wrap (abs_diff_pic_num = MaxPicNum)
             pred = pn;
           }
           lst.erase(lst.begin() + src);
@@ -1210,7 +1213,7 @@ static int encode_clip(const hwgen_params &P, std::vector<uint8_t> &mp4, uint8_t
           // 8.2.1.2 with a one-entry cycle (offset_for_ref_frame[0] = 2): expected POC from frame_num alone
           if (ps.idr) frame_num_offset = 0;
           else if (prev_mmco5) frame_num_offset = 0;
-          else if (prev_frame_num > frame_num) frame_num_offset += 16;
+          else if (prev_frame_num > frame_num) frame_num_offset += 1 << enc.fn_bits();
           int abs_fn = frame_num_offset + frame_num;
           if (!ps.is_ref && abs_fn > 0) abs_fn--;
           int expected = abs_fn > 0 ? 2 * abs_fn : 0;
@@ -1220,7 +1223,7 @@ static int encode_clip(const hwgen_params &P, std::vector<uint8_t> &mp4, uint8_t
         }
         // ---- adaptive reference marking: decided before the picture is coded (it is slice-header syntax), applied after
         std::vector<RefEntry> &dpb = enc.dpb;
-        auto pic_num = [&](const RefEntry &r) { return r.frame_num > frame_num ? r.frame_num - 16 : r.frame_num; };
+        auto pic_num = [&](const RefEntry &r) { return r.frame_num > frame_num ? r.frame_num - (1 << enc.fn_bits()) : r.frame_num; };
         int n_short = 0, n_long = 0;
         for (auto &r : dpb) (r.long_term ? n_long : n_short)++;
         bool cur_long = false; int cur_lt_idx = 0; bool mmco5 = false;
@@ -1315,7 +1318,7 @@ static int encode_clip(const hwgen_params &P, std::vector<uint8_t> &mp4, uint8_t
             poc_base += ps.poc; frame_num = 0; prev_frame_num = 0; prev_mmco5 = true; frame_num_offset = 0;
           }
           dpb.push_back(cur);
-          frame_num = (frame_num + 1) & 15;
+          frame_num = (frame_num + 1) & ((1 << enc.fn_bits()) - 1);
         }
       }
     }

@@ -42,7 +42,8 @@ typedef struct hwgen_params {
   int32_t mixed_slices;    // 1 (needs slices >= 2): every third slice of a P / B picture is an I slice (intra refresh by slice, as some
                            //    hardware encoders do); such pictures write slice_type 0..2 instead of 5..7
   int32_t header_variant;  // 1: parameter-set ids other than 0 (sps 3, pps 7), pic_init_qp_minus26 = -4, num_ref_idx_default_active = 2 / 2 in
-                           //    the PPS (slices override only when they differ), as encoders other than this one write their headers
+                           //    the PPS (slices override only when they differ), 6-bit frame_num and 5-bit pic_order_cnt_lsb (both wrap inside a
+                           //    GOP), as encoders other than this one write their headers
   int32_t reserved[2];
 } hwgen_params;
 
