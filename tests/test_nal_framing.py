@@ -135,3 +135,36 @@ def test_sps_with_full_vui_hrd_and_timing(emu):
     new_avcc = bytes(avcc[:5]) + bytes([0xE1]) + struct.pack('>H', len(sps)) + sps + bytes([len(pps_list)]) + \
         b''.join(struct.pack('>H', len(p)) + p for p in pps_list)
     _decode_both(index, new_avcc, samples, kf)
+
+
+def test_frame_cropping_with_a_top_offset(emu):
+    """frame_crop_top_offset other than 0 (the generator only crops at the right and at the bottom): the same coded
+    pictures shown through a window that starts at luma row 4 -- planar output and RGB24 against libavcodec + the
+    swscale arithmetic.  (A left offset is not compared: libavcodec itself reduces frame_crop_left_offset to a multiple
+    of 32 samples "to preserve alignment", h264_ps.c, so the reference would show a 92-sample-wide picture there.)"""
+    kw = dict(frames=8, gop=4, width=88, height=72, profile=1, seed=63, num_ref=2, bframes=1)  # coded 96x80
+    mp4, index, samples, kf = util.make_clip(**kw)
+    avcc = index.metadata_bytes()
+    nls, sps_list, pps_list = fo.parse_avcc(avcc)
+    b = _Bits()
+    b.u(77, 8); b.u(0x40, 8); b.u(30, 8)
+    b.ue(0); b.ue(0); b.ue(0); b.ue(4)
+    b.ue(2); b.u(0, 1)
+    b.ue(5); b.ue(4); b.u(1, 1); b.u(1, 1)
+    b.u(1, 1); b.ue(0); b.ue(4); b.ue(2); b.ue(2)   # crop 8 luma samples on the right, 4 rows at the top and at the bottom: 96x80 -> 88x72
+    b.u(0, 1)                                       # no VUI at all (output order must not depend on it)
+    sps = bytes([0x67]) + b.rbsp()
+    new_avcc = bytes(avcc[:5]) + bytes([0xE1]) + struct.pack('>H', len(sps)) + sps + bytes([len(pps_list)]) + \
+        b''.join(struct.pack('>H', len(p)) + p for p in pps_list)
+    _decode_both(index, new_avcc, samples, kf)
+    ref = fo.decode_samples(new_avcc, samples, kf)
+    dec = hw.VideoDecoder(0)
+    dec.configure(88, 72, index.format(), new_avcc)
+    for s, k in zip(samples, kf):
+        dec.feed(s, k)
+    dec.feed(None); dec.flush()
+    for i in range(len(samples)):
+        while dec.frames_ready() == 0:
+            pass
+        rgb = np.asarray(dec.get_frame()).reshape(72, 88, 3)
+        assert np.array_equal(rgb, fo.yuv420_to_rgb24(*ref[i])), 'RGB24 frame %d' % i
