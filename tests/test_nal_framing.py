@@ -168,3 +168,75 @@ def test_frame_cropping_with_a_top_offset(emu):
             pass
         rgb = np.asarray(dec.get_frame()).reshape(72, 88, 3)
         assert np.array_equal(rgb, fo.yuv420_to_rgb24(*ref[i])), 'RGB24 frame %d' % i
+
+
+def _scaling_list(b, values, n):
+    """scaling_list() syntax (7.3.2.1.1.1): `values` in zig-zag order; a value of 0 at position j > 0 ends the list (the rest
+    repeats the last value), a value of 0 at position 0 asks for the default matrix."""
+    last = 8
+    for j in range(n):
+        v = values[j] if j < len(values) else 0
+        delta = (v - last + 128) % 256 - 128
+        b.se(delta)
+        if v == 0:
+            return
+        last = v
+
+
+@pytest.mark.parametrize('pps_lists', [False, True])
+def test_sequence_level_scaling_matrices_with_fallback_rules(emu, pps_lists):
+    """seq_scaling_matrix_present_flag = 1 with every way a list can be given (7.4.2.1.1): explicit, explicit but cut
+    short, "use the default matrix", absent -> fall-back rule set A (the previous list, or the default for the first of its
+    kind); the PPS carries no matrices of its own, so the sequence-level ones are what dequantisation uses (4x4 and 8x8,
+    intra and inter).  The encoder quantised with flat matrices, so the pictures drift -- both decoders must drift alike.
+    With pps_lists the picture parameter set carries matrices too (fall-back rule set B).  The matrices stay below twice
+    the flat value: with entries of 60 one frame differed from libavcodec -- levels quantised for a flat matrix then
+    dequantise beyond the 16 bits a conformant stream guarantees, where libavcodec (16-bit coefficients) and this decoder
+    (32-bit) presumably part ways; not pursued."""
+    kw = dict(frames=12, gop=6, width=96, height=80, profile=2, seed=64, num_ref=2, bframes=1, intra_in_p_pct=15)
+    mp4, index, samples, kf = util.make_clip(**kw)
+    avcc = index.metadata_bytes()
+    nls, sps_list, pps_list = fo.parse_avcc(avcc)
+    b = _Bits()
+    b.u(100, 8); b.u(0, 8); b.u(30, 8)
+    b.ue(0)                                         # sps id
+    b.ue(1); b.ue(0); b.ue(0); b.u(0, 1)            # chroma_format_idc 1, 8 bit, no transform bypass
+    b.u(1, 1)                                       # seq_scaling_matrix_present_flag
+    b.u(1, 1); _scaling_list(b, [6 + 2 * j for j in range(16)], 16)          # 0: Intra Y, explicit
+    b.u(0, 1)                                                                 # 1: Intra Cb <- list 0
+    b.u(1, 1); _scaling_list(b, [0], 16)                                      # 2: Intra Cr: default matrix
+    b.u(1, 1); _scaling_list(b, [40 - 2 * j for j in range(16)], 16)         # 3: Inter Y, explicit
+    b.u(0, 1)                                                                 # 4: Inter Cb <- list 3
+    b.u(1, 1); _scaling_list(b, [12, 14, 16, 18, 20], 16)                     # 5: Inter Cr: cut short after five values
+    b.u(0, 1)                                                                 # 6: 8x8 Intra: absent -> default
+    b.u(1, 1); _scaling_list(b, [9 + (j * 7) % 40 for j in range(64)], 64)    # 7: 8x8 Inter, explicit
+    b.ue(0); b.ue(0); b.ue(4)                       # log2_max_frame_num_minus4, poc type 0, 8-bit lsb
+    b.ue(2); b.u(0, 1)
+    b.ue(5); b.ue(4); b.u(1, 1); b.u(1, 1)
+    b.u(0, 1)                                       # no cropping (96x80)
+    b.u(1, 1)                                       # VUI: bitstream restriction only
+    b.u(0, 1); b.u(0, 1); b.u(0, 1); b.u(0, 1); b.u(0, 1); b.u(0, 1); b.u(0, 1); b.u(0, 1)
+    b.u(1, 1); b.u(1, 1); b.ue(0); b.ue(0); b.ue(16); b.ue(16); b.ue(1); b.ue(2)
+    sps = bytes([0x67]) + b.rbsp()
+    if pps_lists:
+        # ... and a picture parameter set with matrices of its own: absent lists fall back to the SEQUENCE-level list
+        # (rule set B) for the first of each kind and to the previous list otherwise
+        q = _Bits()
+        q.ue(0); q.ue(0); q.u(1, 1); q.u(0, 1); q.ue(0)    # ids, CABAC, no field order, one slice group
+        q.ue(0); q.ue(0); q.u(0, 1); q.u(0, 2)            # default reference counts, no weighted prediction
+        q.se(0); q.se(0); q.se(0)                         # init qp / qs, chroma_qp_index_offset
+        q.u(1, 1); q.u(0, 1); q.u(0, 1)                   # deblocking control present, no constrained intra, no redundant pictures
+        q.u(1, 1); q.u(1, 1)                              # transform_8x8_mode, pic_scaling_matrix_present
+        q.u(0, 1)                                                                 # 0: <- sequence-level list 0 (rule B)
+        q.u(1, 1); _scaling_list(q, [26 - j for j in range(16)], 16)              # 1: explicit
+        q.u(0, 1)                                                                 # 2: <- list 1
+        q.u(0, 1)                                                                 # 3: <- sequence-level list 3 (rule B)
+        q.u(1, 1); _scaling_list(q, [0], 16)                                      # 4: default matrix
+        q.u(0, 1)                                                                 # 5: <- list 4
+        q.u(0, 1)                                                                 # 6: <- sequence-level 8x8 intra
+        q.u(1, 1); _scaling_list(q, [12 + (j * 3) % 17 for j in range(64)], 64)   # 7: explicit
+        q.se(-1)                                          # second_chroma_qp_index_offset (as tools/h264gen writes it)
+        pps_list = [bytes([0x68]) + q.rbsp()]
+    new_avcc = bytes(avcc[:5]) + bytes([0xE1]) + struct.pack('>H', len(sps)) + sps + bytes([len(pps_list)]) + \
+        b''.join(struct.pack('>H', len(p)) + p for p in pps_list)
+    _decode_both(index, new_avcc, samples, kf)
