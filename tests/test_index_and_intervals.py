@@ -267,3 +267,70 @@ def test_index_of_mdat_first_variant(emu, name):
             ref = json.loads(subprocess.run([tool, 'index', f.name], capture_output=True, text=True, timeout=60).stdout)
         assert 'error' not in ref, ref
         assert (ref['offsets'], ref['sizes'], ref['keyframes']) == (vi.sample_offsets(), vi.sample_sizes(), vi.keyframe_indices())
+
+
+def _box(typ, payload):
+    return struct.pack('>I4s', 8 + len(payload), typ) + payload
+
+
+def _audio_trak(track_id=1, samples=5):
+    """A minimal sound track (handler 'soun', one chunk of `samples` 100-byte samples at offset 0x1000)."""
+    tkhd = _box(b'tkhd', struct.pack('>IIIII', 7, 0, 0, track_id, 0) + bytes(60))
+    mdhd = _box(b'mdhd', struct.pack('>IIIIIHH', 0, 0, 0, 44100, 44100 * 2, 0x55C4, 0))
+    hdlr = _box(b'hdlr', struct.pack('>II4s', 0, 0, b'soun') + bytes(12) + b'snd\0')
+    mp4a = _box(b'mp4a', bytes(6) + struct.pack('>H', 1) + bytes(8) + struct.pack('>HHHHI', 2, 16, 0, 0, 44100 << 16))
+    stbl = _box(b'stbl', _box(b'stsd', struct.pack('>II', 0, 1) + mp4a) + _box(b'stts', struct.pack('>IIII', 0, 1, samples, 1024)) +
+                _box(b'stsc', struct.pack('>IIIII', 0, 1, 1, samples, 1)) + _box(b'stsz', struct.pack('>III', 0, 100, samples)) +
+                _box(b'stco', struct.pack('>III', 0, 1, 0x1000)))
+    minf = _box(b'minf', _box(b'smhd', bytes(8)) + _box(b'dinf', _box(b'dref', struct.pack('>II', 0, 1) + _box(b'url ', struct.pack('>I', 1)))) + stbl)
+    return _box(b'trak', tkhd + _box(b'mdia', mdhd + hdlr + minf))
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_index_of_a_file_with_a_sound_track_first_extra_boxes_and_a_64_bit_mdat(emu, name):
+    """What muxers other than ours write around the video track: a sound track AHEAD of it inside moov, `free` / `udta`
+    boxes, an `edts` box inside the video track, and an mdat box with a 64-bit size field.  The video index must be the
+    same table, shifted; checked against the reference's own indexer when it is built here."""
+    mp4, g = load(name)
+    ri = g['reference_index']
+    buf = bytes(mp4)
+    top = _boxes(buf, 0, len(buf))
+    names = [t for t, _, _ in top]
+    if b'moof' in names or b'mdat' not in names or names.index(b'moov') > names.index(b'mdat'):
+        pytest.skip('fragmented or mdat-first layout')
+    (_, mp, msize), (_, dp, dsize) = next(b for b in top if b[0] == b'moov'), next(b for b in top if b[0] == b'mdat')
+    moov_kids = _boxes(buf, mp + 8, mp + msize)
+    _, tp, tsize = next(b for b in moov_kids if b[0] == b'trak')
+    edts = _box(b'edts', _box(b'elst', struct.pack('>IIIiI', 0, 1, 1000, 0, 0x10000)))
+    trak_kids = _boxes(buf, tp + 8, tp + tsize)
+    _, kp, ksize = trak_kids[0]  # tkhd first, edts right behind it
+    video_trak = _box(b'trak', buf[tp + 8:kp + ksize] + edts + buf[kp + ksize:tp + tsize])
+    new_moov_payload = buf[mp + 8:tp] + _audio_trak(track_id=7) + video_trak + buf[tp + tsize:mp + msize] + \
+        _box(b'udta', _box(b'meta', bytes(4) + _box(b'hdlr', bytes(24))))
+    free = _box(b'free', bytes(37))
+    new_mdat = struct.pack('>I4sQ', 1, b'mdat', dsize + 8) + buf[dp + 8:dp + dsize]  # largesize form
+    head = buf[:mp] + _box(b'moov', new_moov_payload) + buf[mp + msize:dp] + free
+    delta = len(head) + 16 - (dp + 8)  # where the media data starts now minus where it started
+    out = bytearray(head + new_mdat + buf[dp + dsize:])
+    # the video track's chunk offsets move by delta (they sit in the last stco of the file: the sound track's comes first)
+    sp = bytes(out).rfind(b'stco')
+    n = struct.unpack('>I', out[sp + 8:sp + 12])[0]
+    offs = struct.unpack('>%dI' % n, out[sp + 12:sp + 12 + 4 * n])
+    out[sp + 12:sp + 12 + 4 * n] = struct.pack('>%dI' % n, *[o + delta for o in offs])
+    out = bytes(out)
+    ic = run_indexer(out)
+    assert not ic.is_error(), ic.error_message()
+    vi = ic.get_video_index()
+    assert vi.sample_offsets() == [o + delta for o in ri['offsets']]
+    assert vi.sample_sizes() == ri['sizes'] and vi.keyframe_indices() == ri['keyframes']
+    assert (vi.frame_width(), vi.frame_height()) == (ri['width'], ri['height'])
+    for o, s in zip(vi.sample_offsets(), vi.sample_sizes()):  # the table points at the same bytes as before
+        assert out[o:o + s] == buf[o - delta:o - delta + s]
+    tool = os.path.join(os.path.dirname(GOLDEN), '..', 'oracle', '_ref', 'ref_tool')
+    if os.path.exists(tool):
+        import subprocess, tempfile
+        with tempfile.NamedTemporaryFile(suffix='.mp4') as f:
+            f.write(out); f.flush()
+            ref = json.loads(subprocess.run([tool, 'index', f.name], capture_output=True, text=True, timeout=60).stdout)
+        if 'error' not in ref:  # the reference indexer may refuse what it does not know; when it answers, the answers must agree
+            assert (ref['offsets'], ref['sizes'], ref['keyframes']) == (vi.sample_offsets(), vi.sample_sizes(), vi.keyframe_indices())
