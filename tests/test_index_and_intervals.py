@@ -334,3 +334,34 @@ def test_index_of_a_file_with_a_sound_track_first_extra_boxes_and_a_64_bit_mdat(
             ref = json.loads(subprocess.run([tool, 'index', f.name], capture_output=True, text=True, timeout=60).stdout)
         if 'error' not in ref:  # the reference indexer may refuse what it does not know; when it answers, the answers must agree
             assert (ref['offsets'], ref['sizes'], ref['keyframes']) == (vi.sample_offsets(), vi.sample_sizes(), vi.keyframe_indices())
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_index_of_an_hevc_sample_entry(emu, name):
+    """The reference indexes HEVC files too (hev1 / hvcC, mp4_index_creator.cpp:454-469; its decode tests use one): the
+    index -- table, format string, configuration record -- does not depend on the codec.  Decoding such a file is
+    refused with the reference's "Unsupported video codec" wording."""
+    mp4, g = load(name)
+    ri = g['reference_index']
+    assert mp4.count(b'avc1') >= 1 and mp4.count(b'avcC') == 1
+    hevc = mp4.replace(b'avcC', b'hvcC')
+    i = hevc.find(b'stsd')
+    j = hevc.find(b'avc1', i)
+    hevc = hevc[:j] + b'hev1' + hevc[j + 4:]
+    ic = run_indexer(hevc)
+    assert not ic.is_error(), ic.error_message()
+    vi = ic.get_video_index()
+    assert vi.format() == 'hev1'
+    assert vi.sample_offsets() == ri['offsets'] and vi.sample_sizes() == ri['sizes'] and vi.keyframe_indices() == ri['keyframes']
+    assert vi.metadata_bytes() == hw.index_video(io.BytesIO(mp4)).metadata_bytes()
+    tool = os.path.join(os.path.dirname(GOLDEN), '..', 'oracle', '_ref', 'ref_tool')
+    if os.path.exists(tool):
+        import subprocess, tempfile
+        with tempfile.NamedTemporaryFile(suffix='.mp4') as f:
+            f.write(hevc); f.flush()
+            ref = json.loads(subprocess.run([tool, 'index', f.name], capture_output=True, text=True, timeout=60).stdout)
+        assert 'error' not in ref, ref
+        assert (ref['offsets'], ref['sizes'], ref['keyframes'], ref['format']) == (vi.sample_offsets(), vi.sample_sizes(), vi.keyframe_indices(), 'hev1')
+    dec = hw.VideoDecoder(0)
+    with pytest.raises(RuntimeError, match='Unsupported video codec'):
+        dec.configure(vi.frame_width(), vi.frame_height(), vi.format(), vi.metadata_bytes())
