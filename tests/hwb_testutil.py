@@ -123,6 +123,11 @@ CPU_SYNTAX_CLIPS = {
                                         weighted=3, rplm_pct=40, mmco=1),
     'header_variant_b_pyramid_mixed_slices': dict(frames=26, gop=13, width=176, height=144, profile=2, seed=123, num_ref=4, bframes=3, b_pyramid=1,
                                                   header_variant=1, weighted=3, direct_spatial=0, slices=2, mixed_slices=1),
+    # long GOPs with a B pyramid, MMCO / long-term references and temporal direct prediction: more than 16 reference pictures per
+    # GOP, so frame_num must be wider than 4 bits for libavcodec to be a usable oracle here (it maps co-located references by
+    # frame_num: DESIGN.md 6)
+    'mmco_long_term_b_temporal_long_gop': dict(frames=80, gop=40, width=80, height=64, profile=2, seed=124, num_ref=3, bframes=2, b_pyramid=1, mmco=1,
+                                               direct_spatial=0, header_variant=1, slices=2, qp_jitter=4),
     'mixed_slice_types_b_spatial_cavlc_constrained': dict(frames=24, gop=12, width=176, height=144, profile=2, seed=119, num_ref=3, bframes=2,
                                                           slices=2, mixed_slices=1, cabac=0, constrained_intra=1, weighted=2),
 }

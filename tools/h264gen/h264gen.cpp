@@ -328,7 +328,18 @@ struct Encoder {
       for (auto &r : dpb) if (r.slot == s) used = true;
       if (!used && (best < 0 || slot_stamp[s] < slot_stamp[best])) best = s;
     }
-    if (best >= 0) slot_stamp[best] = ++stamp;
+    if (best >= 0) {
+      slot_stamp[best] = ++stamp;
+      // ... and least-recently-used is not enough with a B pyramid and four references (found by tools/param_sweep.py): a
+      // picture still in the DPB may name a reference that left long ago.  Whatever still names the slot that is handed
+      // out now is made unmatchable, so that temporal direct prediction finds "no such picture in list 0" (index 0) exactly
+      // as a decoder does, which knows pictures by identity and not by buffer.
+      for (auto &r : dpb)
+        for (int l = 0; l < 2; ++l) {
+          int16_t *po = pic_refpic(c, r.slot, l);
+          for (int i = 0; i < nmb * 4; ++i) if (po[i] == best) po[i] = -2;
+        }
+    }
     return best;
   }
   const uint8_t *src_plane(int p) const { return p == 0 ? srcY.data() : (p == 1 ? srcU.data() : srcV.data()); }

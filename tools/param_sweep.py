@@ -1,0 +1,64 @@
+"""Randomised closed-loop check on the CPU: random combinations of the generator's options (profiles, entropy modes,
+B pictures / pyramid, slices, weights, direct modes, list modification, MMCO, POC types, short reference lists, mixed
+slice types, header variant, scaling lists, deblocking modes ...) -> (a) the generator's own reconstruction, (b)
+libavcodec, (c) the decode core in host emulation must all agree frame by frame.  Finds interactions no hand-written
+clip list covers.   python tools/param_sweep.py [combinations] [seed]"""
+import io, os, random, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
+import numpy as np
+from hwang_b200 import _lib, build
+_lib.use_library(os.environ.get('HWB_FUZZ_LIB') or build.EMU)
+import hwang_b200 as hw
+from hwang_b200.testing import streamgen
+import hwb_testutil as util
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+rng = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+t0 = time.time()
+fails = 0
+for it in range(N):
+    profile = rng.choice([0, 1, 1, 2, 2, 2])
+    bframes = 0 if profile == 0 else rng.choice([0, 0, 1, 2, 3])
+    kw = dict(width=rng.choice([64, 80, 96, 112, 176]), height=rng.choice([48, 64, 72, 80, 144]), profile=profile, bframes=bframes,
+              seed=rng.randrange(1, 1 << 30), qp=rng.choice([18, 24, 28, 34, 40]), slices=rng.choice([1, 1, 2, 3, 4]),
+              num_ref=rng.choice([1, 2, 3, 4]), qp_jitter=rng.choice([0, 0, 2, 4]), intra_in_p_pct=rng.choice([0, 2, 10, 30]),
+              ipcm_per_100k=rng.choice([0, 0, 1500]), deblock=rng.choice([0, 0, 1, 2, 3]), constrained_intra=rng.choice([0, 0, 1]),
+              cabac_init_idc=rng.choice([-1, 0, 1, 2]), chroma_qp_offset=rng.choice([0, 0, -2, 3]), direct_spatial=rng.choice([0, 1]),
+              rplm_pct=rng.choice([0, 0, 40, 80]), mmco=rng.choice([0, 0, 1]), pad_refs=rng.choice([0, 0, 1]),
+              mixed_slices=rng.choice([0, 0, 1]), header_variant=rng.choice([0, 0, 1]), fragmented=rng.choice([0, 0, 1]))
+    if profile >= 1: kw['cabac'] = rng.choice([-1, -1, 0])
+    if profile == 2: kw['scaling_lists'] = rng.choice([0, 0, 1])
+    kw['weighted'] = rng.choice([0, 0, 1, 2, 3]) if profile >= 1 else 0
+    if bframes == 0 and kw['weighted'] >= 2: kw['weighted'] = 1
+    kw['b_pyramid'] = 1 if (bframes >= 2 and rng.random() < 0.5) else 0
+    if kw['b_pyramid'] and kw['num_ref'] < 3: kw['num_ref'] = 3
+    kw['poc_type'] = rng.choice([0, 0, 1, 2]) if bframes == 0 else rng.choice([0, 0, 1])
+    # Known difference, kept out of the sweep: libavcodec maps a co-located block's reference into list 0 by frame_num
+    # (h264_direct.c fill_colmap), so with a 4-bit frame_num that wraps inside a GOP while an older (long-term or not yet
+    # dropped) reference is alive it picks a different picture than the standard's rule (picture identity), which this
+    # decoder and the generator follow.  40 random clips of that kind: 18 differ from libavcodec with a 4-bit frame_num, none
+    # with 6 bits.
+    if kw['mmco'] and bframes and not kw['direct_spatial']: kw['header_variant'] = 1
+    gop = rng.choice([4, 7, 12, 20, 40]); gop = max(gop, bframes + 2)
+    kw['gop'] = gop; kw['frames'] = gop * rng.choice([1, 2, 2])
+    try:
+        mp4, recon = streamgen.generate(want_recon=True, **kw)
+    except RuntimeError as e:
+        print('skip (generator refuses):', str(e)[:80], flush=True); continue
+    index = hw.index_video(io.BytesIO(mp4))
+    offs, sizes, kfs = index.sample_offsets(), index.sample_sizes(), set(index.keyframe_indices())
+    samples = [mp4[o:o + s] for o, s in zip(offs, sizes)]
+    keyflags = [i in kfs for i in range(len(samples))]
+    ref = util.oracle_frames(index, samples, keyflags)
+    bad_gen = [i for i, r in enumerate(ref) if not np.array_equal(recon[i], util.flat(r))] if len(ref) == kw['frames'] else ['count %d' % len(ref)]
+    try:
+        got, _ = util.decode_yuv(index, samples, keyflags)
+        bad_dec = [i for i, (g, r) in enumerate(zip(got, ref)) if not np.array_equal(g, util.flat(r))]
+    except Exception as e:
+        bad_dec = ['ERROR ' + str(e)[:90]]
+    if bad_gen or bad_dec:
+        fails += 1
+        print('MISMATCH generator!=libavcodec at %s, decoder!=libavcodec at %s\n   %s' % (bad_gen[:5], bad_dec[:5], kw), flush=True)
+print('param sweep: %d combinations, %d mismatches, %.0f s' % (N, fails, time.time() - t0))  # a generator-only mismatch is a tooling bug (round 2: stale buffer names, fixed), a decoder mismatch a product bug
+sys.exit(1 if fails else 0)
