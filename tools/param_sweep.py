@@ -20,9 +20,9 @@ fails = 0
 for it in range(N):
     profile = rng.choice([0, 1, 1, 2, 2, 2])
     bframes = 0 if profile == 0 else rng.choice([0, 0, 1, 2, 3])
-    kw = dict(width=rng.choice([64, 80, 96, 112, 176]), height=rng.choice([48, 64, 72, 80, 144]), profile=profile, bframes=bframes,
-              seed=rng.randrange(1, 1 << 30), qp=rng.choice([18, 24, 28, 34, 40]), slices=rng.choice([1, 1, 2, 3, 4]),
-              num_ref=rng.choice([1, 2, 3, 4]), qp_jitter=rng.choice([0, 0, 2, 4]), intra_in_p_pct=rng.choice([0, 2, 10, 30]),
+    kw = dict(width=rng.choice([16, 64, 80, 96, 112, 176, 352]), height=rng.choice([16, 48, 64, 72, 80, 144, 288]), profile=profile, bframes=bframes,
+              seed=rng.randrange(1, 1 << 30), qp=rng.choice([12, 18, 24, 28, 34, 40, 44]), slices=rng.choice([1, 1, 2, 3, 4, 8]),
+              num_ref=rng.choice([1, 2, 3, 4]), qp_jitter=rng.choice([0, 0, 2, 4]), intra_in_p_pct=rng.choice([0, 2, 10, 30, 60]),
               ipcm_per_100k=rng.choice([0, 0, 1500]), deblock=rng.choice([0, 0, 1, 2, 3]), constrained_intra=rng.choice([0, 0, 1]),
               cabac_init_idc=rng.choice([-1, 0, 1, 2]), chroma_qp_offset=rng.choice([0, 0, -2, 3]), direct_spatial=rng.choice([0, 1]),
               rplm_pct=rng.choice([0, 0, 40, 80]), mmco=rng.choice([0, 0, 1]), pad_refs=rng.choice([0, 0, 1]),
@@ -40,8 +40,9 @@ for it in range(N):
     # decoder and the generator follow.  40 random clips of that kind: 18 differ from libavcodec with a 4-bit frame_num, none
     # with 6 bits.
     if kw['mmco'] and bframes and not kw['direct_spatial']: kw['header_variant'] = 1
-    gop = rng.choice([4, 7, 12, 20, 40]); gop = max(gop, bframes + 2)
-    kw['gop'] = gop; kw['frames'] = gop * rng.choice([1, 2, 2])
+    gop = rng.choice([4, 7, 12, 20, 40, 40, 70, 100]); gop = max(gop, bframes + 2)
+    kw['gop'] = gop; kw['frames'] = gop * (rng.choice([1, 2, 2]) if gop < 70 else 1)
+    if kw['slices'] > max(1, (kw['width'] + 15) // 16 * ((kw['height'] + 15) // 16)): kw['slices'] = 1  # a slice holds at least one macroblock
     try:
         mp4, recon = streamgen.generate(want_recon=True, **kw)
     except RuntimeError as e:
