@@ -12,6 +12,7 @@ _lib.use_library(os.environ.get('HWB_FUZZ_LIB') or build.EMU)
 import hwang_b200 as hw
 from hwang_b200.testing import streamgen
 import hwb_testutil as util
+from oracle import ffmpeg_oracle as fo
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 rng = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
@@ -58,6 +59,22 @@ for it in range(N):
         bad_dec = [i for i, (g, r) in enumerate(zip(got, ref)) if not np.array_equal(g, util.flat(r))]
     except Exception as e:
         bad_dec = ['ERROR ' + str(e)[:90]]
+    # ... and the python API on a random row set (sparse, dense, clustered): interval slicing, hints (unrequested
+    # non-reference pictures and GOP tails are not decoded), RGB24 against the swscale arithmetic
+    if not bad_dec and rng.random() < 0.6:
+        n = kw['frames']
+        style = rng.choice(['sparse', 'dense', 'cluster', 'single'])
+        if style == 'sparse': rows = sorted(rng.sample(range(n), max(1, n // rng.choice([3, 7, 17]))))
+        elif style == 'dense': rows = list(range(rng.randrange(n), n))
+        elif style == 'cluster': a = rng.randrange(n); rows = sorted(set(list(range(a, min(n, a + 5))) + [rng.randrange(n) for _ in range(3)]))
+        else: rows = [rng.randrange(n)]
+        try:
+            frames = hw.Decoder(io.BytesIO(mp4), video_index=index).retrieve(rows)
+            bad_rows = [r for r, f in zip(rows, frames) if not np.array_equal(np.asarray(f), fo.yuv420_to_rgb24(*ref[r]))]
+            if len(frames) != len(rows): bad_rows.append('count')
+        except Exception as e:
+            bad_rows = ['ERROR ' + str(e)[:90]]
+        if bad_rows: bad_dec = ['retrieve(%s rows) wrong at %s' % (style, bad_rows[:5])]
     if bad_gen or bad_dec:
         fails += 1
         print('MISMATCH generator!=libavcodec at %s, decoder!=libavcodec at %s\n   %s' % (bad_gen[:5], bad_dec[:5], kw), flush=True)
