@@ -13,11 +13,13 @@ import hwang_b200 as hw
 from hwang_b200.testing import streamgen
 import hwb_testutil as util
 from oracle import ffmpeg_oracle as fo
+from hwang_b200 import batch as hwbatch
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 rng = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 t0 = time.time()
 fails = 0
+POOLS = {}
 for it in range(N):
     profile = rng.choice([0, 1, 1, 2, 2, 2])
     bframes = 0 if profile == 0 else rng.choice([0, 0, 1, 2, 3])
@@ -75,6 +77,21 @@ for it in range(N):
         except Exception as e:
             bad_rows = ['ERROR ' + str(e)[:90]]
         if bad_rows: bad_dec = ['retrieve(%s rows) wrong at %s' % (style, bad_rows[:5])]
+    # ... and batch retrieval across clips: the last few clips of this geometry in ONE retrieve_many call (their intervals share GPU
+    # batches, hwang_b200/batch.py), every returned frame against the oracle of its own clip
+    if not bad_dec:
+        pool = POOLS.setdefault((kw['width'], kw['height']), [])
+        pool.append((mp4, ref, kw['frames']))
+        del pool[:-4]
+        if len(pool) >= 2 and rng.random() < 0.3:
+            reqs = [(m, sorted(rng.sample(range(n), rng.randrange(1, n + 1)))) for m, _, n in pool]
+            try:
+                outs = hwbatch.retrieve_many(reqs, devices=[0])
+                for (m, rows), frames, (_, rf, _) in zip(reqs, outs, pool):
+                    if len(frames) != len(rows) or any(not np.array_equal(np.asarray(f), fo.yuv420_to_rgb24(*rf[r])) for r, f in zip(rows, frames)):
+                        bad_dec = ['retrieve_many over %d clips wrong' % len(pool)]
+            except Exception as e:
+                bad_dec = ['retrieve_many ERROR ' + str(e)[:90]]
     if bad_gen or bad_dec:
         fails += 1
         print('MISMATCH generator!=libavcodec at %s, decoder!=libavcodec at %s\n   %s' % (bad_gen[:5], bad_dec[:5], kw), flush=True)
