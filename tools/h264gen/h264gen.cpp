@@ -768,7 +768,7 @@ struct Encoder {
       // mixed_slices: every third slice of an inter picture is an I slice
       const int stype = (P.mixed_slices && P.slices >= 2 && ps.type != SLICE_I && (sl + ps.t) % 3 == 1) ? (int)SLICE_I : (int)ps.type;
       sd.pic = slot; sd.first_mb = first_mb; sd.slice_type = (uint8_t)stype;
-      sd.qp = (uint8_t)clip3(10, 44, P.qp + (stype == SLICE_B ? 2 : (stype == SLICE_I ? -2 : 0)) + (P.qp_jitter ? rng.range(-1, 1) : 0));
+      sd.qp = (uint8_t)clip3(P.qp < 10 ? 0 : 10, P.qp > 44 ? 51 : 44, P.qp + (stype == SLICE_B ? 2 : (stype == SLICE_I ? -2 : 0)) + (P.qp_jitter ? rng.range(-1, 1) : 0));
       sd.cabac_init_idc = (uint8_t)(P.cabac_init_idc >= 0 ? P.cabac_init_idc : rng.below(3));
       sd.disable_deblock = (uint8_t)(P.deblock == 1 ? 1 : (P.deblock == 2 ? 2 : 0));
       if (P.deblock == 3) { sd.alpha_off = (int8_t)(rng.range(-3, 3) * 2); sd.beta_off = (int8_t)(rng.range(-3, 3) * 2); if (rng.pct(15)) sd.disable_deblock = (uint8_t)rng.range(1, 2); }
@@ -851,7 +851,7 @@ struct Encoder {
     const int stype = sd.slice_type;  // the slice's type (a picture may mix I slices in)
     const bool B = stype == SLICE_B;
     int want_qp = s.qp;
-    if (P.qp_jitter && rng.pct(20)) want_qp = clip3(8, 46, s.qp + rng.range(-P.qp_jitter, P.qp_jitter));
+    if (P.qp_jitter && rng.pct(20)) want_qp = clip3(P.qp < 10 ? 0 : 8, P.qp > 44 ? 51 : 46, s.qp + rng.range(-P.qp_jitter, P.qp_jitter));  // (the full range only for extreme base QPs: older clips keep their streams)
     bool intra = stype == SLICE_I || rng.pct(P.intra_in_p_pct);
     Levels L;
     memset(&L, 0, sizeof(L));
