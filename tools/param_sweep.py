@@ -23,7 +23,7 @@ POOLS = {}
 for it in range(N):
     profile = rng.choice([0, 1, 1, 2, 2, 2])
     bframes = 0 if profile == 0 else rng.choice([0, 0, 1, 2, 3])
-    kw = dict(width=rng.choice([16, 64, 80, 96, 112, 176, 352]), height=rng.choice([16, 48, 64, 72, 80, 144, 288]), profile=profile, bframes=bframes,
+    kw = dict(width=rng.choice([16, 24, 64, 80, 88, 96, 104, 112, 176, 352]), height=rng.choice([16, 18, 48, 56, 64, 72, 80, 90, 144, 288]), profile=profile, bframes=bframes,
               seed=rng.randrange(1, 1 << 30), qp=rng.choice([0, 3, 6, 9, 12, 18, 24, 28, 34, 40, 44, 47, 49, 51]), slices=rng.choice([1, 1, 2, 3, 4, 8]),
               num_ref=rng.choice([1, 2, 3, 4]), qp_jitter=rng.choice([0, 0, 2, 4]), intra_in_p_pct=rng.choice([0, 2, 10, 30, 60]),
               ipcm_per_100k=rng.choice([0, 0, 1500]), deblock=rng.choice([0, 0, 1, 2, 3]), constrained_intra=rng.choice([0, 0, 1]),
