@@ -14,7 +14,7 @@ class GenParams(ctypes.Structure):
         [('seed', ctypes.c_uint32)] + [(n, ctypes.c_int32) for n in (
             'weighted', 'direct_spatial', 'deblock', 'constrained_intra', 'ipcm_per_100k', 'intra_in_p_pct',
             'cabac_init_idc', 'chroma_qp_offset', 'scaling_lists', 'poc_type', 'fragmented', 'threads',
-            'qp_jitter', 'b_pyramid', 'rplm_pct', 'mmco', 'pad_refs', 'mixed_slices', 'header_variant')] + [('reserved', ctypes.c_int32 * 2)]
+            'qp_jitter', 'b_pyramid', 'rplm_pct', 'mmco', 'pad_refs', 'mixed_slices', 'header_variant', 'direct_4x4')] + [('reserved', ctypes.c_int32 * 1)]
 
 
 _lib = None

@@ -128,6 +128,10 @@ CPU_SYNTAX_CLIPS = {
     # frame_num: DESIGN.md 6)
     'mmco_long_term_b_temporal_long_gop': dict(frames=80, gop=40, width=80, height=64, profile=2, seed=124, num_ref=3, bframes=2, b_pyramid=1, mmco=1,
                                                direct_spatial=0, header_variant=1, slices=2, qp_jitter=4),
+    # direct_8x8_inference_flag = 0: direct prediction per 4x4 block (spatial and temporal), no 8x8 transform in macroblocks with direct parts
+    'direct_4x4_spatial_high': dict(frames=24, gop=12, width=96, height=80, profile=2, seed=125, num_ref=3, bframes=2, direct_4x4=1, weighted=2, slices=2, qp_jitter=2),
+    'direct_4x4_temporal_pyramid_cavlc': dict(frames=26, gop=13, width=96, height=80, profile=2, seed=126, num_ref=4, bframes=3, b_pyramid=1, direct_4x4=1,
+                                              direct_spatial=0, cabac=0, qp_jitter=2),
     'mixed_slice_types_b_spatial_cavlc_constrained': dict(frames=24, gop=12, width=176, height=144, profile=2, seed=119, num_ref=3, bframes=2,
                                                           slices=2, mixed_slices=1, cabac=0, constrained_intra=1, weighted=2),
 }

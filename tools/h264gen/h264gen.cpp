@@ -259,7 +259,7 @@ struct Encoder {
     b.put1(0);
     b.ue((uint32_t)(mb_w - 1)); b.ue((uint32_t)(mb_h - 1));
     b.put1(1);  // frame_mbs_only
-    b.put1(1);  // direct_8x8_inference
+    b.put1(P.direct_4x4 ? 0 : 1);  // direct_8x8_inference
     bool crop = wc != W || hc != H;
     b.put1(crop);
     if (crop) { b.ue(0); b.ue((uint32_t)((wc - W) / 2)); b.ue(0); b.ue((uint32_t)((hc - H) / 2)); }
@@ -697,7 +697,7 @@ struct Encoder {
     memset(&pd, 0, sizeof(pd));
     pd.frame = slot; pd.first_slice = slot * MAXSL; pd.num_slices = P.slices; pd.poc = ps.poc;
     pd.cabac = cabac; pd.transform8x8_mode = high; pd.constrained_intra_pred = P.constrained_intra != 0;
-    pd.direct_8x8_inference = 1; pd.weighted_pred = P.weighted >= 1; pd.weighted_bipred_idc = P.weighted >= 2 ? 2 : 0;
+    pd.direct_8x8_inference = P.direct_4x4 ? 0 : 1; pd.weighted_pred = P.weighted >= 1; pd.weighted_bipred_idc = P.weighted >= 2 ? 2 : 0;
     pd.is_ref = ps.is_ref; pd.has_inter = ps.type == SLICE_I ? 0 : (ps.type == SLICE_P ? 1 : 2);
     pd.chroma_qp_offset[0] = (int8_t)P.chroma_qp_offset; pd.chroma_qp_offset[1] = (int8_t)(high ? P.chroma_qp_offset - 1 : P.chroma_qp_offset);
     memcpy(pd.scaling4, scaling4, sizeof(scaling4)); memcpy(pd.scaling8, scaling8, sizeof(scaling8));
@@ -1033,6 +1033,8 @@ struct Encoder {
     if (high) {
       bool allowed = true;
       if ((!B && m.mbt >= 3) || (B && m.mbt == 22)) for (int q = 0; q < 4; ++q) { int t = m.sub[q]; if (B ? (t >= 4) : (t != 0)) allowed = false; }
+      // without direct_8x8_inference a macroblock with direct parts (whose motion may change every 4x4 block) has no 8x8 transform
+      if (B && !pd_of(slot).direct_8x8_inference) { if (m.mbt == 0) allowed = false; if (m.mbt == 22) for (int q = 0; q < 4; ++q) if (m.sub[q] == 0) allowed = false; }
       t8 = allowed && rng.pct(50);
     }
     const int qpc0 = chroma_qp(want_qp, pd_of(slot).chroma_qp_offset[0]), qpc1 = chroma_qp(want_qp, pd_of(slot).chroma_qp_offset[1]);

@@ -44,7 +44,9 @@ typedef struct hwgen_params {
   int32_t header_variant;  // 1: parameter-set ids other than 0 (sps 3, pps 7), pic_init_qp_minus26 = -4, num_ref_idx_default_active = 2 / 2 in
                            //    the PPS (slices override only when they differ), 6-bit frame_num and 5-bit pic_order_cnt_lsb (both wrap inside a
                            //    GOP), as encoders other than this one write their headers
-  int32_t reserved[2];
+  int32_t direct_4x4;      // 1: direct_8x8_inference_flag = 0 (direct prediction takes the co-located motion per 4x4 block; no 8x8 transform
+                           //    in macroblocks with direct parts), as Baseline-era encoders write it
+  int32_t reserved[1];
 } hwgen_params;
 
 void hwgen_default_params(hwgen_params *p);

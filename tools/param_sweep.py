@@ -29,7 +29,7 @@ for it in range(N):
               ipcm_per_100k=rng.choice([0, 0, 1500]), deblock=rng.choice([0, 0, 1, 2, 3]), constrained_intra=rng.choice([0, 0, 1]),
               cabac_init_idc=rng.choice([-1, 0, 1, 2]), chroma_qp_offset=rng.choice([0, 0, -2, 3]), direct_spatial=rng.choice([0, 1]),
               rplm_pct=rng.choice([0, 0, 40, 80]), mmco=rng.choice([0, 0, 1]), pad_refs=rng.choice([0, 0, 1]),
-              mixed_slices=rng.choice([0, 0, 1]), header_variant=rng.choice([0, 0, 1]), fragmented=rng.choice([0, 0, 1]))
+              mixed_slices=rng.choice([0, 0, 1]), header_variant=rng.choice([0, 0, 1]), direct_4x4=rng.choice([0, 0, 1]), fragmented=rng.choice([0, 0, 1]))
     if profile >= 1: kw['cabac'] = rng.choice([-1, -1, 0])
     if profile == 2: kw['scaling_lists'] = rng.choice([0, 0, 1])
     kw['weighted'] = rng.choice([0, 0, 1, 2, 3]) if profile >= 1 else 0
