@@ -851,7 +851,14 @@ struct Encoder {
     const int stype = sd.slice_type;  // the slice's type (a picture may mix I slices in)
     const bool B = stype == SLICE_B;
     int want_qp = s.qp;
-    if (P.qp_jitter && rng.pct(20)) want_qp = clip3(P.qp < 10 ? 0 : 8, P.qp > 44 ? 51 : 46, s.qp + rng.range(-P.qp_jitter, P.qp_jitter));  // (the full range only for extreme base QPs: older clips keep their streams)
+    // (the full QP range only for extreme base QPs: older clips keep their streams.  There the walk also crosses the 0 / 51 boundary:
+    // QP_Y = (QP_Y,pred + mb_qp_delta + 52) % 52, with the short way round as the coded difference)
+    const bool full_range = P.qp < 10 || P.qp > 44;
+    if (P.qp_jitter && rng.pct(20)) {
+      const int walk = s.qp + rng.range(-P.qp_jitter, P.qp_jitter);
+      want_qp = full_range ? (walk + 52) % 52 : clip3(8, 46, walk);
+    }
+    auto qp_delta = [&](int want, int pred) { int d = want - pred; if (d > 25) d -= 52; if (d < -26) d += 52; return d; };
     bool intra = stype == SLICE_I || rng.pct(P.intra_in_p_pct);
     Levels L;
     memset(&L, 0, sizeof(L));
@@ -914,7 +921,7 @@ struct Encoder {
       }
       m.mbt = m.imbt + (stype == SLICE_I ? 0 : (stype == SLICE_P ? 5 : 23));
       m.cbp = o.cbp;
-      if (o.cbp || !nxn) { m.dqp = want_qp - s.qp; o.qp = (uint8_t)want_qp; }
+      if (o.cbp || !nxn) { m.dqp = qp_delta(want_qp, s.qp); o.qp = (uint8_t)want_qp; }
       else { m.dqp = 0; o.qp = (uint8_t)s.qp; }
       mbs[addr] = o;
       rs = saved;
@@ -1043,7 +1050,7 @@ struct Encoder {
     emit_levels(s, o, false, t8, L);
     if (t8 && (o.cbp & 15)) { o.flags |= MBF_T8x8; m.t8 = true; }
     m.cbp = o.cbp;
-    if (o.cbp) { m.dqp = want_qp - s.qp; o.qp = (uint8_t)want_qp; }
+    if (o.cbp) { m.dqp = qp_delta(want_qp, s.qp); o.qp = (uint8_t)want_qp; }
     else { m.dqp = 0; o.qp = (uint8_t)s.qp; }
     if (!o.cbp && try_skip) { m.skipped = true; o.flags |= MBF_SKIP; }
     mbs[addr] = o;
